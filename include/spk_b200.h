@@ -1,0 +1,129 @@
+/* spk_b200.h — C ABI of the B200-native numeric factor/solve engine for Sparspak.jl's
+ * supernodal LU (SparseSolver) and LDL^T (SparseSpdSolver).
+ *
+ * Every pointer below is HOST memory owned by the caller (in the reference: Julia
+ * `Vector`s of the `_SparseBase` / `_SparseSpdBase` structs).  Index arrays are the
+ * reference's own 1-based Int64 arrays, passed unmodified.  Nothing is retained past a
+ * call except inside an explicit plan handle.  No torch / CUDA types appear here.
+ *
+ * Array lengths (SpkSparseBase.jl:99-125):
+ *   xsuper, xlindx : nsuper+1      snode, ipvt : n      xlnz, xunz : n+1
+ *   lindx : xlindx[nsuper]-1 (nsub)  lnz : xlnz[n]-1    unz : xunz[n]-1
+ *
+ * Return value of the factor entry points = the reference's `iflag`
+ * (SpkLUFactor.jl:29-34):  0 ok,  -1 zero pivot (ANY supernode — a documented superset of
+ * the reference, which keeps only the last supernode's status, SpkLUFactor.jl:230-233),
+ * -2 insufficient workspace (never produced here), and new codes
+ * -100 - cudaError for device/runtime failures (see spk_last_error()).  The library never aborts
+ * the calling process.
+ */
+#ifndef SPK_B200_H
+#define SPK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SPK_API __attribute__((visibility("default")))
+#else
+#define SPK_API
+#endif
+
+/* ---- stateless drop-ins: one call = upload, compute on the GPU, download ------------- */
+
+/* replaces _lufactor!(n,nsuper,xsuper,snode,xlindx,lindx,xlnz,lnz,xunz,unz,ipvt)
+ * src/SparseMethod/SpkLUFactor.jl:60-255, called from _factor! SpkSparseBase.jl:384 */
+SPK_API int64_t spk_lufactor_f64(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* snode,
+                                 const int64_t* xlindx, const int64_t* lindx, const int64_t* xlnz, double* lnz,
+                                 const int64_t* xunz, double* unz, int64_t* ipvt);
+
+/* replaces _lulsolve!(nsuper,xsuper,xlindx,lindx,xlnz,lnz,ipiv,rhs)  SpkLUFactor.jl:269-323
+ * (called from _triangularsolve! SpkSparseBase.jl:409).  rhs: length n = xsuper[nsuper]-1, permuted
+ * order, in place. */
+SPK_API int64_t spk_lulsolve_f64(int64_t nsuper, const int64_t* xsuper, const int64_t* xlindx,
+                                 const int64_t* lindx, const int64_t* xlnz, const double* lnz,
+                                 const int64_t* ipiv, double* rhs);
+
+/* replaces _luusolve!(n,nsuper,xsuper,xlindx,lindx,xlnz,lnz,xunz,unz,rhs)  SpkLUFactor.jl:325-377
+ * (SpkSparseBase.jl:411) */
+SPK_API int64_t spk_luusolve_f64(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* xlindx,
+                                 const int64_t* lindx, const int64_t* xlnz, const double* lnz,
+                                 const int64_t* xunz, const double* unz, double* rhs);
+
+/* replaces _ldltfactor!(n,nsuper,xsuper,snode,xlindx,lindx,xlnz,lnz)
+ * src/SparseSpdMethod/SpkLDLtFactor.jl:58-246, called from _factor! SpkSparseSpdBase.jl:325.
+ * Computes the INTENDED LDL^T (the reference code as written is defective: SURVEY.md §8a S3/S4). */
+SPK_API int64_t spk_ldltfactor_f64(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* snode,
+                                   const int64_t* xlindx, const int64_t* lindx, const int64_t* xlnz, double* lnz);
+
+/* replaces _ldltsolve!(nsuper,xsuper,xlindx,lindx,xlnz,lnz,rhs)  SpkLDLtFactor.jl:266-293
+ * (SpkSparseSpdBase.jl:351) */
+SPK_API int64_t spk_ldltsolve_f64(int64_t nsuper, const int64_t* xsuper, const int64_t* xlindx,
+                                  const int64_t* lindx, const int64_t* xlnz, const double* lnz, double* rhs);
+
+/* ---- stateful plan: structure + factors stay resident in HBM --------------------------
+ * One plan per symbolic factorisation (rebuild when symbolicfactor! reruns,
+ * SpkSparseSolver.jl:163-175).  Re-entrant per handle; every call is synchronous at return. */
+typedef struct spk_plan spk_plan;
+
+#define SPK_LU   0   /* xunz != NULL: supernodal LU with in-supernode partial pivoting */
+#define SPK_LDLT 1   /* xunz == NULL: supernodal LDL^T */
+
+/* device: CUDA ordinal.  part/nparts: elimination-subtree partition for multi-GPU
+ * (part 0 of 1 = whole matrix).  Returns NULL on failure (see spk_last_error()). */
+SPK_API spk_plan* spk_plan_create(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* snode,
+                                  const int64_t* xlindx, const int64_t* lindx, const int64_t* xlnz,
+                                  const int64_t* xunz_or_null, int32_t device, int32_t part, int32_t nparts);
+SPK_API void spk_plan_destroy(spk_plan* p);
+
+/* _inmatrix! on the device (SpkSparseBase.jl:302-372 / SpkSparseSpdBase.jl:234-311): zero lnz/unz,
+ * then lnz[dest[k]-1] += nzval[k] (dest>0) or unz[-dest[k]-1] += nzval[k] (dest<0); dest==0 skipped.
+ * dest is uploaded once per plan (pass NULL afterwards to reuse it). */
+SPK_API int64_t spk_plan_inmatrix(spk_plan* p, int64_t nnz, const int64_t* dest_or_null, const double* nzval);
+
+/* upload assembled lnz/unz (what _inmatrix! produced on the host) */
+SPK_API int64_t spk_plan_set_values(spk_plan* p, const double* lnz, const double* unz_or_null);
+
+/* numeric factorisation of the resident values; returns iflag */
+SPK_API int64_t spk_plan_factor(spk_plan* p);
+
+/* download factors in the reference layout (any pointer may be NULL to skip) */
+SPK_API int64_t spk_plan_get_factors(spk_plan* p, double* lnz, double* unz, int64_t* ipvt);
+/* upload factors computed elsewhere (stateless solve entry points use this) */
+SPK_API int64_t spk_plan_set_factors(spk_plan* p, const double* lnz, const double* unz_or_null, const int64_t* ipvt_or_null);
+
+/* forward+backward solve of nrhs right-hand sides held column-major (ld = ldrhs >= n) in the
+ * PERMUTED order the reference's numeric routines use; in place.
+ * which: 0 = both sweeps, 1 = forward only (_lulsolve!), 2 = backward only (_luusolve!). */
+SPK_API int64_t spk_plan_solve(spk_plan* p, double* rhs, int64_t nrhs, int64_t ldrhs, int32_t which);
+
+/* _triangularsolve! (SpkSparseBase.jl:400-416): x := P^T solve(P b) with the 1-based
+ * permutations given once (rperm, rinvp: length n); b in original order, in place. */
+SPK_API int64_t spk_plan_set_perm(spk_plan* p, const int64_t* rperm, const int64_t* rinvp);
+SPK_API int64_t spk_plan_triangularsolve(spk_plan* p, double* b, int64_t nrhs, int64_t ldb);
+
+/* ---- device-resident variants used by bench.py / multi-GPU drivers -------------------- */
+SPK_API void*   spk_plan_device_ptr(spk_plan* p, int32_t what);   /* 0 lnz, 1 unz, 2 ipiv(int32), 3 tail lnz, 4 tail unz */
+SPK_API int64_t spk_plan_device_len(spk_plan* p, int32_t what);   /* element counts of the above */
+SPK_API int64_t spk_plan_factor_phase(spk_plan* p, int32_t phase); /* multi-GPU: 0 local subtrees, 1 top set */
+SPK_API int64_t spk_plan_solve_device(spk_plan* p, double* d_rhs, int64_t nrhs, int64_t ldrhs, int32_t which);
+
+/* ---- introspection --------------------------------------------------------------------- */
+/* what: 0 kernel launches of the last factor, 1 of the last solve, 2 #fronts, 3 #levels,
+ *       4 device bytes held, 5 #big fronts, 6 update-matrix (S) doubles */
+SPK_API int64_t spk_plan_stat(spk_plan* p, int32_t what);
+/* what: 0 structural factor flops (sum cc^2 for LDLT, 2 sum cc^2 - sum cc for LU), 1 nnz(L)=sum cc,
+ *       2 ms of the last factor (CUDA events), 3 ms of the last solve,
+ *       4 flops executed by the dominant GEMM kernel in the last factor, 5 ms spent in it */
+SPK_API double  spk_plan_statf(spk_plan* p, int32_t what);
+SPK_API const char* spk_last_error(void);
+SPK_API int32_t spk_device_count(void);
+SPK_API const char* spk_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPK_B200_H */
