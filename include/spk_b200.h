@@ -84,6 +84,9 @@ SPK_API void spk_plan_destroy(spk_plan* p);
  * dest is uploaded once per plan (pass NULL afterwards to reuse it). */
 SPK_API int64_t spk_plan_inmatrix(spk_plan* p, int64_t nnz, const int64_t* dest_or_null, const double* nzval);
 
+/* the same with the values already resident from the last spk_plan_inmatrix (no host traffic; asynchronous) */
+SPK_API int64_t spk_plan_reassemble(spk_plan* p);
+
 /* upload assembled lnz/unz (what _inmatrix! produced on the host) */
 SPK_API int64_t spk_plan_set_values(spk_plan* p, const double* lnz, const double* unz_or_null);
 
@@ -117,7 +120,8 @@ SPK_API int64_t spk_plan_solve_device(spk_plan* p, double* d_rhs, int64_t nrhs, 
 SPK_API int64_t spk_plan_stat(spk_plan* p, int32_t what);
 /* what: 0 structural factor flops (sum cc^2 for LDLT, 2 sum cc^2 - sum cc for LU), 1 nnz(L)=sum cc,
  *       2 ms of the last factor (CUDA events), 3 ms of the last solve,
- *       4 flops executed by the dominant GEMM kernel in the last factor, 5 ms spent in it */
+ *       4 flops executed by the DMMA trailing-update kernels in the last factor, 5 ms spent in them
+ *       (5 and 10+kind / 30+kind = ms / launches per kernel kind need profiling mode: spk_plan_stat(p, 100)) */
 SPK_API double  spk_plan_statf(spk_plan* p, int32_t what);
 SPK_API const char* spk_last_error(void);
 SPK_API int32_t spk_device_count(void);

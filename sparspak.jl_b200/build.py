@@ -1,5 +1,4 @@
-"""In-tree builds: the CUDA C-ABI library (sm_100a), the host structure library and
-the oracle.  Built artefacts are git-ignored but travel to the GPU box with the
+"""In-tree builds: the CUDA C-ABI library (sm_100a) and the host structure library.  Built artefacts are git-ignored but travel to the GPU box with the
 gpurun snapshot, so nothing is JIT-compiled there."""
 import os
 import shutil
@@ -10,12 +9,10 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 HOST = os.path.join(PKG_DIR, "host")
-ORACLE = os.path.join(ROOT, "oracle")
 INCLUDE = os.path.join(ROOT, "include")
 
 LIB_CUDA = os.path.join(CSRC, "libspkb200.so")
 LIB_HOST = os.path.join(HOST, "libspkhost.so")
-LIB_ORACLE = os.path.join(ORACLE, "libspkoracle.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
@@ -46,20 +43,13 @@ def build_host(force=False):
     return LIB_HOST
 
 
-def build_oracle(force=False):
-    src = [os.path.join(ORACLE, "spk_oracle.c")]
-    if force or _stale(LIB_ORACLE, src):
-        _run(["gcc", "-O2", "-std=c11", "-shared", "-fPIC", "-fvisibility=hidden", "-o", LIB_ORACLE] + src + ["-ldl", "-lm"])
-    return LIB_ORACLE
-
-
 def cuda_sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
 def build_cuda(force=False, verbose=False):
     srcs = cuda_sources()
-    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh", ".hpp"))]
     deps += [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)]
     if not (force or _stale(LIB_CUDA, deps)):
         return LIB_CUDA
@@ -76,10 +66,9 @@ def build_cuda(force=False, verbose=False):
 
 def build_all(force=False):
     build_host(force)
-    build_oracle(force)
     build_cuda(force)
 
 
 if __name__ == "__main__":
     build_all(force="--force" in sys.argv)
-    print("built:", LIB_HOST, LIB_ORACLE, LIB_CUDA)
+    print("built:", LIB_HOST, LIB_CUDA)

@@ -1,0 +1,493 @@
+// kernels.cuh — sm_100a kernels of the multifrontal supernodal LU / LDL^T engine.
+//
+// All kernels are "task-list" kernels: one launch executes a list of independent tasks
+// built at plan time (plan.hpp); a thread block finds its task by binary search in a
+// block-prefix array.  Dense work happens in frontal matrices held in a device arena;
+// the reference layout (lnz / unz, SpkSparseBase.jl:1-87) is gathered from / scattered to
+// by k_load_chunks / k_store_chunks, and read directly by the triangular solves.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "plan.hpp"
+
+namespace spk {
+
+struct DFront {
+    int64_t fofs, relofs, wofs, F0;
+    int32_t W, R, m, ld, parent, child0, nchild, pad;
+};
+struct DChunk {
+    int64_t lofs, uofs, posofs, fofs;
+    int32_t nj, jlen, o, ld;
+};
+
+struct DevCtx {
+    double* F;                       // frontal-matrix arena
+    double* lnz; double* unz; double* w;
+    int32_t* ipiv; int32_t* iflag;
+    const DFront* fronts; const DChunk* chunks; const PStep* psteps; const int32_t* subw;
+    const int32_t* childlist; const int32_t* rel; const int32_t* pos;
+    const SolveTask* solvet;
+    int64_t wlen;
+    int32_t lu;
+};
+
+__device__ __forceinline__ int find_task(const int32_t* __restrict__ pfx, int count, int b) {
+    int lo = 0, hi = count;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (pfx[mid] <= b) lo = mid; else hi = mid; }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------------
+// inmatrix on the device (SpkSparseBase.jl:302-372): scatter A's values
+// straight into the frontal matrices through a destination map built once per pattern.
+// A duplicate-free CSC gives unique destinations, so no atomics are needed.
+__global__ void k_scatter_values(int64_t nnz, const int64_t* __restrict__ dest, const double* __restrict__ v,
+                                 double* __restrict__ F) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nnz) return;
+    int64_t d = dest[k];
+    if (d >= 0) F[d] += v[k];
+}
+
+// reference layout -> fronts (values assembled by the host _inmatrix!) and back (factors)
+constexpr int CHUNK_EPB = 1024;      // entries per block
+template <bool STORE>
+__global__ void __launch_bounds__(256) k_chunks(DevCtx c, const int32_t* __restrict__ pfx, int count) {
+    int t = find_task(pfx, count, blockIdx.x);
+    int lb = blockIdx.x - pfx[t];
+    const DChunk ch = c.chunks[t];
+    const int32_t* __restrict__ pos = c.pos + ch.posofs;
+    double* __restrict__ F = c.F + ch.fofs;
+    const int64_t nl = (int64_t)ch.jlen * ch.nj;
+    const int64_t nu = c.lu ? (int64_t)(ch.jlen - ch.nj) * ch.nj : 0;
+    const int ldu = ch.jlen - ch.nj;
+    for (int it = 0; it < CHUNK_EPB / 256; ++it) {
+        int64_t e = (int64_t)lb * CHUNK_EPB + it * 256 + threadIdx.x;
+        if (e < nl) {
+            int j = (int)(e / ch.jlen), i = (int)(e - (int64_t)j * ch.jlen);
+            int64_t f = (int64_t)pos[i] + (int64_t)(ch.o + j) * ch.ld;
+            if (STORE) c.lnz[ch.lofs + e] = F[f]; else F[f] = c.lnz[ch.lofs + e];
+        } else if (e - nl < nu) {
+            int64_t eu = e - nl;
+            int j = (int)(eu / ldu), i = (int)(eu - (int64_t)j * ldu);
+            int64_t f = (int64_t)(ch.o + j) + (int64_t)pos[ch.nj + i] * ch.ld;
+            if (STORE) c.unz[ch.uofs + eu] = F[f]; else F[f] = c.unz[ch.uofs + eu];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Extend-add of one child's update matrix into its parent front (the reference's
+// _assmb!/_mmpyi! scatter through relative indices, SpkSpdMMOps.jl:41-49,125-143,
+// re-expressed child -> parent).  Entry (i,j) of S_child goes to exactly one place.
+__device__ __forceinline__ void asm_entry(const DevCtx& c, const DFront& C, const DFront& P,
+                                          const int32_t* __restrict__ rel, int64_t e) {
+    const int32_t m = C.m;
+    const int32_t j = (int32_t)(e / m), i = (int32_t)(e - (int64_t)j * m);
+    if (!c.lu && i < j) return;                       // LDL^T: lower triangle only
+    const double v = c.F[C.fofs + (int64_t)(C.W + i) + (int64_t)(C.W + j) * C.ld];
+    c.F[P.fofs + (int64_t)rel[i] + (int64_t)rel[j] * P.ld] += v;
+}
+
+__global__ void __launch_bounds__(ASM_TPB) k_assemble(DevCtx c, const AsmTask* __restrict__ tasks,
+                                                     const int32_t* __restrict__ pfx, int count) {
+    int t = find_task(pfx, count, blockIdx.x);
+    int lb = blockIdx.x - pfx[t];
+    AsmTask a = tasks[t];
+    const DFront C = c.fronts[a.child], P = c.fronts[a.parent];
+    const int32_t* rel = c.rel + C.relofs;
+    int64_t total = (int64_t)C.m * C.m;
+    int64_t e = (int64_t)lb * (ASM_TPB * ASM_EPT) + threadIdx.x;
+#pragma unroll
+    for (int it = 0; it < ASM_EPT; ++it, e += ASM_TPB)
+        if (e < total) asm_entry(c, C, P, rel, e);
+}
+
+// parents with more than ASM_ROUNDS children: one block walks the remaining children in order
+__global__ void __launch_bounds__(256) k_assemble_tail(DevCtx c, const AsmTask* __restrict__ tasks, int count) {
+    AsmTask a = tasks[blockIdx.x];
+    const DFront P = c.fronts[a.parent];
+    for (int r = ASM_ROUNDS; r < P.nchild; ++r) {
+        const DFront C = c.fronts[c.childlist[P.child0 + r]];
+        const int32_t* rel = c.rel + C.relofs;
+        int64_t total = (int64_t)C.m * C.m;
+        for (int64_t e = threadIdx.x; e < total; e += blockDim.x) asm_entry(c, C, P, rel, e);
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Diagonal block of a panel step (w x w, one or more chunks).
+// LU: partial pivoting restricted to each chunk's own rows, first maximum wins (ggetrf!,
+// GenericBlasLapackFragments.jl:64-74 == LAPACK idamax); row interchanges are applied from the
+// chunk's first column rightwards (never to L entries of earlier chunks), ipiv is chunk-local
+// 1-based (SpkLUFactor.jl:230).  LDL^T: the intended _pchole! in-block part
+// (SpkLDLtFactor.jl:351-362).
+template <bool LU>
+__device__ void diag_factor(double* A, int lda, int w, const int32_t* __restrict__ subw, int nsub,
+                            int32_t* ipiv, int32_t* iflag, int32_t* s_piv, double* s_pv) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (LU) {
+        int s0 = 0;
+        for (int b = 0; b < nsub; ++b) {
+            const int s1 = s0 + subw[b];
+            for (int k = s0; k < s1; ++k) {
+                if (tid < 32) {
+                    double best = -1.0; int bi = 0x7fffffff;
+                    for (int i = k + tid; i < s1; i += 32) {
+                        double v = fabs(A[i + (size_t)k * lda]);
+                        if (v > best) { best = v; bi = i; }
+                    }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        double ob = __shfl_xor_sync(0xffffffffu, best, off);
+                        int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                    }
+                    if (tid == 0) {
+                        if (bi == 0x7fffffff) bi = k;                  // only NaNs: keep the diagonal
+                        double pv0 = A[bi + (size_t)k * lda];
+                        *s_piv = bi; *s_pv = pv0; ipiv[k] = bi - s0 + 1;
+                        if (pv0 == 0.0) atomicExch(iflag, -1);
+                    }
+                }
+                __syncthreads();
+                const int kp = *s_piv;
+                const double pv = *s_pv;
+                if (kp != k && pv != 0.0)
+                    for (int j = s0 + tid; j < w; j += nt) {
+                        double t = A[k + (size_t)j * lda]; A[k + (size_t)j * lda] = A[kp + (size_t)j * lda]; A[kp + (size_t)j * lda] = t;
+                    }
+                __syncthreads();
+                if (pv != 0.0) {
+                    const double inv = 1.0 / A[k + (size_t)k * lda];
+                    for (int i = k + 1 + tid; i < w; i += nt) A[i + (size_t)k * lda] *= inv;
+                }
+                __syncthreads();
+                const int rem = w - k - 1;
+                for (int e = tid; e < rem * rem; e += nt) {
+                    int j = k + 1 + e / rem, i = k + 1 + e % rem;
+                    A[i + (size_t)j * lda] -= A[i + (size_t)k * lda] * A[k + (size_t)j * lda];
+                }
+                __syncthreads();
+            }
+            s0 = s1;
+        }
+    } else {
+        for (int k = 0; k < w; ++k) {
+            const double d = A[k + (size_t)k * lda];
+            if (tid == 0 && d == 0.0) atomicExch(iflag, -1);
+            __syncthreads();
+            for (int i = k + 1 + tid; i < w; i += nt) A[i + (size_t)k * lda] /= d;
+            __syncthreads();
+            const int rem = w - k - 1;
+            for (int e = tid; e < rem * rem; e += nt) {
+                int s = k + 1 + e / rem, r = k + 1 + e % rem;
+                if (r >= s) A[r + (size_t)s * lda] -= (A[s + (size_t)k * lda] * d) * A[r + (size_t)k * lda];
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <bool LU>
+__global__ void __launch_bounds__(256) k_diag(DevCtx c, const int32_t* __restrict__ pslist, int smem_w) {
+    extern __shared__ double sm[];
+    __shared__ int32_t s_piv;
+    __shared__ double s_pv;
+    const PStep ps = c.psteps[pslist[blockIdx.x]];
+    double* G = c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld;
+    const int w = ps.w, ld = ps.ld;
+    int32_t* ipiv = c.ipiv + ps.col0;
+    const int32_t* subw = c.subw + ps.sub0;
+    if (w <= smem_w) {
+        const int lds = w | 1;                          // odd leading dimension: conflict-free columns
+        for (int e = threadIdx.x; e < w * w; e += blockDim.x) { int j = e / w, i = e % w; sm[i + j * lds] = G[i + (size_t)j * ld]; }
+        __syncthreads();
+        diag_factor<LU>(sm, lds, w, subw, ps.nsub, ipiv, c.iflag, &s_piv, &s_pv);
+        for (int e = threadIdx.x; e < w * w; e += blockDim.x) { int j = e / w, i = e % w; G[i + (size_t)j * ld] = sm[i + j * lds]; }
+    } else {
+        diag_factor<LU>(G, ld, w, subw, ps.nsub, ipiv, c.iflag, &s_piv, &s_pv);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Panels of a panel step: one thread per front row below (L side) / per front column to the right (U side).
+//   LU  L-side: X = A21 * inv(U11)                     (dtrsm 'r','u','n','n', SpkLUFactor.jl:235)
+//   LU  U-side: per chunk, apply its row interchanges then inv(L11)  (:238-240, _luswap! SpkSpdMMOps.jl:168-175)
+//   LDLT:       X = A21 * inv(L11^T), then each column / D  (SpkLDLtFactor.jl:367-377)
+template <bool LU>
+__global__ void __launch_bounds__(PANEL_ROWS) k_panel(DevCtx c, const int32_t* __restrict__ pslist,
+                                                      const int32_t* __restrict__ pfx, int count) {
+    int t = find_task(pfx, count, blockIdx.x);
+    int lb = blockIdx.x - pfx[t];
+    const PStep ps = c.psteps[pslist[t]];
+    const int w = ps.w, ld = ps.ld, e0 = ps.o + ps.w;
+    const int below = ps.R - e0;
+    const int nb = (below + PANEL_ROWS - 1) / PANEL_ROWS;
+    double* Fm = c.F + ps.fofs;
+    const double* __restrict__ T = Fm + (int64_t)ps.o + (int64_t)ps.o * ld;   // factored w x w block
+    if (lb < nb) {
+        int i = lb * PANEL_ROWS + threadIdx.x;
+        if (i >= below) return;
+        double* X = Fm + (int64_t)(e0 + i) + (int64_t)ps.o * ld;               // row of the L panel, stride ld
+        if (LU) {
+            for (int j = 0; j < w; ++j) {
+                double acc = X[(size_t)j * ld];
+                for (int k = 0; k < j; ++k) acc -= T[k + (size_t)j * ld] * X[(size_t)k * ld];
+                X[(size_t)j * ld] = (1.0 / T[j + (size_t)j * ld]) * acc;
+            }
+        } else {
+            for (int j = 0; j < w; ++j) {
+                double acc = X[(size_t)j * ld];
+                for (int k = 0; k < j; ++k) acc -= T[j + (size_t)k * ld] * X[(size_t)k * ld];
+                X[(size_t)j * ld] = acc;
+            }
+            for (int j = 0; j < w; ++j) X[(size_t)j * ld] /= T[j + (size_t)j * ld];
+        }
+    } else if (LU) {
+        int i = (lb - nb) * PANEL_ROWS + threadIdx.x;
+        if (i >= below) return;
+        double* Y = Fm + (int64_t)ps.o + (int64_t)(e0 + i) * ld;               // column of the U panel: w contiguous entries
+        const int32_t* ipiv = c.ipiv + ps.col0;
+        const int32_t* subw = c.subw + ps.sub0;
+        int s0 = 0;
+        for (int b = 0; b < ps.nsub; ++b) {
+            const int s1 = s0 + subw[b];
+            for (int j = s0; j < s1; ++j) {                                    // contributions of earlier chunks (unswapped rows)
+                double acc = Y[j];
+                for (int k = 0; k < s0; ++k) acc -= T[j + (size_t)k * ld] * Y[k];
+                Y[j] = acc;
+            }
+            for (int k = s0; k < s1; ++k) {                                    // this chunk's interchanges
+                int ip = s0 + ipiv[k] - 1;
+                if (ip != k) { double tmp = Y[k]; Y[k] = Y[ip]; Y[ip] = tmp; }
+            }
+            for (int j = s0; j < s1; ++j) {                                    // unit-lower solve inside the chunk
+                double acc = Y[j];
+                for (int k = s0; k < j; ++k) acc -= T[j + (size_t)k * ld] * Y[k];
+                Y[j] = acc;
+            }
+            s0 = s1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// C -= A * B inside a frontal matrix (small-tile DFMA kernel; 64x64 tile, 4x4 per thread).
+// The big-tile DMMA kernels live in gemm_dmma.cuh.
+__global__ void __launch_bounds__(256) k_gemm_small(DevCtx c, const GemmTask* __restrict__ tasks,
+                                                    const int32_t* __restrict__ pfx, int count) {
+    constexpr int TM = GEMM_TM, TN = GEMM_TN, TK = 16;
+    __shared__ double As[TK][TM + 4];
+    __shared__ double Bs[TK][TN + 4];
+    int t = find_task(pfx, count, blockIdx.x);
+    int lb = blockIdx.x - pfx[t];
+    const GemmTask g = tasks[t];
+    const int mt = (g.m + TM - 1) / TM;
+    const int row0 = (lb % mt) * TM, col0 = (lb / mt) * TN;
+    if (g.lower && row0 + TM - 1 + g.roff < col0) return;   // tile strictly above the diagonal
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    const double* __restrict__ A = c.F + g.a0;
+    const double* __restrict__ B = c.F + g.b0;
+    const double* __restrict__ D = c.F + g.d0;
+    const int ld = g.ld;
+    for (int k0 = 0; k0 < g.k; k0 += TK) {
+        {   // A tile: rows contiguous
+            const int lr = tid & 63, lk = tid >> 6;
+#pragma unroll
+            for (int p = 0; p < TK / 4; ++p) {
+                int kk = lk + p * 4, kg = k0 + kk;
+                double a = 0.0;
+                if (kg < g.k && row0 + lr < g.m) a = A[(size_t)(row0 + lr) + (size_t)kg * ld];
+                As[kk][lr] = a;
+                if (!g.bk) {
+                    double b = 0.0;
+                    if (kg < g.k && col0 + lr < g.n) b = B[(size_t)(col0 + lr) + (size_t)kg * ld] * D[(size_t)kg * (ld + 1)];
+                    Bs[kk][lr] = b;
+                }
+            }
+        }
+        if (g.bk) {  // B tile: k contiguous
+            const int kk = tid & 15, ln = tid >> 4;
+#pragma unroll
+            for (int p = 0; p < TN / 16; ++p) {
+                int nn = ln + p * 16, kg = k0 + kk;
+                double b = 0.0;
+                if (kg < g.k && col0 + nn < g.n) b = B[(size_t)kg + (size_t)(col0 + nn) * ld];
+                Bs[kk][nn] = b;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < TK; ++kk) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = As[kk][tx * 4 + i]; b[i] = Bs[kk][ty * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+        }
+        __syncthreads();
+    }
+    double* __restrict__ C = c.F + g.c0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int cc = col0 + ty * 4 + j;
+        if (cc >= g.n) continue;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int r = row0 + tx * 4 + i;
+            if (r < g.m && !(g.lower && r + g.roff < cc)) C[(size_t)r + (size_t)cc * ld] -= acc[i][j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Triangular solves (SpkLUFactor.jl:269-377, SpkLDLtFactor.jl:266-293), level-scheduled over
+// the front tree, reading lnz / unz in the reference layout.  Each front owns a work vector
+// w_f indexed by front row: [unknowns of the front (W) ; contributions / values of the rows below (m)].
+// blockIdx.y = right-hand side.
+__global__ void __launch_bounds__(256) k_fwd_gather(DevCtx c, const int32_t* __restrict__ flist,
+                                                    const double* __restrict__ rhs, int64_t ldrhs) {
+    const DFront F = c.fronts[flist[blockIdx.x]];
+    double* w = c.w + (size_t)blockIdx.y * c.wlen + F.wofs;
+    const double* b = rhs + (size_t)blockIdx.y * ldrhs + F.F0;
+    for (int i = threadIdx.x; i < F.R; i += blockDim.x) w[i] = i < F.W ? b[i] : 0.0;
+    __syncthreads();
+    for (int r = 0; r < F.nchild; ++r) {
+        const DFront C = c.fronts[c.childlist[F.child0 + r]];
+        const double* wc = c.w + (size_t)blockIdx.y * c.wlen + C.wofs + C.W;
+        const int32_t* rel = c.rel + C.relofs;
+        for (int i = threadIdx.x; i < C.m; i += blockDim.x) w[rel[i]] += wc[i];
+        __syncthreads();
+    }
+}
+
+template <bool LU>
+__global__ void __launch_bounds__(128) k_fwd_diag(DevCtx c, const int32_t* __restrict__ clist) {
+    const SolveTask t = c.solvet[clist[blockIdx.x]];
+    double* x = c.w + (size_t)blockIdx.y * c.wlen + t.wofs + t.o;
+    const double* __restrict__ T = c.lnz + t.lofs;
+    if (LU) {
+        if (threadIdx.x == 0) {
+            const int32_t* ipiv = c.ipiv + t.col0;
+            for (int k = 0; k < t.nj; ++k) { int ip = ipiv[k] - 1; if (ip != k) { double tmp = x[k]; x[k] = x[ip]; x[ip] = tmp; } }
+        }
+        __syncthreads();
+    }
+    for (int k = 0; k < t.nj - 1; ++k) {
+        double xk = x[k];
+        for (int i = k + 1 + threadIdx.x; i < t.nj; i += blockDim.x) x[i] -= xk * T[i + (size_t)k * t.ld];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(UPD_ROWS) k_fwd_update(DevCtx c, const int32_t* __restrict__ clist,
+                                                         const int32_t* __restrict__ pfx, int count) {
+    int ti = find_task(pfx, count, blockIdx.x);
+    int lb = blockIdx.x - pfx[ti];
+    const SolveTask t = c.solvet[clist[ti]];
+    int i = lb * UPD_ROWS + threadIdx.x;
+    if (i >= t.m) return;
+    double* wf = c.w + (size_t)blockIdx.y * c.wlen + t.wofs;
+    const double* xk = wf + t.o;
+    const double* __restrict__ L = c.lnz + t.lofs + t.nj + i;
+    double acc = 0.0;
+    for (int k = 0; k < t.nj; ++k) acc += (-xk[k]) * L[(size_t)k * t.ld];
+    wf[c.pos[t.posofs + t.nj + i]] += acc;
+}
+
+__global__ void __launch_bounds__(256) k_bwd_gather(DevCtx c, const int32_t* __restrict__ flist,
+                                                    const int32_t* __restrict__ pfx, int count) {
+    int ti = find_task(pfx, count, blockIdx.x);
+    int lb = blockIdx.x - pfx[ti];
+    const DFront F = c.fronts[flist[ti]];
+    int i = lb * 256 + threadIdx.x;
+    if (i >= F.m) return;
+    const DFront P = c.fronts[F.parent];
+    const double* wp = c.w + (size_t)blockIdx.y * c.wlen + P.wofs;
+    double* w = c.w + (size_t)blockIdx.y * c.wlen + F.wofs;
+    w[F.W + i] = wp[c.rel[F.relofs + i]];
+}
+
+// one warp per column k of the chunk: x_k -= sum_i B[i,k] * x_below[i]
+template <bool LU>
+__global__ void __launch_bounds__(BWD_COLS * 32) k_bwd_update(DevCtx c, const int32_t* __restrict__ clist,
+                                                              const int32_t* __restrict__ pfx, int count) {
+    int ti = find_task(pfx, count, blockIdx.x);
+    int lb = blockIdx.x - pfx[ti];
+    const SolveTask t = c.solvet[clist[ti]];
+    int k = lb * BWD_COLS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (k >= t.nj) return;
+    double* wf = c.w + (size_t)blockIdx.y * c.wlen + t.wofs;
+    const double* __restrict__ B = LU ? c.unz + t.uofs + (size_t)k * t.ldu : c.lnz + t.lofs + t.nj + (size_t)k * t.ld;
+    const int32_t* __restrict__ pos = c.pos + t.posofs + t.nj;
+    double s = 0.0;
+    for (int i = lane; i < t.m; i += 32) s += B[i] * wf[pos[i]];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) {
+        double* xk = wf + t.o + k;
+        if (LU) *xk += -s;
+        else *xk = *xk / c.lnz[t.lofs + k + (size_t)k * t.ld] - s;
+    }
+}
+
+template <bool LU>
+__global__ void __launch_bounds__(128) k_bwd_diag(DevCtx c, const int32_t* __restrict__ clist,
+                                                  double* __restrict__ rhs, int64_t ldrhs) {
+    const SolveTask t = c.solvet[clist[blockIdx.x]];
+    double* x = c.w + (size_t)blockIdx.y * c.wlen + t.wofs + t.o;
+    const double* __restrict__ T = c.lnz + t.lofs;
+    for (int k = t.nj - 1; k >= 0; --k) {
+        if (LU) {
+            if (threadIdx.x == 0) x[k] /= T[k + (size_t)k * t.ld];
+            __syncthreads();
+            double xk = x[k];
+            for (int i = threadIdx.x; i < k; i += blockDim.x) x[i] -= xk * T[i + (size_t)k * t.ld];
+        } else {
+            double xk = x[k];
+            for (int i = threadIdx.x; i < k; i += blockDim.x) x[i] -= xk * T[k + (size_t)i * t.ld];
+        }
+        __syncthreads();
+    }
+    double* out = rhs + (size_t)blockIdx.y * ldrhs + t.col0;
+    for (int k = threadIdx.x; k < t.nj; k += blockDim.x) out[k] = x[k];
+}
+
+// forward-only result / backward-only input: copy between rhs and the front vectors
+__global__ void k_copy_front_x(DevCtx c, int nfronts, double* __restrict__ rhs, int64_t ldrhs, int to_rhs) {
+    int f = blockIdx.x;
+    if (f >= nfronts) return;
+    const DFront F = c.fronts[f];
+    double* w = c.w + (size_t)blockIdx.y * c.wlen + F.wofs;
+    double* b = rhs + (size_t)blockIdx.y * ldrhs + F.F0;
+    for (int i = threadIdx.x; i < F.W; i += blockDim.x) { if (to_rhs) b[i] = w[i]; else w[i] = b[i]; }
+}
+
+// rhs permutation gathers of _triangularsolve! (SpkSparseBase.jl:406-413): out[i] = in[idx[i]-1]
+__global__ void k_perm_gather(int64_t n, const int64_t* __restrict__ idx, const double* __restrict__ in,
+                              double* __restrict__ out, int64_t ldin, int64_t ldout) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[(size_t)blockIdx.y * ldout + i] = in[(size_t)blockIdx.y * ldin + idx[i] - 1];
+}
+
+__global__ void k_ipiv_widen(int64_t n, const int32_t* __restrict__ in, int64_t* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+__global__ void k_ipiv_narrow(int64_t n, const int64_t* __restrict__ in, int32_t* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int32_t)in[i];
+}
+
+} // namespace spk

@@ -1,0 +1,481 @@
+// plan.hpp — host-side static analysis of a symbolic factorisation into a device schedule.
+//
+// Input: the reference's flat 1-based arrays (xsuper, snode, xlindx, lindx, xlnz, xunz;
+// SpkSparseBase.jl:99-125).  Output:
+//   * FRONTS: chains of consecutive reference supernodes ("chunks") whose row structures nest
+//     (exactly = the fundamental supernodes the reference split at ~maxblocksize,
+//     SpkSymFct.jl:415-464; or up to a few extra rows = relaxed chains, which absorb the long
+//     runs of one-column supernodes a 7-point nested dissection produces).  Each front is a dense
+//     R x R frontal matrix (column-major, padded ld) in a private device arena:
+//         [ F11 (W x W)   F12 = U12 ]      W = columns of the front,
+//         [ F21 = L21     S         ]      S = update matrix handed to the parent front.
+//   * the front tree with relative-index maps (child below-rows -> parent rows),
+//   * per-chunk position maps (stored row of the reference layout -> front row),
+//   * per-level LAUNCH lists of independent TASKS.
+// The reference's own layout (lnz / unz) is what goes in and what comes out: values are
+// gathered into the fronts and the factors are scattered back, so the caller sees exactly
+// the arrays `_lufactor!` / `_ldltfactor!` would have produced.
+//
+// Pure C++ (no CUDA) so tests can execute the same task lists on the host
+// (tests/hostsim) to validate the schedule independently of the kernels.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+namespace spk {
+
+struct Chunk {            // one reference supernode
+    int64_t fj;           // first column (0-based)
+    int64_t lofs, uofs;   // start of its block in lnz / unz (0-based)
+    int64_t posofs;       // pos[posofs + i] = front row of stored row i (i < jlen)
+    int64_t fofs;         // owning front's matrix
+    int32_t nj, jlen;     // width, rows
+    int32_t front, o;     // owning front, column offset inside the front
+    int32_t ld, pad;      // owning front's leading dimension
+};
+
+struct Front {
+    int64_t F0;           // first column (0-based)
+    int64_t fofs;         // frontal matrix in the arena (doubles), ld below
+    int64_t relofs;       // rel[relofs + i] = row of below-row i in the PARENT front
+    int64_t wofs;         // solve work vector (R entries)
+    int32_t c0, nch;      // chunk range
+    int32_t W, R, m, ld;  // columns, rows, m = R - W, leading dimension (R padded)
+    int32_t parent, level;
+    int32_t child0, nchild;
+    int32_t ps0, nps;     // panel steps
+};
+
+// One panel step of the dense partial factorisation of a front: columns [o, o+w), made of
+// `nsub` consecutive chunks (pivoting is restricted to each chunk's own diagonal block,
+// SpkLUFactor.jl:230).  ob_end = first column after the outer block this step belongs to.
+struct PStep {
+    int64_t fofs, col0;   // front matrix; global first column (ipiv index)
+    int32_t ld, R, o, w, ob_end, sub0, nsub, front;
+};
+
+struct GemmTask {         // C -= A * B   inside one frontal matrix (offsets relative to the arena)
+    int64_t a0, b0, c0, d0;   // element offsets of A(0,0), B(0,0), C(0,0), D(0) (LDL^T scaling)
+    int32_t ld, m, n, k;
+    int32_t roff;         // row index of C(0,0) minus its column index inside the front (for `lower`)
+    uint8_t bk;           // 1: B(k,n) at b0 + k + n*ld (LU: a row block of U);  0: B(n,k) at b0 + n + k*ld, scaled by D
+    uint8_t lower;        // only entries on/below the front's diagonal are needed / written
+    uint8_t pad0, pad1;
+};
+struct AsmTask { int32_t child, parent; };
+struct SolveTask {        // one chunk of a triangular sweep (values read from lnz / unz)
+    int64_t lofs, uofs, col0, wofs, posofs;
+    int32_t ld, ldu, nj, m, o, front;
+};
+
+enum Kind : int32_t {
+    K_ASM = 0, K_ASM_TAIL, K_DIAG, K_PANEL, K_GEMM, K_GEMM_B64, K_GEMM_B128,
+    K_FWD_GATHER, K_FWD_DIAG, K_FWD_UPDATE, K_BWD_GATHER, K_BWD_UPDATE, K_BWD_DIAG
+};
+struct Launch {
+    int32_t kind;
+    int32_t first, count;     // task range in the kind's task array
+    int32_t nblocks;          // total thread blocks
+    int64_t pfx;              // block prefix: blkpfx[pfx .. pfx+count] (count+1 entries)
+    double  flops;            // executed flops (GEMM launches)
+    int32_t level, step;
+};
+
+constexpr int ASM_ROUNDS = 8;      // children handled by per-round launches; the rest by a tail kernel
+constexpr int ASM_TPB = 256, ASM_EPT = 4;
+constexpr int PANEL_ROWS = 128;    // rows (L side) / columns (U side) per panel block
+constexpr int GEMM_TM = 64, GEMM_TN = 64;   // C tile of the small-tile kernel
+constexpr int BIG_TM = 128;                 // C tile rows of the DMMA kernels (TN = 64 or 128)
+constexpr int UPD_ROWS = 256;      // rows per block in the forward-solve update
+constexpr int BWD_COLS = 8;        // columns (warps) per block in the backward-solve update
+constexpr int PS_WIDTH = 64;       // target panel-step width (a wider single chunk stays alone)
+constexpr int OB_WIDTH = 256;      // target outer-block width (delayed trailing update)
+constexpr int RELAX_ABS = 4;       // a chunk joins the chain if it adds at most this many rows ...
+constexpr double RELAX_FRAC = 0.02;//   ... or this fraction of its rows
+
+struct Plan {
+    bool lu = false;
+    int64_t n = 0, nsuper = 0, nsub = 0, nlnz = 0, nunz = 0;
+    std::vector<Chunk> chunks;
+    std::vector<Front> fronts;
+    std::vector<PStep> psteps;
+    std::vector<int32_t> subw;                // pivot sub-block widths of all panel steps
+    std::vector<int32_t> childlist;
+    std::vector<int32_t> rel;                 // relative indices, all fronts
+    std::vector<int32_t> pos;                 // per-chunk stored-row -> front-row maps
+    std::vector<int32_t> col2chunk;
+    int64_t arena = 0, wlen = 0;
+    int32_t nlevels = 0, maxnj = 0, maxR = 0, maxpw = 0;
+    double flops_struct = 0, nnzL = 0;        // sum cc^2 (or 2 sum cc^2 - sum cc), sum cc
+    bool use_dmma = true;
+    int relax_abs = RELAX_ABS; double relax_frac = RELAX_FRAC;
+    // schedules
+    std::vector<AsmTask> asmt;
+    std::vector<GemmTask> gemmt;
+    std::vector<int32_t> pslist;              // panel-step ids, grouped per DIAG/PANEL launch
+    std::vector<SolveTask> solvet;            // one per chunk
+    std::vector<int32_t> gathert;
+    std::vector<int32_t> blkpfx;
+    std::vector<Launch> factor_launches, fwd_launches, bwd_launches;
+    std::string error;
+};
+
+inline int32_t cdiv(int64_t a, int64_t b) { return (int32_t)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------
+inline bool analyze(Plan& P, int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* snode,
+                    const int64_t* xlindx, const int64_t* lindx, const int64_t* xlnz, const int64_t* xunz) {
+    (void)snode;
+    P.lu = (xunz != nullptr);
+    P.n = n; P.nsuper = nsuper;
+    if (n <= 0 || nsuper <= 0) { P.error = "empty problem"; return false; }
+    P.nsub = xlindx[nsuper] - 1;
+    P.nlnz = xlnz[n] - 1;
+    P.nunz = P.lu ? xunz[n] - 1 : 0;
+
+    P.chunks.resize(nsuper);
+    int64_t posofs = 0;
+    for (int64_t s = 0; s < nsuper; ++s) {
+        Chunk& c = P.chunks[s];
+        c.fj = xsuper[s] - 1;
+        c.nj = (int32_t)(xsuper[s + 1] - xsuper[s]);
+        c.jlen = (int32_t)(xlindx[s + 1] - xlindx[s]);
+        if ((int64_t)c.jlen != xlnz[c.fj + 1] - xlnz[c.fj] || c.nj <= 0 || c.jlen < c.nj) { P.error = "inconsistent supernode storage"; return false; }
+        c.lofs = xlnz[c.fj] - 1;
+        c.uofs = P.lu ? xunz[c.fj] - 1 : 0;
+        c.posofs = posofs; posofs += c.jlen;
+        P.maxnj = std::max(P.maxnj, c.nj);
+    }
+    P.pos.assign(posofs, 0);
+    P.col2chunk.assign(n, 0);
+    for (int64_t s = 0; s < nsuper; ++s) for (int32_t j = 0; j < P.chunks[s].nj; ++j) P.col2chunk[P.chunks[s].fj + j] = (int32_t)s;
+
+    // fronts: chunk e+1 joins the chain of chunk e iff it is e's parent (first below-row of e is
+    // its first column) and it adds at most a few rows to what e hands down.
+    for (int64_t s = 0; s < nsuper;) {
+        Front f{};
+        f.c0 = (int32_t)s; f.F0 = P.chunks[s].fj;
+        int32_t o = 0; int64_t e = s;
+        for (;;) {
+            Chunk& c = P.chunks[e];
+            c.front = (int32_t)P.fronts.size(); c.o = o; o += c.nj;
+            bool more = false;
+            if (e + 1 < nsuper && c.jlen > c.nj && lindx[xlindx[e] - 1 + c.nj] == P.chunks[e + 1].fj + 1) {
+                const Chunk& d = P.chunks[e + 1];
+                int32_t extra = d.jlen - (c.jlen - c.nj);
+                int32_t lim = std::max<int32_t>(P.relax_abs, (int32_t)(P.relax_frac * d.jlen));
+                if (extra <= lim) more = true;
+            }
+            ++e;
+            if (!more) break;
+        }
+        f.nch = (int32_t)(e - s); f.W = o;
+        const Chunk& last = P.chunks[e - 1];
+        f.m = last.jlen - last.nj; f.R = f.W + f.m;
+        f.ld = (f.R + 1) & ~1;                     // even leading dimension (16-byte aligned columns)
+        f.parent = -1;
+        P.maxR = std::max(P.maxR, f.R);
+        P.fronts.push_back(f);
+        s = e;
+    }
+    const int32_t nf = (int32_t)P.fronts.size();
+    // per-chunk position maps: own columns map to o..o+nj-1; below rows are located in the front's
+    // row list = [columns of the chain] ++ [below rows of the last chunk]
+    for (int32_t f = 0; f < nf; ++f) {
+        const Front& F = P.fronts[f];
+        const Chunk& last = P.chunks[F.c0 + F.nch - 1];
+        const int64_t* below = lindx + (xlindx[F.c0 + F.nch - 1] - 1) + last.nj;   // m entries, 1-based, sorted
+        for (int32_t t = 0; t < F.nch; ++t) {
+            const Chunk& c = P.chunks[F.c0 + t];
+            int32_t* pos = P.pos.data() + c.posofs;
+            const int64_t* rows = lindx + (xlindx[F.c0 + t] - 1);
+            int32_t q = 0;
+            for (int32_t i = 0; i < c.jlen; ++i) {
+                int64_t r = rows[i] - 1;            // 0-based global row
+                if (r < F.F0 + F.W) {               // a column of the chain
+                    if (r < c.fj) { P.error = "row above supernode"; return false; }
+                    pos[i] = (int32_t)(r - F.F0);
+                } else {
+                    while (q < F.m && below[q] - 1 < r) ++q;
+                    if (q >= F.m || below[q] - 1 != r) { P.error = "chain rows do not nest"; return false; }
+                    pos[i] = F.W + q;
+                }
+            }
+        }
+    }
+    // front tree, relative indices, arena
+    int64_t relofs = 0, fofs = 0, wofs = 0;
+    std::vector<int32_t> nchild(nf, 0);
+    for (int32_t f = 0; f < nf; ++f) {
+        Front& F = P.fronts[f];
+        F.relofs = relofs; F.fofs = fofs; F.wofs = wofs;
+        relofs += F.m; fofs += (int64_t)F.ld * F.R; fofs = (fofs + 1) & ~(int64_t)1; wofs += F.R;
+        for (int32_t t = 0; t < F.nch; ++t) { P.chunks[F.c0 + t].fofs = F.fofs; P.chunks[F.c0 + t].ld = F.ld; }
+        if (F.m > 0) {
+            const Chunk& last = P.chunks[F.c0 + F.nch - 1];
+            int64_t prow = lindx[(xlindx[F.c0 + F.nch - 1] - 1) + last.nj] - 1;
+            F.parent = P.chunks[P.col2chunk[prow]].front;
+            if (F.parent <= f) { P.error = "front tree not topologically ordered"; return false; }
+            ++nchild[F.parent];
+        }
+    }
+    P.arena = fofs; P.wlen = wofs;
+    P.rel.assign(relofs, 0);
+    for (int32_t f = 0; f < nf; ++f) {
+        const Front& F = P.fronts[f];
+        if (F.m == 0) continue;
+        const Front& Pa = P.fronts[F.parent];
+        const Chunk& last = P.chunks[F.c0 + F.nch - 1];
+        const int64_t* fr = lindx + (xlindx[F.c0 + F.nch - 1] - 1) + last.nj;
+        const Chunk& plast = P.chunks[Pa.c0 + Pa.nch - 1];
+        const int64_t* pbelow = lindx + (xlindx[Pa.c0 + Pa.nch - 1] - 1) + plast.nj;
+        int32_t q = 0;
+        for (int32_t i = 0; i < F.m; ++i) {
+            int64_t r = fr[i] - 1;
+            if (r < Pa.F0 + Pa.W) {
+                if (r < Pa.F0) { P.error = "child row before parent"; return false; }
+                P.rel[F.relofs + i] = (int32_t)(r - Pa.F0);
+            } else {
+                while (q < Pa.m && pbelow[q] - 1 < r) ++q;
+                if (q >= Pa.m || pbelow[q] - 1 != r) { P.error = "child rows not contained in parent rows"; return false; }
+                P.rel[F.relofs + i] = Pa.W + q;
+            }
+        }
+    }
+    int32_t acc = 0;
+    for (int32_t f = 0; f < nf; ++f) { P.fronts[f].child0 = acc; acc += nchild[f]; P.fronts[f].nchild = 0; P.fronts[f].level = 0; }
+    P.childlist.assign(acc, 0);
+    for (int32_t f = 0; f < nf; ++f) {
+        int32_t p = P.fronts[f].parent;
+        if (p >= 0) {
+            Front& Pa = P.fronts[p];
+            P.childlist[Pa.child0 + Pa.nchild++] = f;
+            Pa.level = std::max(Pa.level, P.fronts[f].level + 1);
+        }
+    }
+    P.nlevels = 0;
+    for (int32_t f = 0; f < nf; ++f) P.nlevels = std::max(P.nlevels, P.fronts[f].level + 1);
+    // panel steps: greedy groups of consecutive chunks up to PS_WIDTH columns; outer blocks up to OB_WIDTH
+    for (int32_t f = 0; f < nf; ++f) {
+        Front& F = P.fronts[f];
+        F.ps0 = (int32_t)P.psteps.size();
+        int32_t t = 0;
+        while (t < F.nch) {
+            PStep ps{}; ps.fofs = F.fofs; ps.ld = F.ld; ps.R = F.R; ps.front = f;
+            ps.o = P.chunks[F.c0 + t].o; ps.col0 = P.chunks[F.c0 + t].fj; ps.sub0 = (int32_t)P.subw.size();
+            int32_t w = 0, ns = 0;
+            while (t < F.nch && (ns == 0 || w + P.chunks[F.c0 + t].nj <= PS_WIDTH)) { w += P.chunks[F.c0 + t].nj; P.subw.push_back(P.chunks[F.c0 + t].nj); ++ns; ++t; }
+            ps.w = w; ps.nsub = ns;
+            P.maxpw = std::max(P.maxpw, w);
+            P.psteps.push_back(ps);
+        }
+        F.nps = (int32_t)P.psteps.size() - F.ps0;
+        int32_t j = 0;
+        while (j < F.nps) {
+            int32_t j0 = j, w = 0;
+            while (j < F.nps && (j == j0 || w + P.psteps[F.ps0 + j].w <= OB_WIDTH)) { w += P.psteps[F.ps0 + j].w; ++j; }
+            int32_t ob_end = P.psteps[F.ps0 + j0].o + w;
+            for (int32_t q = j0; q < j; ++q) P.psteps[F.ps0 + q].ob_end = ob_end;
+        }
+    }
+    // structural work: cc_j for column j of a chunk = jlen - j
+    double s1 = 0, s2 = 0;
+    for (int64_t s = 0; s < nsuper; ++s) {
+        const Chunk& c = P.chunks[s];
+        for (int32_t j = 0; j < c.nj; ++j) { double cc = c.jlen - j; s1 += cc; s2 += cc * cc; }
+    }
+    P.nnzL = s1;
+    P.flops_struct = P.lu ? 2.0 * s2 - s1 : s2;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------
+struct LaunchBuilder {
+    Plan& P; std::vector<Launch>& out;
+    Launch cur{};
+    LaunchBuilder(Plan& p, std::vector<Launch>& o) : P(p), out(o) {}
+    void begin(int32_t kind, int32_t first, int32_t level, int32_t step) {
+        cur = Launch{}; cur.kind = kind; cur.first = first; cur.count = 0; cur.nblocks = 0;
+        cur.pfx = (int64_t)P.blkpfx.size(); cur.flops = 0; cur.level = level; cur.step = step;
+        P.blkpfx.push_back(0);
+    }
+    void add(int32_t nblocks, double flops = 0) {
+        cur.count++; cur.nblocks += nblocks; cur.flops += flops; P.blkpfx.push_back(cur.nblocks);
+    }
+    void end() {
+        if (cur.count > 0 && cur.nblocks > 0) out.push_back(cur);
+        else P.blkpfx.resize(cur.pfx);
+    }
+};
+
+inline int32_t gemm_blocks(const GemmTask& t, int tm, int tn) { return cdiv(t.m, tm) * cdiv(t.n, tn); }
+
+struct GemmBatch {
+    struct Item { GemmTask t; double flops; };
+    std::vector<Item> small, b64, b128;
+    void add(const Plan& P, const GemmTask& t, double flops) {
+        if (t.m <= 0 || t.n <= 0 || t.k <= 0) return;
+        if (P.use_dmma && t.m >= 128 && t.n > 64) b128.push_back({t, flops});
+        else if (P.use_dmma && t.m >= 128 && t.n > 16) b64.push_back({t, flops});
+        else small.push_back({t, flops});
+    }
+    void emit(Plan& P, LaunchBuilder& fb, int32_t lev, int32_t step) {
+        auto one = [&](std::vector<Item>& v, int32_t kind, int tm, int tn) {
+            if (v.empty()) return;
+            fb.begin(kind, (int32_t)P.gemmt.size(), lev, step);
+            for (const Item& it : v) { P.gemmt.push_back(it.t); fb.add(gemm_blocks(it.t, tm, tn), it.flops); }
+            fb.end();
+            v.clear();
+        };
+        one(small, K_GEMM, GEMM_TM, GEMM_TN);
+        one(b64, K_GEMM_B64, BIG_TM, 64);
+        one(b128, K_GEMM_B128, BIG_TM, 128);
+    }
+};
+
+// C(r0.., c0..) [m x n] -= A(r0.., k0..k0+k) * B(k0.., c0..)   inside front F
+inline GemmTask front_gemm(const Plan& P, const Front& F, int32_t r0, int32_t m, int32_t c0, int32_t n, int32_t k0, int32_t k) {
+    GemmTask g{};
+    g.ld = F.ld; g.m = m; g.n = n; g.k = k;
+    g.a0 = F.fofs + (int64_t)r0 + (int64_t)k0 * F.ld;
+    g.c0 = F.fofs + (int64_t)r0 + (int64_t)c0 * F.ld;
+    if (P.lu) { g.bk = 1; g.b0 = F.fofs + (int64_t)k0 + (int64_t)c0 * F.ld; g.lower = 0; g.d0 = 0; }
+    else { g.bk = 0; g.b0 = F.fofs + (int64_t)c0 + (int64_t)k0 * F.ld; g.d0 = F.fofs + (int64_t)k0 + (int64_t)k0 * F.ld; g.lower = 1; }
+    g.roff = r0 - c0;
+    return g;
+}
+inline double gemm_flops(const GemmTask& g) {
+    double f = 2.0 * g.m * g.n * g.k;
+    if (g.lower && g.roff < g.n) {                 // entries above the diagonal are skipped
+        double t = (double)(g.n - std::max(g.roff, 0));
+        f -= t * t * g.k;
+    }
+    return f;
+}
+
+inline void build_schedule(Plan& P) {
+    const int32_t nf = (int32_t)P.fronts.size();
+    std::vector<std::vector<int32_t>> bylevel(P.nlevels);
+    for (int32_t f = 0; f < nf; ++f) bylevel[P.fronts[f].level].push_back(f);
+    const bool lu = P.lu;
+
+    P.solvet.resize(P.chunks.size());
+    for (size_t s = 0; s < P.chunks.size(); ++s) {
+        const Chunk& c = P.chunks[s]; const Front& F = P.fronts[c.front];
+        SolveTask t{}; t.lofs = c.lofs; t.uofs = c.uofs; t.col0 = c.fj; t.wofs = F.wofs; t.posofs = c.posofs;
+        t.ld = c.jlen; t.ldu = c.jlen - c.nj; t.nj = c.nj; t.m = c.jlen - c.nj; t.o = c.o; t.front = c.front;
+        P.solvet[s] = t;
+    }
+
+    LaunchBuilder fb(P, P.factor_launches);
+    for (int32_t lev = 0; lev < P.nlevels; ++lev) {
+        const std::vector<int32_t>& fr = bylevel[lev];
+        int32_t maxch = 0, maxnps = 0;
+        for (int32_t f : fr) { maxch = std::max(maxch, P.fronts[f].nchild); maxnps = std::max(maxnps, P.fronts[f].nps); }
+        // ---- extend-add of the children's update matrices
+        for (int32_t r = 0; r < std::min(maxch, ASM_ROUNDS); ++r) {
+            fb.begin(K_ASM, (int32_t)P.asmt.size(), lev, r);
+            for (int32_t f : fr) {
+                const Front& F = P.fronts[f];
+                if (F.nchild <= r) continue;
+                int32_t c = P.childlist[F.child0 + r];
+                int64_t mc = P.fronts[c].m;
+                P.asmt.push_back(AsmTask{c, f});
+                fb.add(cdiv(mc * mc, ASM_TPB * ASM_EPT));
+            }
+            fb.end();
+        }
+        if (maxch > ASM_ROUNDS) {
+            fb.begin(K_ASM_TAIL, (int32_t)P.asmt.size(), lev, ASM_ROUNDS);
+            for (int32_t f : fr) if (P.fronts[f].nchild > ASM_ROUNDS) { P.asmt.push_back(AsmTask{-1, f}); fb.add(1); }
+            fb.end();
+        }
+        // ---- dense partial factorisation, panel step by panel step
+        for (int32_t j = 0; j < maxnps; ++j) {
+            fb.begin(K_DIAG, (int32_t)P.pslist.size(), lev, j);
+            for (int32_t f : fr) if (P.fronts[f].nps > j) { P.pslist.push_back(P.fronts[f].ps0 + j); fb.add(1); }
+            fb.end();
+            fb.begin(K_PANEL, (int32_t)P.pslist.size(), lev, j);
+            for (int32_t f : fr) if (P.fronts[f].nps > j) {
+                const PStep& ps = P.psteps[P.fronts[f].ps0 + j];
+                int32_t below = ps.R - ps.o - ps.w;
+                if (below <= 0) continue;
+                P.pslist.push_back(P.fronts[f].ps0 + j);
+                fb.add(cdiv(below, PANEL_ROWS) * (lu ? 2 : 1));
+            }
+            fb.end();
+            GemmBatch gb;
+            for (int32_t f : fr) if (P.fronts[f].nps > j) {
+                const Front& F = P.fronts[f];
+                const PStep& ps = P.psteps[F.ps0 + j];
+                const int32_t e = ps.o + ps.w;             // first column after the panel
+                if (e >= F.R) continue;
+                if (e < ps.ob_end) {
+                    // inside the outer block: eager update of the block's remaining columns (and rows, LU)
+                    GemmTask g = front_gemm(P, F, e, F.R - e, e, ps.ob_end - e, ps.o, ps.w);
+                    gb.add(P, g, gemm_flops(g));
+                    if (lu && ps.ob_end < F.R) {
+                        GemmTask h = front_gemm(P, F, e, ps.ob_end - e, ps.ob_end, F.R - ps.ob_end, ps.o, ps.w);
+                        gb.add(P, h, gemm_flops(h));
+                    }
+                } else {
+                    // last step of an outer block: delayed update of everything behind the block
+                    int32_t ob0 = ps.o;
+                    for (int32_t q = j; q >= 0 && P.psteps[F.ps0 + q].ob_end == ps.ob_end; --q) ob0 = P.psteps[F.ps0 + q].o;
+                    GemmTask g = front_gemm(P, F, e, F.R - e, e, F.R - e, ob0, e - ob0);
+                    gb.add(P, g, gemm_flops(g));
+                }
+            }
+            gb.emit(P, fb, lev, j);
+        }
+    }
+
+    // ---- solves (on lnz / unz in the reference layout)
+    LaunchBuilder sf(P, P.fwd_launches);
+    for (int32_t lev = 0; lev < P.nlevels; ++lev) {
+        const std::vector<int32_t>& fr = bylevel[lev];
+        int32_t maxnch = 0;
+        sf.begin(K_FWD_GATHER, (int32_t)P.gathert.size(), lev, 0);
+        for (int32_t f : fr) { P.gathert.push_back(f); sf.add(1); maxnch = std::max(maxnch, P.fronts[f].nch); }
+        sf.end();
+        for (int32_t t = 0; t < maxnch; ++t) {
+            sf.begin(K_FWD_DIAG, (int32_t)P.gathert.size(), lev, t);
+            for (int32_t f : fr) if (P.fronts[f].nch > t) { P.gathert.push_back(P.fronts[f].c0 + t); sf.add(1); }
+            sf.end();
+            sf.begin(K_FWD_UPDATE, (int32_t)P.gathert.size(), lev, t);
+            for (int32_t f : fr) if (P.fronts[f].nch > t) {
+                const Chunk& c = P.chunks[P.fronts[f].c0 + t];
+                if (c.jlen > c.nj) { P.gathert.push_back(P.fronts[f].c0 + t); sf.add(cdiv(c.jlen - c.nj, UPD_ROWS)); }
+            }
+            sf.end();
+        }
+    }
+    LaunchBuilder sb(P, P.bwd_launches);
+    for (int32_t lev = P.nlevels - 1; lev >= 0; --lev) {
+        const std::vector<int32_t>& fr = bylevel[lev];
+        int32_t maxnch = 0;
+        sb.begin(K_BWD_GATHER, (int32_t)P.gathert.size(), lev, 0);
+        for (int32_t f : fr) {
+            maxnch = std::max(maxnch, P.fronts[f].nch);
+            if (P.fronts[f].m > 0) { P.gathert.push_back(f); sb.add(cdiv(P.fronts[f].m, 256)); }
+        }
+        sb.end();
+        for (int32_t t = maxnch - 1; t >= 0; --t) {
+            sb.begin(K_BWD_UPDATE, (int32_t)P.gathert.size(), lev, t);
+            for (int32_t f : fr) if (P.fronts[f].nch > t) {
+                const Chunk& c = P.chunks[P.fronts[f].c0 + t];
+                // LDL^T: the D^-1 scaling of the block's unknowns happens here, so every chunk gets a task
+                if (c.jlen > c.nj || !lu) { P.gathert.push_back(P.fronts[f].c0 + t); sb.add(cdiv(c.nj, BWD_COLS)); }
+            }
+            sb.end();
+            sb.begin(K_BWD_DIAG, (int32_t)P.gathert.size(), lev, t);
+            for (int32_t f : fr) if (P.fronts[f].nch > t) { P.gathert.push_back(P.fronts[f].c0 + t); sb.add(1); }
+            sb.end();
+        }
+    }
+}
+
+} // namespace spk

@@ -1,0 +1,631 @@
+// spk_b200.cu — C ABI (include/spk_b200.h) and plan runtime of the B200 numeric engine.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <mutex>
+#include <cuda_runtime.h>
+#include "spk_b200.h"
+#include "plan.hpp"
+#include "kernels.cuh"
+#include "gemm_dmma.cuh"
+
+using namespace spk;
+
+static thread_local std::string g_err;
+static void set_err(const std::string& s) { g_err = s; }
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            set_err(std::string(#call) + ": " + cudaGetErrorString(e_));                      \
+            return -100 - (int64_t)e_;                                                        \
+        }                                                                                     \
+    } while (0)
+
+template <class T>
+static cudaError_t upload(T** d, const std::vector<T>& h) {
+    *d = nullptr;
+    size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+    cudaError_t e = cudaMalloc((void**)d, bytes);
+    if (e != cudaSuccess) return e;
+    if (!h.empty()) e = cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return e;
+}
+
+struct spk_plan {
+    Plan P;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evg0 = nullptr, evg1 = nullptr;
+    // device state
+    double *d_F = nullptr, *d_lnz = nullptr, *d_unz = nullptr, *d_w = nullptr, *d_rhs = nullptr, *d_tmp = nullptr;
+    int32_t *d_ipiv = nullptr, *d_iflag = nullptr;
+    DFront* d_fronts = nullptr; DChunk* d_chunks = nullptr; PStep* d_psteps = nullptr;
+    int32_t *d_subw = nullptr, *d_childlist = nullptr, *d_rel = nullptr, *d_pos = nullptr, *d_blkpfx = nullptr,
+            *d_gathert = nullptr, *d_pslist = nullptr, *d_chunkpfx = nullptr;
+    int64_t *d_dest = nullptr, *d_rperm = nullptr, *d_rinvp = nullptr;
+    double* d_nzval = nullptr; int64_t nzcap = 0, nz_last = 0;
+    AsmTask* d_asmt = nullptr; GemmTask* d_gemmt = nullptr; SolveTask* d_solvet = nullptr;
+    int32_t chunk_blocks = 0;
+    bool values_in_fronts = false;      // inmatrix scattered straight into the fronts
+    int64_t w_nrhs = 0, rhs_cap = 0;
+    size_t dev_bytes = 0;
+    int diag_smem_nj = 0; size_t diag_smem_bytes = 0;
+    bool have_perm = false, factored = false;
+    // stats
+    int64_t launches_factor = 0, launches_solve = 0;
+    double ms_factor = 0, ms_solve = 0, gemm_flops = 0, gemm_ms = 0;
+    std::vector<float> launch_ms;       // optional per-launch timing (profiling mode)
+    double kind_ms[16] = {0}; int64_t kind_n[16] = {0};
+    bool profile = false;
+};
+
+static DevCtx make_ctx(spk_plan* p) {
+    DevCtx c{};
+    c.F = p->d_F; c.lnz = p->d_lnz; c.unz = p->d_unz; c.w = p->d_w;
+    c.ipiv = p->d_ipiv; c.iflag = p->d_iflag;
+    c.fronts = p->d_fronts; c.chunks = p->d_chunks; c.psteps = p->d_psteps; c.subw = p->d_subw;
+    c.childlist = p->d_childlist; c.rel = p->d_rel; c.pos = p->d_pos;
+    c.solvet = p->d_solvet; c.wlen = p->P.wlen; c.lu = p->P.lu ? 1 : 0;
+    return c;
+}
+
+extern "C" {
+
+SPK_API const char* spk_last_error(void) { return g_err.c_str(); }
+SPK_API const char* spk_version(void) { return "sparspak.jl_b200 0.1.0 (sm_100a)"; }
+SPK_API int32_t spk_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+SPK_API void spk_plan_destroy(spk_plan* p) {
+    if (!p) return;
+    if (p->device >= 0) {
+        cudaSetDevice(p->device);
+        void* ptrs[] = {p->d_F, p->d_lnz, p->d_unz, p->d_w, p->d_rhs, p->d_tmp, p->d_ipiv, p->d_iflag, p->d_fronts,
+                        p->d_chunks, p->d_psteps, p->d_subw, p->d_childlist, p->d_rel, p->d_pos, p->d_blkpfx,
+                        p->d_gathert, p->d_pslist, p->d_chunkpfx, p->d_dest, p->d_rperm, p->d_rinvp, p->d_nzval,
+                        p->d_asmt, p->d_gemmt, p->d_solvet};
+        for (void* q : ptrs) if (q) cudaFree(q);
+        if (p->ev0) cudaEventDestroy(p->ev0);
+        if (p->ev1) cudaEventDestroy(p->ev1);
+        if (p->evg0) cudaEventDestroy(p->evg0);
+        if (p->evg1) cudaEventDestroy(p->evg1);
+        if (p->stream) cudaStreamDestroy(p->stream);
+    }
+    delete p;
+}
+
+static int64_t plan_upload(spk_plan* p) {
+    Plan& P = p->P;
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&p->ev0)); CK(cudaEventCreate(&p->ev1));
+    CK(cudaEventCreate(&p->evg0)); CK(cudaEventCreate(&p->evg1));
+    std::vector<DFront> df(P.fronts.size());
+    for (size_t i = 0; i < df.size(); ++i) {
+        const Front& F = P.fronts[i];
+        df[i] = DFront{F.fofs, F.relofs, F.wofs, F.F0, F.W, F.R, F.m, F.ld, F.parent, F.child0, F.nchild, 0};
+    }
+    std::vector<DChunk> dc(P.chunks.size());
+    std::vector<int32_t> cpfx(P.chunks.size() + 1, 0);
+    for (size_t i = 0; i < dc.size(); ++i) {
+        const Chunk& C = P.chunks[i];
+        dc[i] = DChunk{C.lofs, C.uofs, C.posofs, C.fofs, C.nj, C.jlen, C.o, C.ld};
+        int64_t ne = (int64_t)C.jlen * C.nj + (P.lu ? (int64_t)(C.jlen - C.nj) * C.nj : 0);
+        cpfx[i + 1] = cpfx[i] + cdiv(ne, CHUNK_EPB);
+    }
+    p->chunk_blocks = cpfx.back();
+    CK(upload(&p->d_fronts, df));
+    CK(upload(&p->d_chunks, dc));
+    CK(upload(&p->d_chunkpfx, cpfx));
+    CK(upload(&p->d_psteps, P.psteps));
+    CK(upload(&p->d_subw, P.subw));
+    CK(upload(&p->d_childlist, P.childlist));
+    CK(upload(&p->d_rel, P.rel));
+    CK(upload(&p->d_pos, P.pos));
+    CK(upload(&p->d_blkpfx, P.blkpfx));
+    CK(upload(&p->d_gathert, P.gathert));
+    CK(upload(&p->d_pslist, P.pslist));
+    CK(upload(&p->d_asmt, P.asmt));
+    CK(upload(&p->d_gemmt, P.gemmt));
+    CK(upload(&p->d_solvet, P.solvet));
+    CK(cudaMalloc((void**)&p->d_F, std::max<int64_t>(P.arena, 1) * sizeof(double)));
+    CK(cudaMalloc((void**)&p->d_lnz, std::max<int64_t>(P.nlnz, 1) * sizeof(double)));
+    CK(cudaMalloc((void**)&p->d_unz, std::max<int64_t>(P.nunz, 1) * sizeof(double)));
+    CK(cudaMalloc((void**)&p->d_ipiv, P.n * sizeof(int32_t)));
+    CK(cudaMalloc((void**)&p->d_iflag, sizeof(int32_t)));
+    CK(cudaMemset(p->d_ipiv, 0, P.n * sizeof(int32_t)));
+    p->dev_bytes = (size_t)(P.nlnz + P.nunz + P.arena) * 8 + (size_t)P.n * 4 + (P.rel.size() + P.pos.size()) * 4 +
+                   P.blkpfx.size() * 4 + P.gemmt.size() * sizeof(GemmTask) + P.solvet.size() * sizeof(SolveTask) +
+                   dc.size() * sizeof(DChunk) + df.size() * sizeof(DFront);
+    // diagonal-block kernel: shared-memory copy of the block when it fits
+    int maxnj = P.maxpw;
+    size_t need = (size_t)maxnj * (maxnj | 1) * sizeof(double);
+    size_t cap = 200 * 1024;
+    if (need > cap) { int q = 1; while ((size_t)(q + 1) * ((q + 1) | 1) * 8 <= cap) ++q; p->diag_smem_nj = q; need = (size_t)q * (q | 1) * 8; }
+    else p->diag_smem_nj = maxnj;
+    p->diag_smem_bytes = need;
+    if (need > 48 * 1024) {
+        CK(cudaFuncSetAttribute(k_diag<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+        CK(cudaFuncSetAttribute(k_diag<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    }
+    CK(gemm_dmma_init());
+    return 0;
+}
+
+SPK_API spk_plan* spk_plan_create(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* snode,
+                                  const int64_t* xlindx, const int64_t* lindx, const int64_t* xlnz,
+                                  const int64_t* xunz_or_null, int32_t device, int32_t part, int32_t nparts) {
+    (void)part; (void)nparts;
+    spk_plan* p = new spk_plan();
+    p->device = device;
+    if (!analyze(p->P, n, nsuper, xsuper, snode, xlindx, lindx, xlnz, xunz_or_null)) {
+        set_err("analyze: " + p->P.error); delete p; return nullptr;
+    }
+ {
+        const char* e = getenv("SPK_NO_DMMA");
+        p->P.use_dmma = !(e && e[0] == '1');
+    }
+    build_schedule(p->P);
+    if (device < 0) return p;                      // host-only plan: structure statistics without a GPU
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device) {
+        cudaGetLastError();
+        set_err("no CUDA device " + std::to_string(device) + " (the numeric path has no CPU fallback)");
+        delete p; return nullptr;
+    }
+    if (plan_upload(p) != 0) { spk_plan_destroy(p); return nullptr; }
+    return p;
+}
+
+#define NEED_DEV(p) do { if (!(p) || (p)->device < 0) { set_err("plan has no device"); return -100; } CK(cudaSetDevice((p)->device)); } while (0)
+
+SPK_API int64_t spk_plan_set_values(spk_plan* p, const double* lnz, const double* unz) {
+    NEED_DEV(p);
+    CK(cudaMemcpyAsync(p->d_lnz, lnz, p->P.nlnz * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    if (p->P.lu && p->P.nunz > 0) {
+        if (!unz) { set_err("unz required for LU"); return -100; }
+        CK(cudaMemcpyAsync(p->d_unz, unz, p->P.nunz * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    }
+    CK(cudaStreamSynchronize(p->stream));
+    p->factored = false; p->values_in_fronts = false;
+    return 0;
+}
+
+SPK_API int64_t spk_plan_set_factors(spk_plan* p, const double* lnz, const double* unz, const int64_t* ipvt) {
+    int64_t rc = spk_plan_set_values(p, lnz, unz);
+    if (rc) return rc;
+    if (p->P.lu && ipvt) {
+        int64_t* tmp = nullptr;
+        CK(cudaMalloc((void**)&tmp, p->P.n * sizeof(int64_t)));
+        CK(cudaMemcpy(tmp, ipvt, p->P.n * sizeof(int64_t), cudaMemcpyHostToDevice));
+        k_ipiv_narrow<<<cdiv(p->P.n, 256), 256, 0, p->stream>>>(p->P.n, tmp, p->d_ipiv);
+        CK(cudaStreamSynchronize(p->stream));
+        CK(cudaFree(tmp));
+    }
+    p->factored = true;
+    return 0;
+}
+
+// destination slot in the reference layout (1-based lnz slot, or -(1-based unz slot)) -> arena element
+static int64_t slot_to_arena(const Plan& P, int64_t d) {
+    if (d == 0) return -1;
+    if (d > 0) {
+        int64_t slot = d - 1;
+        size_t lo = 0, hi = P.chunks.size();
+        while (hi - lo > 1) { size_t mid = (lo + hi) >> 1; if (P.chunks[mid].lofs <= slot) lo = mid; else hi = mid; }
+        const Chunk& c = P.chunks[lo];
+        int64_t e = slot - c.lofs;
+        int64_t j = e / c.jlen, i = e - j * c.jlen;
+        if (j >= c.nj) return -2;
+        return c.fofs + P.pos[c.posofs + i] + (int64_t)(c.o + j) * c.ld;
+    }
+    int64_t slot = -d - 1;
+    size_t lo = 0, hi = P.chunks.size();
+    while (hi - lo > 1) { size_t mid = (lo + hi) >> 1; if (P.chunks[mid].uofs <= slot) lo = mid; else hi = mid; }
+    const Chunk& c = P.chunks[lo];
+    int64_t ldu = c.jlen - c.nj, e = slot - c.uofs;
+    if (ldu <= 0) return -2;
+    int64_t j = e / ldu, i = e - j * ldu;
+    if (j >= c.nj) return -2;
+    return c.fofs + (int64_t)(c.o + j) + (int64_t)P.pos[c.posofs + c.nj + i] * c.ld;
+}
+
+SPK_API int64_t spk_plan_inmatrix(spk_plan* p, int64_t nnz, const int64_t* dest, const double* nzval) {
+    NEED_DEV(p);
+    if (nnz > p->nzcap || !p->d_dest) {
+        if (p->d_nzval) cudaFree(p->d_nzval);
+        if (p->d_dest) cudaFree(p->d_dest);
+        p->d_nzval = nullptr; p->d_dest = nullptr; p->nzcap = 0;
+        if (!dest) { set_err("destination map required on first inmatrix"); return -100; }
+        CK(cudaMalloc((void**)&p->d_nzval, std::max<int64_t>(nnz, 1) * sizeof(double)));
+        CK(cudaMalloc((void**)&p->d_dest, std::max<int64_t>(nnz, 1) * sizeof(int64_t)));
+        p->nzcap = nnz;
+    }
+    if (dest) {
+        std::vector<int64_t> ad(nnz);
+        for (int64_t k = 0; k < nnz; ++k) {
+            ad[k] = slot_to_arena(p->P, dest[k]);
+            if (ad[k] == -2) { set_err("inmatrix: destination outside the factor structure"); return -100; }
+        }
+        CK(cudaMemcpy(p->d_dest, ad.data(), nnz * sizeof(int64_t), cudaMemcpyHostToDevice));
+    }
+    CK(cudaMemcpyAsync(p->d_nzval, nzval, nnz * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaMemsetAsync(p->d_F, 0, p->P.arena * sizeof(double), p->stream));
+    if (nnz > 0) k_scatter_values<<<cdiv(nnz, 256), 256, 0, p->stream>>>(nnz, p->d_dest, p->d_nzval, p->d_F);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(p->stream));
+    p->factored = false; p->values_in_fronts = true; p->nz_last = nnz;
+    return 0;
+}
+
+// zero the fronts and re-scatter the values uploaded by the last spk_plan_inmatrix (no host traffic)
+SPK_API int64_t spk_plan_reassemble(spk_plan* p) {
+    NEED_DEV(p);
+    if (!p->d_dest || p->nz_last <= 0) { set_err("spk_plan_inmatrix has not been called"); return -100; }
+    CK(cudaMemsetAsync(p->d_F, 0, p->P.arena * sizeof(double), p->stream));
+    k_scatter_values<<<cdiv(p->nz_last, 256), 256, 0, p->stream>>>(p->nz_last, p->d_dest, p->d_nzval, p->d_F);
+    CK(cudaGetLastError());
+    p->factored = false; p->values_in_fronts = true;
+    return 0;
+}
+
+// ---- factor ---------------------------------------------------------------------------
+static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L) {
+    const int32_t* pfx = p->d_blkpfx + L.pfx;
+    cudaStream_t st = p->stream;
+    const bool lu = p->P.lu;
+    switch (L.kind) {
+    case K_ASM:
+        k_assemble<<<L.nblocks, ASM_TPB, 0, st>>>(c, p->d_asmt + L.first, pfx, L.count); break;
+    case K_ASM_TAIL:
+        k_assemble_tail<<<L.count, 256, 0, st>>>(c, p->d_asmt + L.first, L.count); break;
+    case K_DIAG:
+        if (lu) k_diag<true><<<L.count, 256, p->diag_smem_bytes, st>>>(c, p->d_pslist + L.first, p->diag_smem_nj);
+        else k_diag<false><<<L.count, 256, p->diag_smem_bytes, st>>>(c, p->d_pslist + L.first, p->diag_smem_nj);
+        break;
+    case K_PANEL:
+        if (lu) k_panel<true><<<L.nblocks, PANEL_ROWS, 0, st>>>(c, p->d_pslist + L.first, pfx, L.count);
+        else k_panel<false><<<L.nblocks, PANEL_ROWS, 0, st>>>(c, p->d_pslist + L.first, pfx, L.count);
+        break;
+    case K_GEMM:
+        k_gemm_small<<<L.nblocks, 256, 0, st>>>(c, p->d_gemmt + L.first, pfx, L.count); break;
+    case K_GEMM_B64:
+    case K_GEMM_B128:
+        gemm_dmma_kernel(L.kind, lu)<<<L.nblocks, DM_THREADS, gemm_dmma_smem(L.kind), st>>>(
+            c, p->d_gemmt + L.first, pfx, L.count);
+        break;
+    default:
+        set_err("bad launch kind"); return -100;
+    }
+    return 0;
+}
+
+SPK_API int64_t spk_plan_factor_phase(spk_plan* p, int32_t phase) {
+    (void)phase;
+    NEED_DEV(p);
+    Plan& P = p->P;
+    DevCtx c = make_ctx(p);
+    cudaStream_t st = p->stream;
+    CK(cudaEventRecord(p->ev0, st));
+    CK(cudaMemsetAsync(p->d_iflag, 0, sizeof(int32_t), st));
+    p->launches_factor = 0; p->gemm_flops = 0; p->gemm_ms = 0;
+    if (!p->values_in_fronts) {
+        // gather the assembled matrix (reference layout) into the zeroed frontal matrices
+        CK(cudaMemsetAsync(p->d_F, 0, P.arena * sizeof(double), st));
+        k_chunks<false><<<p->chunk_blocks, 256, 0, st>>>(c, p->d_chunkpfx, (int)P.chunks.size());
+        ++p->launches_factor;
+    }
+    std::vector<cudaEvent_t> evs;
+    if (p->profile) { evs.resize(P.factor_launches.size() + 1); for (auto& e : evs) cudaEventCreate(&e); cudaEventRecord(evs[0], st); }
+    size_t li = 0;
+    for (const Launch& L : P.factor_launches) {
+        int64_t rc = run_factor_launch(p, c, L);
+        if (rc) return rc;
+        ++p->launches_factor;
+        if (L.kind == K_GEMM_B64 || L.kind == K_GEMM_B128) p->gemm_flops += L.flops;
+        if (p->profile) cudaEventRecord(evs[++li], st);
+    }
+    // scatter the factors back into the reference layout (lnz / unz)
+    k_chunks<true><<<p->chunk_blocks, 256, 0, st>>>(c, p->d_chunkpfx, (int)P.chunks.size());
+    ++p->launches_factor;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(p->ev1, st));
+    CK(cudaStreamSynchronize(st));
+    p->values_in_fronts = false;
+    float ms = 0; CK(cudaEventElapsedTime(&ms, p->ev0, p->ev1)); p->ms_factor = ms;
+    if (p->profile) {
+        p->launch_ms.assign(P.factor_launches.size(), 0.f);
+        for (int k = 0; k < 16; ++k) { p->kind_ms[k] = 0; p->kind_n[k] = 0; }
+        for (size_t i = 0; i < P.factor_launches.size(); ++i) {
+            cudaEventElapsedTime(&p->launch_ms[i], evs[i], evs[i + 1]);
+            p->kind_ms[P.factor_launches[i].kind & 15] += p->launch_ms[i]; p->kind_n[P.factor_launches[i].kind & 15]++;
+            if (P.factor_launches[i].kind == K_GEMM_B64 || P.factor_launches[i].kind == K_GEMM_B128) p->gemm_ms += p->launch_ms[i];
+        }
+        for (auto& e : evs) cudaEventDestroy(e);
+    }
+    int32_t flag = 0;
+    CK(cudaMemcpy(&flag, p->d_iflag, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    p->factored = true;
+    return flag;
+}
+
+SPK_API int64_t spk_plan_factor(spk_plan* p) { return spk_plan_factor_phase(p, -1); }
+
+SPK_API int64_t spk_plan_get_factors(spk_plan* p, double* lnz, double* unz, int64_t* ipvt) {
+    NEED_DEV(p);
+    if (lnz) CK(cudaMemcpyAsync(lnz, p->d_lnz, p->P.nlnz * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (unz && p->P.nunz > 0) CK(cudaMemcpyAsync(unz, p->d_unz, p->P.nunz * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (ipvt && p->P.lu) {
+        int64_t* tmp = nullptr;
+        CK(cudaMalloc((void**)&tmp, p->P.n * sizeof(int64_t)));
+        k_ipiv_widen<<<cdiv(p->P.n, 256), 256, 0, p->stream>>>(p->P.n, p->d_ipiv, tmp);
+        CK(cudaMemcpyAsync(ipvt, tmp, p->P.n * sizeof(int64_t), cudaMemcpyDeviceToHost, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
+        CK(cudaFree(tmp));
+    }
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+// ---- solve ----------------------------------------------------------------------------
+static int64_t ensure_w(spk_plan* p, int64_t nrhs) {
+    if (nrhs > p->w_nrhs) {
+        if (p->d_w) cudaFree(p->d_w);
+        p->d_w = nullptr; p->w_nrhs = 0;
+        CK(cudaMalloc((void**)&p->d_w, (size_t)p->P.wlen * nrhs * sizeof(double)));
+        p->w_nrhs = nrhs;
+    }
+    return 0;
+}
+
+static int64_t run_solve_launches(spk_plan* p, const DevCtx& c, const std::vector<Launch>& Ls, double* d_rhs,
+                                  int64_t nrhs, int64_t ldrhs) {
+    cudaStream_t st = p->stream;
+    const bool lu = p->P.lu;
+    for (const Launch& L : Ls) {
+        const int32_t* pfx = p->d_blkpfx + L.pfx;
+        const int32_t* list = p->d_gathert + L.first;
+        dim3 grid(L.nblocks, (unsigned)nrhs);
+        switch (L.kind) {
+        case K_FWD_GATHER: k_fwd_gather<<<dim3(L.count, (unsigned)nrhs), 256, 0, st>>>(c, list, d_rhs, ldrhs); break;
+        case K_FWD_DIAG:
+            if (lu) k_fwd_diag<true><<<dim3(L.count, (unsigned)nrhs), 128, 0, st>>>(c, list);
+            else k_fwd_diag<false><<<dim3(L.count, (unsigned)nrhs), 128, 0, st>>>(c, list);
+            break;
+        case K_FWD_UPDATE: k_fwd_update<<<grid, UPD_ROWS, 0, st>>>(c, list, pfx, L.count); break;
+        case K_BWD_GATHER: k_bwd_gather<<<grid, 256, 0, st>>>(c, list, pfx, L.count); break;
+        case K_BWD_UPDATE:
+            if (lu) k_bwd_update<true><<<grid, BWD_COLS * 32, 0, st>>>(c, list, pfx, L.count);
+            else k_bwd_update<false><<<grid, BWD_COLS * 32, 0, st>>>(c, list, pfx, L.count);
+            break;
+        case K_BWD_DIAG:
+            if (lu) k_bwd_diag<true><<<dim3(L.count, (unsigned)nrhs), 128, 0, st>>>(c, list, d_rhs, ldrhs);
+            else k_bwd_diag<false><<<dim3(L.count, (unsigned)nrhs), 128, 0, st>>>(c, list, d_rhs, ldrhs);
+            break;
+        default: set_err("bad solve launch kind"); return -100;
+        }
+        ++p->launches_solve;
+    }
+    return 0;
+}
+
+// d_rhs: device, permuted order, column-major ld = ldrhs
+SPK_API int64_t spk_plan_solve_device(spk_plan* p, double* d_rhs, int64_t nrhs, int64_t ldrhs, int32_t which) {
+    NEED_DEV(p);
+    if (nrhs <= 0) return 0;
+    const int64_t maxbatch = 32;                       // bounds the work-vector arena
+    cudaStream_t st = p->stream;
+    CK(cudaEventRecord(p->ev0, st));
+    p->launches_solve = 0;
+    for (int64_t r0 = 0; r0 < nrhs; r0 += maxbatch) {
+        int64_t nb = std::min(maxbatch, nrhs - r0);
+        int64_t rc = ensure_w(p, nb); if (rc) return rc;
+        DevCtx c = make_ctx(p);
+        double* b = d_rhs + (size_t)r0 * ldrhs;
+        const int nf = (int)p->P.fronts.size();
+        if (which == 2) { k_copy_front_x<<<dim3(nf, (unsigned)nb), 64, 0, st>>>(c, nf, b, ldrhs, 0); ++p->launches_solve; }
+        if (which == 0 || which == 1) { rc = run_solve_launches(p, c, p->P.fwd_launches, b, nb, ldrhs); if (rc) return rc; }
+        if (which == 1) { k_copy_front_x<<<dim3(nf, (unsigned)nb), 64, 0, st>>>(c, nf, b, ldrhs, 1); ++p->launches_solve; }
+        if (which == 0 || which == 2) { rc = run_solve_launches(p, c, p->P.bwd_launches, b, nb, ldrhs); if (rc) return rc; }
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(p->ev1, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, p->ev0, p->ev1)); p->ms_solve = ms;
+    return 0;
+}
+
+static int64_t ensure_rhs(spk_plan* p, int64_t nrhs) {
+    int64_t need = p->P.n * nrhs;
+    if (need > p->rhs_cap) {
+        if (p->d_rhs) cudaFree(p->d_rhs);
+        if (p->d_tmp) cudaFree(p->d_tmp);
+        p->d_rhs = p->d_tmp = nullptr; p->rhs_cap = 0;
+        CK(cudaMalloc((void**)&p->d_rhs, need * sizeof(double)));
+        CK(cudaMalloc((void**)&p->d_tmp, need * sizeof(double)));
+        p->rhs_cap = need;
+    }
+    return 0;
+}
+
+SPK_API int64_t spk_plan_solve(spk_plan* p, double* rhs, int64_t nrhs, int64_t ldrhs, int32_t which) {
+    NEED_DEV(p);
+    if (nrhs <= 0) return 0;
+    const int64_t n = p->P.n;
+    int64_t rc = ensure_rhs(p, nrhs); if (rc) return rc;
+    CK(cudaMemcpy2DAsync(p->d_rhs, n * sizeof(double), rhs, ldrhs * sizeof(double), n * sizeof(double), nrhs,
+                         cudaMemcpyHostToDevice, p->stream));
+    rc = spk_plan_solve_device(p, p->d_rhs, nrhs, n, which); if (rc) return rc;
+    CK(cudaMemcpy2DAsync(rhs, ldrhs * sizeof(double), p->d_rhs, n * sizeof(double), n * sizeof(double), nrhs,
+                         cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+SPK_API int64_t spk_plan_set_perm(spk_plan* p, const int64_t* rperm, const int64_t* rinvp) {
+    NEED_DEV(p);
+    const int64_t n = p->P.n;
+    if (!p->d_rperm) { CK(cudaMalloc((void**)&p->d_rperm, n * sizeof(int64_t))); CK(cudaMalloc((void**)&p->d_rinvp, n * sizeof(int64_t))); }
+    CK(cudaMemcpy(p->d_rperm, rperm, n * sizeof(int64_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(p->d_rinvp, rinvp, n * sizeof(int64_t), cudaMemcpyHostToDevice));
+    p->have_perm = true;
+    return 0;
+}
+
+SPK_API int64_t spk_plan_triangularsolve(spk_plan* p, double* b, int64_t nrhs, int64_t ldb) {
+    NEED_DEV(p);
+    if (!p->have_perm) { set_err("spk_plan_set_perm not called"); return -100; }
+    if (nrhs <= 0) return 0;
+    const int64_t n = p->P.n;
+    int64_t rc = ensure_rhs(p, nrhs); if (rc) return rc;
+    cudaStream_t st = p->stream;
+    CK(cudaMemcpy2DAsync(p->d_tmp, n * sizeof(double), b, ldb * sizeof(double), n * sizeof(double), nrhs,
+                         cudaMemcpyHostToDevice, st));
+    k_perm_gather<<<dim3(cdiv(n, 256), (unsigned)nrhs), 256, 0, st>>>(n, p->d_rperm, p->d_tmp, p->d_rhs, n, n);
+    rc = spk_plan_solve_device(p, p->d_rhs, nrhs, n, 0); if (rc) return rc;
+    k_perm_gather<<<dim3(cdiv(n, 256), (unsigned)nrhs), 256, 0, st>>>(n, p->d_rinvp, p->d_rhs, p->d_tmp, n, n);
+    CK(cudaMemcpy2DAsync(b, ldb * sizeof(double), p->d_tmp, n * sizeof(double), n * sizeof(double), nrhs,
+                         cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- introspection ----------------------------------------------------------------------
+SPK_API void* spk_plan_device_ptr(spk_plan* p, int32_t what) {
+    if (!p) return nullptr;
+    switch (what) { case 0: return p->d_lnz; case 1: return p->d_unz; case 2: return p->d_ipiv; default: return nullptr; }
+}
+SPK_API int64_t spk_plan_device_len(spk_plan* p, int32_t what) {
+    if (!p) return 0;
+    switch (what) { case 0: return p->P.nlnz; case 1: return p->P.nunz; case 2: return p->P.n; default: return 0; }
+}
+SPK_API int64_t spk_plan_stat(spk_plan* p, int32_t what) {
+    if (!p) return 0;
+    switch (what) {
+    case 0: return p->launches_factor;
+    case 1: return p->launches_solve;
+    case 2: return (int64_t)p->P.fronts.size();
+    case 3: return p->P.nlevels;
+    case 4: return (int64_t)p->dev_bytes;
+    case 5: { int64_t k = 0; for (const Front& f : p->P.fronts) if (f.nch > 1) ++k; return k; }
+    case 6: return p->P.arena;
+    case 7: return (int64_t)p->P.factor_launches.size();
+    case 8: return (int64_t)(p->P.fwd_launches.size() + p->P.bwd_launches.size());
+    case 9: return p->P.wlen;
+    case 10: return p->P.maxpw;
+    case 11: return p->P.maxR;
+    case 100: p->profile = true; return 0;
+    case 101: p->profile = false; return 0;
+    default: return 0;
+    }
+}
+SPK_API double spk_plan_statf(spk_plan* p, int32_t what) {
+    if (!p) return 0;
+    switch (what) {
+    case 0: return p->P.flops_struct;
+    case 1: return p->P.nnzL;
+    case 2: return p->ms_factor;
+    case 3: return p->ms_solve;
+    case 4: return p->gemm_flops;
+    case 5: return p->gemm_ms;
+    default:
+        if (what >= 10 && what < 26) return p->kind_ms[what - 10];
+        if (what >= 30 && what < 46) return (double)p->kind_n[what - 30];
+        return 0;
+    }
+}
+
+// ---- stateless drop-ins -------------------------------------------------------------------
+static int64_t n_from_xsuper(int64_t nsuper, const int64_t* xsuper) { return xsuper[nsuper] - 1; }
+
+SPK_API int64_t spk_lufactor_f64(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* snode,
+                                 const int64_t* xlindx, const int64_t* lindx, const int64_t* xlnz, double* lnz,
+                                 const int64_t* xunz, double* unz, int64_t* ipvt) {
+    spk_plan* p = spk_plan_create(n, nsuper, xsuper, snode, xlindx, lindx, xlnz, xunz, 0, 0, 1);
+    if (!p) return -100;
+    int64_t rc = spk_plan_set_values(p, lnz, unz);
+    int64_t flag = 0;
+    if (!rc) { flag = spk_plan_factor(p); if (flag < -1) rc = flag; }
+    if (!rc) rc = spk_plan_get_factors(p, lnz, unz, ipvt);
+    spk_plan_destroy(p);
+    return rc ? rc : flag;
+}
+
+SPK_API int64_t spk_ldltfactor_f64(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* snode,
+                                   const int64_t* xlindx, const int64_t* lindx, const int64_t* xlnz, double* lnz) {
+    spk_plan* p = spk_plan_create(n, nsuper, xsuper, snode, xlindx, lindx, xlnz, nullptr, 0, 0, 1);
+    if (!p) return -100;
+    int64_t rc = spk_plan_set_values(p, lnz, nullptr);
+    int64_t flag = 0;
+    if (!rc) { flag = spk_plan_factor(p); if (flag < -1) rc = flag; }
+    if (!rc) rc = spk_plan_get_factors(p, lnz, nullptr, nullptr);
+    spk_plan_destroy(p);
+    return rc ? rc : flag;
+}
+
+// the solve drop-ins get no snode / (for _lulsolve!) no xunz: rebuild what the plan needs
+static spk_plan* solve_plan(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* xlindx,
+                            const int64_t* lindx, const int64_t* xlnz, bool lu) {
+    std::vector<int64_t> snode(n), xunz;
+    for (int64_t s = 0; s < nsuper; ++s) for (int64_t j = xsuper[s]; j < xsuper[s + 1]; ++j) snode[j - 1] = s + 1;
+    if (lu) {
+        xunz.resize(n + 1);
+        int64_t up = 1;
+        for (int64_t s = 0; s < nsuper; ++s) {
+            int64_t w = xsuper[s + 1] - xsuper[s], len = xlindx[s + 1] - xlindx[s];
+            for (int64_t j = xsuper[s]; j < xsuper[s + 1]; ++j) { xunz[j - 1] = up; up += len - w; }
+        }
+        xunz[n] = up;
+    }
+    return spk_plan_create(n, nsuper, xsuper, snode.data(), xlindx, lindx, xlnz, lu ? xunz.data() : nullptr, 0, 0, 1);
+}
+
+SPK_API int64_t spk_lulsolve_f64(int64_t nsuper, const int64_t* xsuper, const int64_t* xlindx, const int64_t* lindx,
+                                 const int64_t* xlnz, const double* lnz, const int64_t* ipiv, double* rhs) {
+    int64_t n = n_from_xsuper(nsuper, xsuper);
+    spk_plan* p = solve_plan(n, nsuper, xsuper, xlindx, lindx, xlnz, true);
+    if (!p) return -100;
+    // the forward sweep reads lnz and ipiv only; unz is left unset
+    int64_t rc = 0;
+    if (cudaMemcpy(p->d_lnz, lnz, p->P.nlnz * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) rc = -100;
+    if (!rc) {
+        std::vector<int32_t> ip(n);
+        for (int64_t i = 0; i < n; ++i) ip[i] = (int32_t)ipiv[i];
+        if (cudaMemcpy(p->d_ipiv, ip.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) rc = -100;
+    }
+    if (!rc) rc = spk_plan_solve(p, rhs, 1, n, 1);
+    spk_plan_destroy(p);
+    return rc ? rc : 1;
+}
+
+SPK_API int64_t spk_luusolve_f64(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* xlindx,
+                                 const int64_t* lindx, const int64_t* xlnz, const double* lnz, const int64_t* xunz,
+                                 const double* unz, double* rhs) {
+    (void)xunz;
+    spk_plan* p = solve_plan(n, nsuper, xsuper, xlindx, lindx, xlnz, true);
+    if (!p) return -100;
+    int64_t rc = spk_plan_set_factors(p, lnz, unz, nullptr);
+    if (!rc) rc = spk_plan_solve(p, rhs, 1, n, 2);
+    spk_plan_destroy(p);
+    return rc ? rc : 1;
+}
+
+SPK_API int64_t spk_ldltsolve_f64(int64_t nsuper, const int64_t* xsuper, const int64_t* xlindx, const int64_t* lindx,
+                                  const int64_t* xlnz, const double* lnz, double* rhs) {
+    int64_t n = n_from_xsuper(nsuper, xsuper);
+    spk_plan* p = solve_plan(n, nsuper, xsuper, xlindx, lindx, xlnz, false);
+    if (!p) return -100;
+    int64_t rc = spk_plan_set_factors(p, lnz, nullptr, nullptr);
+    if (!rc) rc = spk_plan_solve(p, rhs, 1, n, 0);
+    spk_plan_destroy(p);
+    return rc ? rc : 1;
+}
+
+} // extern "C"

@@ -323,10 +323,24 @@ SPKH_API int spkh_mmd(I n, const I* xadj0, const I* adj0, I* perm0, I* invp0) {
 namespace {
 struct NdCtx { I nx, ny, nz, dof, leaf; I* perm; I next; };
 
+inline void nd_node(NdCtx& c, I x, I y, I z) {
+    for (I d = 0; d < c.dof; ++d) c.perm[c.next++] = ((z * c.ny + y) * c.nx + x) * c.dof + d + 1;
+}
 void nd_emit(NdCtx& c, I x0, I x1, I y0, I y1, I z0, I z1) {
-    for (I z = z0; z < z1; ++z) for (I y = y0; y < y1; ++y) for (I x = x0; x < x1; ++x)
-        for (I d = 0; d < c.dof; ++d)
-            c.perm[c.next++] = ((z * c.ny + y) * c.nx + x) * c.dof + d + 1;
+    for (I z = z0; z < z1; ++z) for (I y = y0; y < y1; ++y) for (I x = x0; x < x1; ++x) nd_node(c, x, y, z);
+}
+// Separator plane: nodes that touch a face of the box lying on an ANCESTOR separator (any box face
+// that is not on the domain boundary) are numbered last.  Each of them brings one new row into the
+// structure when it is eliminated, so numbering them last keeps the rest of the plane one
+// fundamental supernode instead of breaking it every few columns.
+void nd_emit_sep(NdCtx& c, I x0, I x1, I y0, I y1, I z0, I z1, I bx0, I bx1, I by0, I by1, I bz0, I bz1) {
+    auto touches = [&](I x, I y, I z) {
+        return (x == bx0 && bx0 > 0) || (x == bx1 - 1 && bx1 < c.nx) || (y == by0 && by0 > 0) ||
+               (y == by1 - 1 && by1 < c.ny) || (z == bz0 && bz0 > 0) || (z == bz1 - 1 && bz1 < c.nz);
+    };
+    for (int pass = 0; pass < 2; ++pass)
+        for (I z = z0; z < z1; ++z) for (I y = y0; y < y1; ++y) for (I x = x0; x < x1; ++x)
+            if ((int)touches(x, y, z) == pass) nd_node(c, x, y, z);
 }
 void nd_rec(NdCtx& c, I x0, I x1, I y0, I y1, I z0, I z1) {
     I lx = x1 - x0, ly = y1 - y0, lz = z1 - z0;
@@ -335,15 +349,15 @@ void nd_rec(NdCtx& c, I x0, I x1, I y0, I y1, I z0, I z1) {
     if (lx >= ly && lx >= lz) {
         I m = x0 + lx / 2;
         nd_rec(c, x0, m, y0, y1, z0, z1); nd_rec(c, m + 1, x1, y0, y1, z0, z1);
-        nd_emit(c, m, m + 1, y0, y1, z0, z1);
+        nd_emit_sep(c, m, m + 1, y0, y1, z0, z1, x0, x1, y0, y1, z0, z1);
     } else if (ly >= lz) {
         I m = y0 + ly / 2;
         nd_rec(c, x0, x1, y0, m, z0, z1); nd_rec(c, x0, x1, m + 1, y1, z0, z1);
-        nd_emit(c, x0, x1, m, m + 1, z0, z1);
+        nd_emit_sep(c, x0, x1, m, m + 1, z0, z1, x0, x1, y0, y1, z0, z1);
     } else {
         I m = z0 + lz / 2;
         nd_rec(c, x0, x1, y0, y1, z0, m); nd_rec(c, x0, x1, y0, y1, m + 1, z1);
-        nd_emit(c, x0, x1, y0, y1, m, m + 1);
+        nd_emit_sep(c, x0, x1, y0, y1, m, m + 1, x0, x1, y0, y1, z0, z1);
     }
 }
 } // namespace

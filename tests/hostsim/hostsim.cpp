@@ -1,0 +1,242 @@
+// TEST INFRASTRUCTURE — sequential host executor of the device schedule built by
+// sparspak.jl_b200/csrc/plan.hpp.  It runs the SAME task lists the CUDA kernels run
+// (load / assemble / diag / panel / GEMM / store / solve steps) with plain loops, so the
+// schedule (fronts, relative indices, position maps, blocking) can be validated against the
+// oracle on a machine without a GPU.  Never linked into the product library.
+#include <cmath>
+#include <cstdio>
+#include <vector>
+#include "plan.hpp"
+using namespace spk;
+#define API extern "C" __attribute__((visibility("default")))
+
+struct Sim {
+    Plan P;
+    std::vector<double> F, lnz, unz, w;
+    std::vector<int32_t> ipiv;
+    int iflag = 0;
+};
+
+static void chunks_io(Sim& s, bool store) {
+    Plan& P = s.P;
+    for (const Chunk& c : P.chunks) {
+        const int32_t* pos = P.pos.data() + c.posofs;
+        double* F = s.F.data() + c.fofs;
+        for (int j = 0; j < c.nj; ++j)
+            for (int i = 0; i < c.jlen; ++i) {
+                double& f = F[(int64_t)pos[i] + (int64_t)(c.o + j) * c.ld];
+                double& l = s.lnz[c.lofs + i + (int64_t)j * c.jlen];
+                if (store) l = f; else f = l;
+            }
+        if (P.lu) {
+            int ldu = c.jlen - c.nj;
+            for (int j = 0; j < c.nj; ++j)
+                for (int i = 0; i < ldu; ++i) {
+                    double& f = F[(int64_t)(c.o + j) + (int64_t)pos[c.nj + i] * c.ld];
+                    double& u = s.unz[c.uofs + i + (int64_t)j * ldu];
+                    if (store) u = f; else f = u;
+                }
+        }
+    }
+}
+
+static void assemble(Sim& s, const Front& C, const Front& Pa) {
+    Plan& P = s.P;
+    const int32_t* rel = P.rel.data() + C.relofs;
+    for (int j = 0; j < C.m; ++j)
+        for (int i = 0; i < C.m; ++i) {
+            if (!P.lu && i < j) continue;
+            s.F[Pa.fofs + (int64_t)rel[i] + (int64_t)rel[j] * Pa.ld] += s.F[C.fofs + (int64_t)(C.W + i) + (int64_t)(C.W + j) * C.ld];
+        }
+}
+
+static void diag(Sim& s, const PStep& ps) {
+    Plan& P = s.P;
+    double* A = s.F.data() + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld;
+    const int ld = ps.ld, w = ps.w;
+    if (P.lu) {
+        int32_t* ip = s.ipiv.data() + ps.col0;
+        int s0 = 0;
+        for (int b = 0; b < ps.nsub; ++b) {
+            int s1 = s0 + P.subw[ps.sub0 + b];
+            for (int k = s0; k < s1; ++k) {
+                int kp = k; double best = std::fabs(A[k + (size_t)k * ld]);
+                for (int i = k + 1; i < s1; ++i) { double v = std::fabs(A[i + (size_t)k * ld]); if (v > best) { best = v; kp = i; } }
+                ip[k] = kp - s0 + 1;
+                double pv = A[kp + (size_t)k * ld];
+                if (pv == 0.0) s.iflag = -1;
+                if (pv != 0.0) {
+                    if (kp != k) for (int j = s0; j < w; ++j) std::swap(A[k + (size_t)j * ld], A[kp + (size_t)j * ld]);
+                    double inv = 1.0 / A[k + (size_t)k * ld];
+                    for (int i = k + 1; i < w; ++i) A[i + (size_t)k * ld] *= inv;
+                }
+                for (int j = k + 1; j < w; ++j) for (int i = k + 1; i < w; ++i) A[i + (size_t)j * ld] -= A[i + (size_t)k * ld] * A[k + (size_t)j * ld];
+            }
+            s0 = s1;
+        }
+    } else {
+        for (int k = 0; k < w; ++k) {
+            double d = A[k + (size_t)k * ld];
+            if (d == 0.0) s.iflag = -1;
+            for (int i = k + 1; i < w; ++i) A[i + (size_t)k * ld] /= d;
+            for (int c = k + 1; c < w; ++c) for (int r = c; r < w; ++r) A[r + (size_t)c * ld] -= (A[c + (size_t)k * ld] * d) * A[r + (size_t)k * ld];
+        }
+    }
+}
+
+static void panel(Sim& s, const PStep& ps) {
+    Plan& P = s.P;
+    const int w = ps.w, ld = ps.ld, e0 = ps.o + ps.w, below = ps.R - e0;
+    double* Fm = s.F.data() + ps.fofs;
+    const double* T = Fm + (int64_t)ps.o + (int64_t)ps.o * ld;
+    for (int i = 0; i < below; ++i) {
+        double* X = Fm + (int64_t)(e0 + i) + (int64_t)ps.o * ld;
+        if (P.lu) {
+            for (int j = 0; j < w; ++j) {
+                double acc = X[(size_t)j * ld];
+                for (int k = 0; k < j; ++k) acc -= T[k + (size_t)j * ld] * X[(size_t)k * ld];
+                X[(size_t)j * ld] = (1.0 / T[j + (size_t)j * ld]) * acc;
+            }
+            double* Y = Fm + (int64_t)ps.o + (int64_t)(e0 + i) * ld;
+            const int32_t* ip = s.ipiv.data() + ps.col0;
+            int s0 = 0;
+            for (int b = 0; b < ps.nsub; ++b) {
+                int s1 = s0 + P.subw[ps.sub0 + b];
+                for (int j = s0; j < s1; ++j) { double acc = Y[j]; for (int k = 0; k < s0; ++k) acc -= T[j + (size_t)k * ld] * Y[k]; Y[j] = acc; }
+                for (int k = s0; k < s1; ++k) { int q = s0 + ip[k] - 1; if (q != k) std::swap(Y[k], Y[q]); }
+                for (int j = s0; j < s1; ++j) { double acc = Y[j]; for (int k = s0; k < j; ++k) acc -= T[j + (size_t)k * ld] * Y[k]; Y[j] = acc; }
+                s0 = s1;
+            }
+        } else {
+            for (int j = 0; j < w; ++j) {
+                double acc = X[(size_t)j * ld];
+                for (int k = 0; k < j; ++k) acc -= T[j + (size_t)k * ld] * X[(size_t)k * ld];
+                X[(size_t)j * ld] = acc;
+            }
+            for (int j = 0; j < w; ++j) X[(size_t)j * ld] /= T[j + (size_t)j * ld];
+        }
+    }
+}
+
+static void gemm(Sim& s, const GemmTask& g) {
+    std::vector<double> acc((size_t)g.m * g.n, 0.0);
+    const double* A = s.F.data() + g.a0; const double* B = s.F.data() + g.b0; const double* D = s.F.data() + g.d0;
+    for (int k = 0; k < g.k; ++k)
+        for (int j = 0; j < g.n; ++j) {
+            double b = g.bk ? B[(size_t)k + (size_t)j * g.ld] : B[(size_t)j + (size_t)k * g.ld] * D[(size_t)k * (g.ld + 1)];
+            for (int i = 0; i < g.m; ++i) acc[i + (size_t)j * g.m] += A[i + (size_t)k * g.ld] * b;
+        }
+    double* C = s.F.data() + g.c0;
+    for (int j = 0; j < g.n; ++j) for (int i = 0; i < g.m; ++i) if (!(g.lower && i + g.roff < j)) C[i + (size_t)j * g.ld] -= acc[i + (size_t)j * g.m];
+}
+
+API void* sim_create(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* snode, const int64_t* xlindx,
+                     const int64_t* lindx, const int64_t* xlnz, const int64_t* xunz, int use_dmma_buckets,
+                     int relax_abs, double relax_frac, int alloc) {
+    Sim* s = new Sim();
+    s->P.relax_abs = relax_abs; s->P.relax_frac = relax_frac;
+    if (!analyze(s->P, n, nsuper, xsuper, snode, xlindx, lindx, xlnz, xunz)) { fprintf(stderr, "analyze: %s\n", s->P.error.c_str()); delete s; return nullptr; }
+    s->P.use_dmma = use_dmma_buckets != 0;
+    build_schedule(s->P);
+    if (alloc) {
+        s->F.assign(std::max<int64_t>(s->P.arena, 1), 0.0);
+        s->w.assign(std::max<int64_t>(s->P.wlen, 1), 0.0);
+        s->ipiv.assign(n, 0);
+    }
+    return s;
+}
+API void sim_destroy(void* h) { delete (Sim*)h; }
+API int64_t sim_stat(void* h, int what) {
+    Sim* s = (Sim*)h; Plan& P = s->P;
+    switch (what) {
+    case 0: return (int64_t)P.fronts.size(); case 1: return P.nlevels; case 2: return P.arena; case 3: return P.wlen;
+    case 4: return (int64_t)P.factor_launches.size(); case 5: return (int64_t)(P.fwd_launches.size() + P.bwd_launches.size());
+    case 6: return (int64_t)P.gemmt.size(); case 7: return P.maxpw; case 8: return P.maxR;
+    case 9: { int64_t k = 0; for (auto& f : P.fronts) if (f.nch > 1) ++k; return k; }
+    case 10: { int64_t k = 0; for (auto& L : P.factor_launches) k += L.nblocks; return k; }
+    case 11: return (int64_t)P.psteps.size();
+    case 12: { int64_t k = 0; for (auto& f : P.fronts) k += (int64_t)f.m * f.m; return k; }
+    default: return 0; }
+}
+API double sim_statf(void* h, int what) {
+    Sim* s = (Sim*)h; Plan& P = s->P;
+    if (what == 0) return P.flops_struct; if (what == 1) return P.nnzL;
+    if (what == 2) { double f = 0; for (auto& L : P.factor_launches) f += L.flops; return f; }
+    if (what == 3) { double f = 0; for (auto& L : P.factor_launches) if (L.kind == K_GEMM_B64 || L.kind == K_GEMM_B128) f += L.flops; return f; }
+    return 0;
+}
+
+API int64_t sim_factor(void* h, double* lnz, double* unz, int64_t* ipvt) {
+    Sim* s = (Sim*)h; Plan& P = s->P;
+    s->lnz.assign(lnz, lnz + P.nlnz);
+    if (P.lu) s->unz.assign(unz, unz + P.nunz);
+    std::fill(s->F.begin(), s->F.end(), 0.0);
+    s->iflag = 0;
+    chunks_io(*s, false);
+    for (const Launch& L : P.factor_launches) {
+        switch (L.kind) {
+        case K_ASM:
+            for (int t = 0; t < L.count; ++t) { AsmTask a = P.asmt[L.first + t]; assemble(*s, P.fronts[a.child], P.fronts[a.parent]); } break;
+        case K_ASM_TAIL:
+            for (int t = 0; t < L.count; ++t) {
+                const Front& Pa = P.fronts[P.asmt[L.first + t].parent];
+                for (int r = ASM_ROUNDS; r < Pa.nchild; ++r) assemble(*s, P.fronts[P.childlist[Pa.child0 + r]], Pa);
+            } break;
+        case K_DIAG: for (int t = 0; t < L.count; ++t) diag(*s, P.psteps[P.pslist[L.first + t]]); break;
+        case K_PANEL: for (int t = 0; t < L.count; ++t) panel(*s, P.psteps[P.pslist[L.first + t]]); break;
+        case K_GEMM: case K_GEMM_B64: case K_GEMM_B128: for (int t = 0; t < L.count; ++t) gemm(*s, P.gemmt[L.first + t]); break;
+        default: return -100;
+        }
+    }
+    chunks_io(*s, true);
+    std::copy(s->lnz.begin(), s->lnz.end(), lnz);
+    if (P.lu) { std::copy(s->unz.begin(), s->unz.end(), unz); for (int64_t i = 0; i < P.n; ++i) ipvt[i] = s->ipiv[i]; }
+    return s->iflag;
+}
+
+// rhs in permuted order, in place; factors as left by sim_factor
+API int64_t sim_solve(void* h, double* rhs) {
+    Sim* s = (Sim*)h; Plan& P = s->P; const bool lu = P.lu;
+    double* w = s->w.data();
+    for (const Launch& L : P.fwd_launches) {
+        const int32_t* list = P.gathert.data() + L.first;
+        for (int ti = 0; ti < L.count; ++ti) {
+            if (L.kind == K_FWD_GATHER) {
+                const Front& F = P.fronts[list[ti]]; double* wf = w + F.wofs;
+                for (int i = 0; i < F.R; ++i) wf[i] = i < F.W ? rhs[F.F0 + i] : 0.0;
+                for (int r = 0; r < F.nchild; ++r) { const Front& C = P.fronts[P.childlist[F.child0 + r]]; for (int i = 0; i < C.m; ++i) wf[P.rel[C.relofs + i]] += w[C.wofs + C.W + i]; }
+            } else if (L.kind == K_FWD_DIAG) {
+                const SolveTask& t = P.solvet[list[ti]]; double* x = w + t.wofs + t.o; const double* T = s->lnz.data() + t.lofs;
+                if (lu) for (int k = 0; k < t.nj; ++k) { int q = s->ipiv[t.col0 + k] - 1; if (q != k) std::swap(x[k], x[q]); }
+                for (int k = 0; k < t.nj; ++k) for (int i = k + 1; i < t.nj; ++i) x[i] -= x[k] * T[i + (size_t)k * t.ld];
+            } else if (L.kind == K_FWD_UPDATE) {
+                const SolveTask& t = P.solvet[list[ti]]; double* wf = w + t.wofs;
+                for (int i = 0; i < t.m; ++i) { double acc = 0; for (int k = 0; k < t.nj; ++k) acc += (-wf[t.o + k]) * s->lnz[t.lofs + t.nj + i + (size_t)k * t.ld]; wf[P.pos[t.posofs + t.nj + i]] += acc; }
+            } else return -100;
+        }
+    }
+    for (const Launch& L : P.bwd_launches) {
+        const int32_t* list = P.gathert.data() + L.first;
+        for (int ti = 0; ti < L.count; ++ti) {
+            if (L.kind == K_BWD_GATHER) {
+                const Front& F = P.fronts[list[ti]]; const Front& Pa = P.fronts[F.parent];
+                for (int i = 0; i < F.m; ++i) w[F.wofs + F.W + i] = w[Pa.wofs + P.rel[F.relofs + i]];
+            } else if (L.kind == K_BWD_UPDATE) {
+                const SolveTask& t = P.solvet[list[ti]]; double* wf = w + t.wofs;
+                for (int k = 0; k < t.nj; ++k) {
+                    double sum = 0;
+                    for (int i = 0; i < t.m; ++i) sum += (lu ? s->unz[t.uofs + i + (size_t)k * t.ldu] : s->lnz[t.lofs + t.nj + i + (size_t)k * t.ld]) * wf[P.pos[t.posofs + t.nj + i]];
+                    if (lu) wf[t.o + k] += -sum; else wf[t.o + k] = wf[t.o + k] / s->lnz[t.lofs + k + (size_t)k * t.ld] - sum;
+                }
+            } else if (L.kind == K_BWD_DIAG) {
+                const SolveTask& t = P.solvet[list[ti]]; double* x = w + t.wofs + t.o; const double* T = s->lnz.data() + t.lofs;
+                for (int k = t.nj - 1; k >= 0; --k) {
+                    if (lu) { x[k] /= T[k + (size_t)k * t.ld]; for (int i = 0; i < k; ++i) x[i] -= x[k] * T[i + (size_t)k * t.ld]; }
+                    else for (int i = 0; i < k; ++i) x[i] -= x[k] * T[k + (size_t)i * t.ld];
+                }
+                for (int k = 0; k < t.nj; ++k) rhs[t.col0 + k] = x[k];
+            } else return -100;
+        }
+    }
+    return 0;
+}

@@ -1,0 +1,229 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same
+inputs.  Bars (north_star): pivot sequence and all integer structure bit-exact, factor entries
+to a relative 1e-11, solve residual ||Ax-b||/||b|| <= 1e-12."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import sparspak_jl_b200 as spk
+from sparspak_jl_b200 import _cudalib
+import oracle
+from common import (CASES, prepare, oracle_factor, spd_mask, rel_err, residual, M, maketridiagproblem,
+                    FACTOR_RTOL, RESID_TOL)
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_factor_plan(b):
+    plan = _cudalib.Plan(b)
+    plan.set_values(b.lnz, None if b.spd else b.unz)
+    fl = plan.factor()
+    nl = int(b.xlnz[b.n]) - 1
+    lnz = np.zeros(b.lnz.size); unz = np.zeros(b.unz.size); ipiv = np.zeros(b.n, np.int64)
+    plan.get_factors(lnz, None if b.spd else unz, None if b.spd else ipiv)
+    return plan, lnz, unz, ipiv, fl
+
+
+@pytest.mark.parametrize("name,build,spd,order,maxblk", CASES, ids=[c[0] for c in CASES])
+def test_factor_and_solve_match_oracle(name, build, spd, order, maxblk):
+    A = build()
+    s = prepare(A, spd, order() if order else None, maxblk)
+    b = s.slvr
+    lo, uo, po, fo = oracle_factor(b)
+    plan, lg, ug, pg, fg = gpu_factor_plan(b)
+    assert fg == fo == 0
+    assert rel_err(lg, lo, spd_mask(b)) < FACTOR_RTOL
+    if not spd:
+        assert np.array_equal(pg, po), "pivot sequence differs from the reference rule"
+        assert rel_err(ug, uo) < FACTOR_RTOL
+    bb = M.rhs_for(A)
+    x = bb.copy()
+    plan.set_perm(b.order.rperm, b.order.rinvp)
+    plan.triangularsolve(x)
+    xo = oracle.triangularsolve(b, lo, uo, po, bb)
+    assert residual(A, x, bb) < RESID_TOL
+    assert np.linalg.norm(x - xo) / np.linalg.norm(xo) < 1e-10
+    plan.destroy()
+
+
+def test_golden_tridiagonal_factors_on_gpu():
+    # test/test_sparse_method.jl:219-227 directly against the CUDA path
+    from test_oracle_golden import GOLD_LNZ
+    s = prepare(maketridiagproblem(11), False)
+    plan, lg, ug, pg, fg = gpu_factor_plan(s.slvr)
+    g = np.array(GOLD_LNZ)
+    assert np.linalg.norm(lg - g) / np.linalg.norm(g) < 1e-14
+    assert np.abs(ug + 1.0).max() == 0.0
+    assert pg.tolist() == [1] * 10 + [2]
+
+
+@pytest.mark.parametrize("spd", [False, True])
+def test_stateless_dropins(spd):
+    """spk_lufactor_f64 / spk_lulsolve_f64 / spk_luusolve_f64 / spk_ldltfactor_f64 / spk_ldltsolve_f64:
+    the Julia signatures of _lufactor! etc. (SpkSparseBase.jl:384,409-411; SpkSparseSpdBase.jl:325,351)."""
+    A = M.convdiff3d(9) if not spd else M.laplacian3d(9)
+    s = prepare(A, spd, spk.nd_grid_order(9, 9, 9))
+    b = s.slvr
+    L = _cudalib.lib()
+    lo, uo, po, _ = oracle_factor(b)
+    lnz = b.lnz.copy(); unz = b.unz.copy(); ipiv = np.zeros(b.n, np.int64)
+    bb = M.rhs_for(A)
+    rhs = np.ascontiguousarray(bb[b.order.rperm - 1])
+    if spd:
+        assert L.spk_ldltfactor_f64(b.n, b.nsuper, b.xsuper, b.snode, b.xlindx, b.lindx, b.xlnz, lnz) == 0
+        assert rel_err(lnz, lo, spd_mask(b)) < FACTOR_RTOL
+        assert L.spk_ldltsolve_f64(b.nsuper, b.xsuper, b.xlindx, b.lindx, b.xlnz, lnz, rhs) == 1
+    else:
+        assert L.spk_lufactor_f64(b.n, b.nsuper, b.xsuper, b.snode, b.xlindx, b.lindx, b.xlnz, lnz, b.xunz, unz, ipiv) == 0
+        assert np.array_equal(ipiv, po) and rel_err(lnz, lo) < FACTOR_RTOL and rel_err(unz, uo) < FACTOR_RTOL
+        # forward sweep alone == oracle's _lulsolve!
+        fw = rhs.copy(); fo = rhs.copy()
+        assert L.spk_lulsolve_f64(b.nsuper, b.xsuper, b.xlindx, b.lindx, b.xlnz, lnz, ipiv, fw) == 1
+        oracle.lib().spko_lulsolve(b.nsuper, b.xsuper, b.xlindx, b.lindx, b.xlnz, lo, po, fo)
+        assert np.linalg.norm(fw - fo) / np.linalg.norm(fo) < 1e-12
+        assert L.spk_luusolve_f64(b.n, b.nsuper, b.xsuper, b.xlindx, b.lindx, b.xlnz, lnz, b.xunz, unz, fw) == 1
+        rhs = fw
+    x = rhs[b.order.rinvp - 1]
+    assert residual(A, x, bb) < RESID_TOL
+
+
+def test_solver_api_dropin_lu():
+    """The reference call sequence (findorder!/symbolicfactor!/inmatrix!/factor!/triangularsolve!/solve!)
+    through the host mirror; lnz/unz/ipiv of the solver are overwritten in place as in the reference."""
+    p = maketridiagproblem(1101)
+    s = spk.SparseSolver(p)
+    assert spk.solve(s)
+    import scipy.sparse.linalg as spla
+    xr = spla.spsolve(p.csc().tocsc(), p.rhs)
+    assert np.linalg.norm(p.x - xr) / np.linalg.norm(xr) < 1e-6          # the reference's own bar
+    assert residual(p.csc(), p.x, p.rhs) < RESID_TOL
+    lo, uo, po, _ = None, None, None, None
+    assert s._factordone and s._trisolvedone
+    assert s.slvr.ipiv.min() >= 1
+
+
+def test_solver_api_dropin_spd_and_nd_callback():
+    A = M.laplacian2d(40)
+    s = spk.SparseSpdSolver(A)
+    spk.findorder(s, spk.nd_grid_order(40, 40))
+    spk.symbolicfactor(s); spk.inmatrix(s); spk.factor(s)
+    b = M.rhs_for(A)
+    x = b.copy()
+    spk.triangularsolve(s, x)
+    assert residual(A, x, b) < RESID_TOL
+    assert np.allclose(x, np.arange(1, 1601), rtol=1e-9)
+
+
+def test_csc_interface_refactor_and_pattern_change():
+    # test/test_cscinterface.jl:100-201: sparspaklu / sparspaklu! / ldiv! / backslash
+    A = M.convdiff3d(7)
+    lu = spk.sparspaklu(A)
+    b = M.rhs_for(A)
+    x = spk.backslash(lu, b)
+    assert residual(A, x, b) < RESID_TOL
+    A2 = A.copy(); A2.data = A2.data * 1.5                      # same pattern, new values
+    order_before = lu.slvr.order.rperm.copy()
+    spk.sparspaklu_(lu, A2)
+    assert np.array_equal(order_before, lu.slvr.order.rperm)   # ordering + symbolic reused
+    x2 = np.zeros_like(b); spk.ldiv(x2, lu, b)
+    assert residual(A2, x2, b) < RESID_TOL
+    A3 = sp.csc_matrix(A2 + sp.eye(A.shape[0], k=5) * 0.01)     # pattern change
+    with pytest.raises(RuntimeError):
+        spk.sparspaklu_(lu, A3, allow_pattern_change=False)
+    spk.sparspaklu_(lu, A3)
+    assert residual(A3, spk.backslash(lu, b), b) < RESID_TOL
+    lu0 = spk.sparspaklu(A, factorize=False)
+    with pytest.raises(spk.SequenceError):
+        spk.triangularsolve(lu0, b.copy())
+
+
+def test_device_inmatrix_and_refactor():
+    """values scattered on the device through the once-built index map; a
+    refactorisation uploads nnz(A) values only."""
+    A = M.laplacian3d(10)
+    s = prepare(A, True, spk.nd_grid_order(10, 10, 10))
+    b = s.slvr
+    dest, nzval = b._inmatrix_map(A)
+    plan = _cudalib.Plan(b)
+    plan.inmatrix(nzval, dest)
+    assert plan.factor() == 0
+    lg = np.zeros(b.lnz.size); plan.get_factors(lg)
+    lo, _, _, _ = oracle_factor(b)
+    assert rel_err(lg, lo, spd_mask(b)) < FACTOR_RTOL
+    plan.inmatrix(nzval * 2.0)                                   # same pattern, map reused
+    assert plan.factor() == 0
+    plan.get_factors(lg)
+    b.lnz *= 2.0
+    lo2, _, _, _ = oracle_factor(b)
+    assert rel_err(lg, lo2, spd_mask(b)) < FACTOR_RTOL
+    plan.destroy()
+
+
+@pytest.mark.parametrize("spd", [False, True])
+def test_multi_rhs(spd):
+    """Extension over the reference (single-RHS only, SpkSparseSolver.jl:266): a block of right-hand
+    sides; every column must equal the single-RHS solve."""
+    A = M.convdiff3d(8) if not spd else M.laplacian3d(8)
+    s = prepare(A, spd, spk.nd_grid_order(8, 8, 8))
+    b = s.slvr
+    plan = _cudalib.Plan(b)
+    plan.set_values(b.lnz, None if spd else b.unz); assert plan.factor() == 0
+    plan.set_perm(b.order.rperm, b.order.rinvp)
+    rng = np.random.default_rng(9876)
+    B = np.asfortranarray(rng.random((b.n, 37)))
+    X = B.copy(order="F")
+    plan.triangularsolve(X)
+    for j in (0, 17, 36):
+        xj = B[:, j].copy(); plan.triangularsolve(xj)
+        assert np.array_equal(xj, X[:, j])
+        assert residual(A, X[:, j], B[:, j]) < RESID_TOL
+    plan.destroy()
+
+
+def test_zero_pivot_flag():
+    # iflag = -1 on a zero pivot (SpkLUFactor.jl:29-34); the host mirror turns it into an error (SpkSparseBase.jl:386-389)
+    A = sp.csc_matrix(np.array([[0.0, 0, 0], [0, 2.0, 1.0], [0, 1.0, 2.0]]))
+    A[0, 0] = 0.0
+    A = sp.csc_matrix(([0.0, 2.0, 1.0, 1.0, 2.0], ([0, 1, 2, 1, 2], [0, 1, 1, 2, 2])), shape=(3, 3))
+    s = prepare(A, False)
+    plan = _cudalib.Plan(s.slvr)
+    plan.set_values(s.slvr.lnz, s.slvr.unz)
+    assert plan.factor() == -1
+    with pytest.raises(RuntimeError):
+        spk.factor(s)
+
+
+def test_pivoting_fuzz_on_gpu():
+    # test/test_structunsymm.jl:60-90 against the CUDA path: ipiv identical to the oracle's on every case
+    rng = np.random.default_rng(4321)
+    done = 0
+    for k in range(60):
+        n = int(rng.integers(4, 40))
+        a = sp.random(n, n, density=min(0.9, 3.0 / n + 0.1), random_state=rng, format="csc", data_rvs=rng.random) + sp.identity(n, format="csc")
+        a = sp.csc_matrix(a); a.eliminate_zeros()
+        if np.linalg.cond(a.toarray()) > 1e8:
+            continue
+        s = prepare(a, False, maxblocksize=int(rng.integers(2, 12)))
+        lo, uo, po, _ = oracle_factor(s.slvr)
+        plan, lg, ug, pg, fg = gpu_factor_plan(s.slvr)
+        assert np.array_equal(pg, po)
+        assert rel_err(lg, lo) < 1e-9 and rel_err(ug, uo) < 1e-9
+        bvec = rng.random(n); x = bvec.copy()
+        plan.set_perm(s.slvr.order.rperm, s.slvr.order.rinvp); plan.triangularsolve(x)
+        assert np.linalg.norm(x - np.linalg.solve(a.toarray(), bvec)) < 1e-9
+        plan.destroy(); done += 1
+    assert done > 30
+
+
+def test_dmma_and_dfma_kernels_agree(monkeypatch):
+    """The DMMA trailing-update kernels and the small-tile DFMA kernel compute the same factors."""
+    A = M.laplacian3d(16)
+    s = prepare(A, True, spk.nd_grid_order(16, 16, 16))
+    b = s.slvr
+    _, l1, _, _, f1 = gpu_factor_plan(b)
+    monkeypatch.setenv("SPK_NO_DMMA", "1")
+    _, l2, _, _, f2 = gpu_factor_plan(b)
+    assert f1 == f2 == 0
+    assert rel_err(l1, l2, spd_mask(b)) < 1e-12
+    lo, _, _, _ = oracle_factor(b)
+    assert rel_err(l1, lo, spd_mask(b)) < FACTOR_RTOL

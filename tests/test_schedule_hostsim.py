@@ -1,0 +1,54 @@
+"""The device schedule (plan.hpp: fronts, relaxed chains, relative indices, panel steps, outer
+blocks, solve steps) executed on the host by tests/hostsim must reproduce the oracle."""
+import numpy as np
+import pytest
+
+import sparspak_jl_b200 as spk
+import oracle
+from common import CASES, prepare, oracle_factor, spd_mask, rel_err, residual, HostSim, M
+
+
+@pytest.mark.parametrize("name,build,spd,order,maxblk", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("relax", [(0, 0.0), (4, 0.02)], ids=["fundamental", "relaxed"])
+def test_hostsim_matches_oracle(name, build, spd, order, maxblk, relax):
+    A = build()
+    s = prepare(A, spd, order() if order else None, maxblk)
+    b = s.slvr
+    lo, uo, po, fo = oracle_factor(b)
+    sim = HostSim(b, relax[0], relax[1])
+    ls, us, ps, fs = sim.factor()
+    assert fs == fo == 0
+    nl = int(b.xlnz[b.n]) - 1
+    assert rel_err(ls, lo[:nl], spd_mask(b)[:nl]) < 1e-12
+    if not spd:
+        assert np.array_equal(ps, po)
+        assert rel_err(us, uo) < 1e-12
+    bb = M.rhs_for(A)
+    rhs = np.ascontiguousarray(bb[b.order.rperm - 1])
+    x = sim.solve(rhs)[b.order.rinvp - 1]
+    assert residual(A, x, bb) < 1e-13
+
+
+def test_hostsim_many_children_tail_path():
+    # arrow matrix: the root front has n-1 children -> exercises the assemble tail kernel path
+    import scipy.sparse as sp
+    n = 40
+    A = sp.lil_matrix((n, n)); A.setdiag(4.0); A[n - 1, :] = -0.1; A[:, n - 1] = -0.1; A[n - 1, n - 1] = 10.0
+    A = sp.csc_matrix(A)
+    for spd in (False, True):
+        s = prepare(A, spd)
+        lo, uo, po, _ = oracle_factor(s.slvr)
+        ls, us, ps, _ = HostSim(s.slvr).factor()
+        nl = int(s.slvr.xlnz[n]) - 1
+        assert rel_err(ls, lo[:nl], spd_mask(s.slvr)[:nl]) < 1e-13
+
+
+def test_plan_statistics_cfg1():
+    # config 1 (2-D 5-point 100x100, SPD, nested dissection): structure figures used by DESIGN.md
+    A = M.laplacian2d(100)
+    s = spk.SparseSpdSolver(A)
+    spk.findorder(s, spk.nd_grid_order(100, 100)); spk.symbolicfactor(s)
+    sim = HostSim(s.slvr, alloc=False)
+    assert s.slvr.n == 10000
+    assert sim.stat(0) < s.slvr.nsuper            # relaxed chains merge supernodes into fewer fronts
+    assert sim.stat(1) < 40                       # few front levels
