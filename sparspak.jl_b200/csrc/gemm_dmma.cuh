@@ -34,7 +34,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
@@ -155,18 +155,32 @@ k_gemm_dmma(DevCtx c, const GemmTask* __restrict__ tasks, const int32_t* __restr
     }
     cp_async_wait<0>();
 
-    // epilogue: C -= acc   (fragment (i,j): rows wm0+8i+lr, cols wn0+8j+2*lk+{0,1})
+    // epilogue: C -= acc   (fragment (i,j): rows wm0+8i+lr, cols wn0+8j+2*lk+{0,1}).
+    // All loads of one column pair are issued before the first store: a plain `C[..] -= acc` loop
+    // serialises on load->store->load ordering (the compiler must assume the addresses alias) and
+    // left the tensor pipe idle for longer than the whole k loop (ncu: long-scoreboard stalls on the DADDs).
     double* __restrict__ C = c.F + g.c0;
 #pragma unroll
     for (int j = 0; j < FN; ++j) {
+        double cv[2][FM];
+        bool ok[2][FM];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int cc = col0 + wn0 + j * 8 + 2 * lk + h;
-            if (cc >= g.n) continue;
 #pragma unroll
             for (int i = 0; i < FM; ++i) {
                 const int r = row0 + wm0 + i * 8 + lr;
-                if (r < g.m && !(g.lower && r + g.roff < cc)) C[(size_t)r + (size_t)cc * ld] -= acc[i][j][h];
+                ok[h][i] = (cc < g.n) && (r < g.m) && !(g.lower && r + g.roff < cc);
+                cv[h][i] = ok[h][i] ? __ldcg(C + (size_t)r + (size_t)cc * ld) : 0.0;
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int cc = col0 + wn0 + j * 8 + 2 * lk + h;
+#pragma unroll
+            for (int i = 0; i < FM; ++i) {
+                const int r = row0 + wm0 + i * 8 + lr;
+                if (ok[h][i]) __stcg(C + (size_t)r + (size_t)cc * ld, cv[h][i] - acc[i][j][h]);
             }
         }
     }

@@ -14,7 +14,7 @@ namespace spk {
 
 struct DFront {
     int64_t fofs, relofs, wofs, F0;
-    int32_t W, R, m, ld, parent, child0, nchild, pad;
+    int32_t W, R, m, ld, parent, child0, nchild, c0, nch, pad;
 };
 struct DChunk {
     int64_t lofs, uofs, posofs, fofs;
@@ -128,6 +128,7 @@ template <bool LU>
 __device__ void diag_factor(double* A, int lda, int w, const int32_t* __restrict__ subw, int nsub,
                             int32_t* ipiv, int32_t* iflag, int32_t* s_piv, double* s_pv) {
     const int tid = threadIdx.x, nt = blockDim.x;
+    const int tx = tid & 15, ty = tid >> 4;               // 16 x 16 layout for the rank-1 updates (blockDim.x == 256)
     if (LU) {
         int s0 = 0;
         for (int b = 0; b < nsub; ++b) {
@@ -165,10 +166,9 @@ __device__ void diag_factor(double* A, int lda, int w, const int32_t* __restrict
                     for (int i = k + 1 + tid; i < w; i += nt) A[i + (size_t)k * lda] *= inv;
                 }
                 __syncthreads();
-                const int rem = w - k - 1;
-                for (int e = tid; e < rem * rem; e += nt) {
-                    int j = k + 1 + e / rem, i = k + 1 + e % rem;
-                    A[i + (size_t)j * lda] -= A[i + (size_t)k * lda] * A[k + (size_t)j * lda];
+                for (int j = k + 1 + ty; j < w; j += 16) {
+                    const double akj = A[k + (size_t)j * lda];
+                    for (int i = k + 1 + tx; i < w; i += 16) A[i + (size_t)j * lda] -= A[i + (size_t)k * lda] * akj;
                 }
                 __syncthreads();
             }
@@ -181,10 +181,9 @@ __device__ void diag_factor(double* A, int lda, int w, const int32_t* __restrict
             __syncthreads();
             for (int i = k + 1 + tid; i < w; i += nt) A[i + (size_t)k * lda] /= d;
             __syncthreads();
-            const int rem = w - k - 1;
-            for (int e = tid; e < rem * rem; e += nt) {
-                int s = k + 1 + e / rem, r = k + 1 + e % rem;
-                if (r >= s) A[r + (size_t)s * lda] -= (A[s + (size_t)k * lda] * d) * A[r + (size_t)k * lda];
+            for (int s = k + 1 + ty; s < w; s += 16) {
+                const double f = A[s + (size_t)k * lda] * d;
+                for (int r = s + tx; r < w; r += 16) A[r + (size_t)s * lda] -= f * A[r + (size_t)k * lda];
             }
             __syncthreads();
         }
@@ -213,64 +212,90 @@ __global__ void __launch_bounds__(256) k_diag(DevCtx c, const int32_t* __restric
 }
 
 // ------------------------------------------------------------------------------------
-// Panels of a panel step: one thread per front row below (L side) / per front column to the right (U side).
+// Panels of a panel step.  One block = PANEL_ROWS front rows below the block (L side) or PANEL_ROWS
+// front columns to its right (U side); the factored w x w block T and the block's slice of the
+// panel are staged in shared memory (coalesced both ways), one thread then owns one row / column:
 //   LU  L-side: X = A21 * inv(U11)                     (dtrsm 'r','u','n','n', SpkLUFactor.jl:235)
 //   LU  U-side: per chunk, apply its row interchanges then inv(L11)  (:238-240, _luswap! SpkSpdMMOps.jl:168-175)
 //   LDLT:       X = A21 * inv(L11^T), then each column / D  (SpkLDLtFactor.jl:367-377)
+// Shared layout: Ts[w*w] (column-major), Xs[w][PANEL_ROWS] (element k of thread t at Xs[k*PANEL_ROWS + t]).
+inline size_t panel_smem_bytes(int w) { return ((size_t)w * w + (size_t)w * PANEL_ROWS) * sizeof(double); }
+
 template <bool LU>
 __global__ void __launch_bounds__(PANEL_ROWS) k_panel(DevCtx c, const int32_t* __restrict__ pslist,
                                                       const int32_t* __restrict__ pfx, int count) {
+    extern __shared__ double psm[];
     int t = find_task(pfx, count, blockIdx.x);
     int lb = blockIdx.x - pfx[t];
     const PStep ps = c.psteps[pslist[t]];
     const int w = ps.w, ld = ps.ld, e0 = ps.o + ps.w;
     const int below = ps.R - e0;
     const int nb = (below + PANEL_ROWS - 1) / PANEL_ROWS;
+    const int tid = threadIdx.x;
     double* Fm = c.F + ps.fofs;
     const double* __restrict__ T = Fm + (int64_t)ps.o + (int64_t)ps.o * ld;   // factored w x w block
-    if (lb < nb) {
-        int i = lb * PANEL_ROWS + threadIdx.x;
-        if (i >= below) return;
-        double* X = Fm + (int64_t)(e0 + i) + (int64_t)ps.o * ld;               // row of the L panel, stride ld
-        if (LU) {
-            for (int j = 0; j < w; ++j) {
-                double acc = X[(size_t)j * ld];
-                for (int k = 0; k < j; ++k) acc -= T[k + (size_t)j * ld] * X[(size_t)k * ld];
-                X[(size_t)j * ld] = (1.0 / T[j + (size_t)j * ld]) * acc;
+    double* Ts = psm;
+    double* Xs = psm + w * w;
+    for (int e = tid; e < w * w; e += PANEL_ROWS) { int j = e / w, i = e - j * w; Ts[e] = T[i + (size_t)j * ld]; }
+    const bool lside = lb < nb;
+    const int i0 = (lside ? lb : lb - nb) * PANEL_ROWS;
+    const int cnt = min(PANEL_ROWS, below - i0);
+    if (lside) {
+        double* X0 = Fm + (int64_t)(e0 + i0) + (int64_t)ps.o * ld;             // rows contiguous
+        for (int k = 0; k < w; ++k) if (tid < cnt) Xs[k * PANEL_ROWS + tid] = X0[tid + (size_t)k * ld];
+    } else {
+        double* Y0 = Fm + (int64_t)ps.o + (int64_t)(e0 + i0) * ld;             // each column: w contiguous entries
+        for (int e = tid; e < w * cnt; e += PANEL_ROWS) { int col = e / w, k = e - col * w; Xs[k * PANEL_ROWS + col] = Y0[k + (size_t)col * ld]; }
+    }
+    __syncthreads();
+    if (tid < cnt) {
+        double* x = Xs + tid;                                                  // x[k * PANEL_ROWS]
+        if (lside) {
+            if (LU) {
+                for (int j = 0; j < w; ++j) {
+                    double acc = x[j * PANEL_ROWS];
+                    for (int k = 0; k < j; ++k) acc -= Ts[k + j * w] * x[k * PANEL_ROWS];
+                    x[j * PANEL_ROWS] = (1.0 / Ts[j + j * w]) * acc;
+                }
+            } else {
+                for (int j = 0; j < w; ++j) {
+                    double acc = x[j * PANEL_ROWS];
+                    for (int k = 0; k < j; ++k) acc -= Ts[j + k * w] * x[k * PANEL_ROWS];
+                    x[j * PANEL_ROWS] = acc;
+                }
+                for (int j = 0; j < w; ++j) x[j * PANEL_ROWS] /= Ts[j + j * w];
             }
-        } else {
-            for (int j = 0; j < w; ++j) {
-                double acc = X[(size_t)j * ld];
-                for (int k = 0; k < j; ++k) acc -= T[j + (size_t)k * ld] * X[(size_t)k * ld];
-                X[(size_t)j * ld] = acc;
+        } else if (LU) {
+            const int32_t* ipiv = c.ipiv + ps.col0;
+            const int32_t* subw = c.subw + ps.sub0;
+            int s0 = 0;
+            for (int b = 0; b < ps.nsub; ++b) {
+                const int s1 = s0 + subw[b];
+                for (int j = s0; j < s1; ++j) {                                // contributions of earlier chunks (unswapped rows)
+                    double acc = x[j * PANEL_ROWS];
+                    for (int k = 0; k < s0; ++k) acc -= Ts[j + k * w] * x[k * PANEL_ROWS];
+                    x[j * PANEL_ROWS] = acc;
+                }
+                for (int k = s0; k < s1; ++k) {                                // this chunk's interchanges
+                    int ip = s0 + ipiv[k] - 1;
+                    if (ip != k) { double tmp = x[k * PANEL_ROWS]; x[k * PANEL_ROWS] = x[ip * PANEL_ROWS]; x[ip * PANEL_ROWS] = tmp; }
+                }
+                for (int j = s0; j < s1; ++j) {                                // unit-lower solve inside the chunk
+                    double acc = x[j * PANEL_ROWS];
+                    for (int k = s0; k < j; ++k) acc -= Ts[j + k * w] * x[k * PANEL_ROWS];
+                    x[j * PANEL_ROWS] = acc;
+                }
+                s0 = s1;
             }
-            for (int j = 0; j < w; ++j) X[(size_t)j * ld] /= T[j + (size_t)j * ld];
         }
+    }
+    __syncthreads();
+    if (lside) {
+        double* X0 = Fm + (int64_t)(e0 + i0) + (int64_t)ps.o * ld;
+        for (int k = 0; k < w; ++k) if (tid < cnt) X0[tid + (size_t)k * ld] = Xs[k * PANEL_ROWS + tid];
     } else if (LU) {
-        int i = (lb - nb) * PANEL_ROWS + threadIdx.x;
-        if (i >= below) return;
-        double* Y = Fm + (int64_t)ps.o + (int64_t)(e0 + i) * ld;               // column of the U panel: w contiguous entries
-        const int32_t* ipiv = c.ipiv + ps.col0;
-        const int32_t* subw = c.subw + ps.sub0;
-        int s0 = 0;
-        for (int b = 0; b < ps.nsub; ++b) {
-            const int s1 = s0 + subw[b];
-            for (int j = s0; j < s1; ++j) {                                    // contributions of earlier chunks (unswapped rows)
-                double acc = Y[j];
-                for (int k = 0; k < s0; ++k) acc -= T[j + (size_t)k * ld] * Y[k];
-                Y[j] = acc;
-            }
-            for (int k = s0; k < s1; ++k) {                                    // this chunk's interchanges
-                int ip = s0 + ipiv[k] - 1;
-                if (ip != k) { double tmp = Y[k]; Y[k] = Y[ip]; Y[ip] = tmp; }
-            }
-            for (int j = s0; j < s1; ++j) {                                    // unit-lower solve inside the chunk
-                double acc = Y[j];
-                for (int k = s0; k < j; ++k) acc -= T[j + (size_t)k * ld] * Y[k];
-                Y[j] = acc;
-            }
-            s0 = s1;
-        }
+        double* Y0 = Fm + (int64_t)ps.o + (int64_t)(e0 + i0) * ld;
+        for (int e = tid; e < w * cnt; e += PANEL_ROWS) { int col = e / w, k = e - col * w; Y0[k + (size_t)col * ld] = Xs[k * PANEL_ROWS + col]; }
     }
 }
 
@@ -338,16 +363,22 @@ __global__ void __launch_bounds__(256) k_gemm_small(DevCtx c, const GemmTask* __
         __syncthreads();
     }
     double* __restrict__ C = c.F + g.c0;
+    double cv[4][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        int cc = col0 + ty * 4 + j;
-        if (cc >= g.n) continue;
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            int r = row0 + tx * 4 + i;
-            if (r < g.m && !(g.lower && r + g.roff < cc)) C[(size_t)r + (size_t)cc * ld] -= acc[i][j];
+            const int cc = col0 + ty * 4 + j, r = row0 + tx * 4 + i;
+            const bool ok = cc < g.n && r < g.m && !(g.lower && r + g.roff < cc);
+            cv[i][j] = ok ? C[(size_t)r + (size_t)cc * ld] : 0.0;
         }
-    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int cc = col0 + ty * 4 + j, r = row0 + tx * 4 + i;
+            if (cc < g.n && r < g.m && !(g.lower && r + g.roff < cc)) C[(size_t)r + (size_t)cc * ld] = cv[i][j] - acc[i][j];
+        }
 }
 
 // ------------------------------------------------------------------------------------
@@ -461,6 +492,77 @@ __global__ void __launch_bounds__(128) k_bwd_diag(DevCtx c, const int32_t* __res
     }
     double* out = rhs + (size_t)blockIdx.y * ldrhs + t.col0;
     for (int k = threadIdx.x; k < t.nj; k += blockDim.x) out[k] = x[k];
+}
+
+// Small fronts: one block walks all chunks of the front (same arithmetic as the per-chunk kernels).
+template <bool LU>
+__global__ void __launch_bounds__(256) k_fwd_front(DevCtx c, const int32_t* __restrict__ flist) {
+    const DFront F = c.fronts[flist[blockIdx.x]];
+    double* wf = c.w + (size_t)blockIdx.y * c.wlen + F.wofs;
+    for (int tc = 0; tc < F.nch; ++tc) {
+        const SolveTask t = c.solvet[F.c0 + tc];
+        double* x = wf + t.o;
+        const double* __restrict__ T = c.lnz + t.lofs;
+        if (LU) {
+            if (threadIdx.x == 0) {
+                const int32_t* ipiv = c.ipiv + t.col0;
+                for (int k = 0; k < t.nj; ++k) { int ip = ipiv[k] - 1; if (ip != k) { double tmp = x[k]; x[k] = x[ip]; x[ip] = tmp; } }
+            }
+            __syncthreads();
+        }
+        for (int k = 0; k < t.nj - 1; ++k) {
+            double xk = x[k];
+            for (int i = k + 1 + threadIdx.x; i < t.nj; i += blockDim.x) x[i] -= xk * T[i + (size_t)k * t.ld];
+            __syncthreads();
+        }
+        const int32_t* __restrict__ pos = c.pos + t.posofs + t.nj;
+        for (int i = threadIdx.x; i < t.m; i += blockDim.x) {
+            const double* __restrict__ L = T + t.nj + i;
+            double acc = 0.0;
+            for (int k = 0; k < t.nj; ++k) acc += (-x[k]) * L[(size_t)k * t.ld];
+            wf[pos[i]] += acc;
+        }
+        __syncthreads();
+    }
+}
+
+template <bool LU>
+__global__ void __launch_bounds__(256) k_bwd_front(DevCtx c, const int32_t* __restrict__ flist,
+                                                   double* __restrict__ rhs, int64_t ldrhs) {
+    const DFront F = c.fronts[flist[blockIdx.x]];
+    double* wf = c.w + (size_t)blockIdx.y * c.wlen + F.wofs;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int tc = F.nch - 1; tc >= 0; --tc) {
+        const SolveTask t = c.solvet[F.c0 + tc];
+        double* x = wf + t.o;
+        const double* __restrict__ T = c.lnz + t.lofs;
+        const int32_t* __restrict__ pos = c.pos + t.posofs + t.nj;
+        if (t.m > 0 || !LU) {
+            for (int k = warp; k < t.nj; k += 8) {
+                const double* __restrict__ B = LU ? c.unz + t.uofs + (size_t)k * t.ldu : T + t.nj + (size_t)k * t.ld;
+                double s = 0.0;
+                for (int i = lane; i < t.m; i += 32) s += B[i] * wf[pos[i]];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+                if (lane == 0) { if (LU) x[k] += -s; else x[k] = x[k] / T[k + (size_t)k * t.ld] - s; }
+            }
+            __syncthreads();
+        }
+        for (int k = t.nj - 1; k >= 0; --k) {
+            if (LU) {
+                if (threadIdx.x == 0) x[k] /= T[k + (size_t)k * t.ld];
+                __syncthreads();
+                double xk = x[k];
+                for (int i = threadIdx.x; i < k; i += blockDim.x) x[i] -= xk * T[i + (size_t)k * t.ld];
+            } else {
+                double xk = x[k];
+                for (int i = threadIdx.x; i < k; i += blockDim.x) x[i] -= xk * T[k + (size_t)i * t.ld];
+            }
+            __syncthreads();
+        }
+    }
+    double* out = rhs + (size_t)blockIdx.y * ldrhs + F.F0;
+    for (int k = threadIdx.x; k < F.W; k += blockDim.x) out[k] = wf[k];
 }
 
 // forward-only result / backward-only input: copy between rhs and the front vectors

@@ -20,6 +20,7 @@
 // (tests/hostsim) to validate the schedule independently of the kernels.
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -73,7 +74,7 @@ struct SolveTask {        // one chunk of a triangular sweep (values read from l
 
 enum Kind : int32_t {
     K_ASM = 0, K_ASM_TAIL, K_DIAG, K_PANEL, K_GEMM, K_GEMM_B64, K_GEMM_B128,
-    K_FWD_GATHER, K_FWD_DIAG, K_FWD_UPDATE, K_BWD_GATHER, K_BWD_UPDATE, K_BWD_DIAG
+    K_FWD_GATHER, K_FWD_DIAG, K_FWD_UPDATE, K_BWD_GATHER, K_BWD_UPDATE, K_BWD_DIAG, K_FWD_FRONT, K_BWD_FRONT
 };
 struct Launch {
     int32_t kind;
@@ -93,6 +94,7 @@ constexpr int UPD_ROWS = 256;      // rows per block in the forward-solve update
 constexpr int BWD_COLS = 8;        // columns (warps) per block in the backward-solve update
 constexpr int PS_WIDTH = 64;       // target panel-step width (a wider single chunk stays alone)
 constexpr int OB_WIDTH = 256;      // target outer-block width (delayed trailing update)
+constexpr int64_t SOLVE_SMALL = 65536;  // fronts with at most this many stored L entries are solved by one block
 constexpr int RELAX_ABS = 4;       // a chunk joins the chain if it adds at most this many rows ...
 constexpr double RELAX_FRAC = 0.02;//   ... or this fraction of its rows
 
@@ -111,6 +113,7 @@ struct Plan {
     int32_t nlevels = 0, maxnj = 0, maxR = 0, maxpw = 0;
     double flops_struct = 0, nnzL = 0;        // sum cc^2 (or 2 sum cc^2 - sum cc), sum cc
     bool use_dmma = true;
+    int64_t solve_small = SOLVE_SMALL;
     int relax_abs = RELAX_ABS; double relax_frac = RELAX_FRAC;
     // schedules
     std::vector<AsmTask> asmt;
@@ -356,6 +359,11 @@ inline double gemm_flops(const GemmTask& g) {
     return f;
 }
 
+inline void plan_env_overrides(Plan& P) {        // test / tuning knobs
+    if (const char* e = getenv("SPK_NO_DMMA")) P.use_dmma = !(e[0] == '1');
+    if (const char* e = getenv("SPK_SOLVE_SMALL")) P.solve_small = atoll(e);
+}
+
 inline void build_schedule(Plan& P) {
     const int32_t nf = (int32_t)P.fronts.size();
     std::vector<std::vector<int32_t>> bylevel(P.nlevels);
@@ -433,20 +441,27 @@ inline void build_schedule(Plan& P) {
         }
     }
 
-    // ---- solves (on lnz / unz in the reference layout)
+    // ---- solves (on lnz / unz in the reference layout).  Small fronts: one block walks all chunks of the
+    // front; large fronts: one launch pair per chunk step so that many blocks share the panel.
+    auto front_entries = [&](const Front& F) { int64_t e = 0; for (int32_t t = 0; t < F.nch; ++t) { const Chunk& c = P.chunks[F.c0 + t]; e += (int64_t)c.jlen * c.nj; } return e; };
+    std::vector<uint8_t> small(nf);
+    for (int32_t f = 0; f < nf; ++f) small[f] = front_entries(P.fronts[f]) <= P.solve_small;
     LaunchBuilder sf(P, P.fwd_launches);
     for (int32_t lev = 0; lev < P.nlevels; ++lev) {
         const std::vector<int32_t>& fr = bylevel[lev];
         int32_t maxnch = 0;
         sf.begin(K_FWD_GATHER, (int32_t)P.gathert.size(), lev, 0);
-        for (int32_t f : fr) { P.gathert.push_back(f); sf.add(1); maxnch = std::max(maxnch, P.fronts[f].nch); }
+        for (int32_t f : fr) { P.gathert.push_back(f); sf.add(1); if (!small[f]) maxnch = std::max(maxnch, P.fronts[f].nch); }
+        sf.end();
+        sf.begin(K_FWD_FRONT, (int32_t)P.gathert.size(), lev, 0);
+        for (int32_t f : fr) if (small[f]) { P.gathert.push_back(f); sf.add(1); }
         sf.end();
         for (int32_t t = 0; t < maxnch; ++t) {
             sf.begin(K_FWD_DIAG, (int32_t)P.gathert.size(), lev, t);
-            for (int32_t f : fr) if (P.fronts[f].nch > t) { P.gathert.push_back(P.fronts[f].c0 + t); sf.add(1); }
+            for (int32_t f : fr) if (!small[f] && P.fronts[f].nch > t) { P.gathert.push_back(P.fronts[f].c0 + t); sf.add(1); }
             sf.end();
             sf.begin(K_FWD_UPDATE, (int32_t)P.gathert.size(), lev, t);
-            for (int32_t f : fr) if (P.fronts[f].nch > t) {
+            for (int32_t f : fr) if (!small[f] && P.fronts[f].nch > t) {
                 const Chunk& c = P.chunks[P.fronts[f].c0 + t];
                 if (c.jlen > c.nj) { P.gathert.push_back(P.fronts[f].c0 + t); sf.add(cdiv(c.jlen - c.nj, UPD_ROWS)); }
             }
@@ -459,20 +474,23 @@ inline void build_schedule(Plan& P) {
         int32_t maxnch = 0;
         sb.begin(K_BWD_GATHER, (int32_t)P.gathert.size(), lev, 0);
         for (int32_t f : fr) {
-            maxnch = std::max(maxnch, P.fronts[f].nch);
+            if (!small[f]) maxnch = std::max(maxnch, P.fronts[f].nch);
             if (P.fronts[f].m > 0) { P.gathert.push_back(f); sb.add(cdiv(P.fronts[f].m, 256)); }
         }
         sb.end();
+        sb.begin(K_BWD_FRONT, (int32_t)P.gathert.size(), lev, 0);
+        for (int32_t f : fr) if (small[f]) { P.gathert.push_back(f); sb.add(1); }
+        sb.end();
         for (int32_t t = maxnch - 1; t >= 0; --t) {
             sb.begin(K_BWD_UPDATE, (int32_t)P.gathert.size(), lev, t);
-            for (int32_t f : fr) if (P.fronts[f].nch > t) {
+            for (int32_t f : fr) if (!small[f] && P.fronts[f].nch > t) {
                 const Chunk& c = P.chunks[P.fronts[f].c0 + t];
                 // LDL^T: the D^-1 scaling of the block's unknowns happens here, so every chunk gets a task
                 if (c.jlen > c.nj || !lu) { P.gathert.push_back(P.fronts[f].c0 + t); sb.add(cdiv(c.nj, BWD_COLS)); }
             }
             sb.end();
             sb.begin(K_BWD_DIAG, (int32_t)P.gathert.size(), lev, t);
-            for (int32_t f : fr) if (P.fronts[f].nch > t) { P.gathert.push_back(P.fronts[f].c0 + t); sb.add(1); }
+            for (int32_t f : fr) if (!small[f] && P.fronts[f].nch > t) { P.gathert.push_back(P.fronts[f].c0 + t); sb.add(1); }
             sb.end();
         }
     }

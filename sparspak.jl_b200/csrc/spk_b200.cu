@@ -53,7 +53,7 @@ struct spk_plan {
     bool values_in_fronts = false;      // inmatrix scattered straight into the fronts
     int64_t w_nrhs = 0, rhs_cap = 0;
     size_t dev_bytes = 0;
-    int diag_smem_nj = 0; size_t diag_smem_bytes = 0;
+    int diag_smem_nj = 0; size_t diag_smem_bytes = 0, panel_smem = 0;
     bool have_perm = false, factored = false;
     // stats
     int64_t launches_factor = 0, launches_solve = 0;
@@ -110,7 +110,7 @@ static int64_t plan_upload(spk_plan* p) {
     std::vector<DFront> df(P.fronts.size());
     for (size_t i = 0; i < df.size(); ++i) {
         const Front& F = P.fronts[i];
-        df[i] = DFront{F.fofs, F.relofs, F.wofs, F.F0, F.W, F.R, F.m, F.ld, F.parent, F.child0, F.nchild, 0};
+        df[i] = DFront{F.fofs, F.relofs, F.wofs, F.F0, F.W, F.R, F.m, F.ld, F.parent, F.child0, F.nchild, F.c0, F.nch, 0};
     }
     std::vector<DChunk> dc(P.chunks.size());
     std::vector<int32_t> cpfx(P.chunks.size() + 1, 0);
@@ -155,6 +155,12 @@ static int64_t plan_upload(spk_plan* p) {
         CK(cudaFuncSetAttribute(k_diag<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
         CK(cudaFuncSetAttribute(k_diag<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
     }
+    p->panel_smem = panel_smem_bytes(P.maxpw);
+    if (p->panel_smem > 220 * 1024) { set_err("panel step too wide for shared memory (reduce maxblocksize)"); return -100; }
+    if (p->panel_smem > 48 * 1024) {
+        CK(cudaFuncSetAttribute(k_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->panel_smem));
+        CK(cudaFuncSetAttribute(k_panel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->panel_smem));
+    }
     CK(gemm_dmma_init());
     return 0;
 }
@@ -168,10 +174,7 @@ SPK_API spk_plan* spk_plan_create(int64_t n, int64_t nsuper, const int64_t* xsup
     if (!analyze(p->P, n, nsuper, xsuper, snode, xlindx, lindx, xlnz, xunz_or_null)) {
         set_err("analyze: " + p->P.error); delete p; return nullptr;
     }
- {
-        const char* e = getenv("SPK_NO_DMMA");
-        p->P.use_dmma = !(e && e[0] == '1');
-    }
+    plan_env_overrides(p->P);
     build_schedule(p->P);
     if (device < 0) return p;                      // host-only plan: structure statistics without a GPU
     int ndev = 0;
@@ -291,8 +294,8 @@ static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L) 
         else k_diag<false><<<L.count, 256, p->diag_smem_bytes, st>>>(c, p->d_pslist + L.first, p->diag_smem_nj);
         break;
     case K_PANEL:
-        if (lu) k_panel<true><<<L.nblocks, PANEL_ROWS, 0, st>>>(c, p->d_pslist + L.first, pfx, L.count);
-        else k_panel<false><<<L.nblocks, PANEL_ROWS, 0, st>>>(c, p->d_pslist + L.first, pfx, L.count);
+        if (lu) k_panel<true><<<L.nblocks, PANEL_ROWS, p->panel_smem, st>>>(c, p->d_pslist + L.first, pfx, L.count);
+        else k_panel<false><<<L.nblocks, PANEL_ROWS, p->panel_smem, st>>>(c, p->d_pslist + L.first, pfx, L.count);
         break;
     case K_GEMM:
         k_gemm_small<<<L.nblocks, 256, 0, st>>>(c, p->d_gemmt + L.first, pfx, L.count); break;
@@ -400,6 +403,14 @@ static int64_t run_solve_launches(spk_plan* p, const DevCtx& c, const std::vecto
             else k_fwd_diag<false><<<dim3(L.count, (unsigned)nrhs), 128, 0, st>>>(c, list);
             break;
         case K_FWD_UPDATE: k_fwd_update<<<grid, UPD_ROWS, 0, st>>>(c, list, pfx, L.count); break;
+        case K_FWD_FRONT:
+            if (lu) k_fwd_front<true><<<dim3(L.count, (unsigned)nrhs), 256, 0, st>>>(c, list);
+            else k_fwd_front<false><<<dim3(L.count, (unsigned)nrhs), 256, 0, st>>>(c, list);
+            break;
+        case K_BWD_FRONT:
+            if (lu) k_bwd_front<true><<<dim3(L.count, (unsigned)nrhs), 256, 0, st>>>(c, list, d_rhs, ldrhs);
+            else k_bwd_front<false><<<dim3(L.count, (unsigned)nrhs), 256, 0, st>>>(c, list, d_rhs, ldrhs);
+            break;
         case K_BWD_GATHER: k_bwd_gather<<<grid, 256, 0, st>>>(c, list, pfx, L.count); break;
         case K_BWD_UPDATE:
             if (lu) k_bwd_update<true><<<grid, BWD_COLS * 32, 0, st>>>(c, list, pfx, L.count);

@@ -5,6 +5,7 @@
 // oracle on a machine without a GPU.  Never linked into the product library.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 #include "plan.hpp"
 using namespace spk;
@@ -137,6 +138,7 @@ API void* sim_create(int64_t n, int64_t nsuper, const int64_t* xsuper, const int
     s->P.relax_abs = relax_abs; s->P.relax_frac = relax_frac;
     if (!analyze(s->P, n, nsuper, xsuper, snode, xlindx, lindx, xlnz, xunz)) { fprintf(stderr, "analyze: %s\n", s->P.error.c_str()); delete s; return nullptr; }
     s->P.use_dmma = use_dmma_buckets != 0;
+    if (const char* e = getenv("SPK_SOLVE_SMALL")) s->P.solve_small = atoll(e);
     build_schedule(s->P);
     if (alloc) {
         s->F.assign(std::max<int64_t>(s->P.arena, 1), 0.0);
@@ -194,6 +196,33 @@ API int64_t sim_factor(void* h, double* lnz, double* unz, int64_t* ipvt) {
     return s->iflag;
 }
 
+static void fwd_diag(Sim& s, const SolveTask& t) {
+    double* x = s.w.data() + t.wofs + t.o; const double* T = s.lnz.data() + t.lofs;
+    if (s.P.lu) for (int k = 0; k < t.nj; ++k) { int q = s.ipiv[t.col0 + k] - 1; if (q != k) std::swap(x[k], x[q]); }
+    for (int k = 0; k < t.nj; ++k) for (int i = k + 1; i < t.nj; ++i) x[i] -= x[k] * T[i + (size_t)k * t.ld];
+}
+static void fwd_update(Sim& s, const SolveTask& t) {
+    double* wf = s.w.data() + t.wofs;
+    for (int i = 0; i < t.m; ++i) { double acc = 0; for (int k = 0; k < t.nj; ++k) acc += (-wf[t.o + k]) * s.lnz[t.lofs + t.nj + i + (size_t)k * t.ld]; wf[s.P.pos[t.posofs + t.nj + i]] += acc; }
+}
+static void bwd_update(Sim& s, const SolveTask& t) {
+    double* wf = s.w.data() + t.wofs; const bool lu = s.P.lu;
+    if (t.m == 0 && lu) return;
+    for (int k = 0; k < t.nj; ++k) {
+        double sum = 0;
+        for (int i = 0; i < t.m; ++i) sum += (lu ? s.unz[t.uofs + i + (size_t)k * t.ldu] : s.lnz[t.lofs + t.nj + i + (size_t)k * t.ld]) * wf[s.P.pos[t.posofs + t.nj + i]];
+        if (lu) wf[t.o + k] += -sum; else wf[t.o + k] = wf[t.o + k] / s.lnz[t.lofs + k + (size_t)k * t.ld] - sum;
+    }
+}
+static void bwd_diag(Sim& s, const SolveTask& t, double* rhs) {
+    double* x = s.w.data() + t.wofs + t.o; const double* T = s.lnz.data() + t.lofs; const bool lu = s.P.lu;
+    for (int k = t.nj - 1; k >= 0; --k) {
+        if (lu) { x[k] /= T[k + (size_t)k * t.ld]; for (int i = 0; i < k; ++i) x[i] -= x[k] * T[i + (size_t)k * t.ld]; }
+        else for (int i = 0; i < k; ++i) x[i] -= x[k] * T[k + (size_t)i * t.ld];
+    }
+    for (int k = 0; k < t.nj; ++k) rhs[t.col0 + k] = x[k];
+}
+
 // rhs in permuted order, in place; factors as left by sim_factor
 API int64_t sim_solve(void* h, double* rhs) {
     Sim* s = (Sim*)h; Plan& P = s->P; const bool lu = P.lu;
@@ -206,12 +235,12 @@ API int64_t sim_solve(void* h, double* rhs) {
                 for (int i = 0; i < F.R; ++i) wf[i] = i < F.W ? rhs[F.F0 + i] : 0.0;
                 for (int r = 0; r < F.nchild; ++r) { const Front& C = P.fronts[P.childlist[F.child0 + r]]; for (int i = 0; i < C.m; ++i) wf[P.rel[C.relofs + i]] += w[C.wofs + C.W + i]; }
             } else if (L.kind == K_FWD_DIAG) {
-                const SolveTask& t = P.solvet[list[ti]]; double* x = w + t.wofs + t.o; const double* T = s->lnz.data() + t.lofs;
-                if (lu) for (int k = 0; k < t.nj; ++k) { int q = s->ipiv[t.col0 + k] - 1; if (q != k) std::swap(x[k], x[q]); }
-                for (int k = 0; k < t.nj; ++k) for (int i = k + 1; i < t.nj; ++i) x[i] -= x[k] * T[i + (size_t)k * t.ld];
+                fwd_diag(*s, P.solvet[list[ti]]);
             } else if (L.kind == K_FWD_UPDATE) {
-                const SolveTask& t = P.solvet[list[ti]]; double* wf = w + t.wofs;
-                for (int i = 0; i < t.m; ++i) { double acc = 0; for (int k = 0; k < t.nj; ++k) acc += (-wf[t.o + k]) * s->lnz[t.lofs + t.nj + i + (size_t)k * t.ld]; wf[P.pos[t.posofs + t.nj + i]] += acc; }
+                fwd_update(*s, P.solvet[list[ti]]);
+            } else if (L.kind == K_FWD_FRONT) {
+                const Front& F = P.fronts[list[ti]];
+                for (int tc = 0; tc < F.nch; ++tc) { fwd_diag(*s, P.solvet[F.c0 + tc]); fwd_update(*s, P.solvet[F.c0 + tc]); }
             } else return -100;
         }
     }
@@ -222,19 +251,12 @@ API int64_t sim_solve(void* h, double* rhs) {
                 const Front& F = P.fronts[list[ti]]; const Front& Pa = P.fronts[F.parent];
                 for (int i = 0; i < F.m; ++i) w[F.wofs + F.W + i] = w[Pa.wofs + P.rel[F.relofs + i]];
             } else if (L.kind == K_BWD_UPDATE) {
-                const SolveTask& t = P.solvet[list[ti]]; double* wf = w + t.wofs;
-                for (int k = 0; k < t.nj; ++k) {
-                    double sum = 0;
-                    for (int i = 0; i < t.m; ++i) sum += (lu ? s->unz[t.uofs + i + (size_t)k * t.ldu] : s->lnz[t.lofs + t.nj + i + (size_t)k * t.ld]) * wf[P.pos[t.posofs + t.nj + i]];
-                    if (lu) wf[t.o + k] += -sum; else wf[t.o + k] = wf[t.o + k] / s->lnz[t.lofs + k + (size_t)k * t.ld] - sum;
-                }
+                bwd_update(*s, P.solvet[list[ti]]);
             } else if (L.kind == K_BWD_DIAG) {
-                const SolveTask& t = P.solvet[list[ti]]; double* x = w + t.wofs + t.o; const double* T = s->lnz.data() + t.lofs;
-                for (int k = t.nj - 1; k >= 0; --k) {
-                    if (lu) { x[k] /= T[k + (size_t)k * t.ld]; for (int i = 0; i < k; ++i) x[i] -= x[k] * T[i + (size_t)k * t.ld]; }
-                    else for (int i = 0; i < k; ++i) x[i] -= x[k] * T[k + (size_t)i * t.ld];
-                }
-                for (int k = 0; k < t.nj; ++k) rhs[t.col0 + k] = x[k];
+                bwd_diag(*s, P.solvet[list[ti]], rhs);
+            } else if (L.kind == K_BWD_FRONT) {
+                const Front& F = P.fronts[list[ti]];
+                for (int tc = F.nch - 1; tc >= 0; --tc) { bwd_update(*s, P.solvet[F.c0 + tc]); bwd_diag(*s, P.solvet[F.c0 + tc], rhs); }
             } else return -100;
         }
     }

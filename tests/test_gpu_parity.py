@@ -227,3 +227,19 @@ def test_dmma_and_dfma_kernels_agree(monkeypatch):
     assert rel_err(l1, l2, spd_mask(b)) < 1e-12
     lo, _, _, _ = oracle_factor(b)
     assert rel_err(l1, lo, spd_mask(b)) < FACTOR_RTOL
+
+
+@pytest.mark.parametrize("spd", [False, True])
+def test_large_front_solve_path(spd, monkeypatch):
+    """Every front forced onto the per-chunk (multi-block) solve path used for large fronts."""
+    monkeypatch.setenv("SPK_SOLVE_SMALL", "0")
+    A = M.convdiff3d(10) if not spd else M.laplacian3d(10)
+    s = prepare(A, spd, spk.nd_grid_order(10, 10, 10), 6)
+    b = s.slvr
+    plan, lg, ug, pg, fg = gpu_factor_plan(b)
+    bb = M.rhs_for(A)
+    x = bb.copy()
+    plan.set_perm(b.order.rperm, b.order.rinvp)
+    plan.triangularsolve(x)
+    assert residual(A, x, bb) < RESID_TOL
+    plan.destroy()

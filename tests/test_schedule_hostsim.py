@@ -52,3 +52,18 @@ def test_plan_statistics_cfg1():
     assert s.slvr.n == 10000
     assert sim.stat(0) < s.slvr.nsuper            # relaxed chains merge supernodes into fewer fronts
     assert sim.stat(1) < 40                       # few front levels
+
+
+@pytest.mark.parametrize("spd", [False, True])
+def test_hostsim_large_front_solve_path(spd, monkeypatch):
+    # force every front onto the per-chunk (multi-block) solve path used for large fronts
+    monkeypatch.setenv("SPK_SOLVE_SMALL", "0")
+    A = M.convdiff3d(8) if not spd else M.laplacian3d(8)
+    s = prepare(A, spd, spk.nd_grid_order(8, 8, 8), 6)
+    b = s.slvr
+    sim = HostSim(b)
+    sim.factor()
+    bb = M.rhs_for(A)
+    rhs = np.ascontiguousarray(bb[b.order.rperm - 1])
+    x = sim.solve(rhs)[b.order.rinvp - 1]
+    assert residual(A, x, bb) < 1e-13
