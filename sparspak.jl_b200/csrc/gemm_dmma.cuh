@@ -154,34 +154,46 @@ k_gemm_dmma(DevCtx c, const GemmTask* __restrict__ tasks, const int32_t* __restr
         }
     }
     cp_async_wait<0>();
+    __syncthreads();                                   // every warp is done reading the last stage
 
-    // epilogue: C -= acc   (fragment (i,j): rows wm0+8i+lr, cols wn0+8j+2*lk+{0,1}).
-    // All loads of one column pair are issued before the first store: a plain `C[..] -= acc` loop
-    // serialises on load->store->load ordering (the compiler must assume the addresses alias) and
-    // left the tensor pipe idle for longer than the whole k loop (ncu: long-scoreboard stalls on the DADDs).
+    // Epilogue: C -= acc, staged through shared memory (the pipeline ring is free now).
+    //  1. accumulator fragments -> Cs[col][row]      (fragment (i,j): rows wm0+8i+lr, cols wn0+8j+2*lk+{0,1})
+    //  2. coalesced read-modify-write of C: consecutive threads own consecutive rows of one column, with
+    //     EPI_U independent loads in flight per thread.  (A direct `C[..] -= acc` from the fragments keeps
+    //     ~64 dependent, 64-byte-granular global round trips per thread on the critical path: ncu showed the
+    //     tensor pipe idle for longer than the whole k loop, all warps in long-scoreboard stalls on the DADDs.)
+    constexpr int LDC = TM + 4;
+    static_assert((size_t)TN * LDC * sizeof(double) <= Cfg::SMEM, "C tile must fit in the pipeline ring");
+    double* Cs = smem;
+#pragma unroll
+    for (int j = 0; j < FN; ++j)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int i = 0; i < FM; ++i)
+                Cs[(wn0 + j * 8 + 2 * lk + h) * LDC + wm0 + i * 8 + lr] = acc[i][j][h];
+    __syncthreads();
+
     double* __restrict__ C = c.F + g.c0;
+    constexpr int COLS_PER_PASS = DM_THREADS / TM;     // 2 columns per pass with 256 threads
+    constexpr int EPI_U = 8;
+    const int er = tid % TM, ec = tid / TM;
+    const int r = row0 + er;
+    const bool rok = r < g.m;
+#pragma unroll 1
+    for (int p0 = 0; p0 < TN / COLS_PER_PASS; p0 += EPI_U) {
+        double cv[EPI_U];
+        bool ok[EPI_U];
 #pragma unroll
-    for (int j = 0; j < FN; ++j) {
-        double cv[2][FM];
-        bool ok[2][FM];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int cc = col0 + wn0 + j * 8 + 2 * lk + h;
-#pragma unroll
-            for (int i = 0; i < FM; ++i) {
-                const int r = row0 + wm0 + i * 8 + lr;
-                ok[h][i] = (cc < g.n) && (r < g.m) && !(g.lower && r + g.roff < cc);
-                cv[h][i] = ok[h][i] ? __ldcg(C + (size_t)r + (size_t)cc * ld) : 0.0;
-            }
+        for (int u = 0; u < EPI_U; ++u) {
+            const int cl = (p0 + u) * COLS_PER_PASS + ec, cc = col0 + cl;
+            ok[u] = rok && cc < g.n && !(g.lower && r + g.roff < cc);
+            cv[u] = ok[u] ? __ldcg(C + (size_t)r + (size_t)cc * ld) : 0.0;
         }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int cc = col0 + wn0 + j * 8 + 2 * lk + h;
-#pragma unroll
-            for (int i = 0; i < FM; ++i) {
-                const int r = row0 + wm0 + i * 8 + lr;
-                if (ok[h][i]) __stcg(C + (size_t)r + (size_t)cc * ld, cv[h][i] - acc[i][j][h]);
-            }
+        for (int u = 0; u < EPI_U; ++u) {
+            const int cl = (p0 + u) * COLS_PER_PASS + ec, cc = col0 + cl;
+            if (ok[u]) __stcg(C + (size_t)r + (size_t)cc * ld, cv[u] - Cs[cl * LDC + er]);
         }
     }
 }

@@ -449,23 +449,32 @@ __global__ void __launch_bounds__(256) k_bwd_gather(DevCtx c, const int32_t* __r
     w[F.W + i] = wp[c.rel[F.relofs + i]];
 }
 
-// one warp per column k of the chunk: x_k -= sum_i B[i,k] * x_below[i]
+// one block per column k of the chunk: x_k -= sum_i B[i,k] * x_below[i]   (fixed-order block reduction)
 template <bool LU>
-__global__ void __launch_bounds__(BWD_COLS * 32) k_bwd_update(DevCtx c, const int32_t* __restrict__ clist,
-                                                              const int32_t* __restrict__ pfx, int count) {
+__global__ void __launch_bounds__(256) k_bwd_update(DevCtx c, const int32_t* __restrict__ clist,
+                                                    const int32_t* __restrict__ pfx, int count) {
+    __shared__ double red[8];
     int ti = find_task(pfx, count, blockIdx.x);
-    int lb = blockIdx.x - pfx[ti];
+    const int k = blockIdx.x - pfx[ti];
     const SolveTask t = c.solvet[clist[ti]];
-    int k = lb * BWD_COLS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (k >= t.nj) return;
     double* wf = c.w + (size_t)blockIdx.y * c.wlen + t.wofs;
     const double* __restrict__ B = LU ? c.unz + t.uofs + (size_t)k * t.ldu : c.lnz + t.lofs + t.nj + (size_t)k * t.ld;
     const int32_t* __restrict__ pos = c.pos + t.posofs + t.nj;
-    double s = 0.0;
-    for (int i = lane; i < t.m; i += 32) s += B[i] * wf[pos[i]];
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int i = threadIdx.x;
+    for (; i + 768 < t.m; i += 1024) {
+        s0 += B[i] * wf[pos[i]]; s1 += B[i + 256] * wf[pos[i + 256]];
+        s2 += B[i + 512] * wf[pos[i + 512]]; s3 += B[i + 768] * wf[pos[i + 768]];
+    }
+    for (; i < t.m; i += 256) s0 += B[i] * wf[pos[i]];
+    double s = (s0 + s1) + (s2 + s3);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    if (lane == 0) {
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
         double* xk = wf + t.o + k;
         if (LU) *xk += -s;
         else *xk = *xk / c.lnz[t.lofs + k + (size_t)k * t.ld] - s;

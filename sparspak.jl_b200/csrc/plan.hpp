@@ -91,7 +91,7 @@ constexpr int PANEL_ROWS = 128;    // rows (L side) / columns (U side) per panel
 constexpr int GEMM_TM = 64, GEMM_TN = 64;   // C tile of the small-tile kernel
 constexpr int BIG_TM = 128;                 // C tile rows of the DMMA kernels (TN = 64 or 128)
 constexpr int UPD_ROWS = 256;      // rows per block in the forward-solve update
-constexpr int BWD_COLS = 8;        // columns (warps) per block in the backward-solve update
+constexpr int BWD_COLS = 1;        // columns per block in the backward-solve update (one block reduces one column)
 constexpr int PS_WIDTH = 64;       // target panel-step width (a wider single chunk stays alone)
 constexpr int OB_WIDTH = 256;      // target outer-block width (delayed trailing update)
 constexpr int64_t SOLVE_SMALL = 65536;  // fronts with at most this many stored L entries are solved by one block

@@ -413,8 +413,8 @@ static int64_t run_solve_launches(spk_plan* p, const DevCtx& c, const std::vecto
             break;
         case K_BWD_GATHER: k_bwd_gather<<<grid, 256, 0, st>>>(c, list, pfx, L.count); break;
         case K_BWD_UPDATE:
-            if (lu) k_bwd_update<true><<<grid, BWD_COLS * 32, 0, st>>>(c, list, pfx, L.count);
-            else k_bwd_update<false><<<grid, BWD_COLS * 32, 0, st>>>(c, list, pfx, L.count);
+            if (lu) k_bwd_update<true><<<grid, 256, 0, st>>>(c, list, pfx, L.count);
+            else k_bwd_update<false><<<grid, 256, 0, st>>>(c, list, pfx, L.count);
             break;
         case K_BWD_DIAG:
             if (lu) k_bwd_diag<true><<<dim3(L.count, (unsigned)nrhs), 128, 0, st>>>(c, list, d_rhs, ldrhs);
