@@ -176,9 +176,8 @@ __device__ void diag_factor(double* A, int lda, int w, const int32_t* __restrict
         }
     } else {
         for (int k = 0; k < w; ++k) {
-            const double d = A[k + (size_t)k * lda];
+            const double d = A[k + (size_t)k * lda];          // final since the previous step's barrier; not written below
             if (tid == 0 && d == 0.0) atomicExch(iflag, -1);
-            __syncthreads();
             for (int i = k + 1 + tid; i < w; i += nt) A[i + (size_t)k * lda] /= d;
             __syncthreads();
             for (int s = k + 1 + ty; s < w; s += 16) {
@@ -241,11 +240,25 @@ __global__ void __launch_bounds__(PANEL_ROWS) k_panel(DevCtx c, const int32_t* _
     const int i0 = (lside ? lb : lb - nb) * PANEL_ROWS;
     const int cnt = min(PANEL_ROWS, below - i0);
     if (lside) {
-        double* X0 = Fm + (int64_t)(e0 + i0) + (int64_t)ps.o * ld;             // rows contiguous
-        for (int k = 0; k < w; ++k) if (tid < cnt) Xs[k * PANEL_ROWS + tid] = X0[tid + (size_t)k * ld];
+        const double* X0 = Fm + (int64_t)(e0 + i0) + (int64_t)ps.o * ld;       // rows contiguous
+        if (tid < cnt)
+            for (int k0 = 0; k0 < w; k0 += 8) {                                // 8 independent loads in flight
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = (k0 + u < w) ? __ldcg(X0 + tid + (size_t)(k0 + u) * ld) : 0.0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) if (k0 + u < w) Xs[(k0 + u) * PANEL_ROWS + tid] = v[u];
+            }
     } else {
-        double* Y0 = Fm + (int64_t)ps.o + (int64_t)(e0 + i0) * ld;             // each column: w contiguous entries
-        for (int e = tid; e < w * cnt; e += PANEL_ROWS) { int col = e / w, k = e - col * w; Xs[k * PANEL_ROWS + col] = Y0[k + (size_t)col * ld]; }
+        const double* Y0 = Fm + (int64_t)ps.o + (int64_t)(e0 + i0) * ld;       // each column: w contiguous entries
+        const int tot = w * cnt;
+        for (int e0i = tid; e0i < tot; e0i += 8 * PANEL_ROWS) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { int e = e0i + u * PANEL_ROWS; int col = e / w, k = e - col * w; v[u] = (e < tot) ? __ldcg(Y0 + k + (size_t)col * ld) : 0.0; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { int e = e0i + u * PANEL_ROWS; int col = e / w, k = e - col * w; if (e < tot) Xs[k * PANEL_ROWS + col] = v[u]; }
+        }
     }
     __syncthreads();
     if (tid < cnt) {
@@ -254,12 +267,14 @@ __global__ void __launch_bounds__(PANEL_ROWS) k_panel(DevCtx c, const int32_t* _
             if (LU) {
                 for (int j = 0; j < w; ++j) {
                     double acc = x[j * PANEL_ROWS];
+#pragma unroll 8
                     for (int k = 0; k < j; ++k) acc -= Ts[k + j * w] * x[k * PANEL_ROWS];
                     x[j * PANEL_ROWS] = (1.0 / Ts[j + j * w]) * acc;
                 }
             } else {
                 for (int j = 0; j < w; ++j) {
                     double acc = x[j * PANEL_ROWS];
+#pragma unroll 8
                     for (int k = 0; k < j; ++k) acc -= Ts[j + k * w] * x[k * PANEL_ROWS];
                     x[j * PANEL_ROWS] = acc;
                 }
