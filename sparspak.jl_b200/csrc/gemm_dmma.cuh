@@ -1,8 +1,8 @@
 // gemm_dmma.cuh — FP64 tensor-core (DMMA, mma.sync.m8n8k4.f64) trailing-update kernel.
 //
-//   C[m x n] -= A[m x k] * B        inside one frontal matrix (uniform leading dimension)
-//     LU   : B = a row block of U           (B(k,n) contiguous along k)
-//     LDLT : B = (L21' * diag(D))^T         (B(n,k) contiguous along n, scaled on the fly)
+//   C[m x n] -= A[m x k] * B[k x n]        inside one frontal matrix (uniform leading dimension)
+//     A = a column block of L (rows contiguous), B = a row block of U (k contiguous).
+//     LDL^T fronts keep U = D * L^T in their upper triangle, so both factorisations use this form.
 //
 // This is the Schur-complement / in-front update of the supernodal factorisation (the
 // reference's dgemm('n','t') call sites, SpkLUFactor.jl:152-209, SpkLDLtFactor.jl:145-205).
@@ -21,7 +21,6 @@ namespace spk {
 
 constexpr int DM_TK = 16;            // k per pipeline stage
 constexpr int DM_STAGES = 4;
-constexpr int DM_THREADS = 256;
 constexpr int DM_LDBK = DM_TK + 4;   // row stride of the k-contiguous B tile (conflict-free fragment loads)
 
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem, bool valid) {
@@ -32,30 +31,34 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem, bool val
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+        : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
 template <int TM, int TN>
 struct DmmaCfg {
-    static constexpr int LDA = TM + 4, LDB = TN + 4;               // +4 doubles: conflict-free fragment loads
+    static constexpr int LDA = TM + 4;                              // +4 doubles: conflict-free fragment loads
+    static constexpr int LDC = TM + 4;
     static constexpr int A_DOUBLES = DM_TK * LDA;
-    static constexpr int B_DOUBLES = (DM_TK * LDB > TN * DM_LDBK) ? DM_TK * LDB : TN * DM_LDBK;
-    static constexpr int STAGE_DOUBLES = A_DOUBLES + B_DOUBLES + DM_TK;   // A tile, B tile, D slice
-    static constexpr size_t SMEM = (size_t)DM_STAGES * STAGE_DOUBLES * sizeof(double);
+    static constexpr int B_DOUBLES = TN * DM_LDBK;
+    static constexpr int STAGE_DOUBLES = A_DOUBLES + B_DOUBLES;
+    static constexpr int RING_DOUBLES = DM_STAGES * STAGE_DOUBLES;
+    static constexpr int C_DOUBLES = TN * LDC;
+    static constexpr size_t SMEM = sizeof(double) * (size_t)(RING_DOUBLES > C_DOUBLES ? RING_DOUBLES : C_DOUBLES);
 };
 
-// WARPS_M x WARPS_N warps, each owning a (TM/WARPS_M) x (TN/WARPS_N) sub-tile.
-// BK: B is k-contiguous (LU) instead of n-contiguous + D-scaled (LDL^T).
-template <int TM, int TN, int WARPS_M, int WARPS_N, bool BK>
-__global__ void __launch_bounds__(DM_THREADS, 1)
+// WARPS_M x WARPS_N warps, each owning a (TM/WARPS_M) x (TN/WARPS_N) sub-tile of the block's C tile.
+template <int TM, int TN, int WARPS_M, int WARPS_N>
+__global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, 1)
 k_gemm_dmma(DevCtx c, const GemmTask* __restrict__ tasks, const int32_t* __restrict__ pfx, int count) {
-    static_assert(WARPS_M * WARPS_N * 32 == DM_THREADS, "warp layout");
     using Cfg = DmmaCfg<TM, TN>;
+    constexpr int NT = WARPS_M * WARPS_N * 32;
     constexpr int WM = TM / WARPS_M, WN = TN / WARPS_N;
     constexpr int FM = WM / 8, FN = WN / 8;
+    static_assert(NT % TM == 0 && (TN * DM_TK) % NT == 0 && (TM * DM_TK) % NT == 0, "loader shapes");
     extern __shared__ double smem[];
 
     int t = find_task(pfx, count, blockIdx.x);
@@ -63,7 +66,7 @@ k_gemm_dmma(DevCtx c, const GemmTask* __restrict__ tasks, const int32_t* __restr
     const GemmTask g = tasks[t];
     const int mt = (g.m + TM - 1) / TM;
     const int row0 = (lb % mt) * TM, col0 = (lb / mt) * TN;
-    if (g.lower && row0 + TM - 1 + g.roff < col0) return;
+    if (g.lower && row0 + TM - 1 + g.roff < col0) return;          // tile strictly above the diagonal
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wm0 = (warp % WARPS_M) * WM, wn0 = (warp / WARPS_M) * WN;
@@ -71,7 +74,17 @@ k_gemm_dmma(DevCtx c, const GemmTask* __restrict__ tasks, const int32_t* __restr
     const int ld = g.ld;
     const double* __restrict__ A = c.F + g.a0;
     const double* __restrict__ B = c.F + g.b0;
-    const double* __restrict__ D = c.F + g.d0;
+    double* __restrict__ C = c.F + g.c0;
+
+    // pull the C tile towards L2 while the k loop runs (it is read once, in the epilogue)
+    {
+        constexpr int LINES_PER_COL = TM / 16;                      // 128-byte lines per tile column
+        for (int e = tid; e < TN * LINES_PER_COL; e += NT) {
+            const int cl = e / LINES_PER_COL, rl = (e % LINES_PER_COL) * 16;
+            const int r = row0 + rl, cc = col0 + cl;
+            if (r < g.m && cc < g.n && !(g.lower && r + 15 + g.roff < cc)) prefetch_l2(C + (size_t)r + (size_t)cc * ld);
+        }
+    }
 
     double acc[FM][FN][2];
 #pragma unroll
@@ -85,36 +98,19 @@ k_gemm_dmma(DevCtx c, const GemmTask* __restrict__ tasks, const int32_t* __restr
         const int stage = tile % DM_STAGES, k0 = tile * DM_TK;
         double* As = smem + (size_t)stage * Cfg::STAGE_DOUBLES;
         double* Bs = As + Cfg::A_DOUBLES;
-        double* Ds = Bs + Cfg::B_DOUBLES;
 #pragma unroll
-        for (int e = tid; e < TM * DM_TK; e += DM_THREADS) {       // consecutive threads -> consecutive rows
+        for (int e = tid; e < TM * DM_TK; e += NT) {                // consecutive threads -> consecutive rows
             int r = e % TM, kk = e / TM, kg = k0 + kk;
             bool ok = (row0 + r < g.m) && (kg < g.k);
             const double* src = ok ? A + (size_t)(row0 + r) + (size_t)kg * ld : A;
             cp_async8(As + kk * Cfg::LDA + r, src, ok);
         }
-        if (BK) {
 #pragma unroll
-            for (int e = tid; e < TN * DM_TK; e += DM_THREADS) {   // consecutive threads -> consecutive k
-                int kk = e % DM_TK, r = e / DM_TK, kg = k0 + kk;
-                bool ok = (col0 + r < g.n) && (kg < g.k);
-                const double* src = ok ? B + (size_t)kg + (size_t)(col0 + r) * ld : B;
-                cp_async8(Bs + r * DM_LDBK + kk, src, ok);
-            }
-        } else {
-#pragma unroll
-            for (int e = tid; e < TN * DM_TK; e += DM_THREADS) {
-                int r = e % TN, kk = e / TN, kg = k0 + kk;
-                bool ok = (col0 + r < g.n) && (kg < g.k);
-                const double* src = ok ? B + (size_t)(col0 + r) + (size_t)kg * ld : B;
-                cp_async8(Bs + kk * Cfg::LDB + r, src, ok);
-            }
-            if (tid < DM_TK) {
-                int kg = k0 + tid;
-                bool ok = kg < g.k;
-                const double* src = ok ? D + (size_t)kg * (ld + 1) : D;
-                cp_async8(Ds + tid, src, ok);
-            }
+        for (int e = tid; e < TN * DM_TK; e += NT) {                // consecutive threads -> consecutive k
+            int kk = e % DM_TK, r = e / DM_TK, kg = k0 + kk;
+            bool ok = (col0 + r < g.n) && (kg < g.k);
+            const double* src = ok ? B + (size_t)kg + (size_t)(col0 + r) * ld : B;
+            cp_async8(Bs + r * DM_LDBK + kk, src, ok);
         }
     };
 
@@ -132,21 +128,14 @@ k_gemm_dmma(DevCtx c, const GemmTask* __restrict__ tasks, const int32_t* __restr
         const int stage = tile % DM_STAGES;
         const double* As = smem + (size_t)stage * Cfg::STAGE_DOUBLES;
         const double* Bs = As + Cfg::A_DOUBLES;
-        const double* Ds = Bs + Cfg::B_DOUBLES;
 #pragma unroll
         for (int k4 = 0; k4 < DM_TK / 4; ++k4) {
             const int kk = k4 * 4 + lk;
             double a[FM], b[FN];
 #pragma unroll
             for (int i = 0; i < FM; ++i) a[i] = As[kk * Cfg::LDA + wm0 + i * 8 + lr];
-            if (BK) {
 #pragma unroll
-                for (int j = 0; j < FN; ++j) b[j] = Bs[(wn0 + j * 8 + lr) * DM_LDBK + kk];
-            } else {
-                const double d = Ds[kk];
-#pragma unroll
-                for (int j = 0; j < FN; ++j) b[j] = Bs[kk * Cfg::LDB + wn0 + j * 8 + lr] * d;
-            }
+            for (int j = 0; j < FN; ++j) b[j] = Bs[(wn0 + j * 8 + lr) * DM_LDBK + kk];
 #pragma unroll
             for (int i = 0; i < FM; ++i)
 #pragma unroll
@@ -162,8 +151,6 @@ k_gemm_dmma(DevCtx c, const GemmTask* __restrict__ tasks, const int32_t* __restr
     //     EPI_U independent loads in flight per thread.  (A direct `C[..] -= acc` from the fragments keeps
     //     ~64 dependent, 64-byte-granular global round trips per thread on the critical path: ncu showed the
     //     tensor pipe idle for longer than the whole k loop, all warps in long-scoreboard stalls on the DADDs.)
-    constexpr int LDC = TM + 4;
-    static_assert((size_t)TN * LDC * sizeof(double) <= Cfg::SMEM, "C tile must fit in the pipeline ring");
     double* Cs = smem;
 #pragma unroll
     for (int j = 0; j < FN; ++j)
@@ -171,17 +158,17 @@ k_gemm_dmma(DevCtx c, const GemmTask* __restrict__ tasks, const int32_t* __restr
         for (int h = 0; h < 2; ++h)
 #pragma unroll
             for (int i = 0; i < FM; ++i)
-                Cs[(wn0 + j * 8 + 2 * lk + h) * LDC + wm0 + i * 8 + lr] = acc[i][j][h];
+                Cs[(wn0 + j * 8 + 2 * lk + h) * Cfg::LDC + wm0 + i * 8 + lr] = acc[i][j][h];
     __syncthreads();
 
-    double* __restrict__ C = c.F + g.c0;
-    constexpr int COLS_PER_PASS = DM_THREADS / TM;     // 2 columns per pass with 256 threads
-    constexpr int EPI_U = 8;
+    constexpr int COLS_PER_PASS = NT / TM;
+    constexpr int NPASS = TN / COLS_PER_PASS;
+    constexpr int EPI_U = NPASS < 16 ? NPASS : 16;
     const int er = tid % TM, ec = tid / TM;
     const int r = row0 + er;
     const bool rok = r < g.m;
 #pragma unroll 1
-    for (int p0 = 0; p0 < TN / COLS_PER_PASS; p0 += EPI_U) {
+    for (int p0 = 0; p0 < NPASS; p0 += EPI_U) {
         double cv[EPI_U];
         bool ok[EPI_U];
 #pragma unroll
@@ -193,28 +180,30 @@ k_gemm_dmma(DevCtx c, const GemmTask* __restrict__ tasks, const int32_t* __restr
 #pragma unroll
         for (int u = 0; u < EPI_U; ++u) {
             const int cl = (p0 + u) * COLS_PER_PASS + ec, cc = col0 + cl;
-            if (ok[u]) __stcg(C + (size_t)r + (size_t)cc * ld, cv[u] - Cs[cl * LDC + er]);
+            if (ok[u]) __stcg(C + (size_t)r + (size_t)cc * ld, cv[u] - Cs[cl * Cfg::LDC + er]);
         }
     }
 }
 
+// Kernel variants.  `wide` = 16 warps per block (4 per scheduler) instead of 8: more DMMA issuers per SM.
 using GemmKernel = void (*)(DevCtx, const GemmTask*, const int32_t*, int);
-inline GemmKernel gemm_dmma_kernel(int kind, bool lu) {
-    if (kind == K_GEMM_B128) return lu ? k_gemm_dmma<BIG_TM, 128, 2, 4, true> : k_gemm_dmma<BIG_TM, 128, 2, 4, false>;
-    return lu ? k_gemm_dmma<BIG_TM, 64, 4, 2, true> : k_gemm_dmma<BIG_TM, 64, 4, 2, false>;
-}
-inline size_t gemm_dmma_smem(int kind) {
-    return kind == K_GEMM_B128 ? DmmaCfg<BIG_TM, 128>::SMEM : DmmaCfg<BIG_TM, 64>::SMEM;
+struct GemmVariant { GemmKernel fn; int threads; size_t smem; };
+inline GemmVariant gemm_dmma_variant(int kind, bool wide) {
+    if (kind == K_GEMM_B128) {
+        if (wide) return {k_gemm_dmma<BIG_TM, 128, 4, 4>, 512, DmmaCfg<BIG_TM, 128>::SMEM};
+        return {k_gemm_dmma<BIG_TM, 128, 2, 4>, 256, DmmaCfg<BIG_TM, 128>::SMEM};
+    }
+    if (wide) return {k_gemm_dmma<BIG_TM, 64, 4, 4>, 512, DmmaCfg<BIG_TM, 64>::SMEM};
+    return {k_gemm_dmma<BIG_TM, 64, 4, 2>, 256, DmmaCfg<BIG_TM, 64>::SMEM};
 }
 inline cudaError_t gemm_dmma_init() {
-    cudaError_t e;
-    e = cudaFuncSetAttribute(k_gemm_dmma<BIG_TM, 128, 2, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DmmaCfg<BIG_TM, 128>::SMEM);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_gemm_dmma<BIG_TM, 128, 2, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DmmaCfg<BIG_TM, 128>::SMEM);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_gemm_dmma<BIG_TM, 64, 4, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DmmaCfg<BIG_TM, 64>::SMEM);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_gemm_dmma<BIG_TM, 64, 4, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DmmaCfg<BIG_TM, 64>::SMEM);
+    for (int kind : {(int)K_GEMM_B64, (int)K_GEMM_B128})
+        for (int wide = 0; wide < 2; ++wide) {
+            GemmVariant v = gemm_dmma_variant(kind, wide != 0);
+            cudaError_t e = cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem);
+            if (e != cudaSuccess) return e;
+        }
+    return cudaSuccess;
 }
 
 } // namespace spk

@@ -272,13 +272,12 @@ __global__ void __launch_bounds__(PANEL_ROWS) k_panel(DevCtx c, const int32_t* _
                     x[j * PANEL_ROWS] = (1.0 / Ts[j + j * w]) * acc;
                 }
             } else {
-                for (int j = 0; j < w; ++j) {
+                for (int j = 0; j < w; ++j) {                                  // X = A21 * inv(L11^T), kept UNSCALED here
                     double acc = x[j * PANEL_ROWS];
 #pragma unroll 8
                     for (int k = 0; k < j; ++k) acc -= Ts[j + k * w] * x[k * PANEL_ROWS];
                     x[j * PANEL_ROWS] = acc;
                 }
-                for (int j = 0; j < w; ++j) x[j * PANEL_ROWS] /= Ts[j + j * w];
             }
         } else if (LU) {
             const int32_t* ipiv = c.ipiv + ps.col0;
@@ -307,7 +306,15 @@ __global__ void __launch_bounds__(PANEL_ROWS) k_panel(DevCtx c, const int32_t* _
     __syncthreads();
     if (lside) {
         double* X0 = Fm + (int64_t)(e0 + i0) + (int64_t)ps.o * ld;
-        for (int k = 0; k < w; ++k) if (tid < cnt) X0[tid + (size_t)k * ld] = Xs[k * PANEL_ROWS + tid];
+        if (LU) {
+            for (int k = 0; k < w; ++k) if (tid < cnt) X0[tid + (size_t)k * ld] = Xs[k * PANEL_ROWS + tid];
+        } else {
+            // L21 = X / D (SpkLDLtFactor.jl:372-377); U12 = X^T = D * L21^T goes to the upper triangle of the
+            // front, where the trailing-update kernel reads its B operand
+            for (int k = 0; k < w; ++k) if (tid < cnt) X0[tid + (size_t)k * ld] = Xs[k * PANEL_ROWS + tid] / Ts[k + k * w];
+            double* Y0 = Fm + (int64_t)ps.o + (int64_t)(e0 + i0) * ld;
+            for (int e = tid; e < w * cnt; e += PANEL_ROWS) { int col = e / w, k = e - col * w; Y0[k + (size_t)col * ld] = Xs[k * PANEL_ROWS + col]; }
+        }
     } else if (LU) {
         double* Y0 = Fm + (int64_t)ps.o + (int64_t)(e0 + i0) * ld;
         for (int e = tid; e < w * cnt; e += PANEL_ROWS) { int col = e / w, k = e - col * w; Y0[k + (size_t)col * ld] = Xs[k * PANEL_ROWS + col]; }
@@ -336,7 +343,6 @@ __global__ void __launch_bounds__(256) k_gemm_small(DevCtx c, const GemmTask* __
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
     const double* __restrict__ A = c.F + g.a0;
     const double* __restrict__ B = c.F + g.b0;
-    const double* __restrict__ D = c.F + g.d0;
     const int ld = g.ld;
     for (int k0 = 0; k0 < g.k; k0 += TK) {
         {   // A tile: rows contiguous
@@ -347,14 +353,9 @@ __global__ void __launch_bounds__(256) k_gemm_small(DevCtx c, const GemmTask* __
                 double a = 0.0;
                 if (kg < g.k && row0 + lr < g.m) a = A[(size_t)(row0 + lr) + (size_t)kg * ld];
                 As[kk][lr] = a;
-                if (!g.bk) {
-                    double b = 0.0;
-                    if (kg < g.k && col0 + lr < g.n) b = B[(size_t)(col0 + lr) + (size_t)kg * ld] * D[(size_t)kg * (ld + 1)];
-                    Bs[kk][lr] = b;
-                }
             }
         }
-        if (g.bk) {  // B tile: k contiguous
+        {   // B tile: k contiguous
             const int kk = tid & 15, ln = tid >> 4;
 #pragma unroll
             for (int p = 0; p < TN / 16; ++p) {

@@ -59,12 +59,11 @@ struct PStep {
 };
 
 struct GemmTask {         // C -= A * B   inside one frontal matrix (offsets relative to the arena)
-    int64_t a0, b0, c0, d0;   // element offsets of A(0,0), B(0,0), C(0,0), D(0) (LDL^T scaling)
+    int64_t a0, b0, c0;   // element offsets of A(0,0) [A(i,k) at a0 + i + k*ld], B(0,0) [B(k,n) at b0 + k + n*ld], C(0,0)
     int32_t ld, m, n, k;
     int32_t roff;         // row index of C(0,0) minus its column index inside the front (for `lower`)
-    uint8_t bk;           // 1: B(k,n) at b0 + k + n*ld (LU: a row block of U);  0: B(n,k) at b0 + n + k*ld, scaled by D
-    uint8_t lower;        // only entries on/below the front's diagonal are needed / written
-    uint8_t pad0, pad1;
+    uint8_t lower;        // only entries on/below the front's diagonal are needed / written (LDL^T)
+    uint8_t pad0, pad1, pad2;
 };
 struct AsmTask { int32_t child, parent; };
 struct SolveTask {        // one chunk of a triangular sweep (values read from lnz / unz)
@@ -83,6 +82,7 @@ struct Launch {
     int64_t pfx;              // block prefix: blkpfx[pfx .. pfx+count] (count+1 entries)
     double  flops;            // executed flops (GEMM launches)
     int32_t level, step;
+    int32_t maxw;             // widest panel step in a DIAG / PANEL launch (sizes its shared memory)
 };
 
 constexpr int ASM_ROUNDS = 8;      // children handled by per-round launches; the rest by a tail kernel
@@ -305,8 +305,9 @@ struct LaunchBuilder {
         cur.pfx = (int64_t)P.blkpfx.size(); cur.flops = 0; cur.level = level; cur.step = step;
         P.blkpfx.push_back(0);
     }
-    void add(int32_t nblocks, double flops = 0) {
+    void add(int32_t nblocks, double flops = 0, int32_t w = 0) {
         cur.count++; cur.nblocks += nblocks; cur.flops += flops; P.blkpfx.push_back(cur.nblocks);
+        cur.maxw = std::max(cur.maxw, w);
     }
     void end() {
         if (cur.count > 0 && cur.nblocks > 0) out.push_back(cur);
@@ -345,8 +346,10 @@ inline GemmTask front_gemm(const Plan& P, const Front& F, int32_t r0, int32_t m,
     g.ld = F.ld; g.m = m; g.n = n; g.k = k;
     g.a0 = F.fofs + (int64_t)r0 + (int64_t)k0 * F.ld;
     g.c0 = F.fofs + (int64_t)r0 + (int64_t)c0 * F.ld;
-    if (P.lu) { g.bk = 1; g.b0 = F.fofs + (int64_t)k0 + (int64_t)c0 * F.ld; g.lower = 0; g.d0 = 0; }
-    else { g.bk = 0; g.b0 = F.fofs + (int64_t)c0 + (int64_t)k0 * F.ld; g.d0 = F.fofs + (int64_t)k0 + (int64_t)k0 * F.ld; g.lower = 1; }
+    // B is a row block of U.  LDL^T fronts keep U = D * L^T in their (otherwise unused) upper triangle
+    // (written by the panel kernel), so both factorisations run the same kernel with no scaling in the k loop.
+    g.b0 = F.fofs + (int64_t)k0 + (int64_t)c0 * F.ld;
+    g.lower = P.lu ? 0 : 1;
     g.roff = r0 - c0;
     return g;
 }
@@ -404,7 +407,7 @@ inline void build_schedule(Plan& P) {
         // ---- dense partial factorisation, panel step by panel step
         for (int32_t j = 0; j < maxnps; ++j) {
             fb.begin(K_DIAG, (int32_t)P.pslist.size(), lev, j);
-            for (int32_t f : fr) if (P.fronts[f].nps > j) { P.pslist.push_back(P.fronts[f].ps0 + j); fb.add(1); }
+            for (int32_t f : fr) if (P.fronts[f].nps > j) { P.pslist.push_back(P.fronts[f].ps0 + j); fb.add(1, 0, P.psteps[P.fronts[f].ps0 + j].w); }
             fb.end();
             fb.begin(K_PANEL, (int32_t)P.pslist.size(), lev, j);
             for (int32_t f : fr) if (P.fronts[f].nps > j) {
@@ -412,7 +415,7 @@ inline void build_schedule(Plan& P) {
                 int32_t below = ps.R - ps.o - ps.w;
                 if (below <= 0) continue;
                 P.pslist.push_back(P.fronts[f].ps0 + j);
-                fb.add(cdiv(below, PANEL_ROWS) * (lu ? 2 : 1));
+                fb.add(cdiv(below, PANEL_ROWS) * (lu ? 2 : 1), 0, ps.w);
             }
             fb.end();
             GemmBatch gb;

@@ -50,6 +50,7 @@ struct spk_plan {
     double* d_nzval = nullptr; int64_t nzcap = 0, nz_last = 0;
     AsmTask* d_asmt = nullptr; GemmTask* d_gemmt = nullptr; SolveTask* d_solvet = nullptr;
     int32_t chunk_blocks = 0;
+    bool dmma_wide = false;             // 16-warp DMMA blocks (SPK_DMMA_WIDE=1)
     bool values_in_fronts = false;      // inmatrix scattered straight into the fronts
     int64_t w_nrhs = 0, rhs_cap = 0;
     size_t dev_bytes = 0;
@@ -175,6 +176,7 @@ SPK_API spk_plan* spk_plan_create(int64_t n, int64_t nsuper, const int64_t* xsup
         set_err("analyze: " + p->P.error); delete p; return nullptr;
     }
     plan_env_overrides(p->P);
+    if (const char* e = getenv("SPK_DMMA_WIDE")) p->dmma_wide = e[0] == '1';
     build_schedule(p->P);
     if (device < 0) return p;                      // host-only plan: structure statistics without a GPU
     int ndev = 0;
@@ -289,21 +291,28 @@ static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L) 
         k_assemble<<<L.nblocks, ASM_TPB, 0, st>>>(c, p->d_asmt + L.first, pfx, L.count); break;
     case K_ASM_TAIL:
         k_assemble_tail<<<L.count, 256, 0, st>>>(c, p->d_asmt + L.first, L.count); break;
-    case K_DIAG:
-        if (lu) k_diag<true><<<L.count, 256, p->diag_smem_bytes, st>>>(c, p->d_pslist + L.first, p->diag_smem_nj);
-        else k_diag<false><<<L.count, 256, p->diag_smem_bytes, st>>>(c, p->d_pslist + L.first, p->diag_smem_nj);
+    case K_DIAG: {
+        // shared memory sized for the widest block of THIS launch (tiny fronts keep high occupancy)
+        int wl = std::min(L.maxw, p->diag_smem_nj);
+        size_t sm = (size_t)wl * (wl | 1) * sizeof(double);
+        if (lu) k_diag<true><<<L.count, 256, sm, st>>>(c, p->d_pslist + L.first, wl);
+        else k_diag<false><<<L.count, 256, sm, st>>>(c, p->d_pslist + L.first, wl);
         break;
-    case K_PANEL:
-        if (lu) k_panel<true><<<L.nblocks, PANEL_ROWS, p->panel_smem, st>>>(c, p->d_pslist + L.first, pfx, L.count);
-        else k_panel<false><<<L.nblocks, PANEL_ROWS, p->panel_smem, st>>>(c, p->d_pslist + L.first, pfx, L.count);
+    }
+    case K_PANEL: {
+        size_t sm = panel_smem_bytes(L.maxw);
+        if (lu) k_panel<true><<<L.nblocks, PANEL_ROWS, sm, st>>>(c, p->d_pslist + L.first, pfx, L.count);
+        else k_panel<false><<<L.nblocks, PANEL_ROWS, sm, st>>>(c, p->d_pslist + L.first, pfx, L.count);
         break;
+    }
     case K_GEMM:
         k_gemm_small<<<L.nblocks, 256, 0, st>>>(c, p->d_gemmt + L.first, pfx, L.count); break;
     case K_GEMM_B64:
-    case K_GEMM_B128:
-        gemm_dmma_kernel(L.kind, lu)<<<L.nblocks, DM_THREADS, gemm_dmma_smem(L.kind), st>>>(
-            c, p->d_gemmt + L.first, pfx, L.count);
+    case K_GEMM_B128: {
+        GemmVariant v = gemm_dmma_variant(L.kind, p->dmma_wide);
+        v.fn<<<L.nblocks, v.threads, v.smem, st>>>(c, p->d_gemmt + L.first, pfx, L.count);
         break;
+    }
     default:
         set_err("bad launch kind"); return -100;
     }

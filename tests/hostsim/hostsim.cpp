@@ -114,17 +114,18 @@ static void panel(Sim& s, const PStep& ps) {
                 for (int k = 0; k < j; ++k) acc -= T[j + (size_t)k * ld] * X[(size_t)k * ld];
                 X[(size_t)j * ld] = acc;
             }
-            for (int j = 0; j < w; ++j) X[(size_t)j * ld] /= T[j + (size_t)j * ld];
+            double* Y = Fm + (int64_t)ps.o + (int64_t)(e0 + i) * ld;       // U12 = X^T = D * L21^T in the upper triangle
+            for (int j = 0; j < w; ++j) { Y[j] = X[(size_t)j * ld]; X[(size_t)j * ld] /= T[j + (size_t)j * ld]; }
         }
     }
 }
 
 static void gemm(Sim& s, const GemmTask& g) {
     std::vector<double> acc((size_t)g.m * g.n, 0.0);
-    const double* A = s.F.data() + g.a0; const double* B = s.F.data() + g.b0; const double* D = s.F.data() + g.d0;
+    const double* A = s.F.data() + g.a0; const double* B = s.F.data() + g.b0;
     for (int k = 0; k < g.k; ++k)
         for (int j = 0; j < g.n; ++j) {
-            double b = g.bk ? B[(size_t)k + (size_t)j * g.ld] : B[(size_t)j + (size_t)k * g.ld] * D[(size_t)k * (g.ld + 1)];
+            double b = B[(size_t)k + (size_t)j * g.ld];
             for (int i = 0; i < g.m; ++i) acc[i + (size_t)j * g.m] += A[i + (size_t)k * g.ld] * b;
         }
     double* C = s.F.data() + g.c0;
