@@ -51,8 +51,8 @@ struct DmmaCfg {
 };
 
 // WARPS_M x WARPS_N warps, each owning a (TM/WARPS_M) x (TN/WARPS_N) sub-tile of the block's C tile.
-template <int TM, int TN, int WARPS_M, int WARPS_N>
-__global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, 1)
+template <int TM, int TN, int WARPS_M, int WARPS_N, int MINB>
+__global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, MINB)
 k_gemm_dmma(DevCtx c, const GemmTask* __restrict__ tasks, const int32_t* __restrict__ pfx, int count) {
     using Cfg = DmmaCfg<TM, TN>;
     constexpr int NT = WARPS_M * WARPS_N * 32;
@@ -185,21 +185,23 @@ k_gemm_dmma(DevCtx c, const GemmTask* __restrict__ tasks, const int32_t* __restr
     }
 }
 
-// Kernel variants.  `wide` = 16 warps per block (4 per scheduler) instead of 8: more DMMA issuers per SM.
+// Kernel variants (SPK_DMMA_VARIANT): 0 = 8 warps, one block per SM; 1 = 16 warps per block;
+// 2 = 128x64 tiles only, two co-resident blocks per SM (one block's epilogue overlaps the other's k loop).
 using GemmKernel = void (*)(DevCtx, const GemmTask*, const int32_t*, int);
 struct GemmVariant { GemmKernel fn; int threads; size_t smem; };
-inline GemmVariant gemm_dmma_variant(int kind, bool wide) {
+inline GemmVariant gemm_dmma_variant(int kind, int variant) {
     if (kind == K_GEMM_B128) {
-        if (wide) return {k_gemm_dmma<BIG_TM, 128, 4, 4>, 512, DmmaCfg<BIG_TM, 128>::SMEM};
-        return {k_gemm_dmma<BIG_TM, 128, 2, 4>, 256, DmmaCfg<BIG_TM, 128>::SMEM};
+        if (variant == 1) return {k_gemm_dmma<BIG_TM, 128, 4, 4, 1>, 512, DmmaCfg<BIG_TM, 128>::SMEM};
+        return {k_gemm_dmma<BIG_TM, 128, 2, 4, 1>, 256, DmmaCfg<BIG_TM, 128>::SMEM};
     }
-    if (wide) return {k_gemm_dmma<BIG_TM, 64, 4, 4>, 512, DmmaCfg<BIG_TM, 64>::SMEM};
-    return {k_gemm_dmma<BIG_TM, 64, 4, 2>, 256, DmmaCfg<BIG_TM, 64>::SMEM};
+    if (variant == 1) return {k_gemm_dmma<BIG_TM, 64, 4, 4, 1>, 512, DmmaCfg<BIG_TM, 64>::SMEM};
+    if (variant == 2) return {k_gemm_dmma<BIG_TM, 64, 4, 2, 2>, 256, DmmaCfg<BIG_TM, 64>::SMEM};
+    return {k_gemm_dmma<BIG_TM, 64, 4, 2, 1>, 256, DmmaCfg<BIG_TM, 64>::SMEM};
 }
 inline cudaError_t gemm_dmma_init() {
     for (int kind : {(int)K_GEMM_B64, (int)K_GEMM_B128})
-        for (int wide = 0; wide < 2; ++wide) {
-            GemmVariant v = gemm_dmma_variant(kind, wide != 0);
+        for (int variant = 0; variant < 3; ++variant) {
+            GemmVariant v = gemm_dmma_variant(kind, variant);
             cudaError_t e = cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem);
             if (e != cudaSuccess) return e;
         }

@@ -114,6 +114,8 @@ struct Plan {
     double flops_struct = 0, nnzL = 0;        // sum cc^2 (or 2 sum cc^2 - sum cc), sum cc
     bool use_dmma = true;
     int64_t solve_small = SOLVE_SMALL;
+    int ob_width = OB_WIDTH, ps_width = PS_WIDTH;
+    bool no_b128 = false;                     // DMMA tasks all use 128x64 tiles
     int relax_abs = RELAX_ABS; double relax_frac = RELAX_FRAC;
     // schedules
     std::vector<AsmTask> asmt;
@@ -270,7 +272,7 @@ inline bool analyze(Plan& P, int64_t n, int64_t nsuper, const int64_t* xsuper, c
             PStep ps{}; ps.fofs = F.fofs; ps.ld = F.ld; ps.R = F.R; ps.front = f;
             ps.o = P.chunks[F.c0 + t].o; ps.col0 = P.chunks[F.c0 + t].fj; ps.sub0 = (int32_t)P.subw.size();
             int32_t w = 0, ns = 0;
-            while (t < F.nch && (ns == 0 || w + P.chunks[F.c0 + t].nj <= PS_WIDTH)) { w += P.chunks[F.c0 + t].nj; P.subw.push_back(P.chunks[F.c0 + t].nj); ++ns; ++t; }
+            while (t < F.nch && (ns == 0 || w + P.chunks[F.c0 + t].nj <= P.ps_width)) { w += P.chunks[F.c0 + t].nj; P.subw.push_back(P.chunks[F.c0 + t].nj); ++ns; ++t; }
             ps.w = w; ps.nsub = ns;
             P.maxpw = std::max(P.maxpw, w);
             P.psteps.push_back(ps);
@@ -279,7 +281,7 @@ inline bool analyze(Plan& P, int64_t n, int64_t nsuper, const int64_t* xsuper, c
         int32_t j = 0;
         while (j < F.nps) {
             int32_t j0 = j, w = 0;
-            while (j < F.nps && (j == j0 || w + P.psteps[F.ps0 + j].w <= OB_WIDTH)) { w += P.psteps[F.ps0 + j].w; ++j; }
+            while (j < F.nps && (j == j0 || w + P.psteps[F.ps0 + j].w <= P.ob_width)) { w += P.psteps[F.ps0 + j].w; ++j; }
             int32_t ob_end = P.psteps[F.ps0 + j0].o + w;
             for (int32_t q = j0; q < j; ++q) P.psteps[F.ps0 + q].ob_end = ob_end;
         }
@@ -322,7 +324,7 @@ struct GemmBatch {
     std::vector<Item> small, b64, b128;
     void add(const Plan& P, const GemmTask& t, double flops) {
         if (t.m <= 0 || t.n <= 0 || t.k <= 0) return;
-        if (P.use_dmma && t.m >= 128 && t.n > 64) b128.push_back({t, flops});
+        if (P.use_dmma && !P.no_b128 && t.m >= 128 && t.n > 64) b128.push_back({t, flops});
         else if (P.use_dmma && t.m >= 128 && t.n > 16) b64.push_back({t, flops});
         else small.push_back({t, flops});
     }
@@ -365,6 +367,9 @@ inline double gemm_flops(const GemmTask& g) {
 inline void plan_env_overrides(Plan& P) {        // test / tuning knobs
     if (const char* e = getenv("SPK_NO_DMMA")) P.use_dmma = !(e[0] == '1');
     if (const char* e = getenv("SPK_SOLVE_SMALL")) P.solve_small = atoll(e);
+    if (const char* e = getenv("SPK_OB_WIDTH")) P.ob_width = std::max(1, atoi(e));
+    if (const char* e = getenv("SPK_PS_WIDTH")) P.ps_width = std::max(1, atoi(e));
+    if (const char* e = getenv("SPK_DMMA_VARIANT")) P.no_b128 = atoi(e) == 2;
 }
 
 inline void build_schedule(Plan& P) {

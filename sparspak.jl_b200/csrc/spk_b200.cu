@@ -50,7 +50,7 @@ struct spk_plan {
     double* d_nzval = nullptr; int64_t nzcap = 0, nz_last = 0;
     AsmTask* d_asmt = nullptr; GemmTask* d_gemmt = nullptr; SolveTask* d_solvet = nullptr;
     int32_t chunk_blocks = 0;
-    bool dmma_wide = false;             // 16-warp DMMA blocks (SPK_DMMA_WIDE=1)
+    int dmma_variant = 0;               // SPK_DMMA_VARIANT (see gemm_dmma.cuh)
     bool values_in_fronts = false;      // inmatrix scattered straight into the fronts
     int64_t w_nrhs = 0, rhs_cap = 0;
     size_t dev_bytes = 0;
@@ -172,11 +172,12 @@ SPK_API spk_plan* spk_plan_create(int64_t n, int64_t nsuper, const int64_t* xsup
     (void)part; (void)nparts;
     spk_plan* p = new spk_plan();
     p->device = device;
+    plan_env_overrides(p->P);
     if (!analyze(p->P, n, nsuper, xsuper, snode, xlindx, lindx, xlnz, xunz_or_null)) {
         set_err("analyze: " + p->P.error); delete p; return nullptr;
     }
     plan_env_overrides(p->P);
-    if (const char* e = getenv("SPK_DMMA_WIDE")) p->dmma_wide = e[0] == '1';
+    if (const char* e = getenv("SPK_DMMA_VARIANT")) p->dmma_variant = atoi(e);
     build_schedule(p->P);
     if (device < 0) return p;                      // host-only plan: structure statistics without a GPU
     int ndev = 0;
@@ -309,7 +310,7 @@ static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L) 
         k_gemm_small<<<L.nblocks, 256, 0, st>>>(c, p->d_gemmt + L.first, pfx, L.count); break;
     case K_GEMM_B64:
     case K_GEMM_B128: {
-        GemmVariant v = gemm_dmma_variant(L.kind, p->dmma_wide);
+        GemmVariant v = gemm_dmma_variant(L.kind, p->dmma_variant);
         v.fn<<<L.nblocks, v.threads, v.smem, st>>>(c, p->d_gemmt + L.first, pfx, L.count);
         break;
     }

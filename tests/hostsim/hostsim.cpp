@@ -136,6 +136,7 @@ API void* sim_create(int64_t n, int64_t nsuper, const int64_t* xsuper, const int
                      const int64_t* lindx, const int64_t* xlnz, const int64_t* xunz, int use_dmma_buckets,
                      int relax_abs, double relax_frac, int alloc) {
     Sim* s = new Sim();
+    plan_env_overrides(s->P);
     s->P.relax_abs = relax_abs; s->P.relax_frac = relax_frac;
     if (!analyze(s->P, n, nsuper, xsuper, snode, xlindx, lindx, xlnz, xunz)) { fprintf(stderr, "analyze: %s\n", s->P.error.c_str()); delete s; return nullptr; }
     s->P.use_dmma = use_dmma_buckets != 0;
