@@ -117,6 +117,21 @@ __global__ void __launch_bounds__(256) k_assemble_tail(DevCtx c, const AsmTask* 
     }
 }
 
+// Cooperative copy of a w x w block between global memory (leading dimension ld) and shared memory
+// (leading dimension lds), 8 independent loads in flight per thread (a plain load->store loop
+// serialises one global round trip per element on the critical path of every panel step).
+template <int NT>
+__device__ __forceinline__ void block_g2s(double* __restrict__ S, int lds, const double* __restrict__ G, int ld, int w) {
+    const int tot = w * w;
+    for (int e0 = threadIdx.x; e0 < tot; e0 += 8 * NT) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { int e = e0 + u * NT; int j = e / w, i = e - j * w; v[u] = e < tot ? __ldcg(G + i + (size_t)j * ld) : 0.0; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { int e = e0 + u * NT; int j = e / w, i = e - j * w; if (e < tot) S[i + j * lds] = v[u]; }
+    }
+}
+
 // ------------------------------------------------------------------------------------
 // Diagonal block of a panel step (w x w, one or more chunks).
 // LU: partial pivoting restricted to each chunk's own rows, first maximum wins (ggetrf!,
@@ -201,7 +216,7 @@ __global__ void __launch_bounds__(256) k_diag(DevCtx c, const int32_t* __restric
     const int32_t* subw = c.subw + ps.sub0;
     if (w <= smem_w) {
         const int lds = w | 1;                          // odd leading dimension: conflict-free columns
-        for (int e = threadIdx.x; e < w * w; e += blockDim.x) { int j = e / w, i = e % w; sm[i + j * lds] = G[i + (size_t)j * ld]; }
+        block_g2s<256>(sm, lds, G, ld, w);
         __syncthreads();
         diag_factor<LU>(sm, lds, w, subw, ps.nsub, ipiv, c.iflag, &s_piv, &s_pv);
         for (int e = threadIdx.x; e < w * w; e += blockDim.x) { int j = e / w, i = e % w; G[i + (size_t)j * ld] = sm[i + j * lds]; }
@@ -235,7 +250,7 @@ __global__ void __launch_bounds__(PANEL_ROWS) k_panel(DevCtx c, const int32_t* _
     const double* __restrict__ T = Fm + (int64_t)ps.o + (int64_t)ps.o * ld;   // factored w x w block
     double* Ts = psm;
     double* Xs = psm + w * w;
-    for (int e = tid; e < w * w; e += PANEL_ROWS) { int j = e / w, i = e - j * w; Ts[e] = T[i + (size_t)j * ld]; }
+    block_g2s<PANEL_ROWS>(Ts, w, T, ld, w);
     const bool lside = lb < nb;
     const int i0 = (lside ? lb : lb - nb) * PANEL_ROWS;
     const int cnt = min(PANEL_ROWS, below - i0);

@@ -362,6 +362,16 @@ SPK_API int64_t spk_plan_factor_phase(spk_plan* p, int32_t phase) {
             if (P.factor_launches[i].kind == K_GEMM_B64 || P.factor_launches[i].kind == K_GEMM_B128) p->gemm_ms += p->launch_ms[i];
         }
         for (auto& e : evs) cudaEventDestroy(e);
+        if (const char* path = getenv("SPK_DUMP_LAUNCHES")) {       // per-launch CSV for profiles/
+            if (FILE* f = fopen(path, "w")) {
+                fprintf(f, "idx,kind,level,step,tasks,blocks,maxw,flops,ms\n");
+                for (size_t i = 0; i < P.factor_launches.size(); ++i) {
+                    const Launch& L = P.factor_launches[i];
+                    fprintf(f, "%zu,%d,%d,%d,%d,%d,%d,%.6g,%.6f\n", i, L.kind, L.level, L.step, L.count, L.nblocks, L.maxw, L.flops, p->launch_ms[i]);
+                }
+                fclose(f);
+            }
+        }
     }
     int32_t flag = 0;
     CK(cudaMemcpy(&flag, p->d_iflag, sizeof(int32_t), cudaMemcpyDeviceToHost));
