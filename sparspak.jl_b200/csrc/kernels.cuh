@@ -225,6 +225,69 @@ __global__ void __launch_bounds__(256) k_diag(DevCtx c, const int32_t* __restric
     }
 }
 
+// LDL^T of a w x w diagonal block held in REGISTERS: 16 x 16 threads, thread (tx,ty) owns the entries
+// (tx + 16a, ty + 16b), a,b < NB (cyclic, so the shrinking active part stays balanced).  Per column k the
+// owners of that column publish l_r = a_r / d (multiplication by the correctly rounded reciprocal) through a
+// double-buffered shared vector; everybody then updates its own entries from registers: one barrier per column.
+template <int NB>
+__global__ void __launch_bounds__(256) k_diag_ldlt_reg(DevCtx c, const int32_t* __restrict__ pslist) {
+    __shared__ double col[2][16 * NB + 1];
+    const PStep ps = c.psteps[pslist[blockIdx.x]];
+    double* G = c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld;
+    const int w = ps.w, ld = ps.ld;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double v[NB][NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int a = 0; a < NB; ++a) {
+            const int r = tx + 16 * a, s = ty + 16 * b;
+            v[a][b] = (r < w && s < w && r >= s) ? __ldcg(G + r + (size_t)s * ld) : 0.0;
+        }
+    for (int k = 0; k < w; ++k) {
+        double* cb = col[k & 1];
+        const int kb = k >> 4, kt = k & 15;
+        if (ty == kt) {                                     // the 16 owners of column k: one half-warp
+            double dloc = 0.0;
+#pragma unroll
+            for (int a = 0; a < NB; ++a) if (a == kb) dloc = v[a][a];          // meaningful in thread tx == kt only
+            const unsigned half = 0xFFFFu << ((ty & 1) * 16);
+            const double d0 = __shfl_sync(half, dloc, (ty & 1) * 16 + kt);
+            const double rinv = 1.0 / d0;
+            if (tx == kt) { cb[16 * NB] = d0; if (d0 == 0.0) atomicExch(c.iflag, -1); }
+#pragma unroll
+            for (int b = 0; b < NB; ++b) if (b == kb) {
+#pragma unroll
+                for (int a = 0; a < NB; ++a) {
+                    const int r = tx + 16 * a;
+                    if (r > k && r < w) { v[a][b] *= rinv; cb[r] = v[a][b]; }
+                }
+            }
+        }
+        __syncthreads();
+        const double d = cb[16 * NB];
+        double lr[NB], fs[NB];
+#pragma unroll
+        for (int a = 0; a < NB; ++a) { const int r = tx + 16 * a; lr[a] = (r > k && r < w) ? cb[r] : 0.0; }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) { const int s = ty + 16 * b; fs[b] = (s > k && s < w) ? cb[s] * d : 0.0; }
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+#pragma unroll
+            for (int a = 0; a < NB; ++a) {
+                const int r = tx + 16 * a, s = ty + 16 * b;
+                if (r >= s && s > k) v[a][b] -= fs[b] * lr[a];
+            }
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int a = 0; a < NB; ++a) {
+            const int r = tx + 16 * a, s = ty + 16 * b;
+            if (r < w && s < w && r >= s) __stcg(G + r + (size_t)s * ld, v[a][b]);
+        }
+}
+
 // ------------------------------------------------------------------------------------
 // Panels of a panel step.  One block = PANEL_ROWS front rows below the block (L side) or PANEL_ROWS
 // front columns to its right (U side); the factored w x w block T and the block's slice of the
@@ -233,6 +296,58 @@ __global__ void __launch_bounds__(256) k_diag(DevCtx c, const int32_t* __restric
 //   LU  U-side: per chunk, apply its row interchanges then inv(L11)  (:238-240, _luswap! SpkSpdMMOps.jl:168-175)
 //   LDLT:       X = A21 * inv(L11^T), then each column / D  (SpkLDLtFactor.jl:367-377)
 // Shared layout: Ts[w*w] (column-major), Xs[w][PANEL_ROWS] (element k of thread t at Xs[k*PANEL_ROWS + t]).
+// Triangular substitution on one thread's vector x (element k at x[k * PANEL_ROWS]) against the staged
+// block Ts (w x w, column-major).  Columns are processed 8 at a time: the contributions of already final
+// unknowns run as 8 independent FMA chains (throughput-bound), only the 8 x 8 in-block part is a dependent
+// chain.  Per unknown the terms are still subtracted in ascending k, exactly as a plain column loop would.
+//   UPPER: x_j = (a_j - sum_{k<j} x_k T[k,j]) / T[j,j]     (right solve with U11)
+//   else : x_j =  a_j - sum_{k<j} x_k T[j,k]               (right solve with unit-lower L11^T / left solve with L11)
+template <bool UPPER>
+__device__ __forceinline__ double ts_coef(const double* __restrict__ Ts, int w, int k, int j) {
+    return UPPER ? Ts[k + j * w] : Ts[j + k * w];
+}
+// x_j -= sum_{k in [k0,k1)} coef(k,j) x_k  for j in [j0,j1);  requires k1 <= j0
+template <bool UPPER>
+__device__ __forceinline__ void ts_accum(double* x, const double* __restrict__ Ts, int w, int j0, int j1, int k0, int k1) {
+    for (int jb = j0; jb < j1; jb += 8) {
+        const int nb = min(8, j1 - jb);
+        double acc[8];
+#pragma unroll
+        for (int cidx = 0; cidx < 8; ++cidx) acc[cidx] = cidx < nb ? x[(jb + cidx) * PANEL_ROWS] : 0.0;
+        for (int k = k0; k < k1; ++k) {
+            const double xk = x[k * PANEL_ROWS];
+#pragma unroll
+            for (int cidx = 0; cidx < 8; ++cidx) if (cidx < nb) acc[cidx] -= ts_coef<UPPER>(Ts, w, k, jb + cidx) * xk;
+        }
+#pragma unroll
+        for (int cidx = 0; cidx < 8; ++cidx) if (cidx < nb) x[(jb + cidx) * PANEL_ROWS] = acc[cidx];
+    }
+}
+// triangular solve restricted to [j0,j1): unknowns before j0 contribute nothing here
+template <bool UPPER>
+__device__ __forceinline__ void ts_solve(double* x, const double* __restrict__ Ts, int w, int j0, int j1) {
+    for (int jb = j0; jb < j1; jb += 8) {
+        const int nb = min(8, j1 - jb);
+        double acc[8];
+#pragma unroll
+        for (int cidx = 0; cidx < 8; ++cidx) acc[cidx] = cidx < nb ? x[(jb + cidx) * PANEL_ROWS] : 0.0;
+        for (int k = j0; k < jb; ++k) {
+            const double xk = x[k * PANEL_ROWS];
+#pragma unroll
+            for (int cidx = 0; cidx < 8; ++cidx) if (cidx < nb) acc[cidx] -= ts_coef<UPPER>(Ts, w, k, jb + cidx) * xk;
+        }
+#pragma unroll
+        for (int cidx = 0; cidx < 8; ++cidx) {
+            if (cidx < nb) {
+#pragma unroll
+                for (int c2 = 0; c2 < 8; ++c2) if (c2 < cidx) acc[cidx] -= ts_coef<UPPER>(Ts, w, jb + c2, jb + cidx) * acc[c2];
+                if (UPPER) acc[cidx] = (1.0 / Ts[(jb + cidx) + (jb + cidx) * w]) * acc[cidx];
+                x[(jb + cidx) * PANEL_ROWS] = acc[cidx];
+            }
+        }
+    }
+}
+
 inline size_t panel_smem_bytes(int w) { return ((size_t)w * w + (size_t)w * PANEL_ROWS) * sizeof(double); }
 
 template <bool LU>
@@ -279,41 +394,20 @@ __global__ void __launch_bounds__(PANEL_ROWS) k_panel(DevCtx c, const int32_t* _
     if (tid < cnt) {
         double* x = Xs + tid;                                                  // x[k * PANEL_ROWS]
         if (lside) {
-            if (LU) {
-                for (int j = 0; j < w; ++j) {
-                    double acc = x[j * PANEL_ROWS];
-#pragma unroll 8
-                    for (int k = 0; k < j; ++k) acc -= Ts[k + j * w] * x[k * PANEL_ROWS];
-                    x[j * PANEL_ROWS] = (1.0 / Ts[j + j * w]) * acc;
-                }
-            } else {
-                for (int j = 0; j < w; ++j) {                                  // X = A21 * inv(L11^T), kept UNSCALED here
-                    double acc = x[j * PANEL_ROWS];
-#pragma unroll 8
-                    for (int k = 0; k < j; ++k) acc -= Ts[j + k * w] * x[k * PANEL_ROWS];
-                    x[j * PANEL_ROWS] = acc;
-                }
-            }
+            if (LU) ts_solve<true>(x, Ts, w, 0, w);                            // X = A21 * inv(U11)
+            else ts_solve<false>(x, Ts, w, 0, w);                              // X = A21 * inv(L11^T), kept UNSCALED here
         } else if (LU) {
             const int32_t* ipiv = c.ipiv + ps.col0;
             const int32_t* subw = c.subw + ps.sub0;
             int s0 = 0;
             for (int b = 0; b < ps.nsub; ++b) {
                 const int s1 = s0 + subw[b];
-                for (int j = s0; j < s1; ++j) {                                // contributions of earlier chunks (unswapped rows)
-                    double acc = x[j * PANEL_ROWS];
-                    for (int k = 0; k < s0; ++k) acc -= Ts[j + k * w] * x[k * PANEL_ROWS];
-                    x[j * PANEL_ROWS] = acc;
-                }
+                ts_accum<false>(x, Ts, w, s0, s1, 0, s0);                      // contributions of earlier chunks (unswapped rows)
                 for (int k = s0; k < s1; ++k) {                                // this chunk's interchanges
                     int ip = s0 + ipiv[k] - 1;
                     if (ip != k) { double tmp = x[k * PANEL_ROWS]; x[k * PANEL_ROWS] = x[ip * PANEL_ROWS]; x[ip * PANEL_ROWS] = tmp; }
                 }
-                for (int j = s0; j < s1; ++j) {                                // unit-lower solve inside the chunk
-                    double acc = x[j * PANEL_ROWS];
-                    for (int k = s0; k < j; ++k) acc -= Ts[j + k * w] * x[k * PANEL_ROWS];
-                    x[j * PANEL_ROWS] = acc;
-                }
+                ts_solve<false>(x, Ts, w, s0, s1);                             // unit-lower solve inside the chunk
                 s0 = s1;
             }
         }

@@ -50,6 +50,7 @@ struct spk_plan {
     double* d_nzval = nullptr; int64_t nzcap = 0, nz_last = 0;
     AsmTask* d_asmt = nullptr; GemmTask* d_gemmt = nullptr; SolveTask* d_solvet = nullptr;
     int32_t chunk_blocks = 0;
+    bool diag_smem_only = false;        // SPK_DIAG_SMEM=1: always use the shared-memory diagonal kernel
     int dmma_variant = 0;               // SPK_DMMA_VARIANT (see gemm_dmma.cuh)
     bool values_in_fronts = false;      // inmatrix scattered straight into the fronts
     int64_t w_nrhs = 0, rhs_cap = 0;
@@ -178,6 +179,7 @@ SPK_API spk_plan* spk_plan_create(int64_t n, int64_t nsuper, const int64_t* xsup
     }
     plan_env_overrides(p->P);
     if (const char* e = getenv("SPK_DMMA_VARIANT")) p->dmma_variant = atoi(e);
+    if (const char* e = getenv("SPK_DIAG_SMEM")) p->diag_smem_only = e[0] == '1';
     build_schedule(p->P);
     if (device < 0) return p;                      // host-only plan: structure statistics without a GPU
     int ndev = 0;
@@ -297,6 +299,8 @@ static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L) 
         int wl = std::min(L.maxw, p->diag_smem_nj);
         size_t sm = (size_t)wl * (wl | 1) * sizeof(double);
         if (lu) k_diag<true><<<L.count, 256, sm, st>>>(c, p->d_pslist + L.first, wl);
+        else if (L.maxw <= 64 && !p->diag_smem_only) k_diag_ldlt_reg<4><<<L.count, 256, 0, st>>>(c, p->d_pslist + L.first);
+        else if (L.maxw <= 96 && !p->diag_smem_only) k_diag_ldlt_reg<6><<<L.count, 256, 0, st>>>(c, p->d_pslist + L.first);
         else k_diag<false><<<L.count, 256, sm, st>>>(c, p->d_pslist + L.first, wl);
         break;
     }
