@@ -83,6 +83,9 @@ struct Launch {
     double  flops;            // executed flops (GEMM launches)
     int32_t level, step;
     int32_t maxw;             // widest panel step in a DIAG / PANEL launch (sizes its shared memory)
+    // look-ahead: stream 0 = panel stream (diag / panel / in-block updates / next-block strip),
+    // stream 1 = trailing-update stream (the bulk GEMMs).  Listed order is always a valid serial order.
+    uint8_t stream, wait_other, record, pad;   // wait_other: wait for the other stream's last record first
 };
 
 constexpr int ASM_ROUNDS = 8;      // children handled by per-round launches; the rest by a tail kernel
@@ -93,7 +96,8 @@ constexpr int BIG_TM = 128;                 // C tile rows of the DMMA kernels (
 constexpr int UPD_ROWS = 256;      // rows per block in the forward-solve update
 constexpr int BWD_COLS = 1;        // columns per block in the backward-solve update (one block reduces one column)
 constexpr int PS_WIDTH = 64;       // target panel-step width (a wider single chunk stays alone)
-constexpr int OB_WIDTH = 256;      // target outer-block width (delayed trailing update)
+constexpr int OB_WIDTH = 512;      // target outer-block width (delayed trailing update)
+constexpr int OB_STEPS = 8;        // panel steps per outer block (aligned across the fronts of a level for the look-ahead)
 constexpr int64_t SOLVE_SMALL = 65536;  // fronts with at most this many stored L entries are solved by one block
 constexpr int RELAX_ABS = 4;       // a chunk joins the chain if it adds at most this many rows ...
 constexpr double RELAX_FRAC = 0.02;//   ... or this fraction of its rows
@@ -114,7 +118,8 @@ struct Plan {
     double flops_struct = 0, nnzL = 0;        // sum cc^2 (or 2 sum cc^2 - sum cc), sum cc
     bool use_dmma = true;
     int64_t solve_small = SOLVE_SMALL;
-    int ob_width = OB_WIDTH, ps_width = PS_WIDTH;
+    int ob_width = OB_WIDTH, ps_width = PS_WIDTH, ob_steps = OB_STEPS;
+    bool lookahead = true;
     bool no_b128 = false;                     // DMMA tasks all use 128x64 tiles
     int relax_abs = RELAX_ABS; double relax_frac = RELAX_FRAC;
     // schedules
@@ -281,7 +286,7 @@ inline bool analyze(Plan& P, int64_t n, int64_t nsuper, const int64_t* xsuper, c
         int32_t j = 0;
         while (j < F.nps) {
             int32_t j0 = j, w = 0;
-            while (j < F.nps && (j == j0 || w + P.psteps[F.ps0 + j].w <= P.ob_width)) { w += P.psteps[F.ps0 + j].w; ++j; }
+            while (j < F.nps && (j - j0) < P.ob_steps) { w += P.psteps[F.ps0 + j].w; ++j; }   // j0 is a multiple of ob_steps
             int32_t ob_end = P.psteps[F.ps0 + j0].o + w;
             for (int32_t q = j0; q < j; ++q) P.psteps[F.ps0 + q].ob_end = ob_end;
         }
@@ -302,8 +307,9 @@ struct LaunchBuilder {
     Plan& P; std::vector<Launch>& out;
     Launch cur{};
     LaunchBuilder(Plan& p, std::vector<Launch>& o) : P(p), out(o) {}
-    void begin(int32_t kind, int32_t first, int32_t level, int32_t step) {
+    void begin(int32_t kind, int32_t first, int32_t level, int32_t step, int stream = 0, int wait_other = 0, int record = 0) {
         cur = Launch{}; cur.kind = kind; cur.first = first; cur.count = 0; cur.nblocks = 0;
+        cur.stream = (uint8_t)stream; cur.wait_other = (uint8_t)wait_other; cur.record = (uint8_t)record;
         cur.pfx = (int64_t)P.blkpfx.size(); cur.flops = 0; cur.level = level; cur.step = step;
         P.blkpfx.push_back(0);
     }
@@ -328,10 +334,12 @@ struct GemmBatch {
         else if (P.use_dmma && t.m >= 128 && t.n > 16) b64.push_back({t, flops});
         else small.push_back({t, flops});
     }
-    void emit(Plan& P, LaunchBuilder& fb, int32_t lev, int32_t step) {
+    bool empty() const { return small.empty() && b64.empty() && b128.empty(); }
+    // every launch of the batch waits for the other stream (cheap) and records its own completion
+    void emit(Plan& P, LaunchBuilder& fb, int32_t lev, int32_t step, int stream = 0, int wait_other = 0, int record = 0) {
         auto one = [&](std::vector<Item>& v, int32_t kind, int tm, int tn) {
             if (v.empty()) return;
-            fb.begin(kind, (int32_t)P.gemmt.size(), lev, step);
+            fb.begin(kind, (int32_t)P.gemmt.size(), lev, step, stream, wait_other, record);
             for (const Item& it : v) { P.gemmt.push_back(it.t); fb.add(gemm_blocks(it.t, tm, tn), it.flops); }
             fb.end();
             v.clear();
@@ -367,7 +375,8 @@ inline double gemm_flops(const GemmTask& g) {
 inline void plan_env_overrides(Plan& P) {        // test / tuning knobs
     if (const char* e = getenv("SPK_NO_DMMA")) P.use_dmma = !(e[0] == '1');
     if (const char* e = getenv("SPK_SOLVE_SMALL")) P.solve_small = atoll(e);
-    if (const char* e = getenv("SPK_OB_WIDTH")) P.ob_width = std::max(1, atoi(e));
+    if (const char* e = getenv("SPK_OB_STEPS")) P.ob_steps = std::max(1, atoi(e));
+    if (const char* e = getenv("SPK_LOOKAHEAD")) P.lookahead = e[0] != '0';
     if (const char* e = getenv("SPK_PS_WIDTH")) P.ps_width = std::max(1, atoi(e));
     if (const char* e = getenv("SPK_DMMA_VARIANT")) P.no_b128 = atoi(e) == 2;
 }
@@ -393,7 +402,7 @@ inline void build_schedule(Plan& P) {
         for (int32_t f : fr) { maxch = std::max(maxch, P.fronts[f].nchild); maxnps = std::max(maxnps, P.fronts[f].nps); }
         // ---- extend-add of the children's update matrices
         for (int32_t r = 0; r < std::min(maxch, ASM_ROUNDS); ++r) {
-            fb.begin(K_ASM, (int32_t)P.asmt.size(), lev, r);
+            fb.begin(K_ASM, (int32_t)P.asmt.size(), lev, r, 0, 1, 0);
             for (int32_t f : fr) {
                 const Front& F = P.fronts[f];
                 if (F.nchild <= r) continue;
@@ -405,16 +414,16 @@ inline void build_schedule(Plan& P) {
             fb.end();
         }
         if (maxch > ASM_ROUNDS) {
-            fb.begin(K_ASM_TAIL, (int32_t)P.asmt.size(), lev, ASM_ROUNDS);
+            fb.begin(K_ASM_TAIL, (int32_t)P.asmt.size(), lev, ASM_ROUNDS, 0, 1, 0);
             for (int32_t f : fr) if (P.fronts[f].nchild > ASM_ROUNDS) { P.asmt.push_back(AsmTask{-1, f}); fb.add(1); }
             fb.end();
         }
         // ---- dense partial factorisation, panel step by panel step
         for (int32_t j = 0; j < maxnps; ++j) {
-            fb.begin(K_DIAG, (int32_t)P.pslist.size(), lev, j);
+            fb.begin(K_DIAG, (int32_t)P.pslist.size(), lev, j, 0, j == 0 ? 1 : 0, 1);
             for (int32_t f : fr) if (P.fronts[f].nps > j) { P.pslist.push_back(P.fronts[f].ps0 + j); fb.add(1, 0, P.psteps[P.fronts[f].ps0 + j].w); }
             fb.end();
-            fb.begin(K_PANEL, (int32_t)P.pslist.size(), lev, j);
+            fb.begin(K_PANEL, (int32_t)P.pslist.size(), lev, j, 0, 0, 1);
             for (int32_t f : fr) if (P.fronts[f].nps > j) {
                 const PStep& ps = P.psteps[P.fronts[f].ps0 + j];
                 int32_t below = ps.R - ps.o - ps.w;
@@ -423,29 +432,52 @@ inline void build_schedule(Plan& P) {
                 fb.add(cdiv(below, PANEL_ROWS) * (lu ? 2 : 1), 0, ps.w);
             }
             fb.end();
-            GemmBatch gb;
+            // Trailing updates.  Within an outer block (ob_steps panel steps) only the block's own remaining
+            // columns (and rows, LU) are updated eagerly (panel stream).  At a block boundary the delayed
+            // rank-(block width) update is split: the STRIP that the next block's panel steps need goes to the
+            // panel stream, the REST (the bulk of the flops) to the trailing-update stream, where it overlaps
+            // the diagonal / panel kernels of the next block (look-ahead).  A front's last step sends its whole
+            // remaining update (the update matrix S) to the trailing-update stream.
+            GemmBatch gp, gg;
+            const bool boundary = ((j + 1) % P.ob_steps) == 0;
             for (int32_t f : fr) if (P.fronts[f].nps > j) {
                 const Front& F = P.fronts[f];
                 const PStep& ps = P.psteps[F.ps0 + j];
                 const int32_t e = ps.o + ps.w;             // first column after the panel
                 if (e >= F.R) continue;
-                if (e < ps.ob_end) {
-                    // inside the outer block: eager update of the block's remaining columns (and rows, LU)
+                const bool last = (F.nps == j + 1);
+                if (!boundary && !last) {
                     GemmTask g = front_gemm(P, F, e, F.R - e, e, ps.ob_end - e, ps.o, ps.w);
-                    gb.add(P, g, gemm_flops(g));
+                    gp.add(P, g, gemm_flops(g));
                     if (lu && ps.ob_end < F.R) {
                         GemmTask h = front_gemm(P, F, e, ps.ob_end - e, ps.ob_end, F.R - ps.ob_end, ps.o, ps.w);
-                        gb.add(P, h, gemm_flops(h));
+                        gp.add(P, h, gemm_flops(h));
                     }
+                    continue;
+                }
+                int32_t ob0 = ps.o;                         // first column of the (possibly partial) block that ends here
+                for (int32_t q = j; q >= 0 && P.psteps[F.ps0 + q].ob_end == ps.ob_end; --q) ob0 = P.psteps[F.ps0 + q].o;
+                const int32_t kb = e - ob0;
+                if (last) {
+                    GemmTask g = front_gemm(P, F, e, F.R - e, e, F.R - e, ob0, kb);
+                    gg.add(P, g, gemm_flops(g));
                 } else {
-                    // last step of an outer block: delayed update of everything behind the block
-                    int32_t ob0 = ps.o;
-                    for (int32_t q = j; q >= 0 && P.psteps[F.ps0 + q].ob_end == ps.ob_end; --q) ob0 = P.psteps[F.ps0 + q].o;
-                    GemmTask g = front_gemm(P, F, e, F.R - e, e, F.R - e, ob0, e - ob0);
-                    gb.add(P, g, gemm_flops(g));
+                    const int32_t e2 = P.psteps[F.ps0 + j + 1].ob_end;     // end of the next block's columns
+                    GemmTask g = front_gemm(P, F, e, F.R - e, e, e2 - e, ob0, kb);            // column strip
+                    gp.add(P, g, gemm_flops(g));
+                    if (e2 < F.R) {
+                        if (lu) {
+                            GemmTask h = front_gemm(P, F, e, e2 - e, e2, F.R - e2, ob0, kb);  // row strip
+                            gp.add(P, h, gemm_flops(h));
+                        }
+                        GemmTask r = front_gemm(P, F, e2, F.R - e2, e2, F.R - e2, ob0, kb);   // the rest
+                        gg.add(P, r, gemm_flops(r));
+                    }
                 }
             }
-            gb.emit(P, fb, lev, j);
+            // strips must wait for the previous block's REST (same target region); rests wait for this step's panels
+            gp.emit(P, fb, lev, j, 0, boundary ? 1 : 0, 1);
+            gg.emit(P, fb, lev, j, 1, 1, 1);
         }
     }
 

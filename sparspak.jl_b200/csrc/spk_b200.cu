@@ -38,7 +38,8 @@ static cudaError_t upload(T** d, const std::vector<T>& h) {
 struct spk_plan {
     Plan P;
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;   // panel stream (high priority), trailing-update stream
+    cudaEvent_t evs0 = nullptr, evs1 = nullptr;          // last record of each stream
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evg0 = nullptr, evg1 = nullptr;
     // device state
     double *d_F = nullptr, *d_lnz = nullptr, *d_unz = nullptr, *d_w = nullptr, *d_rhs = nullptr, *d_tmp = nullptr;
@@ -98,6 +99,9 @@ SPK_API void spk_plan_destroy(spk_plan* p) {
         if (p->ev1) cudaEventDestroy(p->ev1);
         if (p->evg0) cudaEventDestroy(p->evg0);
         if (p->evg1) cudaEventDestroy(p->evg1);
+        if (p->evs0) cudaEventDestroy(p->evs0);
+        if (p->evs1) cudaEventDestroy(p->evs1);
+        if (p->stream2) cudaStreamDestroy(p->stream2);
         if (p->stream) cudaStreamDestroy(p->stream);
     }
     delete p;
@@ -106,7 +110,14 @@ SPK_API void spk_plan_destroy(spk_plan* p) {
 static int64_t plan_upload(spk_plan* p) {
     Plan& P = p->P;
     CK(cudaSetDevice(p->device));
-    CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&p->stream, cudaStreamNonBlocking, hi));
+        CK(cudaStreamCreateWithPriority(&p->stream2, cudaStreamNonBlocking, lo));
+        CK(cudaEventCreateWithFlags(&p->evs0, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&p->evs1, cudaEventDisableTiming));
+    }
     CK(cudaEventCreate(&p->ev0)); CK(cudaEventCreate(&p->ev1));
     CK(cudaEventCreate(&p->evg0)); CK(cudaEventCreate(&p->evg1));
     std::vector<DFront> df(P.fronts.size());
@@ -285,9 +296,13 @@ SPK_API int64_t spk_plan_reassemble(spk_plan* p) {
 }
 
 // ---- factor ---------------------------------------------------------------------------
-static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L) {
+static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L, bool two_streams) {
     const int32_t* pfx = p->d_blkpfx + L.pfx;
     cudaStream_t st = p->stream;
+    if (two_streams) {
+        st = L.stream ? p->stream2 : p->stream;
+        if (L.wait_other) CK(cudaStreamWaitEvent(st, L.stream ? p->evs0 : p->evs1, 0));
+    }
     const bool lu = p->P.lu;
     switch (L.kind) {
     case K_ASM:
@@ -321,6 +336,7 @@ static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L) 
     default:
         set_err("bad launch kind"); return -100;
     }
+    if (two_streams && L.record) CK(cudaEventRecord(L.stream ? p->evs1 : p->evs0, st));
     return 0;
 }
 
@@ -342,13 +358,16 @@ SPK_API int64_t spk_plan_factor_phase(spk_plan* p, int32_t phase) {
     std::vector<cudaEvent_t> evs;
     if (p->profile) { evs.resize(P.factor_launches.size() + 1); for (auto& e : evs) cudaEventCreate(&e); cudaEventRecord(evs[0], st); }
     size_t li = 0;
+    const bool two = P.lookahead && !p->profile;      // per-launch timing needs the serial order on one stream
+    if (two) { CK(cudaEventRecord(p->evs0, st)); CK(cudaEventRecord(p->evs1, p->stream2)); }
     for (const Launch& L : P.factor_launches) {
-        int64_t rc = run_factor_launch(p, c, L);
+        int64_t rc = run_factor_launch(p, c, L, two);
         if (rc) return rc;
         ++p->launches_factor;
         if (L.kind == K_GEMM_B64 || L.kind == K_GEMM_B128) p->gemm_flops += L.flops;
         if (p->profile) cudaEventRecord(evs[++li], st);
     }
+    if (two) { CK(cudaEventRecord(p->evs1, p->stream2)); CK(cudaStreamWaitEvent(st, p->evs1, 0)); }
     // scatter the factors back into the reference layout (lnz / unz)
     k_chunks<true><<<p->chunk_blocks, 256, 0, st>>>(c, p->d_chunkpfx, (int)P.chunks.size());
     ++p->launches_factor;
