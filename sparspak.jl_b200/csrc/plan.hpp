@@ -120,7 +120,7 @@ struct Plan {
     int64_t solve_small = SOLVE_SMALL;
     int ob_width = OB_WIDTH, ps_width = PS_WIDTH, ob_steps = OB_STEPS;
     bool lookahead = true;
-    bool no_b128 = false;                     // DMMA tasks all use 128x64 tiles
+    bool no_b128 = true;                      // DMMA tasks all use 128x64 tiles, two blocks per SM (measured best)
     int relax_abs = RELAX_ABS; double relax_frac = RELAX_FRAC;
     // schedules
     std::vector<AsmTask> asmt;

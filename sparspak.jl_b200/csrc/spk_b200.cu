@@ -52,7 +52,7 @@ struct spk_plan {
     AsmTask* d_asmt = nullptr; GemmTask* d_gemmt = nullptr; SolveTask* d_solvet = nullptr;
     int32_t chunk_blocks = 0;
     bool diag_smem_only = false;        // SPK_DIAG_SMEM=1: always use the shared-memory diagonal kernel
-    int dmma_variant = 0;               // SPK_DMMA_VARIANT (see gemm_dmma.cuh)
+    int dmma_variant = 2;               // SPK_DMMA_VARIANT (see gemm_dmma.cuh)
     bool values_in_fronts = false;      // inmatrix scattered straight into the fronts
     int64_t w_nrhs = 0, rhs_cap = 0;
     size_t dev_bytes = 0;
