@@ -109,9 +109,14 @@ SPK_API int64_t spk_plan_set_perm(spk_plan* p, const int64_t* rperm, const int64
 SPK_API int64_t spk_plan_triangularsolve(spk_plan* p, double* b, int64_t nrhs, int64_t ldb);
 
 /* ---- device-resident variants used by bench.py / multi-GPU drivers -------------------- */
-SPK_API void*   spk_plan_device_ptr(spk_plan* p, int32_t what);   /* 0 lnz, 1 unz, 2 ipiv(int32), 3 tail lnz, 4 tail unz */
+SPK_API void*   spk_plan_device_ptr(spk_plan* p, int32_t what);   /* 0 lnz, 1 unz, 2 ipiv(int32), 5 frontal arena, 6 solve work vectors */
 SPK_API int64_t spk_plan_device_len(spk_plan* p, int32_t what);   /* element counts of the above */
-SPK_API int64_t spk_plan_factor_phase(spk_plan* p, int32_t phase); /* multi-GPU: 0 local subtrees, 1 top set */
+SPK_API int64_t spk_plan_factor_phase(spk_plan* p, int32_t phase); /* multi-GPU: 0 local subtrees, 1 top set + write-back */
+SPK_API int64_t spk_plan_solve_phase(spk_plan* p, double* d_rhs, int64_t nrhs, int64_t ldrhs, int32_t phase); /* 0 fwd local, 1 top, 2 bwd local */
+/* exchange lists of a multi-part plan (count when out == NULL).  what 0: subtree-root fronts
+ * {owner, arena offset, arena length, w offset, w length, front}; what 1: owned storage ranges
+ * {owner, lnz offset, lnz length, unz offset, unz length, first column, #columns} */
+SPK_API int64_t spk_plan_xchg_info(spk_plan* p, int32_t what, int64_t i, int64_t* out);
 SPK_API int64_t spk_plan_solve_device(spk_plan* p, double* d_rhs, int64_t nrhs, int64_t ldrhs, int32_t which);
 
 /* ---- introspection --------------------------------------------------------------------- */

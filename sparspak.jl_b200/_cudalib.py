@@ -18,7 +18,7 @@ SYMBOLS = [
     "spk_plan_create", "spk_plan_destroy", "spk_plan_inmatrix", "spk_plan_reassemble", "spk_plan_set_values", "spk_plan_factor",
     "spk_plan_get_factors", "spk_plan_set_factors", "spk_plan_solve", "spk_plan_set_perm",
     "spk_plan_triangularsolve", "spk_plan_device_ptr", "spk_plan_device_len", "spk_plan_factor_phase",
-    "spk_plan_solve_device", "spk_plan_stat", "spk_plan_statf", "spk_last_error", "spk_device_count", "spk_version",
+    "spk_plan_solve_device", "spk_plan_solve_phase", "spk_plan_xchg_info", "spk_plan_stat", "spk_plan_statf", "spk_last_error", "spk_device_count", "spk_version",
 ]
 
 
@@ -77,6 +77,10 @@ def lib():
     L.spk_plan_factor_phase.restype = i64
     L.spk_plan_solve_device.argtypes = [vp, vp, i64, i64, i32]
     L.spk_plan_solve_device.restype = i64
+    L.spk_plan_solve_phase.argtypes = [vp, vp, i64, i64, i32]
+    L.spk_plan_solve_phase.restype = i64
+    L.spk_plan_xchg_info.argtypes = [vp, i32, i64, vp]
+    L.spk_plan_xchg_info.restype = i64
     L.spk_plan_stat.argtypes = [vp, i32]
     L.spk_plan_stat.restype = i64
     L.spk_plan_statf.argtypes = [vp, i32]
@@ -100,7 +104,7 @@ class Plan:
     """`spk_plan`: structure + factors resident on one GPU.  `base` is a `_SparseBase`-like object
     (n, nsuper, xsuper, snode, xlindx, lindx, xlnz, xunz, spd)."""
 
-    def __init__(self, base, device=0, host_only=False):
+    def __init__(self, base, device=0, host_only=False, part=0, nparts=1):
         L = lib()
         self.L = L
         self.spd = bool(base.spd)
@@ -109,7 +113,7 @@ class Plan:
         self.nunz = 0 if self.spd else int(base.xunz[base.n]) - 1
         xunz = None if self.spd else base.xunz.ctypes.data
         self.h = L.spk_plan_create(base.n, base.nsuper, base.xsuper, base.snode, base.xlindx, base.lindx,
-                                   base.xlnz, xunz, -1 if host_only else device, 0, 1)
+                                   base.xlnz, xunz, -1 if host_only else device, part, nparts)
         if not self.h:
             raise SpkError("spk_plan_create failed: " + last_error())
         self._perm_set = False
@@ -178,6 +182,25 @@ class Plan:
             nrhs, ld = b.shape[1], b.shape[0]
         self._ck(self.L.spk_plan_triangularsolve(self.h, b.reshape(-1, order="A"), nrhs, ld), "spk_plan_triangularsolve")
         return b
+
+    # -- multi-part (one plan per GPU) -----------------------------------------------------
+    def factor_phase(self, phase):
+        return int(self._ck(self.L.spk_plan_factor_phase(self.h, phase), "spk_plan_factor_phase"))
+
+    def solve_phase(self, d_ptr, nrhs, ld, phase):
+        self._ck(self.L.spk_plan_solve_phase(self.h, d_ptr, nrhs, ld, phase), "spk_plan_solve_phase")
+
+    def xchg_list(self, what):
+        n = int(self.L.spk_plan_xchg_info(self.h, what, 0, None))
+        out = []
+        buf = np.zeros(8, np.int64)
+        for i in range(n):
+            self.L.spk_plan_xchg_info(self.h, what, i, buf.ctypes.data)
+            out.append(buf.copy())
+        return out
+
+    def device_ptr(self, what):
+        return self.L.spk_plan_device_ptr(self.h, what), int(self.L.spk_plan_device_len(self.h, what))
 
     def stat(self, what):
         return int(self.L.spk_plan_stat(self.h, what))

@@ -130,6 +130,14 @@ struct Plan {
     std::vector<int32_t> gathert;
     std::vector<int32_t> blkpfx;
     std::vector<Launch> factor_launches, fwd_launches, bwd_launches;
+    // multi-GPU (elimination-subtree partition): owner[f] = part that factors front f, or -1 for the TOP SET
+    // (the ancestors of all subtree roots), which every part factors redundantly after the exchange.
+    int32_t part = 0, nparts = 1;
+    std::vector<int32_t> owner;
+    std::vector<int32_t> xchg;                 // subtree-root fronts (owner >= 0, parent in the top set)
+    struct Range { int32_t owner; int32_t f0, f1; int64_t lnz0, lnz1, unz0, unz1, col0, col1; };
+    std::vector<Range> ranges;                 // contiguous front / storage ranges owned by one part
+    std::vector<Launch> factor_local, factor_top, fwd_local, fwd_top, bwd_top, bwd_local;
     std::string error;
 };
 
@@ -381,21 +389,15 @@ inline void plan_env_overrides(Plan& P) {        // test / tuning knobs
     if (const char* e = getenv("SPK_DMMA_VARIANT")) P.no_b128 = atoi(e) == 2;
 }
 
-inline void build_schedule(Plan& P) {
+// Launch lists for the fronts selected by `sel` (all of them, one part's subtrees, or the top set).
+inline void build_lists(Plan& P, const std::vector<uint8_t>& sel, std::vector<Launch>& factor_out,
+                        std::vector<Launch>& fwd_out, std::vector<Launch>& bwd_out) {
     const int32_t nf = (int32_t)P.fronts.size();
     std::vector<std::vector<int32_t>> bylevel(P.nlevels);
-    for (int32_t f = 0; f < nf; ++f) bylevel[P.fronts[f].level].push_back(f);
+    for (int32_t f = 0; f < nf; ++f) if (sel[f]) bylevel[P.fronts[f].level].push_back(f);
     const bool lu = P.lu;
 
-    P.solvet.resize(P.chunks.size());
-    for (size_t s = 0; s < P.chunks.size(); ++s) {
-        const Chunk& c = P.chunks[s]; const Front& F = P.fronts[c.front];
-        SolveTask t{}; t.lofs = c.lofs; t.uofs = c.uofs; t.col0 = c.fj; t.wofs = F.wofs; t.posofs = c.posofs;
-        t.ld = c.jlen; t.ldu = c.jlen - c.nj; t.nj = c.nj; t.m = c.jlen - c.nj; t.o = c.o; t.front = c.front;
-        P.solvet[s] = t;
-    }
-
-    LaunchBuilder fb(P, P.factor_launches);
+    LaunchBuilder fb(P, factor_out);
     for (int32_t lev = 0; lev < P.nlevels; ++lev) {
         const std::vector<int32_t>& fr = bylevel[lev];
         int32_t maxch = 0, maxnps = 0;
@@ -486,7 +488,7 @@ inline void build_schedule(Plan& P) {
     auto front_entries = [&](const Front& F) { int64_t e = 0; for (int32_t t = 0; t < F.nch; ++t) { const Chunk& c = P.chunks[F.c0 + t]; e += (int64_t)c.jlen * c.nj; } return e; };
     std::vector<uint8_t> small(nf);
     for (int32_t f = 0; f < nf; ++f) small[f] = front_entries(P.fronts[f]) <= P.solve_small;
-    LaunchBuilder sf(P, P.fwd_launches);
+    LaunchBuilder sf(P, fwd_out);
     for (int32_t lev = 0; lev < P.nlevels; ++lev) {
         const std::vector<int32_t>& fr = bylevel[lev];
         int32_t maxnch = 0;
@@ -508,7 +510,7 @@ inline void build_schedule(Plan& P) {
             sf.end();
         }
     }
-    LaunchBuilder sb(P, P.bwd_launches);
+    LaunchBuilder sb(P, bwd_out);
     for (int32_t lev = P.nlevels - 1; lev >= 0; --lev) {
         const std::vector<int32_t>& fr = bylevel[lev];
         int32_t maxnch = 0;
@@ -534,6 +536,83 @@ inline void build_schedule(Plan& P) {
             sb.end();
         }
     }
+}
+
+// Elimination-subtree partition: split the front tree from the root until there are at
+// least `nparts` subtrees, biggest first; the fronts split off form the top set; subtrees are dealt to
+// parts by decreasing work (LPT).  Subtrees are contiguous front ranges because the reference post-orders
+// the elimination tree (SpkETree.jl:106-139).
+inline void partition(Plan& P) {
+    const int32_t nf = (int32_t)P.fronts.size();
+    P.owner.assign(nf, P.nparts > 1 ? -2 : 0);
+    P.xchg.clear(); P.ranges.clear();
+    if (P.nparts <= 1) return;
+    std::vector<double> work(nf, 0.0);
+    std::vector<int32_t> first(nf);                            // first front of the subtree rooted at f
+    for (int32_t f = 0; f < nf; ++f) {
+        const Front& F = P.fronts[f];
+        double W = F.W, m = F.m;
+        work[f] += W * W * W / 3.0 + W * W * m + W * m * m + 1.0;
+        first[f] = f;
+    }
+    for (int32_t f = 0; f < nf; ++f) {                          // children precede parents
+        for (int32_t q = 0; q < P.fronts[f].nchild; ++q) {
+            int32_t ch = P.childlist[P.fronts[f].child0 + q];
+            work[f] += work[ch]; first[f] = std::min(first[f], first[ch]);
+        }
+    }
+    std::vector<int32_t> roots;
+    for (int32_t f = 0; f < nf; ++f) if (P.fronts[f].parent < 0) roots.push_back(f);
+    for (;;) {
+        if ((int32_t)roots.size() >= P.nparts) break;
+        int32_t best = -1;
+        for (size_t i = 0; i < roots.size(); ++i)
+            if (P.fronts[roots[i]].nchild > 0 && (best < 0 || work[roots[i]] > work[roots[best]])) best = (int32_t)i;
+        if (best < 0) break;
+        int32_t f = roots[best];
+        roots.erase(roots.begin() + best);
+        P.owner[f] = -1;                                        // joins the top set
+        for (int32_t q = 0; q < P.fronts[f].nchild; ++q) roots.push_back(P.childlist[P.fronts[f].child0 + q]);
+    }
+    std::sort(roots.begin(), roots.end(), [&](int32_t a, int32_t b) { return work[a] != work[b] ? work[a] > work[b] : a < b; });
+    std::vector<double> load(P.nparts, 0.0);
+    for (int32_t r : roots) {
+        int32_t tgt = 0;
+        for (int32_t q = 1; q < P.nparts; ++q) if (load[q] < load[tgt]) tgt = q;
+        load[tgt] += work[r];
+        for (int32_t f = first[r]; f <= r; ++f) P.owner[f] = tgt;
+        if (P.fronts[r].parent >= 0) P.xchg.push_back(r);
+        Plan::Range g{};
+        g.owner = tgt; g.f0 = first[r]; g.f1 = r + 1;
+        const Chunk& c0 = P.chunks[P.fronts[first[r]].c0];
+        const Front& Fr = P.fronts[r];
+        const Chunk& c1 = P.chunks[Fr.c0 + Fr.nch - 1];
+        g.lnz0 = c0.lofs; g.lnz1 = c1.lofs + (int64_t)c1.jlen * c1.nj;
+        g.unz0 = c0.uofs; g.unz1 = c1.uofs + (P.lu ? (int64_t)(c1.jlen - c1.nj) * c1.nj : 0);
+        g.col0 = c0.fj; g.col1 = c1.fj + c1.nj;
+        P.ranges.push_back(g);
+    }
+    std::sort(P.xchg.begin(), P.xchg.end());
+    std::sort(P.ranges.begin(), P.ranges.end(), [](const Plan::Range& a, const Plan::Range& b) { return a.f0 < b.f0; });
+}
+
+inline void build_schedule(Plan& P) {
+    const int32_t nf = (int32_t)P.fronts.size();
+    P.solvet.resize(P.chunks.size());
+    for (size_t s = 0; s < P.chunks.size(); ++s) {
+        const Chunk& c = P.chunks[s]; const Front& F = P.fronts[c.front];
+        SolveTask t{}; t.lofs = c.lofs; t.uofs = c.uofs; t.col0 = c.fj; t.wofs = F.wofs; t.posofs = c.posofs;
+        t.ld = c.jlen; t.ldu = c.jlen - c.nj; t.nj = c.nj; t.m = c.jlen - c.nj; t.o = c.o; t.front = c.front;
+        P.solvet[s] = t;
+    }
+    partition(P);
+    std::vector<uint8_t> sel(nf, 1);
+    if (P.nparts <= 1) { build_lists(P, sel, P.factor_launches, P.fwd_launches, P.bwd_launches); return; }
+    std::vector<Launch> unused_f;
+    for (int32_t f = 0; f < nf; ++f) sel[f] = P.owner[f] == P.part;
+    build_lists(P, sel, P.factor_local, P.fwd_local, P.bwd_local);
+    for (int32_t f = 0; f < nf; ++f) sel[f] = P.owner[f] == -1;
+    build_lists(P, sel, P.factor_top, P.fwd_top, P.bwd_top);
 }
 
 } // namespace spk

@@ -51,6 +51,9 @@ struct spk_plan {
     double* d_nzval = nullptr; int64_t nzcap = 0, nz_last = 0;
     AsmTask* d_asmt = nullptr; GemmTask* d_gemmt = nullptr; SolveTask* d_solvet = nullptr;
     int32_t chunk_blocks = 0;
+    bool solve_graphs = true;           // SPK_SOLVE_GRAPH=0 disables CUDA-graph replay of the solve sweeps
+    cudaGraphExec_t sg_exec = nullptr; double* sg_rhs = nullptr; double* sg_w = nullptr;
+    int64_t sg_nrhs = 0, sg_ld = 0, sg_launches = 0; int32_t sg_which = -1;
     bool diag_smem_only = false;        // SPK_DIAG_SMEM=1: always use the shared-memory diagonal kernel
     int dmma_variant = 2;               // SPK_DMMA_VARIANT (see gemm_dmma.cuh)
     bool values_in_fronts = false;      // inmatrix scattered straight into the fronts
@@ -60,7 +63,7 @@ struct spk_plan {
     bool have_perm = false, factored = false;
     // stats
     int64_t launches_factor = 0, launches_solve = 0;
-    double ms_factor = 0, ms_solve = 0, gemm_flops = 0, gemm_ms = 0;
+    double ms_factor = 0, ms_solve = 0, gemm_flops = 0, gemm_ms = 0, ms_phase0 = 0, ms_phase1 = 0;
     std::vector<float> launch_ms;       // optional per-launch timing (profiling mode)
     double kind_ms[16] = {0}; int64_t kind_n[16] = {0};
     bool profile = false;
@@ -99,6 +102,7 @@ SPK_API void spk_plan_destroy(spk_plan* p) {
         if (p->ev1) cudaEventDestroy(p->ev1);
         if (p->evg0) cudaEventDestroy(p->evg0);
         if (p->evg1) cudaEventDestroy(p->evg1);
+        if (p->sg_exec) cudaGraphExecDestroy(p->sg_exec);
         if (p->evs0) cudaEventDestroy(p->evs0);
         if (p->evs1) cudaEventDestroy(p->evs1);
         if (p->stream2) cudaStreamDestroy(p->stream2);
@@ -181,9 +185,10 @@ static int64_t plan_upload(spk_plan* p) {
 SPK_API spk_plan* spk_plan_create(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* snode,
                                   const int64_t* xlindx, const int64_t* lindx, const int64_t* xlnz,
                                   const int64_t* xunz_or_null, int32_t device, int32_t part, int32_t nparts) {
-    (void)part; (void)nparts;
     spk_plan* p = new spk_plan();
     p->device = device;
+    p->P.part = part; p->P.nparts = nparts < 1 ? 1 : nparts;
+    if (part < 0 || part >= p->P.nparts) { set_err("bad part / nparts"); delete p; return nullptr; }
     plan_env_overrides(p->P);
     if (!analyze(p->P, n, nsuper, xsuper, snode, xlindx, lindx, xlnz, xunz_or_null)) {
         set_err("analyze: " + p->P.error); delete p; return nullptr;
@@ -191,6 +196,7 @@ SPK_API spk_plan* spk_plan_create(int64_t n, int64_t nsuper, const int64_t* xsup
     plan_env_overrides(p->P);
     if (const char* e = getenv("SPK_DMMA_VARIANT")) p->dmma_variant = atoi(e);
     if (const char* e = getenv("SPK_DIAG_SMEM")) p->diag_smem_only = e[0] == '1';
+    if (const char* e = getenv("SPK_SOLVE_GRAPH")) p->solve_graphs = e[0] != '0';
     build_schedule(p->P);
     if (device < 0) return p;                      // host-only plan: structure statistics without a GPU
     int ndev = 0;
@@ -340,27 +346,33 @@ static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L, 
     return 0;
 }
 
+// phase -1: everything (single part).  Multi-part plans: phase 0 = this part's subtrees, phase 1 = the
+// top set (after the caller exchanged the subtree-root fronts, see spk_plan_xchg_info) + write-back.
 SPK_API int64_t spk_plan_factor_phase(spk_plan* p, int32_t phase) {
-    (void)phase;
     NEED_DEV(p);
     Plan& P = p->P;
+    if (P.nparts > 1 && phase < 0) { set_err("multi-part plan: call phases 0 and 1 with the exchange in between"); return -100; }
+    if (P.nparts <= 1) phase = -1;
+    const std::vector<Launch>& Ls = phase < 0 ? P.factor_launches : (phase == 0 ? P.factor_local : P.factor_top);
     DevCtx c = make_ctx(p);
     cudaStream_t st = p->stream;
-    CK(cudaEventRecord(p->ev0, st));
-    CK(cudaMemsetAsync(p->d_iflag, 0, sizeof(int32_t), st));
-    p->launches_factor = 0; p->gemm_flops = 0; p->gemm_ms = 0;
-    if (!p->values_in_fronts) {
-        // gather the assembled matrix (reference layout) into the zeroed frontal matrices
-        CK(cudaMemsetAsync(p->d_F, 0, P.arena * sizeof(double), st));
-        k_chunks<false><<<p->chunk_blocks, 256, 0, st>>>(c, p->d_chunkpfx, (int)P.chunks.size());
-        ++p->launches_factor;
+    CK(cudaEventRecord(phase == 1 ? p->evg0 : p->ev0, st));
+    if (phase <= 0) {
+        CK(cudaMemsetAsync(p->d_iflag, 0, sizeof(int32_t), st));
+        p->launches_factor = 0; p->gemm_flops = 0; p->gemm_ms = 0;
+        if (!p->values_in_fronts) {
+            // gather the assembled matrix (reference layout) into the zeroed frontal matrices
+            CK(cudaMemsetAsync(p->d_F, 0, P.arena * sizeof(double), st));
+            k_chunks<false><<<p->chunk_blocks, 256, 0, st>>>(c, p->d_chunkpfx, (int)P.chunks.size());
+            ++p->launches_factor;
+        }
     }
     std::vector<cudaEvent_t> evs;
-    if (p->profile) { evs.resize(P.factor_launches.size() + 1); for (auto& e : evs) cudaEventCreate(&e); cudaEventRecord(evs[0], st); }
+    if (p->profile) { evs.resize(Ls.size() + 1); for (auto& e : evs) cudaEventCreate(&e); cudaEventRecord(evs[0], st); }
     size_t li = 0;
     const bool two = P.lookahead && !p->profile;      // per-launch timing needs the serial order on one stream
     if (two) { CK(cudaEventRecord(p->evs0, st)); CK(cudaEventRecord(p->evs1, p->stream2)); }
-    for (const Launch& L : P.factor_launches) {
+    for (const Launch& L : Ls) {
         int64_t rc = run_factor_launch(p, c, L, two);
         if (rc) return rc;
         ++p->launches_factor;
@@ -368,28 +380,33 @@ SPK_API int64_t spk_plan_factor_phase(spk_plan* p, int32_t phase) {
         if (p->profile) cudaEventRecord(evs[++li], st);
     }
     if (two) { CK(cudaEventRecord(p->evs1, p->stream2)); CK(cudaStreamWaitEvent(st, p->evs1, 0)); }
-    // scatter the factors back into the reference layout (lnz / unz)
-    k_chunks<true><<<p->chunk_blocks, 256, 0, st>>>(c, p->d_chunkpfx, (int)P.chunks.size());
-    ++p->launches_factor;
+    if (phase != 0) {
+        // scatter the factors back into the reference layout (lnz / unz)
+        k_chunks<true><<<p->chunk_blocks, 256, 0, st>>>(c, p->d_chunkpfx, (int)P.chunks.size());
+        ++p->launches_factor;
+    }
     CK(cudaGetLastError());
-    CK(cudaEventRecord(p->ev1, st));
+    CK(cudaEventRecord(phase == 0 ? p->evg1 : p->ev1, st));
     CK(cudaStreamSynchronize(st));
-    p->values_in_fronts = false;
-    float ms = 0; CK(cudaEventElapsedTime(&ms, p->ev0, p->ev1)); p->ms_factor = ms;
+    if (phase != 0) p->values_in_fronts = false;
+    float ms = 0;
+    if (phase < 0) { CK(cudaEventElapsedTime(&ms, p->ev0, p->ev1)); p->ms_factor = ms; }
+    else if (phase == 0) { CK(cudaEventElapsedTime(&ms, p->ev0, p->evg1)); p->ms_factor = ms; p->ms_phase0 = ms; }
+    else { CK(cudaEventElapsedTime(&ms, p->evg0, p->ev1)); p->ms_phase1 = ms; p->ms_factor = p->ms_phase0 + ms; }
     if (p->profile) {
-        p->launch_ms.assign(P.factor_launches.size(), 0.f);
+        p->launch_ms.assign(Ls.size(), 0.f);
         for (int k = 0; k < 16; ++k) { p->kind_ms[k] = 0; p->kind_n[k] = 0; }
-        for (size_t i = 0; i < P.factor_launches.size(); ++i) {
+        for (size_t i = 0; i < Ls.size(); ++i) {
             cudaEventElapsedTime(&p->launch_ms[i], evs[i], evs[i + 1]);
-            p->kind_ms[P.factor_launches[i].kind & 15] += p->launch_ms[i]; p->kind_n[P.factor_launches[i].kind & 15]++;
-            if (P.factor_launches[i].kind == K_GEMM_B64 || P.factor_launches[i].kind == K_GEMM_B128) p->gemm_ms += p->launch_ms[i];
+            p->kind_ms[Ls[i].kind & 15] += p->launch_ms[i]; p->kind_n[Ls[i].kind & 15]++;
+            if (Ls[i].kind == K_GEMM_B64 || Ls[i].kind == K_GEMM_B128) p->gemm_ms += p->launch_ms[i];
         }
         for (auto& e : evs) cudaEventDestroy(e);
         if (const char* path = getenv("SPK_DUMP_LAUNCHES")) {       // per-launch CSV for profiles/
             if (FILE* f = fopen(path, "w")) {
                 fprintf(f, "idx,kind,level,step,tasks,blocks,maxw,flops,ms\n");
-                for (size_t i = 0; i < P.factor_launches.size(); ++i) {
-                    const Launch& L = P.factor_launches[i];
+                for (size_t i = 0; i < Ls.size(); ++i) {
+                    const Launch& L = Ls[i];
                     fprintf(f, "%zu,%d,%d,%d,%d,%d,%d,%.6g,%.6f\n", i, L.kind, L.level, L.step, L.count, L.nblocks, L.maxw, L.flops, p->launch_ms[i]);
                 }
                 fclose(f);
@@ -398,7 +415,7 @@ SPK_API int64_t spk_plan_factor_phase(spk_plan* p, int32_t phase) {
     }
     int32_t flag = 0;
     CK(cudaMemcpy(&flag, p->d_iflag, sizeof(int32_t), cudaMemcpyDeviceToHost));
-    p->factored = true;
+    if (phase != 0) p->factored = true;
     return flag;
 }
 
@@ -471,24 +488,49 @@ static int64_t run_solve_launches(spk_plan* p, const DevCtx& c, const std::vecto
 }
 
 // d_rhs: device, permuted order, column-major ld = ldrhs
-SPK_API int64_t spk_plan_solve_device(spk_plan* p, double* d_rhs, int64_t nrhs, int64_t ldrhs, int32_t which) {
-    NEED_DEV(p);
-    if (nrhs <= 0) return 0;
+static int64_t enqueue_solve(spk_plan* p, double* d_rhs, int64_t nrhs, int64_t ldrhs, int32_t which) {
     const int64_t maxbatch = 32;                       // bounds the work-vector arena
     cudaStream_t st = p->stream;
-    CK(cudaEventRecord(p->ev0, st));
-    p->launches_solve = 0;
     for (int64_t r0 = 0; r0 < nrhs; r0 += maxbatch) {
         int64_t nb = std::min(maxbatch, nrhs - r0);
-        int64_t rc = ensure_w(p, nb); if (rc) return rc;
         DevCtx c = make_ctx(p);
         double* b = d_rhs + (size_t)r0 * ldrhs;
         const int nf = (int)p->P.fronts.size();
+        int64_t rc = 0;
         if (which == 2) { k_copy_front_x<<<dim3(nf, (unsigned)nb), 64, 0, st>>>(c, nf, b, ldrhs, 0); ++p->launches_solve; }
         if (which == 0 || which == 1) { rc = run_solve_launches(p, c, p->P.fwd_launches, b, nb, ldrhs); if (rc) return rc; }
         if (which == 1) { k_copy_front_x<<<dim3(nf, (unsigned)nb), 64, 0, st>>>(c, nf, b, ldrhs, 1); ++p->launches_solve; }
         if (which == 0 || which == 2) { rc = run_solve_launches(p, c, p->P.bwd_launches, b, nb, ldrhs); if (rc) return rc; }
     }
+    return 0;
+}
+
+// d_rhs: device, permuted order, column-major ld = ldrhs.  The launch sequence of a sweep is a pure
+// function of the plan, so it is captured once into a CUDA graph per (buffer, nrhs, ld, which) and
+// replayed: thousands of small dependent launches no longer pay the CPU launch path.
+SPK_API int64_t spk_plan_solve_device(spk_plan* p, double* d_rhs, int64_t nrhs, int64_t ldrhs, int32_t which) {
+    NEED_DEV(p);
+    if (nrhs <= 0) return 0;
+    cudaStream_t st = p->stream;
+    int64_t rc = ensure_w(p, std::min<int64_t>(nrhs, 32)); if (rc) return rc;
+    const bool use_graph = p->solve_graphs;
+    if (use_graph && !(p->sg_exec && p->sg_rhs == d_rhs && p->sg_nrhs == nrhs && p->sg_ld == ldrhs && p->sg_which == which && p->sg_w == p->d_w)) {
+        if (p->sg_exec) { cudaGraphExecDestroy(p->sg_exec); p->sg_exec = nullptr; }
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        p->launches_solve = 0;
+        rc = enqueue_solve(p, d_rhs, nrhs, ldrhs, which);
+        cudaError_t ce = cudaStreamEndCapture(st, &g);
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        CK(ce);
+        CK(cudaGraphInstantiate(&p->sg_exec, g, 0));
+        CK(cudaGraphDestroy(g));
+        p->sg_rhs = d_rhs; p->sg_nrhs = nrhs; p->sg_ld = ldrhs; p->sg_which = which; p->sg_w = p->d_w;
+        p->sg_launches = p->launches_solve;
+    }
+    CK(cudaEventRecord(p->ev0, st));
+    if (use_graph) { CK(cudaGraphLaunch(p->sg_exec, st)); p->launches_solve = p->sg_launches; }
+    else { p->launches_solve = 0; rc = enqueue_solve(p, d_rhs, nrhs, ldrhs, which); if (rc) return rc; }
     CK(cudaGetLastError());
     CK(cudaEventRecord(p->ev1, st));
     CK(cudaStreamSynchronize(st));
@@ -551,14 +593,57 @@ SPK_API int64_t spk_plan_triangularsolve(spk_plan* p, double* b, int64_t nrhs, i
     return 0;
 }
 
+// Multi-part solve: phase 0 = forward sweep over this part's subtrees, phase 1 = forward + backward over the
+// top set (after the caller exchanged the subtree-root work vectors), phase 2 = backward over the subtrees.
+SPK_API int64_t spk_plan_solve_phase(spk_plan* p, double* d_rhs, int64_t nrhs, int64_t ldrhs, int32_t phase) {
+    NEED_DEV(p);
+    if (p->P.nparts <= 1) { set_err("single-part plan"); return -100; }
+    if (nrhs > 32) { set_err("multi-part solve: at most 32 right-hand sides per call"); return -100; }
+    int64_t rc = ensure_w(p, 32); if (rc) return rc;
+    DevCtx c = make_ctx(p);
+    cudaStream_t st = p->stream;
+    CK(cudaEventRecord(p->ev0, st));
+    if (phase == 0) { p->launches_solve = 0; rc = run_solve_launches(p, c, p->P.fwd_local, d_rhs, nrhs, ldrhs); }
+    else if (phase == 1) { rc = run_solve_launches(p, c, p->P.fwd_top, d_rhs, nrhs, ldrhs); if (!rc) rc = run_solve_launches(p, c, p->P.bwd_top, d_rhs, nrhs, ldrhs); }
+    else rc = run_solve_launches(p, c, p->P.bwd_local, d_rhs, nrhs, ldrhs);
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(p->ev1, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+    p->ms_solve = (phase == 0 ? 0.0 : p->ms_solve) + ms;
+    return 0;
+}
+
+// exchange lists of a multi-part plan.  what = 0: subtree-root fronts, out = {owner, F offset, F length,
+// w offset, w length (per right-hand side), front id};  what = 1: storage ranges owned by one part,
+// out = {owner, lnz offset, lnz length, unz offset, unz length, first column, #columns}.  Returns the count
+// when out == NULL.
+SPK_API int64_t spk_plan_xchg_info(spk_plan* p, int32_t what, int64_t i, int64_t* out) {
+    if (!p) return 0;
+    const Plan& P = p->P;
+    if (what == 0) {
+        if (!out) return (int64_t)P.xchg.size();
+        if (i < 0 || i >= (int64_t)P.xchg.size()) return -1;
+        const Front& F = P.fronts[P.xchg[i]];
+        out[0] = P.owner[P.xchg[i]]; out[1] = F.fofs; out[2] = (int64_t)F.ld * F.R; out[3] = F.wofs; out[4] = F.R; out[5] = P.xchg[i];
+        return 0;
+    }
+    if (!out) return (int64_t)P.ranges.size();
+    if (i < 0 || i >= (int64_t)P.ranges.size()) return -1;
+    const Plan::Range& g = P.ranges[i];
+    out[0] = g.owner; out[1] = g.lnz0; out[2] = g.lnz1 - g.lnz0; out[3] = g.unz0; out[4] = g.unz1 - g.unz0; out[5] = g.col0; out[6] = g.col1 - g.col0;
+    return 0;
+}
+
 // ---- introspection ----------------------------------------------------------------------
 SPK_API void* spk_plan_device_ptr(spk_plan* p, int32_t what) {
     if (!p) return nullptr;
-    switch (what) { case 0: return p->d_lnz; case 1: return p->d_unz; case 2: return p->d_ipiv; default: return nullptr; }
+    switch (what) { case 0: return p->d_lnz; case 1: return p->d_unz; case 2: return p->d_ipiv; case 5: return p->d_F; case 6: return p->d_w; default: return nullptr; }
 }
 SPK_API int64_t spk_plan_device_len(spk_plan* p, int32_t what) {
     if (!p) return 0;
-    switch (what) { case 0: return p->P.nlnz; case 1: return p->P.nunz; case 2: return p->P.n; default: return 0; }
+    switch (what) { case 0: return p->P.nlnz; case 1: return p->P.nunz; case 2: return p->P.n; case 5: return p->P.arena; case 6: return p->P.wlen * p->w_nrhs; default: return 0; }
 }
 SPK_API int64_t spk_plan_stat(spk_plan* p, int32_t what) {
     if (!p) return 0;
@@ -575,6 +660,8 @@ SPK_API int64_t spk_plan_stat(spk_plan* p, int32_t what) {
     case 9: return p->P.wlen;
     case 10: return p->P.maxpw;
     case 11: return p->P.maxR;
+    case 12: return p->P.nparts;
+    case 13: { int64_t k = 0; for (int32_t o : p->P.owner) if (o == -1) ++k; return k; }
     case 100: p->profile = true; return 0;
     case 101: p->profile = false; return 0;
     default: return 0;
@@ -589,6 +676,8 @@ SPK_API double spk_plan_statf(spk_plan* p, int32_t what) {
     case 3: return p->ms_solve;
     case 4: return p->gemm_flops;
     case 5: return p->gemm_ms;
+    case 6: return p->ms_phase0;
+    case 7: return p->ms_phase1;
     default:
         if (what >= 10 && what < 26) return p->kind_ms[what - 10];
         if (what >= 30 && what < 46) return (double)p->kind_n[what - 30];

@@ -132,10 +132,19 @@ static void gemm(Sim& s, const GemmTask& g) {
     for (int j = 0; j < g.n; ++j) for (int i = 0; i < g.m; ++i) if (!(g.lower && i + g.roff < j)) C[i + (size_t)j * g.ld] -= acc[i + (size_t)j * g.m];
 }
 
+API void* sim_create2(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* snode, const int64_t* xlindx,
+                      const int64_t* lindx, const int64_t* xlnz, const int64_t* xunz, int use_dmma_buckets,
+                      int relax_abs, double relax_frac, int alloc, int part, int nparts);
 API void* sim_create(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* snode, const int64_t* xlindx,
                      const int64_t* lindx, const int64_t* xlnz, const int64_t* xunz, int use_dmma_buckets,
                      int relax_abs, double relax_frac, int alloc) {
+    return sim_create2(n, nsuper, xsuper, snode, xlindx, lindx, xlnz, xunz, use_dmma_buckets, relax_abs, relax_frac, alloc, 0, 1);
+}
+API void* sim_create2(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* snode, const int64_t* xlindx,
+                      const int64_t* lindx, const int64_t* xlnz, const int64_t* xunz, int use_dmma_buckets,
+                      int relax_abs, double relax_frac, int alloc, int part, int nparts) {
     Sim* s = new Sim();
+    s->P.part = part; s->P.nparts = nparts;
     plan_env_overrides(s->P);
     s->P.relax_abs = relax_abs; s->P.relax_frac = relax_frac;
     if (!analyze(s->P, n, nsuper, xsuper, snode, xlindx, lindx, xlnz, xunz)) { fprintf(stderr, "analyze: %s\n", s->P.error.c_str()); delete s; return nullptr; }
@@ -170,14 +179,9 @@ API double sim_statf(void* h, int what) {
     return 0;
 }
 
-API int64_t sim_factor(void* h, double* lnz, double* unz, int64_t* ipvt) {
-    Sim* s = (Sim*)h; Plan& P = s->P;
-    s->lnz.assign(lnz, lnz + P.nlnz);
-    if (P.lu) s->unz.assign(unz, unz + P.nunz);
-    std::fill(s->F.begin(), s->F.end(), 0.0);
-    s->iflag = 0;
-    chunks_io(*s, false);
-    for (const Launch& L : P.factor_launches) {
+static int64_t run_factor_list(Sim* s, const std::vector<Launch>& Ls) {
+    Plan& P = s->P;
+    for (const Launch& L : Ls) {
         switch (L.kind) {
         case K_ASM:
             for (int t = 0; t < L.count; ++t) { AsmTask a = P.asmt[L.first + t]; assemble(*s, P.fronts[a.child], P.fronts[a.parent]); } break;
@@ -192,6 +196,50 @@ API int64_t sim_factor(void* h, double* lnz, double* unz, int64_t* ipvt) {
         default: return -100;
         }
     }
+    return 0;
+}
+
+API void sim_load(void* h, const double* lnz, const double* unz) {
+    Sim* s = (Sim*)h; Plan& P = s->P;
+    s->lnz.assign(lnz, lnz + P.nlnz);
+    if (P.lu) s->unz.assign(unz, unz + P.nunz);
+    std::fill(s->F.begin(), s->F.end(), 0.0);
+    s->iflag = 0;
+    chunks_io(*s, false);
+}
+API void sim_store(void* h) { chunks_io(*(Sim*)h, true); }
+// which: 0 all, 1 this part's subtrees, 2 top set
+API int64_t sim_factor_list(void* h, int which) {
+    Sim* s = (Sim*)h; Plan& P = s->P;
+    int64_t rc = run_factor_list(s, which == 0 ? P.factor_launches : (which == 1 ? P.factor_local : P.factor_top));
+    return rc ? rc : s->iflag;
+}
+API void* sim_ptr(void* h, int what) {
+    Sim* s = (Sim*)h;
+    switch (what) { case 0: return s->lnz.data(); case 1: return s->unz.data(); case 2: return s->ipiv.data(); case 5: return s->F.data(); case 6: return s->w.data(); default: return nullptr; }
+}
+API int64_t sim_len(void* h, int what) {
+    Sim* s = (Sim*)h;
+    switch (what) { case 0: return (int64_t)s->lnz.size(); case 1: return (int64_t)s->unz.size(); case 2: return (int64_t)s->ipiv.size(); case 5: return (int64_t)s->F.size(); case 6: return (int64_t)s->w.size(); default: return 0; }
+}
+API int64_t sim_xchg_info(void* h, int what, int64_t i, int64_t* out) {
+    Sim* s = (Sim*)h; const Plan& P = s->P;
+    if (what == 0) {
+        if (!out) return (int64_t)P.xchg.size();
+        const Front& F = P.fronts[P.xchg[i]];
+        out[0] = P.owner[P.xchg[i]]; out[1] = F.fofs; out[2] = (int64_t)F.ld * F.R; out[3] = F.wofs; out[4] = F.R; out[5] = P.xchg[i];
+        return 0;
+    }
+    if (!out) return (int64_t)P.ranges.size();
+    const Plan::Range& g = P.ranges[i];
+    out[0] = g.owner; out[1] = g.lnz0; out[2] = g.lnz1 - g.lnz0; out[3] = g.unz0; out[4] = g.unz1 - g.unz0; out[5] = g.col0; out[6] = g.col1 - g.col0;
+    return 0;
+}
+
+API int64_t sim_factor(void* h, double* lnz, double* unz, int64_t* ipvt) {
+    Sim* s = (Sim*)h; Plan& P = s->P;
+    sim_load(h, lnz, unz);
+    if (run_factor_list(s, P.factor_launches)) return -100;
     chunks_io(*s, true);
     std::copy(s->lnz.begin(), s->lnz.end(), lnz);
     if (P.lu) { std::copy(s->unz.begin(), s->unz.end(), unz); for (int64_t i = 0; i < P.n; ++i) ipvt[i] = s->ipiv[i]; }
@@ -225,42 +273,40 @@ static void bwd_diag(Sim& s, const SolveTask& t, double* rhs) {
     for (int k = 0; k < t.nj; ++k) rhs[t.col0 + k] = x[k];
 }
 
-// rhs in permuted order, in place; factors as left by sim_factor
-API int64_t sim_solve(void* h, double* rhs) {
-    Sim* s = (Sim*)h; Plan& P = s->P; const bool lu = P.lu;
-    double* w = s->w.data();
-    for (const Launch& L : P.fwd_launches) {
+static int64_t run_solve_list(Sim* s, const std::vector<Launch>& Ls, double* rhs) {
+    Plan& P = s->P; double* w = s->w.data();
+    for (const Launch& L : Ls) {
         const int32_t* list = P.gathert.data() + L.first;
         for (int ti = 0; ti < L.count; ++ti) {
-            if (L.kind == K_FWD_GATHER) {
+            switch (L.kind) {
+            case K_FWD_GATHER: {
                 const Front& F = P.fronts[list[ti]]; double* wf = w + F.wofs;
                 for (int i = 0; i < F.R; ++i) wf[i] = i < F.W ? rhs[F.F0 + i] : 0.0;
                 for (int r = 0; r < F.nchild; ++r) { const Front& C = P.fronts[P.childlist[F.child0 + r]]; for (int i = 0; i < C.m; ++i) wf[P.rel[C.relofs + i]] += w[C.wofs + C.W + i]; }
-            } else if (L.kind == K_FWD_DIAG) {
-                fwd_diag(*s, P.solvet[list[ti]]);
-            } else if (L.kind == K_FWD_UPDATE) {
-                fwd_update(*s, P.solvet[list[ti]]);
-            } else if (L.kind == K_FWD_FRONT) {
-                const Front& F = P.fronts[list[ti]];
-                for (int tc = 0; tc < F.nch; ++tc) { fwd_diag(*s, P.solvet[F.c0 + tc]); fwd_update(*s, P.solvet[F.c0 + tc]); }
-            } else return -100;
-        }
-    }
-    for (const Launch& L : P.bwd_launches) {
-        const int32_t* list = P.gathert.data() + L.first;
-        for (int ti = 0; ti < L.count; ++ti) {
-            if (L.kind == K_BWD_GATHER) {
-                const Front& F = P.fronts[list[ti]]; const Front& Pa = P.fronts[F.parent];
-                for (int i = 0; i < F.m; ++i) w[F.wofs + F.W + i] = w[Pa.wofs + P.rel[F.relofs + i]];
-            } else if (L.kind == K_BWD_UPDATE) {
-                bwd_update(*s, P.solvet[list[ti]]);
-            } else if (L.kind == K_BWD_DIAG) {
-                bwd_diag(*s, P.solvet[list[ti]], rhs);
-            } else if (L.kind == K_BWD_FRONT) {
-                const Front& F = P.fronts[list[ti]];
-                for (int tc = F.nch - 1; tc >= 0; --tc) { bwd_update(*s, P.solvet[F.c0 + tc]); bwd_diag(*s, P.solvet[F.c0 + tc], rhs); }
-            } else return -100;
+                break; }
+            case K_FWD_DIAG: fwd_diag(*s, P.solvet[list[ti]]); break;
+            case K_FWD_UPDATE: fwd_update(*s, P.solvet[list[ti]]); break;
+            case K_FWD_FRONT: { const Front& F = P.fronts[list[ti]]; for (int tc = 0; tc < F.nch; ++tc) { fwd_diag(*s, P.solvet[F.c0 + tc]); fwd_update(*s, P.solvet[F.c0 + tc]); } break; }
+            case K_BWD_GATHER: { const Front& F = P.fronts[list[ti]]; const Front& Pa = P.fronts[F.parent]; for (int i = 0; i < F.m; ++i) w[F.wofs + F.W + i] = w[Pa.wofs + P.rel[F.relofs + i]]; break; }
+            case K_BWD_UPDATE: bwd_update(*s, P.solvet[list[ti]]); break;
+            case K_BWD_DIAG: bwd_diag(*s, P.solvet[list[ti]], rhs); break;
+            case K_BWD_FRONT: { const Front& F = P.fronts[list[ti]]; for (int tc = F.nch - 1; tc >= 0; --tc) { bwd_update(*s, P.solvet[F.c0 + tc]); bwd_diag(*s, P.solvet[F.c0 + tc], rhs); } break; }
+            default: return -100;
+            }
         }
     }
     return 0;
+}
+// which: 0 fwd local, 1 top (fwd + bwd), 2 bwd local   (multi-part plans)
+API int64_t sim_solve_phase(void* h, double* rhs, int which) {
+    Sim* s = (Sim*)h; Plan& P = s->P;
+    if (which == 0) return run_solve_list(s, P.fwd_local, rhs);
+    if (which == 1) { int64_t rc = run_solve_list(s, P.fwd_top, rhs); return rc ? rc : run_solve_list(s, P.bwd_top, rhs); }
+    return run_solve_list(s, P.bwd_local, rhs);
+}
+// rhs in permuted order, in place; factors as left by sim_factor
+API int64_t sim_solve(void* h, double* rhs) {
+    Sim* s = (Sim*)h; Plan& P = s->P;
+    int64_t rc = run_solve_list(s, P.fwd_launches, rhs);
+    return rc ? rc : run_solve_list(s, P.bwd_launches, rhs);
 }

@@ -1,0 +1,121 @@
+"""world_size-2 (and 4) gloo tests of the multi-GPU orchestration: the same `DistributedSolver`
+that drives the CUDA plans over NCCL is run over gloo with the host simulator of the device
+schedule as the engine (CPU only)."""
+import ctypes as C
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class SimEngine:
+    def __init__(self, b, rank, world):
+        from common import HostSim, I64P, F64P
+        L = HostSim.lib()
+        L.sim_create2.restype = C.c_void_p
+        L.sim_create2.argtypes = [C.c_int64, C.c_int64, I64P, I64P, I64P, I64P, I64P, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int]
+        L.sim_load.argtypes = [C.c_void_p, F64P, C.c_void_p]
+        L.sim_store.argtypes = [C.c_void_p]
+        L.sim_factor_list.argtypes = [C.c_void_p, C.c_int]; L.sim_factor_list.restype = C.c_int64
+        L.sim_solve_phase.argtypes = [C.c_void_p, F64P, C.c_int]; L.sim_solve_phase.restype = C.c_int64
+        L.sim_ptr.argtypes = [C.c_void_p, C.c_int]; L.sim_ptr.restype = C.c_void_p
+        L.sim_len.argtypes = [C.c_void_p, C.c_int]; L.sim_len.restype = C.c_int64
+        L.sim_xchg_info.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p]; L.sim_xchg_info.restype = C.c_int64
+        self.L, self.b, self.lu = L, b, not b.spd
+        self.h = L.sim_create2(b.n, b.nsuper, b.xsuper, b.snode, b.xlindx, b.lindx, b.xlnz,
+                               None if b.spd else b.xunz.ctypes.data, 1, 4, 0.02, 1, rank, world)
+        assert self.h
+        nl = int(b.xlnz[b.n]) - 1
+        L.sim_load(self.h, np.ascontiguousarray(b.lnz[:nl]), None if b.spd else b.unz.ctypes.data)
+
+    def _view(self, what, dtype):
+        n = self.L.sim_len(self.h, what)
+        if n == 0:
+            return torch.empty(0, dtype=torch.float64)
+        ct = C.c_double if dtype == np.float64 else C.c_int32
+        arr = np.ctypeslib.as_array(C.cast(self.L.sim_ptr(self.h, what), C.POINTER(ct)), shape=(n,))
+        return torch.from_numpy(arr)
+
+    def F(self): return self._view(5, np.float64)
+    def w(self): return self._view(6, np.float64)
+    def lnz(self): return self._view(0, np.float64)
+    def unz(self): return self._view(1, np.float64)
+    def ipiv(self): return self._view(2, np.int32)
+
+    def _list(self, what):
+        n = self.L.sim_xchg_info(self.h, what, 0, None)
+        out = []
+        for i in range(n):
+            buf = np.zeros(8, np.int64); self.L.sim_xchg_info(self.h, what, i, buf.ctypes.data); out.append(buf)
+        return out
+
+    def xchg(self): return self._list(0)
+    def ranges(self): return self._list(1)
+
+    def factor_phase(self, phase):
+        fl = int(self.L.sim_factor_list(self.h, 1 if phase == 0 else 2))
+        if phase == 1:
+            self.L.sim_store(self.h)
+        return fl
+
+    def solve_phase(self, rhs, phase):
+        self.L.sim_solve_phase(self.h, rhs.numpy(), phase)
+
+
+def _worker(rank, world, port, spd, q):
+    for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sparspak_jl_b200 as spk
+        from sparspak_jl_b200.multigpu import DistributedSolver
+        from common import prepare, oracle_factor, spd_mask, rel_err, residual, M
+        g = 10
+        A = M.laplacian3d(g) if spd else M.convdiff3d(g)
+        s = prepare(A, spd, spk.nd_grid_order(g, g, g), 8)
+        b = s.slvr
+        eng = SimEngine(b, rank, world)
+        ds = DistributedSolver(eng, rank, world)
+        owners = sorted(set(int(r[0]) for r in ds.rng))
+        flag = ds.factor()
+        ds.gather_factors()
+        lo, uo, po, _ = oracle_factor(b)
+        nl = int(b.xlnz[b.n]) - 1
+        e_l = rel_err(eng.lnz().numpy()[:nl], lo[:nl], spd_mask(b)[:nl])
+        e_u = 0.0 if spd else rel_err(eng.unz().numpy(), uo)
+        piv_ok = True if spd else bool(np.array_equal(eng.ipiv().numpy().astype(np.int64), po))
+        bb = M.rhs_for(A)
+        rhs = torch.from_numpy(np.ascontiguousarray(bb[b.order.rperm - 1]))
+        ds.solve(rhs)
+        x = rhs.numpy()[b.order.rinvp - 1]
+        q.put((rank, flag, e_l, e_u, piv_ok, residual(A, x, bb), owners, len(ds.fronts)))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+@pytest.mark.parametrize("world,spd", [(2, True), (2, False), (4, True)])
+def test_subtree_partition_over_gloo(world, spd):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, spd, q)) for r in range(world)]
+    for p in procs: p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs: p.join(timeout=60)
+    assert all(p.exitcode == 0 for p in procs)
+    for rank, flag, e_l, e_u, piv_ok, resid, owners, nx in res:
+        assert flag == 0 and e_l < 1e-12 and e_u < 1e-12 and piv_ok and resid < 1e-13
+        assert owners == list(range(world))       # every rank owns at least one subtree
+        assert nx >= world                        # and at least that many subtree roots are exchanged
