@@ -19,9 +19,7 @@
 
 namespace spk {
 
-constexpr int DM_TK = 16;            // k per pipeline stage
-constexpr int DM_STAGES = 4;
-constexpr int DM_LDBK = DM_TK + 4;   // row stride of the k-contiguous B tile (conflict-free fragment loads)
+// Pipeline shape is a template parameter pair: TK = k per stage, STAGES = ring depth.
 
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem, bool valid) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -38,12 +36,13 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
         : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-template <int TM, int TN>
+template <int TM, int TN, int DM_TK = 16, int DM_STAGES = 4>
 struct DmmaCfg {
     static constexpr int LDA = TM + 4;                              // +4 doubles: conflict-free fragment loads
     static constexpr int LDC = TM + 4;
+    static constexpr int LDBK = DM_TK + 4;                          // row stride of the k-contiguous B tile
     static constexpr int A_DOUBLES = DM_TK * LDA;
-    static constexpr int B_DOUBLES = TN * DM_LDBK;
+    static constexpr int B_DOUBLES = TN * LDBK;
     static constexpr int STAGE_DOUBLES = A_DOUBLES + B_DOUBLES;
     static constexpr int RING_DOUBLES = DM_STAGES * STAGE_DOUBLES;
     static constexpr int C_DOUBLES = TN * LDC;
@@ -51,10 +50,11 @@ struct DmmaCfg {
 };
 
 // WARPS_M x WARPS_N warps, each owning a (TM/WARPS_M) x (TN/WARPS_N) sub-tile of the block's C tile.
-template <int TM, int TN, int WARPS_M, int WARPS_N, int MINB>
+template <int TM, int TN, int WARPS_M, int WARPS_N, int MINB, int DM_TK = 16, int DM_STAGES = 4>
 __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, MINB)
 k_gemm_dmma(DevCtx c, const GemmTask* __restrict__ tasks, const int32_t* __restrict__ pfx, int count) {
-    using Cfg = DmmaCfg<TM, TN>;
+    using Cfg = DmmaCfg<TM, TN, DM_TK, DM_STAGES>;
+    constexpr int DM_LDBK = Cfg::LDBK;
     constexpr int NT = WARPS_M * WARPS_N * 32;
     constexpr int WM = TM / WARPS_M, WN = TN / WARPS_N;
     constexpr int FM = WM / 8, FN = WN / 8;
@@ -196,11 +196,14 @@ inline GemmVariant gemm_dmma_variant(int kind, int variant) {
     }
     if (variant == 1) return {k_gemm_dmma<BIG_TM, 64, 4, 4, 1>, 512, DmmaCfg<BIG_TM, 64>::SMEM};
     if (variant == 2) return {k_gemm_dmma<BIG_TM, 64, 4, 2, 2>, 256, DmmaCfg<BIG_TM, 64>::SMEM};
+    if (variant == 3) return {k_gemm_dmma<BIG_TM, 64, 4, 2, 2, 32, 2>, 256, DmmaCfg<BIG_TM, 64, 32, 2>::SMEM};
+    if (variant == 4) return {k_gemm_dmma<BIG_TM, 64, 4, 2, 2, 16, 3>, 256, DmmaCfg<BIG_TM, 64, 16, 3>::SMEM};
+    if (variant == 5) return {k_gemm_dmma<BIG_TM, 64, 4, 2, 2, 8, 6>, 256, DmmaCfg<BIG_TM, 64, 8, 6>::SMEM};
     return {k_gemm_dmma<BIG_TM, 64, 4, 2, 1>, 256, DmmaCfg<BIG_TM, 64>::SMEM};
 }
 inline cudaError_t gemm_dmma_init() {
     for (int kind : {(int)K_GEMM_B64, (int)K_GEMM_B128})
-        for (int variant = 0; variant < 3; ++variant) {
+        for (int variant = 0; variant < 6; ++variant) {
             GemmVariant v = gemm_dmma_variant(kind, variant);
             cudaError_t e = cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem);
             if (e != cudaSuccess) return e;

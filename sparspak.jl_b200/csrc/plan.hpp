@@ -386,7 +386,7 @@ inline void plan_env_overrides(Plan& P) {        // test / tuning knobs
     if (const char* e = getenv("SPK_OB_STEPS")) P.ob_steps = std::max(1, atoi(e));
     if (const char* e = getenv("SPK_LOOKAHEAD")) P.lookahead = e[0] != '0';
     if (const char* e = getenv("SPK_PS_WIDTH")) P.ps_width = std::max(1, atoi(e));
-    if (const char* e = getenv("SPK_DMMA_VARIANT")) P.no_b128 = atoi(e) == 2;
+    if (const char* e = getenv("SPK_DMMA_VARIANT")) P.no_b128 = atoi(e) >= 2;
 }
 
 // Launch lists for the fronts selected by `sel` (all of them, one part's subtrees, or the top set).
