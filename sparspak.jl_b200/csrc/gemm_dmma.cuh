@@ -199,11 +199,14 @@ inline GemmVariant gemm_dmma_variant(int kind, int variant) {
     if (variant == 3) return {k_gemm_dmma<BIG_TM, 64, 4, 2, 2, 32, 2>, 256, DmmaCfg<BIG_TM, 64, 32, 2>::SMEM};
     if (variant == 4) return {k_gemm_dmma<BIG_TM, 64, 4, 2, 2, 16, 3>, 256, DmmaCfg<BIG_TM, 64, 16, 3>::SMEM};
     if (variant == 5) return {k_gemm_dmma<BIG_TM, 64, 4, 2, 2, 8, 6>, 256, DmmaCfg<BIG_TM, 64, 8, 6>::SMEM};
+    if (variant == 6) return {k_gemm_dmma<BIG_TM, 64, 4, 2, 2, 16, 2>, 256, DmmaCfg<BIG_TM, 64, 16, 2>::SMEM};
+    if (variant == 7) return {k_gemm_dmma<BIG_TM, 64, 4, 2, 2, 8, 4>, 256, DmmaCfg<BIG_TM, 64, 8, 4>::SMEM};
+    if (variant == 8) return {k_gemm_dmma<BIG_TM, 64, 4, 2, 2, 8, 3>, 256, DmmaCfg<BIG_TM, 64, 8, 3>::SMEM};
     return {k_gemm_dmma<BIG_TM, 64, 4, 2, 1>, 256, DmmaCfg<BIG_TM, 64>::SMEM};
 }
 inline cudaError_t gemm_dmma_init() {
     for (int kind : {(int)K_GEMM_B64, (int)K_GEMM_B128})
-        for (int variant = 0; variant < 6; ++variant) {
+        for (int variant = 0; variant < 9; ++variant) {
             GemmVariant v = gemm_dmma_variant(kind, variant);
             cudaError_t e = cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem);
             if (e != cudaSuccess) return e;

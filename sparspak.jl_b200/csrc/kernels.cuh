@@ -13,8 +13,8 @@
 namespace spk {
 
 struct DFront {
-    int64_t fofs, relofs, wofs, F0;
-    int32_t W, R, m, ld, parent, child0, nchild, c0, nch, pad;
+    int64_t fofs, relofs, wofs, F0, pbofs;
+    int32_t W, R, m, ld, parent, child0, nchild, c0, nch, ps0, nps, pad;
 };
 struct DChunk {
     int64_t lofs, uofs, posofs, fofs;
@@ -23,12 +23,12 @@ struct DChunk {
 
 struct DevCtx {
     double* F;                       // frontal-matrix arena
-    double* lnz; double* unz; double* w;
+    double* lnz; double* unz; double* w; double* pb;   // pb: partial sums of the backward sweep
     int32_t* ipiv; int32_t* iflag;
     const DFront* fronts; const DChunk* chunks; const PStep* psteps; const int32_t* subw;
     const int32_t* childlist; const int32_t* rel; const int32_t* pos;
     const SolveTask* solvet;
-    int64_t wlen;
+    int64_t wlen, pblen;
     int32_t lu;
 };
 
@@ -694,6 +694,211 @@ __global__ void __launch_bounds__(256) k_bwd_front(DevCtx c, const int32_t* __re
             }
             __syncthreads();
         }
+    }
+    double* out = rhs + (size_t)blockIdx.y * ldrhs + F.F0;
+    for (int k = threadIdx.x; k < F.W; k += blockDim.x) out[k] = wf[k];
+}
+
+// ------------------------------------------------------------------------------------
+// Panel-step solves on the frontal matrices.  After the factorisation a front still holds L (below the
+// diagonal, unit) and U (on/above; LDL^T: D on the diagonal) of its own W columns as dense, uniformly
+// strided panels, so one solve step covers a whole panel step (<= ~64 columns, several reference chunks)
+// with dense row-contiguous panels instead of one step per chunk through position maps.
+// Same arithmetic as SpkLUFactor.jl:297-321,350-375 / SpkLDLtFactor.jl:268-291, regrouped.
+//
+// pf_diag: x := inv(L11) P x for the w unknowns of the step (Ts = staged w x w block, xs = staged x).
+// Executed by ONE warp on shared memory (column sweep, __syncwarp between columns): no block barriers.
+template <bool LU>
+__device__ __forceinline__ void pf_diag_warp(const DevCtx& c, const PStep& ps, const double* Ts, double* xs) {
+    const int lane = threadIdx.x & 31, w = ps.w;
+    if (LU) {
+        const int32_t* ipiv = c.ipiv + ps.col0;
+        const int32_t* subw = c.subw + ps.sub0;
+        int s0 = 0;
+        for (int b = 0; b < ps.nsub; ++b) {
+            const int s1 = s0 + subw[b];
+            // all columns k < s0 have been swept over these rows already: apply this chunk's interchanges now
+            if (lane == 0)
+                for (int k = s0; k < s1; ++k) { int ip = s0 + ipiv[k] - 1; if (ip != k) { double t = xs[k]; xs[k] = xs[ip]; xs[ip] = t; } }
+            __syncwarp();
+            for (int k = s0; k < s1; ++k) {
+                const double xk = xs[k];
+                for (int i = k + 1 + lane; i < w; i += 32) xs[i] -= xk * Ts[i + k * w];
+                __syncwarp();
+            }
+            s0 = s1;
+        }
+    } else {
+        for (int k = 0; k < w - 1; ++k) {
+            const double xk = xs[k];
+            for (int i = k + 1 + lane; i < w; i += 32) xs[i] -= xk * Ts[i + k * w];
+            __syncwarp();
+        }
+    }
+}
+// pb_diag: backward in-block solve.  LU: x := inv(U11) y.  LDL^T: x := inv(L11^T) y (y already divided by D).
+template <bool LU>
+__device__ __forceinline__ void pb_diag_warp(const PStep& ps, const double* Ts, double* xs) {
+    const int lane = threadIdx.x & 31, w = ps.w;
+    for (int k = w - 1; k >= 0; --k) {
+        if (LU) { if (lane == 0) xs[k] /= Ts[k + k * w]; __syncwarp(); }
+        const double xk = xs[k];
+        if (LU) { for (int i = lane; i < k; i += 32) xs[i] -= xk * Ts[i + k * w]; }
+        else { for (int i = lane; i < k; i += 32) xs[i] -= xk * Ts[k + i * w]; }
+        __syncwarp();
+    }
+}
+
+// rows [r0, r1) of the front below the step: wf[r] -= sum_k L[r, o+k] x[k]
+__device__ __forceinline__ void pf_update_rows(const DevCtx& c, const PStep& ps, double* wf, const double* xs, int r0, int r1) {
+    const double* __restrict__ Fm = c.F + ps.fofs + (int64_t)ps.o * ps.ld;
+    for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+        double acc = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < ps.w; ++k) acc += Fm[(size_t)r + (size_t)k * ps.ld] * xs[k];
+        wf[r] -= acc;
+    }
+}
+// partial sums over the front indices [r0, r1) beyond the step: out[k] = sum_r coef(r,k) * wf[r]
+//   LU: coef = U[o+k, r] (column r of the U panel: w contiguous entries);  LDL^T: coef = L[r, o+k]
+// red: shared scratch of (blockDim.x/32) * w doubles; the warps' sums are added in a fixed order.
+template <bool LU>
+__device__ __forceinline__ void pb_partial(const DevCtx& c, const PStep& ps, const double* wf, int r0, int r1, double* red, double* out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, w = ps.w;
+    const double* __restrict__ Fm = c.F + ps.fofs;
+    for (int k = threadIdx.x; k < nw * w; k += blockDim.x) red[k] = 0.0;
+    __syncthreads();
+    for (int rb = r0 + warp * 32; rb < r1; rb += nw * 32) {
+        const int r = rb + lane;
+        const double xr = r < r1 ? wf[r] : 0.0;
+        const double* __restrict__ col = LU ? Fm + (int64_t)ps.o + (int64_t)min(r, r1 - 1) * ps.ld
+                                           : Fm + (int64_t)min(r, r1 - 1) + (int64_t)ps.o * ps.ld;
+        for (int k = 0; k < w; ++k) {
+            double v = (LU ? col[k] : col[(size_t)k * ps.ld]) * xr;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            if (lane == 0) red[warp * w + k] += v;
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < w; k += blockDim.x) {
+        double s = 0.0;
+        for (int q = 0; q < nw; ++q) s += red[q * w + k];
+        out[k] = s;
+    }
+}
+
+inline size_t pstep_smem_bytes(int w) { return ((size_t)w * w + (size_t)w + 8 * (size_t)w) * sizeof(double); }
+
+template <bool LU>
+__global__ void __launch_bounds__(128) k_pf_diag(DevCtx c, const int32_t* __restrict__ plist) {
+    extern __shared__ double ssm[];
+    const PStep ps = c.psteps[plist[blockIdx.x]];
+    const DFront F = c.fronts[ps.front];
+    double* wf = c.w + (size_t)blockIdx.y * c.wlen + F.wofs;
+    double* Ts = ssm; double* xs = ssm + ps.w * ps.w;
+    block_g2s<128>(Ts, ps.w, c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld, ps.ld, ps.w);
+    for (int k = threadIdx.x; k < ps.w; k += blockDim.x) xs[k] = wf[ps.o + k];
+    __syncthreads();
+    if (threadIdx.x < 32) pf_diag_warp<LU>(c, ps, Ts, xs);
+    __syncthreads();
+    for (int k = threadIdx.x; k < ps.w; k += blockDim.x) wf[ps.o + k] = xs[k];
+}
+
+__global__ void __launch_bounds__(SV_ROWS) k_pf_update(DevCtx c, const int32_t* __restrict__ plist,
+                                                       const int32_t* __restrict__ pfx, int count) {
+    __shared__ double xs[128];
+    int ti = find_task(pfx, count, blockIdx.x);
+    int lb = blockIdx.x - pfx[ti];
+    const PStep ps = c.psteps[plist[ti]];
+    const DFront F = c.fronts[ps.front];
+    double* wf = c.w + (size_t)blockIdx.y * c.wlen + F.wofs;
+    for (int k = threadIdx.x; k < ps.w; k += blockDim.x) xs[k] = wf[ps.o + k];
+    __syncthreads();
+    const int e0 = ps.o + ps.w;
+    pf_update_rows(c, ps, wf, xs, e0 + lb * SV_ROWS, min(ps.R, e0 + (lb + 1) * SV_ROWS));
+}
+
+template <bool LU>
+__global__ void __launch_bounds__(SV_ROWS) k_pb_update(DevCtx c, const int32_t* __restrict__ plist,
+                                                       const int32_t* __restrict__ pfx, int count, int maxpw) {
+    extern __shared__ double ssm[];
+    int ti = find_task(pfx, count, blockIdx.x);
+    int lb = blockIdx.x - pfx[ti];
+    const PStep ps = c.psteps[plist[ti]];
+    const DFront F = c.fronts[ps.front];
+    const double* wf = c.w + (size_t)blockIdx.y * c.wlen + F.wofs;
+    double* out = c.pb + (size_t)blockIdx.y * c.pblen + F.pbofs + (size_t)lb * maxpw;
+    const int e0 = ps.o + ps.w;
+    pb_partial<LU>(c, ps, wf, e0 + lb * SV_ROWS, min(ps.R, e0 + (lb + 1) * SV_ROWS), ssm, out);
+}
+
+template <bool LU>
+__global__ void __launch_bounds__(128) k_pb_diag(DevCtx c, const int32_t* __restrict__ plist,
+                                                 double* __restrict__ rhs, int64_t ldrhs, int maxpw) {
+    extern __shared__ double ssm[];
+    const PStep ps = c.psteps[plist[blockIdx.x]];
+    const DFront F = c.fronts[ps.front];
+    double* wf = c.w + (size_t)blockIdx.y * c.wlen + F.wofs;
+    const double* pb = c.pb + (size_t)blockIdx.y * c.pblen + F.pbofs;
+    double* Ts = ssm; double* xs = ssm + ps.w * ps.w;
+    block_g2s<128>(Ts, ps.w, c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld, ps.ld, ps.w);
+    const int nblk = (ps.R - ps.o - ps.w + SV_ROWS - 1) / SV_ROWS;
+    __syncthreads();
+    for (int k = threadIdx.x; k < ps.w; k += blockDim.x) {
+        double s = 0.0;
+        for (int q = 0; q < nblk; ++q) s += pb[(size_t)q * maxpw + k];
+        const double y = wf[ps.o + k];
+        xs[k] = LU ? y - s : y / Ts[k + k * ps.w] - s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) pb_diag_warp<LU>(ps, Ts, xs);
+    __syncthreads();
+    double* out = rhs + (size_t)blockIdx.y * ldrhs + ps.col0;
+    for (int k = threadIdx.x; k < ps.w; k += blockDim.x) { wf[ps.o + k] = xs[k]; out[k] = xs[k]; }
+}
+
+// small fronts: one block walks all panel steps of the front
+template <bool LU>
+__global__ void __launch_bounds__(256) k_pf_front(DevCtx c, const int32_t* __restrict__ flist) {
+    extern __shared__ double ssm[];
+    const DFront F = c.fronts[flist[blockIdx.x]];
+    double* wf = c.w + (size_t)blockIdx.y * c.wlen + F.wofs;
+    for (int j = 0; j < F.nps; ++j) {
+        const PStep ps = c.psteps[F.ps0 + j];
+        double* Ts = ssm; double* xs = ssm + ps.w * ps.w;
+        block_g2s<256>(Ts, ps.w, c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld, ps.ld, ps.w);
+        for (int k = threadIdx.x; k < ps.w; k += blockDim.x) xs[k] = wf[ps.o + k];
+        __syncthreads();
+        if (threadIdx.x < 32) pf_diag_warp<LU>(c, ps, Ts, xs);
+        __syncthreads();
+        for (int k = threadIdx.x; k < ps.w; k += blockDim.x) wf[ps.o + k] = xs[k];
+        pf_update_rows(c, ps, wf, xs, ps.o + ps.w, ps.R);
+        __syncthreads();
+    }
+}
+
+template <bool LU>
+__global__ void __launch_bounds__(256) k_pb_front(DevCtx c, const int32_t* __restrict__ flist,
+                                                  double* __restrict__ rhs, int64_t ldrhs) {
+    extern __shared__ double ssm[];
+    const DFront F = c.fronts[flist[blockIdx.x]];
+    double* wf = c.w + (size_t)blockIdx.y * c.wlen + F.wofs;
+    for (int j = F.nps - 1; j >= 0; --j) {
+        const PStep ps = c.psteps[F.ps0 + j];
+        double* Ts = ssm; double* xs = ssm + ps.w * ps.w; double* red = xs + ps.w;
+        block_g2s<256>(Ts, ps.w, c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld, ps.ld, ps.w);
+        pb_partial<LU>(c, ps, wf, ps.o + ps.w, ps.R, red, xs);      // xs[k] = sum over the rows/columns beyond the step
+        __syncthreads();
+        for (int k = threadIdx.x; k < ps.w; k += blockDim.x) {
+            const double y = wf[ps.o + k];
+            xs[k] = LU ? y - xs[k] : y / Ts[k + k * ps.w] - xs[k];
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) pb_diag_warp<LU>(ps, Ts, xs);
+        __syncthreads();
+        for (int k = threadIdx.x; k < ps.w; k += blockDim.x) wf[ps.o + k] = xs[k];
+        __syncthreads();
     }
     double* out = rhs + (size_t)blockIdx.y * ldrhs + F.F0;
     for (int k = threadIdx.x; k < F.W; k += blockDim.x) out[k] = wf[k];

@@ -48,6 +48,7 @@ struct Front {
     int32_t parent, level;
     int32_t child0, nchild;
     int32_t ps0, nps;     // panel steps
+    int64_t pbofs;        // partial-sum scratch of the backward sweep (large fronts)
 };
 
 // One panel step of the dense partial factorisation of a front: columns [o, o+w), made of
@@ -73,7 +74,9 @@ struct SolveTask {        // one chunk of a triangular sweep (values read from l
 
 enum Kind : int32_t {
     K_ASM = 0, K_ASM_TAIL, K_DIAG, K_PANEL, K_GEMM, K_GEMM_B64, K_GEMM_B128,
-    K_FWD_GATHER, K_FWD_DIAG, K_FWD_UPDATE, K_BWD_GATHER, K_BWD_UPDATE, K_BWD_DIAG, K_FWD_FRONT, K_BWD_FRONT
+    K_FWD_GATHER, K_FWD_DIAG, K_FWD_UPDATE, K_BWD_GATHER, K_BWD_UPDATE, K_BWD_DIAG, K_FWD_FRONT, K_BWD_FRONT,
+    // solve on the frontal matrices, one step per PANEL STEP (dense, uniformly strided panels)
+    K_PF_FRONT, K_PF_DIAG, K_PF_UPDATE, K_PB_FRONT, K_PB_UPDATE, K_PB_DIAG
 };
 struct Launch {
     int32_t kind;
@@ -94,6 +97,7 @@ constexpr int PANEL_ROWS = 128;    // rows (L side) / columns (U side) per panel
 constexpr int GEMM_TM = 64, GEMM_TN = 64;   // C tile of the small-tile kernel
 constexpr int BIG_TM = 128;                 // C tile rows of the DMMA kernels (TN = 64 or 128)
 constexpr int UPD_ROWS = 256;      // rows per block in the forward-solve update
+constexpr int SV_ROWS = 256;       // rows / columns per block in the panel-step solve kernels
 constexpr int BWD_COLS = 1;        // columns per block in the backward-solve update (one block reduces one column)
 constexpr int PS_WIDTH = 64;       // target panel-step width (a wider single chunk stays alone)
 constexpr int OB_WIDTH = 512;      // target outer-block width (delayed trailing update)
@@ -113,7 +117,8 @@ struct Plan {
     std::vector<int32_t> rel;                 // relative indices, all fronts
     std::vector<int32_t> pos;                 // per-chunk stored-row -> front-row maps
     std::vector<int32_t> col2chunk;
-    int64_t arena = 0, wlen = 0;
+    int64_t arena = 0, wlen = 0, pblen = 0;
+    bool solve_on_fronts = true;              // solve sweeps read the frontal matrices (panel steps) instead of lnz/unz (chunks)
     int32_t nlevels = 0, maxnj = 0, maxR = 0, maxpw = 0;
     double flops_struct = 0, nnzL = 0;        // sum cc^2 (or 2 sum cc^2 - sum cc), sum cc
     bool use_dmma = true;
@@ -385,6 +390,7 @@ inline void plan_env_overrides(Plan& P) {        // test / tuning knobs
     if (const char* e = getenv("SPK_SOLVE_SMALL")) P.solve_small = atoll(e);
     if (const char* e = getenv("SPK_OB_STEPS")) P.ob_steps = std::max(1, atoi(e));
     if (const char* e = getenv("SPK_LOOKAHEAD")) P.lookahead = e[0] != '0';
+    if (const char* e = getenv("SPK_SOLVE_LNZ")) P.solve_on_fronts = e[0] != '1';
     if (const char* e = getenv("SPK_PS_WIDTH")) P.ps_width = std::max(1, atoi(e));
     if (const char* e = getenv("SPK_DMMA_VARIANT")) P.no_b128 = atoi(e) >= 2;
 }
@@ -483,6 +489,63 @@ inline void build_lists(Plan& P, const std::vector<uint8_t>& sel, std::vector<La
         }
     }
 
+    // ---- solves on the frontal matrices: one step per panel step.  Small fronts: one block walks the whole
+    // front.  Large fronts: a (diag, update) launch pair per panel step.
+    if (P.solve_on_fronts) {
+        std::vector<uint8_t> smallf(nf);
+        for (int32_t f = 0; f < nf; ++f) smallf[f] = (int64_t)P.fronts[f].R * P.fronts[f].W <= P.solve_small;
+        LaunchBuilder sf(P, fwd_out);
+        for (int32_t lev = 0; lev < P.nlevels; ++lev) {
+            const std::vector<int32_t>& fr = bylevel[lev];
+            int32_t maxnps = 0;
+            sf.begin(K_FWD_GATHER, (int32_t)P.gathert.size(), lev, 0);
+            for (int32_t f : fr) { P.gathert.push_back(f); sf.add(1); if (!smallf[f]) maxnps = std::max(maxnps, P.fronts[f].nps); }
+            sf.end();
+            sf.begin(K_PF_FRONT, (int32_t)P.gathert.size(), lev, 0);
+            for (int32_t f : fr) if (smallf[f]) { P.gathert.push_back(f); int32_t mw = 0; for (int32_t q = 0; q < P.fronts[f].nps; ++q) mw = std::max(mw, P.psteps[P.fronts[f].ps0 + q].w); sf.add(1, 0, mw); }
+            sf.end();
+            for (int32_t j = 0; j < maxnps; ++j) {
+                sf.begin(K_PF_DIAG, (int32_t)P.gathert.size(), lev, j);
+                for (int32_t f : fr) if (!smallf[f] && P.fronts[f].nps > j) { P.gathert.push_back(P.fronts[f].ps0 + j); sf.add(1, 0, P.psteps[P.fronts[f].ps0 + j].w); }
+                sf.end();
+                sf.begin(K_PF_UPDATE, (int32_t)P.gathert.size(), lev, j);
+                for (int32_t f : fr) if (!smallf[f] && P.fronts[f].nps > j) {
+                    const PStep& ps = P.psteps[P.fronts[f].ps0 + j];
+                    int32_t below = ps.R - ps.o - ps.w;
+                    if (below > 0) { P.gathert.push_back(P.fronts[f].ps0 + j); sf.add(cdiv(below, SV_ROWS), 0, ps.w); }
+                }
+                sf.end();
+            }
+        }
+        LaunchBuilder sb(P, bwd_out);
+        for (int32_t lev = P.nlevels - 1; lev >= 0; --lev) {
+            const std::vector<int32_t>& fr = bylevel[lev];
+            int32_t maxnps = 0;
+            sb.begin(K_BWD_GATHER, (int32_t)P.gathert.size(), lev, 0);
+            for (int32_t f : fr) {
+                if (!smallf[f]) maxnps = std::max(maxnps, P.fronts[f].nps);
+                if (P.fronts[f].m > 0) { P.gathert.push_back(f); sb.add(cdiv(P.fronts[f].m, 256)); }
+            }
+            sb.end();
+            sb.begin(K_PB_FRONT, (int32_t)P.gathert.size(), lev, 0);
+            for (int32_t f : fr) if (smallf[f]) { P.gathert.push_back(f); int32_t mw = 0; for (int32_t q = 0; q < P.fronts[f].nps; ++q) mw = std::max(mw, P.psteps[P.fronts[f].ps0 + q].w); sb.add(1, 0, mw); }
+            sb.end();
+            for (int32_t j = maxnps - 1; j >= 0; --j) {
+                sb.begin(K_PB_UPDATE, (int32_t)P.gathert.size(), lev, j);
+                for (int32_t f : fr) if (!smallf[f] && P.fronts[f].nps > j) {
+                    const PStep& ps = P.psteps[P.fronts[f].ps0 + j];
+                    int32_t below = ps.R - ps.o - ps.w;
+                    if (below > 0) { P.gathert.push_back(P.fronts[f].ps0 + j); sb.add(cdiv(below, SV_ROWS), 0, ps.w); }
+                }
+                sb.end();
+                sb.begin(K_PB_DIAG, (int32_t)P.gathert.size(), lev, j);
+                for (int32_t f : fr) if (!smallf[f] && P.fronts[f].nps > j) { P.gathert.push_back(P.fronts[f].ps0 + j); sb.add(1, 0, P.psteps[P.fronts[f].ps0 + j].w); }
+                sb.end();
+            }
+        }
+        return;
+    }
+
     // ---- solves (on lnz / unz in the reference layout).  Small fronts: one block walks all chunks of the
     // front; large fronts: one launch pair per chunk step so that many blocks share the panel.
     auto front_entries = [&](const Front& F) { int64_t e = 0; for (int32_t t = 0; t < F.nch; ++t) { const Chunk& c = P.chunks[F.c0 + t]; e += (int64_t)c.jlen * c.nj; } return e; };
@@ -563,17 +626,36 @@ inline void partition(Plan& P) {
     }
     std::vector<int32_t> roots;
     for (int32_t f = 0; f < nf; ++f) if (P.fronts[f].parent < 0) roots.push_back(f);
-    for (;;) {
-        if ((int32_t)roots.size() >= P.nparts) break;
-        int32_t best = -1;
+    // Estimated time of a configuration = (replicated) top-set work + the largest part load under LPT.
+    // Keep splitting the largest splittable subtree (it joins the top set) and remember the best
+    // configuration seen: more subtrees balance better, but everything split off is replicated.
+    auto own = [&](int32_t f) { double W = P.fronts[f].W, m = P.fronts[f].m; return W * W * W / 3.0 + W * W * m + W * m * m + 1.0; };
+    auto lpt_max = [&](std::vector<int32_t> rs) {
+        std::sort(rs.begin(), rs.end(), [&](int32_t a, int32_t b) { return work[a] != work[b] ? work[a] > work[b] : a < b; });
+        std::vector<double> ld(P.nparts, 0.0);
+        for (int32_t r : rs) { int32_t t = 0; for (int32_t q = 1; q < P.nparts; ++q) if (ld[q] < ld[t]) t = q; ld[t] += work[r]; }
+        return *std::max_element(ld.begin(), ld.end());
+    };
+    std::vector<int32_t> top, best_roots = roots, best_top;
+    double topwork = 0.0, best_cost = 1e300;
+    for (int iter = 0; iter < 64; ++iter) {
+        if ((int32_t)roots.size() >= P.nparts) {
+            double cost = topwork + lpt_max(roots);
+            if (cost < best_cost) { best_cost = cost; best_roots = roots; best_top = top; }
+        }
+        int32_t pick = -1;
         for (size_t i = 0; i < roots.size(); ++i)
-            if (P.fronts[roots[i]].nchild > 0 && (best < 0 || work[roots[i]] > work[roots[best]])) best = (int32_t)i;
-        if (best < 0) break;
-        int32_t f = roots[best];
-        roots.erase(roots.begin() + best);
-        P.owner[f] = -1;                                        // joins the top set
+            if (P.fronts[roots[i]].nchild > 0 && (pick < 0 || work[roots[i]] > work[roots[pick]])) pick = (int32_t)i;
+        if (pick < 0) break;
+        int32_t f = roots[pick];
+        roots.erase(roots.begin() + pick);
+        top.push_back(f); topwork += own(f);
         for (int32_t q = 0; q < P.fronts[f].nchild; ++q) roots.push_back(P.childlist[P.fronts[f].child0 + q]);
+        if ((int32_t)roots.size() >= P.nparts && topwork > best_cost) break;   // cannot improve any more
     }
+    if (best_cost >= 1e300) { best_roots = roots; best_top = top; }        // tree too thin to give every part a subtree
+    roots = best_roots;
+    for (int32_t f : best_top) P.owner[f] = -1;
     std::sort(roots.begin(), roots.end(), [&](int32_t a, int32_t b) { return work[a] != work[b] ? work[a] > work[b] : a < b; });
     std::vector<double> load(P.nparts, 0.0);
     for (int32_t r : roots) {
@@ -604,6 +686,12 @@ inline void build_schedule(Plan& P) {
         SolveTask t{}; t.lofs = c.lofs; t.uofs = c.uofs; t.col0 = c.fj; t.wofs = F.wofs; t.posofs = c.posofs;
         t.ld = c.jlen; t.ldu = c.jlen - c.nj; t.nj = c.nj; t.m = c.jlen - c.nj; t.o = c.o; t.front = c.front;
         P.solvet[s] = t;
+    }
+    P.pblen = 0;
+    for (int32_t f = 0; f < nf; ++f) {
+        Front& F = P.fronts[f];
+        F.pbofs = P.pblen;
+        if ((int64_t)F.R * F.W > P.solve_small) P.pblen += (int64_t)cdiv(F.R, SV_ROWS) * P.maxpw;
     }
     partition(P);
     std::vector<uint8_t> sel(nf, 1);

@@ -42,7 +42,7 @@ struct spk_plan {
     cudaEvent_t evs0 = nullptr, evs1 = nullptr;          // last record of each stream
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evg0 = nullptr, evg1 = nullptr;
     // device state
-    double *d_F = nullptr, *d_lnz = nullptr, *d_unz = nullptr, *d_w = nullptr, *d_rhs = nullptr, *d_tmp = nullptr;
+    double *d_pb = nullptr, *d_F = nullptr, *d_lnz = nullptr, *d_unz = nullptr, *d_w = nullptr, *d_rhs = nullptr, *d_tmp = nullptr;
     int32_t *d_ipiv = nullptr, *d_iflag = nullptr;
     DFront* d_fronts = nullptr; DChunk* d_chunks = nullptr; PStep* d_psteps = nullptr;
     int32_t *d_subw = nullptr, *d_childlist = nullptr, *d_rel = nullptr, *d_pos = nullptr, *d_blkpfx = nullptr,
@@ -55,7 +55,7 @@ struct spk_plan {
     cudaGraphExec_t sg_exec = nullptr; double* sg_rhs = nullptr; double* sg_w = nullptr;
     int64_t sg_nrhs = 0, sg_ld = 0, sg_launches = 0; int32_t sg_which = -1;
     bool diag_smem_only = false;        // SPK_DIAG_SMEM=1: always use the shared-memory diagonal kernel
-    int dmma_variant = 2;               // SPK_DMMA_VARIANT (see gemm_dmma.cuh)
+    int dmma_variant = 4;               // SPK_DMMA_VARIANT (see gemm_dmma.cuh)
     bool values_in_fronts = false;      // inmatrix scattered straight into the fronts
     int64_t w_nrhs = 0, rhs_cap = 0;
     size_t dev_bytes = 0;
@@ -71,7 +71,7 @@ struct spk_plan {
 
 static DevCtx make_ctx(spk_plan* p) {
     DevCtx c{};
-    c.F = p->d_F; c.lnz = p->d_lnz; c.unz = p->d_unz; c.w = p->d_w;
+    c.F = p->d_F; c.lnz = p->d_lnz; c.unz = p->d_unz; c.w = p->d_w; c.pb = p->d_pb; c.pblen = p->P.pblen;
     c.ipiv = p->d_ipiv; c.iflag = p->d_iflag;
     c.fronts = p->d_fronts; c.chunks = p->d_chunks; c.psteps = p->d_psteps; c.subw = p->d_subw;
     c.childlist = p->d_childlist; c.rel = p->d_rel; c.pos = p->d_pos;
@@ -93,7 +93,7 @@ SPK_API void spk_plan_destroy(spk_plan* p) {
     if (!p) return;
     if (p->device >= 0) {
         cudaSetDevice(p->device);
-        void* ptrs[] = {p->d_F, p->d_lnz, p->d_unz, p->d_w, p->d_rhs, p->d_tmp, p->d_ipiv, p->d_iflag, p->d_fronts,
+        void* ptrs[] = {p->d_pb, p->d_F, p->d_lnz, p->d_unz, p->d_w, p->d_rhs, p->d_tmp, p->d_ipiv, p->d_iflag, p->d_fronts,
                         p->d_chunks, p->d_psteps, p->d_subw, p->d_childlist, p->d_rel, p->d_pos, p->d_blkpfx,
                         p->d_gathert, p->d_pslist, p->d_chunkpfx, p->d_dest, p->d_rperm, p->d_rinvp, p->d_nzval,
                         p->d_asmt, p->d_gemmt, p->d_solvet};
@@ -127,7 +127,7 @@ static int64_t plan_upload(spk_plan* p) {
     std::vector<DFront> df(P.fronts.size());
     for (size_t i = 0; i < df.size(); ++i) {
         const Front& F = P.fronts[i];
-        df[i] = DFront{F.fofs, F.relofs, F.wofs, F.F0, F.W, F.R, F.m, F.ld, F.parent, F.child0, F.nchild, F.c0, F.nch, 0};
+        df[i] = DFront{F.fofs, F.relofs, F.wofs, F.F0, F.pbofs, F.W, F.R, F.m, F.ld, F.parent, F.child0, F.nchild, F.c0, F.nch, F.ps0, F.nps, 0};
     }
     std::vector<DChunk> dc(P.chunks.size());
     std::vector<int32_t> cpfx(P.chunks.size() + 1, 0);
@@ -177,6 +177,19 @@ static int64_t plan_upload(spk_plan* p) {
     if (p->panel_smem > 48 * 1024) {
         CK(cudaFuncSetAttribute(k_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->panel_smem));
         CK(cudaFuncSetAttribute(k_panel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->panel_smem));
+    }
+    {
+        size_t sm = pstep_smem_bytes(P.maxpw);
+        if (sm > 48 * 1024) {
+            CK(cudaFuncSetAttribute(k_pf_front<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            CK(cudaFuncSetAttribute(k_pf_front<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            CK(cudaFuncSetAttribute(k_pb_front<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            CK(cudaFuncSetAttribute(k_pb_front<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            CK(cudaFuncSetAttribute(k_pf_diag<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            CK(cudaFuncSetAttribute(k_pf_diag<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            CK(cudaFuncSetAttribute(k_pb_diag<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            CK(cudaFuncSetAttribute(k_pb_diag<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        }
     }
     CK(gemm_dmma_init());
     return 0;
@@ -233,6 +246,12 @@ SPK_API int64_t spk_plan_set_factors(spk_plan* p, const double* lnz, const doubl
         k_ipiv_narrow<<<cdiv(p->P.n, 256), 256, 0, p->stream>>>(p->P.n, tmp, p->d_ipiv);
         CK(cudaStreamSynchronize(p->stream));
         CK(cudaFree(tmp));
+    }
+    {   // the solve sweeps read the frontal matrices: rebuild them from the uploaded factors
+        DevCtx c = make_ctx(p);
+        CK(cudaMemsetAsync(p->d_F, 0, p->P.arena * sizeof(double), p->stream));
+        k_chunks<false><<<p->chunk_blocks, 256, 0, p->stream>>>(c, p->d_chunkpfx, (int)p->P.chunks.size());
+        CK(cudaStreamSynchronize(p->stream));
     }
     p->factored = true;
     return 0;
@@ -443,6 +462,9 @@ static int64_t ensure_w(spk_plan* p, int64_t nrhs) {
         if (p->d_w) cudaFree(p->d_w);
         p->d_w = nullptr; p->w_nrhs = 0;
         CK(cudaMalloc((void**)&p->d_w, (size_t)p->P.wlen * nrhs * sizeof(double)));
+        if (p->d_pb) cudaFree(p->d_pb);
+        p->d_pb = nullptr;
+        CK(cudaMalloc((void**)&p->d_pb, std::max<size_t>((size_t)p->P.pblen * nrhs, 1) * sizeof(double)));
         p->w_nrhs = nrhs;
     }
     return 0;
@@ -471,6 +493,37 @@ static int64_t run_solve_launches(spk_plan* p, const DevCtx& c, const std::vecto
             if (lu) k_bwd_front<true><<<dim3(L.count, (unsigned)nrhs), 256, 0, st>>>(c, list, d_rhs, ldrhs);
             else k_bwd_front<false><<<dim3(L.count, (unsigned)nrhs), 256, 0, st>>>(c, list, d_rhs, ldrhs);
             break;
+        case K_PF_FRONT: {
+            size_t sm = pstep_smem_bytes(L.maxw);
+            if (lu) k_pf_front<true><<<dim3(L.count, (unsigned)nrhs), 256, sm, st>>>(c, list);
+            else k_pf_front<false><<<dim3(L.count, (unsigned)nrhs), 256, sm, st>>>(c, list);
+            break;
+        }
+        case K_PB_FRONT: {
+            size_t sm = pstep_smem_bytes(L.maxw);
+            if (lu) k_pb_front<true><<<dim3(L.count, (unsigned)nrhs), 256, sm, st>>>(c, list, d_rhs, ldrhs);
+            else k_pb_front<false><<<dim3(L.count, (unsigned)nrhs), 256, sm, st>>>(c, list, d_rhs, ldrhs);
+            break;
+        }
+        case K_PF_DIAG: {
+            size_t sm = pstep_smem_bytes(L.maxw);
+            if (lu) k_pf_diag<true><<<dim3(L.count, (unsigned)nrhs), 128, sm, st>>>(c, list);
+            else k_pf_diag<false><<<dim3(L.count, (unsigned)nrhs), 128, sm, st>>>(c, list);
+            break;
+        }
+        case K_PF_UPDATE: k_pf_update<<<grid, SV_ROWS, 0, st>>>(c, list, pfx, L.count); break;
+        case K_PB_UPDATE: {
+            size_t sm = (size_t)(SV_ROWS / 32) * L.maxw * sizeof(double);
+            if (lu) k_pb_update<true><<<grid, SV_ROWS, sm, st>>>(c, list, pfx, L.count, p->P.maxpw);
+            else k_pb_update<false><<<grid, SV_ROWS, sm, st>>>(c, list, pfx, L.count, p->P.maxpw);
+            break;
+        }
+        case K_PB_DIAG: {
+            size_t sm = pstep_smem_bytes(L.maxw);
+            if (lu) k_pb_diag<true><<<dim3(L.count, (unsigned)nrhs), 128, sm, st>>>(c, list, d_rhs, ldrhs, p->P.maxpw);
+            else k_pb_diag<false><<<dim3(L.count, (unsigned)nrhs), 128, sm, st>>>(c, list, d_rhs, ldrhs, p->P.maxpw);
+            break;
+        }
         case K_BWD_GATHER: k_bwd_gather<<<grid, 256, 0, st>>>(c, list, pfx, L.count); break;
         case K_BWD_UPDATE:
             if (lu) k_bwd_update<true><<<grid, 256, 0, st>>>(c, list, pfx, L.count);

@@ -273,6 +273,52 @@ static void bwd_diag(Sim& s, const SolveTask& t, double* rhs) {
     for (int k = 0; k < t.nj; ++k) rhs[t.col0 + k] = x[k];
 }
 
+// ---- panel-step solves on the frontal matrices (same semantics as the k_pf_* / k_pb_* kernels)
+static void pf_diag(Sim& s, const PStep& ps) {
+    Plan& P = s.P; const Front& F = P.fronts[ps.front];
+    double* x = s.w.data() + F.wofs + ps.o;
+    const double* T = s.F.data() + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld;
+    const int w = ps.w, ld = ps.ld;
+    if (P.lu) {
+        int s0 = 0;
+        for (int b = 0; b < ps.nsub; ++b) {
+            int s1 = s0 + P.subw[ps.sub0 + b];
+            for (int k = s0; k < s1; ++k) { int q = s0 + s.ipiv[ps.col0 + k] - 1; if (q != k) std::swap(x[k], x[q]); }
+            for (int k = s0; k < s1; ++k) for (int i = k + 1; i < w; ++i) x[i] -= x[k] * T[i + (size_t)k * ld];
+            s0 = s1;
+        }
+    } else {
+        for (int k = 0; k < w; ++k) for (int i = k + 1; i < w; ++i) x[i] -= x[k] * T[i + (size_t)k * ld];
+    }
+}
+static void pf_update(Sim& s, const PStep& ps) {
+    const Front& F = s.P.fronts[ps.front];
+    double* wf = s.w.data() + F.wofs;
+    const double* Fm = s.F.data() + ps.fofs;
+    for (int r = ps.o + ps.w; r < ps.R; ++r) {
+        double acc = 0;
+        for (int k = 0; k < ps.w; ++k) acc += Fm[(size_t)r + (size_t)(ps.o + k) * ps.ld] * wf[ps.o + k];
+        wf[r] -= acc;
+    }
+}
+static void pb_step(Sim& s, const PStep& ps, double* rhs) {
+    Plan& P = s.P; const Front& F = P.fronts[ps.front]; const bool lu = P.lu;
+    double* wf = s.w.data() + F.wofs; double* x = wf + ps.o;
+    const double* Fm = s.F.data() + ps.fofs;
+    const double* T = Fm + (int64_t)ps.o + (int64_t)ps.o * ps.ld;
+    const int w = ps.w, ld = ps.ld;
+    for (int k = 0; k < w; ++k) {
+        double sum = 0;
+        for (int r = ps.o + w; r < ps.R; ++r) sum += (lu ? Fm[(size_t)(ps.o + k) + (size_t)r * ld] : Fm[(size_t)r + (size_t)(ps.o + k) * ld]) * wf[r];
+        x[k] = lu ? x[k] - sum : x[k] / T[k + (size_t)k * ld] - sum;
+    }
+    for (int k = w - 1; k >= 0; --k) {
+        if (lu) { x[k] /= T[k + (size_t)k * ld]; for (int i = 0; i < k; ++i) x[i] -= x[k] * T[i + (size_t)k * ld]; }
+        else for (int i = 0; i < k; ++i) x[i] -= x[k] * T[k + (size_t)i * ld];
+    }
+    for (int k = 0; k < w; ++k) rhs[ps.col0 + k] = x[k];
+}
+
 static int64_t run_solve_list(Sim* s, const std::vector<Launch>& Ls, double* rhs) {
     Plan& P = s->P; double* w = s->w.data();
     for (const Launch& L : Ls) {
@@ -291,6 +337,12 @@ static int64_t run_solve_list(Sim* s, const std::vector<Launch>& Ls, double* rhs
             case K_BWD_UPDATE: bwd_update(*s, P.solvet[list[ti]]); break;
             case K_BWD_DIAG: bwd_diag(*s, P.solvet[list[ti]], rhs); break;
             case K_BWD_FRONT: { const Front& F = P.fronts[list[ti]]; for (int tc = F.nch - 1; tc >= 0; --tc) { bwd_update(*s, P.solvet[F.c0 + tc]); bwd_diag(*s, P.solvet[F.c0 + tc], rhs); } break; }
+            case K_PF_FRONT: { const Front& F = P.fronts[list[ti]]; for (int j = 0; j < F.nps; ++j) { pf_diag(*s, P.psteps[F.ps0 + j]); pf_update(*s, P.psteps[F.ps0 + j]); } break; }
+            case K_PF_DIAG: pf_diag(*s, P.psteps[list[ti]]); break;
+            case K_PF_UPDATE: pf_update(*s, P.psteps[list[ti]]); break;
+            case K_PB_FRONT: { const Front& F = P.fronts[list[ti]]; for (int j = F.nps - 1; j >= 0; --j) pb_step(*s, P.psteps[F.ps0 + j], rhs); break; }
+            case K_PB_UPDATE: break;                          // folded into pb_step at the K_PB_DIAG launch
+            case K_PB_DIAG: pb_step(*s, P.psteps[list[ti]], rhs); break;
             default: return -100;
             }
         }
