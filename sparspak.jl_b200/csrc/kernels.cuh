@@ -858,6 +858,83 @@ __global__ void __launch_bounds__(128) k_pb_diag(DevCtx c, const int32_t* __rest
     for (int k = threadIdx.x; k < ps.w; k += blockDim.x) { wf[ps.o + k] = xs[k]; out[k] = xs[k]; }
 }
 
+// Fused forward step: every block updates its rows beyond step j with x_j; block 0 (whose rows contain all
+// unknowns of step j+1) then also solves the diagonal block of step j+1, so a sweep needs one launch per
+// panel step instead of two.
+template <bool LU>
+__global__ void __launch_bounds__(SV_ROWS) k_pf_step(DevCtx c, const int32_t* __restrict__ plist,
+                                                     const int32_t* __restrict__ pfx, int count) {
+    extern __shared__ double ssm[];
+    int ti = find_task(pfx, count, blockIdx.x);
+    int lb = blockIdx.x - pfx[ti];
+    const int pid = plist[ti];
+    const PStep ps = c.psteps[pid];
+    const DFront F = c.fronts[ps.front];
+    double* wf = c.w + (size_t)blockIdx.y * c.wlen + F.wofs;
+    double* xs = ssm;                                           // x_j (w entries)
+    for (int k = threadIdx.x; k < ps.w; k += blockDim.x) xs[k] = wf[ps.o + k];
+    __syncthreads();
+    const int e0 = ps.o + ps.w;
+    pf_update_rows(c, ps, wf, xs, e0 + lb * SV_ROWS, min(ps.R, e0 + (lb + 1) * SV_ROWS));
+    if (lb == 0 && pid + 1 < F.ps0 + F.nps) {
+        __syncthreads();                                        // this block's rows (incl. step j+1's unknowns) are final
+        const PStep nx = c.psteps[pid + 1];
+        double* Ts = ssm; double* xn = ssm + nx.w * nx.w;
+        block_g2s<SV_ROWS>(Ts, nx.w, c.F + nx.fofs + (int64_t)nx.o + (int64_t)nx.o * nx.ld, nx.ld, nx.w);
+        for (int k = threadIdx.x; k < nx.w; k += blockDim.x) xn[k] = wf[nx.o + k];
+        __syncthreads();
+        if (threadIdx.x < 32) pf_diag_warp<LU>(c, nx, Ts, xn);
+        __syncthreads();
+        for (int k = threadIdx.x; k < nx.w; k += blockDim.x) wf[nx.o + k] = xn[k];
+    }
+}
+
+// Fused backward step: every block writes the partial sums of its rows/columns beyond step j; the block that
+// arrives last (device-wide counter) adds the partials in a fixed order and solves the diagonal block of step j.
+template <bool LU>
+__global__ void __launch_bounds__(SV_ROWS) k_pb_step(DevCtx c, const int32_t* __restrict__ plist,
+                                                     const int32_t* __restrict__ pfx, int count,
+                                                     double* __restrict__ rhs, int64_t ldrhs, int maxpw, int32_t* counters) {
+    extern __shared__ double ssm[];
+    __shared__ int s_last;
+    int ti = find_task(pfx, count, blockIdx.x);
+    int lb = blockIdx.x - pfx[ti];
+    const PStep ps = c.psteps[plist[ti]];
+    const DFront F = c.fronts[ps.front];
+    double* wf = c.w + (size_t)blockIdx.y * c.wlen + F.wofs;
+    double* pb = c.pb + (size_t)blockIdx.y * c.pblen + F.pbofs;
+    const int e0 = ps.o + ps.w, below = ps.R - e0;
+    const int nblk = (below + SV_ROWS - 1) / SV_ROWS;
+    if (nblk > 0) {
+        pb_partial<LU>(c, ps, wf, e0 + lb * SV_ROWS, min(ps.R, e0 + (lb + 1) * SV_ROWS), ssm, pb + (size_t)lb * maxpw);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int32_t* cnt = counters + (size_t)blockIdx.y * gridDim.x + pfx[ti];      // one counter per (rhs, task)
+            int prev = atomicAdd(cnt, 1);
+            s_last = (prev == nblk - 1);
+            if (s_last) *cnt = 0;                                                    // ready for the next sweep
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+    }
+    double* Ts = ssm; double* xs = ssm + ps.w * ps.w;
+    block_g2s<SV_ROWS>(Ts, ps.w, c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld, ps.ld, ps.w);
+    __syncthreads();
+    for (int k = threadIdx.x; k < ps.w; k += blockDim.x) {
+        double sum = 0.0;
+        for (int q = 0; q < nblk; ++q) sum += __ldcg(pb + (size_t)q * maxpw + k);
+        const double y = wf[ps.o + k];
+        xs[k] = LU ? y - sum : y / Ts[k + k * ps.w] - sum;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) pb_diag_warp<LU>(ps, Ts, xs);
+    __syncthreads();
+    double* out = rhs + (size_t)blockIdx.y * ldrhs + ps.col0;
+    for (int k = threadIdx.x; k < ps.w; k += blockDim.x) { wf[ps.o + k] = xs[k]; out[k] = xs[k]; }
+}
+
 // small fronts: one block walks all panel steps of the front
 template <bool LU>
 __global__ void __launch_bounds__(256) k_pf_front(DevCtx c, const int32_t* __restrict__ flist) {

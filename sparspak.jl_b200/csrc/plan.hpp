@@ -76,7 +76,8 @@ enum Kind : int32_t {
     K_ASM = 0, K_ASM_TAIL, K_DIAG, K_PANEL, K_GEMM, K_GEMM_B64, K_GEMM_B128,
     K_FWD_GATHER, K_FWD_DIAG, K_FWD_UPDATE, K_BWD_GATHER, K_BWD_UPDATE, K_BWD_DIAG, K_FWD_FRONT, K_BWD_FRONT,
     // solve on the frontal matrices, one step per PANEL STEP (dense, uniformly strided panels)
-    K_PF_FRONT, K_PF_DIAG, K_PF_UPDATE, K_PB_FRONT, K_PB_UPDATE, K_PB_DIAG
+    K_PF_FRONT, K_PF_DIAG, K_PF_UPDATE, K_PB_FRONT, K_PB_UPDATE, K_PB_DIAG,
+    K_PF_STEP, K_PB_STEP      // fused: update + next diagonal block (forward), partial sums + diagonal block (backward)
 };
 struct Launch {
     int32_t kind;
@@ -505,14 +506,17 @@ inline void build_lists(Plan& P, const std::vector<uint8_t>& sel, std::vector<La
             for (int32_t f : fr) if (smallf[f]) { P.gathert.push_back(f); int32_t mw = 0; for (int32_t q = 0; q < P.fronts[f].nps; ++q) mw = std::max(mw, P.psteps[P.fronts[f].ps0 + q].w); sf.add(1, 0, mw); }
             sf.end();
             for (int32_t j = 0; j < maxnps; ++j) {
-                sf.begin(K_PF_DIAG, (int32_t)P.gathert.size(), lev, j);
-                for (int32_t f : fr) if (!smallf[f] && P.fronts[f].nps > j) { P.gathert.push_back(P.fronts[f].ps0 + j); sf.add(1, 0, P.psteps[P.fronts[f].ps0 + j].w); }
-                sf.end();
-                sf.begin(K_PF_UPDATE, (int32_t)P.gathert.size(), lev, j);
+                if (j == 0) {                       // later diagonal blocks are solved inside the previous fused step
+                    sf.begin(K_PF_DIAG, (int32_t)P.gathert.size(), lev, j);
+                    for (int32_t f : fr) if (!smallf[f] && P.fronts[f].nps > j) { P.gathert.push_back(P.fronts[f].ps0 + j); sf.add(1, 0, P.psteps[P.fronts[f].ps0 + j].w); }
+                    sf.end();
+                }
+                sf.begin(K_PF_STEP, (int32_t)P.gathert.size(), lev, j);
                 for (int32_t f : fr) if (!smallf[f] && P.fronts[f].nps > j) {
                     const PStep& ps = P.psteps[P.fronts[f].ps0 + j];
                     int32_t below = ps.R - ps.o - ps.w;
-                    if (below > 0) { P.gathert.push_back(P.fronts[f].ps0 + j); sf.add(cdiv(below, SV_ROWS), 0, ps.w); }
+                    int32_t wn = P.fronts[f].nps > j + 1 ? P.psteps[P.fronts[f].ps0 + j + 1].w : 0;
+                    if (below > 0) { P.gathert.push_back(P.fronts[f].ps0 + j); sf.add(cdiv(below, SV_ROWS), 0, std::max(ps.w, wn)); }
                 }
                 sf.end();
             }
@@ -531,15 +535,12 @@ inline void build_lists(Plan& P, const std::vector<uint8_t>& sel, std::vector<La
             for (int32_t f : fr) if (smallf[f]) { P.gathert.push_back(f); int32_t mw = 0; for (int32_t q = 0; q < P.fronts[f].nps; ++q) mw = std::max(mw, P.psteps[P.fronts[f].ps0 + q].w); sb.add(1, 0, mw); }
             sb.end();
             for (int32_t j = maxnps - 1; j >= 0; --j) {
-                sb.begin(K_PB_UPDATE, (int32_t)P.gathert.size(), lev, j);
+                sb.begin(K_PB_STEP, (int32_t)P.gathert.size(), lev, j);
                 for (int32_t f : fr) if (!smallf[f] && P.fronts[f].nps > j) {
                     const PStep& ps = P.psteps[P.fronts[f].ps0 + j];
                     int32_t below = ps.R - ps.o - ps.w;
-                    if (below > 0) { P.gathert.push_back(P.fronts[f].ps0 + j); sb.add(cdiv(below, SV_ROWS), 0, ps.w); }
+                    P.gathert.push_back(P.fronts[f].ps0 + j); sb.add(std::max(1, cdiv(below, SV_ROWS)), 0, ps.w);
                 }
-                sb.end();
-                sb.begin(K_PB_DIAG, (int32_t)P.gathert.size(), lev, j);
-                for (int32_t f : fr) if (!smallf[f] && P.fronts[f].nps > j) { P.gathert.push_back(P.fronts[f].ps0 + j); sb.add(1, 0, P.psteps[P.fronts[f].ps0 + j].w); }
                 sb.end();
             }
         }

@@ -43,7 +43,7 @@ struct spk_plan {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evg0 = nullptr, evg1 = nullptr;
     // device state
     double *d_pb = nullptr, *d_F = nullptr, *d_lnz = nullptr, *d_unz = nullptr, *d_w = nullptr, *d_rhs = nullptr, *d_tmp = nullptr;
-    int32_t *d_ipiv = nullptr, *d_iflag = nullptr;
+    int32_t *d_ipiv = nullptr, *d_iflag = nullptr, *d_counters = nullptr;
     DFront* d_fronts = nullptr; DChunk* d_chunks = nullptr; PStep* d_psteps = nullptr;
     int32_t *d_subw = nullptr, *d_childlist = nullptr, *d_rel = nullptr, *d_pos = nullptr, *d_blkpfx = nullptr,
             *d_gathert = nullptr, *d_pslist = nullptr, *d_chunkpfx = nullptr;
@@ -93,7 +93,7 @@ SPK_API void spk_plan_destroy(spk_plan* p) {
     if (!p) return;
     if (p->device >= 0) {
         cudaSetDevice(p->device);
-        void* ptrs[] = {p->d_pb, p->d_F, p->d_lnz, p->d_unz, p->d_w, p->d_rhs, p->d_tmp, p->d_ipiv, p->d_iflag, p->d_fronts,
+        void* ptrs[] = {p->d_counters, p->d_pb, p->d_F, p->d_lnz, p->d_unz, p->d_w, p->d_rhs, p->d_tmp, p->d_ipiv, p->d_iflag, p->d_fronts,
                         p->d_chunks, p->d_psteps, p->d_subw, p->d_childlist, p->d_rel, p->d_pos, p->d_blkpfx,
                         p->d_gathert, p->d_pslist, p->d_chunkpfx, p->d_dest, p->d_rperm, p->d_rinvp, p->d_nzval,
                         p->d_asmt, p->d_gemmt, p->d_solvet};
@@ -157,6 +157,12 @@ static int64_t plan_upload(spk_plan* p) {
     CK(cudaMalloc((void**)&p->d_unz, std::max<int64_t>(P.nunz, 1) * sizeof(double)));
     CK(cudaMalloc((void**)&p->d_ipiv, P.n * sizeof(int32_t)));
     CK(cudaMalloc((void**)&p->d_iflag, sizeof(int32_t)));
+    {   // arrival counters of the fused backward solve step: one per (rhs, block slot) of the largest launch
+        int64_t mx = 1;
+        for (const auto* Ls : {&P.bwd_launches, &P.bwd_local, &P.bwd_top}) for (const Launch& L : *Ls) mx = std::max<int64_t>(mx, L.nblocks);
+        CK(cudaMalloc((void**)&p->d_counters, mx * 32 * sizeof(int32_t)));
+        CK(cudaMemset(p->d_counters, 0, mx * 32 * sizeof(int32_t)));
+    }
     CK(cudaMemset(p->d_ipiv, 0, P.n * sizeof(int32_t)));
     p->dev_bytes = (size_t)(P.nlnz + P.nunz + P.arena) * 8 + (size_t)P.n * 4 + (P.rel.size() + P.pos.size()) * 4 +
                    P.blkpfx.size() * 4 + P.gemmt.size() * sizeof(GemmTask) + P.solvet.size() * sizeof(SolveTask) +
@@ -189,6 +195,10 @@ static int64_t plan_upload(spk_plan* p) {
             CK(cudaFuncSetAttribute(k_pf_diag<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             CK(cudaFuncSetAttribute(k_pb_diag<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             CK(cudaFuncSetAttribute(k_pb_diag<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            CK(cudaFuncSetAttribute(k_pf_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            CK(cudaFuncSetAttribute(k_pf_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            CK(cudaFuncSetAttribute(k_pb_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            CK(cudaFuncSetAttribute(k_pb_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         }
     }
     CK(gemm_dmma_init());
@@ -512,6 +522,18 @@ static int64_t run_solve_launches(spk_plan* p, const DevCtx& c, const std::vecto
             break;
         }
         case K_PF_UPDATE: k_pf_update<<<grid, SV_ROWS, 0, st>>>(c, list, pfx, L.count); break;
+        case K_PF_STEP: {
+            size_t sm = pstep_smem_bytes(L.maxw);
+            if (lu) k_pf_step<true><<<grid, SV_ROWS, sm, st>>>(c, list, pfx, L.count);
+            else k_pf_step<false><<<grid, SV_ROWS, sm, st>>>(c, list, pfx, L.count);
+            break;
+        }
+        case K_PB_STEP: {
+            size_t sm = pstep_smem_bytes(L.maxw);
+            if (lu) k_pb_step<true><<<grid, SV_ROWS, sm, st>>>(c, list, pfx, L.count, d_rhs, ldrhs, p->P.maxpw, p->d_counters);
+            else k_pb_step<false><<<grid, SV_ROWS, sm, st>>>(c, list, pfx, L.count, d_rhs, ldrhs, p->P.maxpw, p->d_counters);
+            break;
+        }
         case K_PB_UPDATE: {
             size_t sm = (size_t)(SV_ROWS / 32) * L.maxw * sizeof(double);
             if (lu) k_pb_update<true><<<grid, SV_ROWS, sm, st>>>(c, list, pfx, L.count, p->P.maxpw);
@@ -795,6 +817,12 @@ SPK_API int64_t spk_lulsolve_f64(int64_t nsuper, const int64_t* xsuper, const in
         std::vector<int32_t> ip(n);
         for (int64_t i = 0; i < n; ++i) ip[i] = (int32_t)ipiv[i];
         if (cudaMemcpy(p->d_ipiv, ip.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) rc = -100;
+    }
+    if (!rc) {   // the sweeps read the frontal matrices: build them from lnz (U is not needed by the forward sweep)
+        DevCtx c = make_ctx(p);
+        if (cudaMemset(p->d_unz, 0, std::max<int64_t>(p->P.nunz, 1) * sizeof(double)) != cudaSuccess) rc = -100;
+        if (!rc && cudaMemset(p->d_F, 0, p->P.arena * sizeof(double)) != cudaSuccess) rc = -100;
+        if (!rc) { k_chunks<false><<<p->chunk_blocks, 256, 0, p->stream>>>(c, p->d_chunkpfx, (int)p->P.chunks.size()); if (cudaStreamSynchronize(p->stream) != cudaSuccess) rc = -100; }
     }
     if (!rc) rc = spk_plan_solve(p, rhs, 1, n, 1);
     spk_plan_destroy(p);
