@@ -708,54 +708,111 @@ __global__ void __launch_bounds__(256) k_bwd_front(DevCtx c, const int32_t* __re
 //
 // pf_diag: x := inv(L11) P x for the w unknowns of the step (Ts = staged w x w block, xs = staged x).
 // Executed by ONE warp on shared memory (column sweep, __syncwarp between columns): no block barriers.
+// Each lane keeps the unknowns lane, lane+32, lane+64 in registers; x_k is broadcast with one shuffle
+// per column, so a column costs a shuffle + FMA instead of a shared-memory round trip (w <= 96).
 template <bool LU>
 __device__ __forceinline__ void pf_diag_warp(const DevCtx& c, const PStep& ps, const double* Ts, double* xs) {
     const int lane = threadIdx.x & 31, w = ps.w;
+    if (w > 96) {                                           // generic shared-memory sweep
+        if (LU) {
+            const int32_t* ipiv = c.ipiv + ps.col0; const int32_t* subw = c.subw + ps.sub0;
+            int s0 = 0;
+            for (int b = 0; b < ps.nsub; ++b) {
+                const int s1 = s0 + subw[b];
+                if (lane == 0) for (int k = s0; k < s1; ++k) { int ip = s0 + ipiv[k] - 1; if (ip != k) { double t = xs[k]; xs[k] = xs[ip]; xs[ip] = t; } }
+                __syncwarp();
+                for (int k = s0; k < s1; ++k) { const double xk = xs[k]; for (int i = k + 1 + lane; i < w; i += 32) xs[i] -= xk * Ts[i + k * w]; __syncwarp(); }
+                s0 = s1;
+            }
+        } else {
+            for (int k = 0; k < w - 1; ++k) { const double xk = xs[k]; for (int i = k + 1 + lane; i < w; i += 32) xs[i] -= xk * Ts[i + k * w]; __syncwarp(); }
+        }
+        return;
+    }
+    double x0 = lane < w ? xs[lane] : 0.0, x1 = lane + 32 < w ? xs[lane + 32] : 0.0, x2 = lane + 64 < w ? xs[lane + 64] : 0.0;
+    auto sweep = [&](int k) {
+        const int slot = k >> 5, src = k & 31;
+        const double xk = __shfl_sync(0xffffffffu, slot == 0 ? x0 : (slot == 1 ? x1 : x2), src);
+        const double* __restrict__ col = Ts + k * w;
+        if (lane > k && lane < w) x0 -= xk * col[lane];
+        if (lane + 32 > k && lane + 32 < w) x1 -= xk * col[lane + 32];
+        if (lane + 64 > k && lane + 64 < w) x2 -= xk * col[lane + 64];
+    };
     if (LU) {
-        const int32_t* ipiv = c.ipiv + ps.col0;
-        const int32_t* subw = c.subw + ps.sub0;
+        const int32_t* ipiv = c.ipiv + ps.col0; const int32_t* subw = c.subw + ps.sub0;
         int s0 = 0;
         for (int b = 0; b < ps.nsub; ++b) {
             const int s1 = s0 + subw[b];
-            // all columns k < s0 have been swept over these rows already: apply this chunk's interchanges now
-            if (lane == 0)
-                for (int k = s0; k < s1; ++k) { int ip = s0 + ipiv[k] - 1; if (ip != k) { double t = xs[k]; xs[k] = xs[ip]; xs[ip] = t; } }
-            __syncwarp();
-            for (int k = s0; k < s1; ++k) {
-                const double xk = xs[k];
-                for (int i = k + 1 + lane; i < w; i += 32) xs[i] -= xk * Ts[i + k * w];
+            bool any = false;
+            for (int k = s0; k < s1; ++k) any |= (s0 + ipiv[k] - 1 != k);
+            if (any) {                                      // interchanges of this chunk: through shared memory
+                if (lane < w) xs[lane] = x0; if (lane + 32 < w) xs[lane + 32] = x1; if (lane + 64 < w) xs[lane + 64] = x2;
                 __syncwarp();
+                if (lane == 0) for (int k = s0; k < s1; ++k) { int ip = s0 + ipiv[k] - 1; if (ip != k) { double t = xs[k]; xs[k] = xs[ip]; xs[ip] = t; } }
+                __syncwarp();
+                x0 = lane < w ? xs[lane] : 0.0; x1 = lane + 32 < w ? xs[lane + 32] : 0.0; x2 = lane + 64 < w ? xs[lane + 64] : 0.0;
             }
+            for (int k = s0; k < s1; ++k) sweep(k);
             s0 = s1;
         }
     } else {
-        for (int k = 0; k < w - 1; ++k) {
-            const double xk = xs[k];
-            for (int i = k + 1 + lane; i < w; i += 32) xs[i] -= xk * Ts[i + k * w];
-            __syncwarp();
-        }
+        for (int k = 0; k < w - 1; ++k) sweep(k);
     }
+    if (lane < w) xs[lane] = x0; if (lane + 32 < w) xs[lane + 32] = x1; if (lane + 64 < w) xs[lane + 64] = x2;
+    __syncwarp();
 }
 // pb_diag: backward in-block solve.  LU: x := inv(U11) y.  LDL^T: x := inv(L11^T) y (y already divided by D).
 template <bool LU>
 __device__ __forceinline__ void pb_diag_warp(const PStep& ps, const double* Ts, double* xs) {
     const int lane = threadIdx.x & 31, w = ps.w;
-    for (int k = w - 1; k >= 0; --k) {
-        if (LU) { if (lane == 0) xs[k] /= Ts[k + k * w]; __syncwarp(); }
-        const double xk = xs[k];
-        if (LU) { for (int i = lane; i < k; i += 32) xs[i] -= xk * Ts[i + k * w]; }
-        else { for (int i = lane; i < k; i += 32) xs[i] -= xk * Ts[k + i * w]; }
-        __syncwarp();
+    if (w > 96) {
+        for (int k = w - 1; k >= 0; --k) {
+            if (LU) { if (lane == 0) xs[k] /= Ts[k + k * w]; __syncwarp(); }
+            const double xk = xs[k];
+            if (LU) { for (int i = lane; i < k; i += 32) xs[i] -= xk * Ts[i + k * w]; }
+            else { for (int i = lane; i < k; i += 32) xs[i] -= xk * Ts[k + i * w]; }
+            __syncwarp();
+        }
+        return;
     }
+    double x0 = lane < w ? xs[lane] : 0.0, x1 = lane + 32 < w ? xs[lane + 32] : 0.0, x2 = lane + 64 < w ? xs[lane + 64] : 0.0;
+    for (int k = w - 1; k >= 0; --k) {
+        const int slot = k >> 5, src = k & 31;
+        double xk = __shfl_sync(0xffffffffu, slot == 0 ? x0 : (slot == 1 ? x1 : x2), src);
+        if (LU) {
+            xk /= Ts[k + k * w];
+            if (lane == src) { if (slot == 0) x0 = xk; else if (slot == 1) x1 = xk; else x2 = xk; }
+            const double* __restrict__ col = Ts + k * w;                     // U[i,k], i < k
+            if (lane < k) x0 -= xk * col[lane];
+            if (lane + 32 < k) x1 -= xk * col[lane + 32];
+            if (lane + 64 < k) x2 -= xk * col[lane + 64];
+        } else {
+            const double* __restrict__ rowk = Ts + k;                        // L[k,i] = Ts[k + i*w], i < k
+            if (lane < k) x0 -= xk * rowk[lane * w];
+            if (lane + 32 < k) x1 -= xk * rowk[(lane + 32) * w];
+            if (lane + 64 < k) x2 -= xk * rowk[(lane + 64) * w];
+        }
+    }
+    if (lane < w) xs[lane] = x0; if (lane + 32 < w) xs[lane + 32] = x1; if (lane + 64 < w) xs[lane + 64] = x2;
+    __syncwarp();
 }
 
 // rows [r0, r1) of the front below the step: wf[r] -= sum_k L[r, o+k] x[k]
+// (16 independent loads in flight per thread: the panel is streamed once from HBM, so the sweep is
+//  latency-bound unless every thread keeps many requests outstanding)
 __device__ __forceinline__ void pf_update_rows(const DevCtx& c, const PStep& ps, double* wf, const double* xs, int r0, int r1) {
     const double* __restrict__ Fm = c.F + ps.fofs + (int64_t)ps.o * ps.ld;
+    const int w = ps.w;
     for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
         double acc = 0.0;
-#pragma unroll 8
-        for (int k = 0; k < ps.w; ++k) acc += Fm[(size_t)r + (size_t)k * ps.ld] * xs[k];
+        const double* __restrict__ row = Fm + r;
+        for (int k0 = 0; k0 < w; k0 += 16) {
+            double v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = (k0 + u < w) ? __ldcs(row + (size_t)(k0 + u) * ps.ld) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) if (k0 + u < w) acc += v[u] * xs[k0 + u];
+        }
         wf[r] -= acc;
     }
 }
@@ -773,11 +830,17 @@ __device__ __forceinline__ void pb_partial(const DevCtx& c, const PStep& ps, con
         const double xr = r < r1 ? wf[r] : 0.0;
         const double* __restrict__ col = LU ? Fm + (int64_t)ps.o + (int64_t)min(r, r1 - 1) * ps.ld
                                            : Fm + (int64_t)min(r, r1 - 1) + (int64_t)ps.o * ps.ld;
-        for (int k = 0; k < w; ++k) {
-            double v = (LU ? col[k] : col[(size_t)k * ps.ld]) * xr;
+        for (int k0 = 0; k0 < w; k0 += 8) {
+            double v[8];
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-            if (lane == 0) red[warp * w + k] += v;
+            for (int u = 0; u < 8; ++u) v[u] = (k0 + u < w) ? __ldcs(LU ? col + (k0 + u) : col + (size_t)(k0 + u) * ps.ld) * xr : 0.0;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] += __shfl_xor_sync(0xffffffffu, v[u], off);
+            if (lane == 0)
+#pragma unroll
+                for (int u = 0; u < 8; ++u) if (k0 + u < w) red[warp * w + k0 + u] += v[u];
         }
     }
     __syncthreads();
