@@ -225,57 +225,60 @@ __global__ void __launch_bounds__(256) k_diag(DevCtx c, const int32_t* __restric
     }
 }
 
-// LDL^T of a w x w diagonal block held in REGISTERS: 16 x 16 threads, thread (tx,ty) owns the entries
-// (tx + 16a, ty + 16b), a,b < NB (cyclic, so the shrinking active part stays balanced).  Per column k the
-// owners of that column publish l_r = a_r / d (multiplication by the correctly rounded reciprocal) through a
-// double-buffered shared vector; everybody then updates its own entries from registers: one barrier per column.
-template <int NB>
-__global__ void __launch_bounds__(256) k_diag_ldlt_reg(DevCtx c, const int32_t* __restrict__ pslist) {
-    __shared__ double col[2][16 * NB + 1];
+// LDL^T of a w x w diagonal block held in REGISTERS: TG x TG threads, thread (tx,ty) owns the entries
+// (tx + TG a, ty + TG b), a,b < NB (cyclic, so the shrinking active part stays balanced).  Per column k the
+// TG owners of that column (consecutive lanes of one warp) get d_k by a shuffle, publish l_r = a_r / d_k
+// (multiplication by the correctly rounded reciprocal) through a double-buffered shared vector; everybody
+// then updates its own entries from registers: one barrier per column.  TG = 8 (two warps, 64 entries per
+// thread) keeps that barrier cheap: the kernel sits on the critical path of every panel step.
+template <int NB, int TG>
+__global__ void __launch_bounds__(TG * TG) k_diag_ldlt_reg(DevCtx c, const int32_t* __restrict__ pslist) {
+    __shared__ double col[2][TG * NB + 1];
     const PStep ps = c.psteps[pslist[blockIdx.x]];
     double* G = c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld;
     const int w = ps.w, ld = ps.ld;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int tx = threadIdx.x % TG, ty = threadIdx.x / TG;
     double v[NB][NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b)
 #pragma unroll
         for (int a = 0; a < NB; ++a) {
-            const int r = tx + 16 * a, s = ty + 16 * b;
+            const int r = tx + TG * a, s = ty + TG * b;
             v[a][b] = (r < w && s < w && r >= s) ? __ldcg(G + r + (size_t)s * ld) : 0.0;
         }
     for (int k = 0; k < w; ++k) {
         double* cb = col[k & 1];
-        const int kb = k >> 4, kt = k & 15;
-        if (ty == kt) {                                     // the 16 owners of column k: one half-warp
+        const int kb = k / TG, kt = k % TG;
+        if (ty == kt) {                                     // the TG owners of column k: consecutive lanes of one warp
             double dloc = 0.0;
 #pragma unroll
             for (int a = 0; a < NB; ++a) if (a == kb) dloc = v[a][a];          // meaningful in thread tx == kt only
-            const unsigned half = 0xFFFFu << ((ty & 1) * 16);
-            const double d0 = __shfl_sync(half, dloc, (ty & 1) * 16 + kt);
+            const int lane0 = (threadIdx.x & 31) - tx;                         // first lane of this owner group
+            const unsigned grp = (TG == 32 ? 0xffffffffu : ((1u << TG) - 1u) << lane0);
+            const double d0 = __shfl_sync(grp, dloc, lane0 + kt);
             const double rinv = 1.0 / d0;
-            if (tx == kt) { cb[16 * NB] = d0; if (d0 == 0.0) atomicExch(c.iflag, -1); }
+            if (tx == kt) { cb[TG * NB] = d0; if (d0 == 0.0) atomicExch(c.iflag, -1); }
 #pragma unroll
             for (int b = 0; b < NB; ++b) if (b == kb) {
 #pragma unroll
                 for (int a = 0; a < NB; ++a) {
-                    const int r = tx + 16 * a;
+                    const int r = tx + TG * a;
                     if (r > k && r < w) { v[a][b] *= rinv; cb[r] = v[a][b]; }
                 }
             }
         }
         __syncthreads();
-        const double d = cb[16 * NB];
+        const double d = cb[TG * NB];
         double lr[NB], fs[NB];
 #pragma unroll
-        for (int a = 0; a < NB; ++a) { const int r = tx + 16 * a; lr[a] = (r > k && r < w) ? cb[r] : 0.0; }
+        for (int a = 0; a < NB; ++a) { const int r = tx + TG * a; lr[a] = (r > k && r < w) ? cb[r] : 0.0; }
 #pragma unroll
-        for (int b = 0; b < NB; ++b) { const int s = ty + 16 * b; fs[b] = (s > k && s < w) ? cb[s] * d : 0.0; }
+        for (int b = 0; b < NB; ++b) { const int s = ty + TG * b; fs[b] = (s > k && s < w) ? cb[s] * d : 0.0; }
 #pragma unroll
         for (int b = 0; b < NB; ++b)
 #pragma unroll
             for (int a = 0; a < NB; ++a) {
-                const int r = tx + 16 * a, s = ty + 16 * b;
+                const int r = tx + TG * a, s = ty + TG * b;
                 if (r >= s && s > k) v[a][b] -= fs[b] * lr[a];
             }
     }
@@ -283,7 +286,7 @@ __global__ void __launch_bounds__(256) k_diag_ldlt_reg(DevCtx c, const int32_t* 
     for (int b = 0; b < NB; ++b)
 #pragma unroll
         for (int a = 0; a < NB; ++a) {
-            const int r = tx + 16 * a, s = ty + 16 * b;
+            const int r = tx + TG * a, s = ty + TG * b;
             if (r < w && s < w && r >= s) __stcg(G + r + (size_t)s * ld, v[a][b]);
         }
 }

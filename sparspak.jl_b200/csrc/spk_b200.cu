@@ -54,6 +54,7 @@ struct spk_plan {
     bool solve_graphs = true;           // SPK_SOLVE_GRAPH=0 disables CUDA-graph replay of the solve sweeps
     cudaGraphExec_t sg_exec = nullptr; double* sg_rhs = nullptr; double* sg_w = nullptr;
     int64_t sg_nrhs = 0, sg_ld = 0, sg_launches = 0; int32_t sg_which = -1;
+    int diag_tg = 8;                    // SPK_DIAG_TG: thread grid of the register LDL^T kernel (8 or 16)
     bool diag_smem_only = false;        // SPK_DIAG_SMEM=1: always use the shared-memory diagonal kernel
     int dmma_variant = 4;               // SPK_DMMA_VARIANT (see gemm_dmma.cuh)
     bool values_in_fronts = false;      // inmatrix scattered straight into the fronts
@@ -220,6 +221,7 @@ SPK_API spk_plan* spk_plan_create(int64_t n, int64_t nsuper, const int64_t* xsup
     if (const char* e = getenv("SPK_DMMA_VARIANT")) p->dmma_variant = atoi(e);
     if (const char* e = getenv("SPK_DIAG_SMEM")) p->diag_smem_only = e[0] == '1';
     if (const char* e = getenv("SPK_SOLVE_GRAPH")) p->solve_graphs = e[0] != '0';
+    if (const char* e = getenv("SPK_DIAG_TG")) p->diag_tg = atoi(e);
     build_schedule(p->P);
     if (device < 0) return p;                      // host-only plan: structure statistics without a GPU
     int ndev = 0;
@@ -349,8 +351,9 @@ static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L, 
         int wl = std::min(L.maxw, p->diag_smem_nj);
         size_t sm = (size_t)wl * (wl | 1) * sizeof(double);
         if (lu) k_diag<true><<<L.count, 256, sm, st>>>(c, p->d_pslist + L.first, wl);
-        else if (L.maxw <= 64 && !p->diag_smem_only) k_diag_ldlt_reg<4><<<L.count, 256, 0, st>>>(c, p->d_pslist + L.first);
-        else if (L.maxw <= 96 && !p->diag_smem_only) k_diag_ldlt_reg<6><<<L.count, 256, 0, st>>>(c, p->d_pslist + L.first);
+        else if (L.maxw <= 64 && !p->diag_smem_only && p->diag_tg == 8) k_diag_ldlt_reg<8, 8><<<L.count, 64, 0, st>>>(c, p->d_pslist + L.first);
+        else if (L.maxw <= 64 && !p->diag_smem_only) k_diag_ldlt_reg<4, 16><<<L.count, 256, 0, st>>>(c, p->d_pslist + L.first);
+        else if (L.maxw <= 96 && !p->diag_smem_only) k_diag_ldlt_reg<6, 16><<<L.count, 256, 0, st>>>(c, p->d_pslist + L.first);
         else k_diag<false><<<L.count, 256, sm, st>>>(c, p->d_pslist + L.first, wl);
         break;
     }
