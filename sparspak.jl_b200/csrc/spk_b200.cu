@@ -54,7 +54,7 @@ struct spk_plan {
     bool solve_graphs = true;           // SPK_SOLVE_GRAPH=0 disables CUDA-graph replay of the solve sweeps
     cudaGraphExec_t sg_exec = nullptr; double* sg_rhs = nullptr; double* sg_w = nullptr;
     int64_t sg_nrhs = 0, sg_ld = 0, sg_launches = 0; int32_t sg_which = -1;
-    int diag_tg = 8;                    // SPK_DIAG_TG: thread grid of the register LDL^T kernel (8 or 16)
+    int diag_tg = 16;                   // SPK_DIAG_TG: thread grid of the register LDL^T kernel (8 or 16)
     bool diag_smem_only = false;        // SPK_DIAG_SMEM=1: always use the shared-memory diagonal kernel
     int dmma_variant = 4;               // SPK_DMMA_VARIANT (see gemm_dmma.cuh)
     bool values_in_fronts = false;      // inmatrix scattered straight into the fronts

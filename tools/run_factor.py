@@ -16,15 +16,26 @@ ap.add_argument("--grid", type=int, default=96)
 ap.add_argument("--kind", default="spd")
 ap.add_argument("--reps", type=int, default=1)
 ap.add_argument("--solve", type=int, default=0)
+ap.add_argument("--nrhs", type=int, default=1)
 ap.add_argument("--profile", action="store_true")
 a = ap.parse_args()
 g = a.grid
-A = spk.matrices.laplacian3d(g) if a.kind == "spd" else spk.matrices.convdiff3d(g)
-s = (spk.SparseSpdSolver if a.kind == "spd" else spk.SparseSolver)(A)
-spk.findorder(s, spk.nd_grid_order(g, g, g)); spk.symbolicfactor(s)
+import time
+t0 = time.time()
+dof = 1
+if a.kind == "spd":
+    A = spk.matrices.laplacian3d(g)
+elif a.kind == "lu":
+    A = spk.matrices.convdiff3d(g)
+else:                                   # "el": config 5, 27-point stencil x 3 dof (LDL^T)
+    A = spk.matrices.elasticity27(g); dof = 3
+s = (spk.SparseSolver if a.kind == "lu" else spk.SparseSpdSolver)(A)
+spk.findorder(s, spk.nd_grid_order(g, g, g, dof)); spk.symbolicfactor(s)
+print(f"host analysis {time.time() - t0:.1f}s: n={s.slvr.n} nnz(A)={A.nnz} nsuper={s.slvr.nsuper} nnz(lnz)={int(s.slvr.xlnz[-1]) - 1:.3e}", flush=True)
 b = s.slvr
 dest, nzval = b._inmatrix_map(A)
 plan = _cudalib.Plan(b)
+print(f"plan: fronts={plan.stat(2)} levels={plan.stat(3)} arena={plan.stat(6) * 8 / 2**30:.1f} GiB flops={plan.statf(0):.3e}", flush=True)
 plan.set_perm(b.order.rperm, b.order.rinvp)
 plan.inmatrix(nzval, dest)
 if a.profile:
@@ -40,5 +51,12 @@ for r in range(a.reps):
         print(f"   dmma: {plan.statf(4) / max(plan.statf(5), 1e-9) / 1e9:.2f} TFLOP/s")
 bb = spk.matrices.rhs_for(A)
 for r in range(a.solve):
-    x = bb.copy(); plan.triangularsolve(x)
-    print(f"solve {r}: {plan.statf(3):.2f} ms, launches {plan.stat(1)}, residual {np.linalg.norm(A @ x - bb) / np.linalg.norm(bb):.2e}", flush=True)
+    if a.nrhs == 1:
+        x = bb.copy(); plan.triangularsolve(x)
+        res = np.linalg.norm(A @ x - bb) / np.linalg.norm(bb)
+    else:
+        rng = np.random.default_rng(9876)
+        B = np.asfortranarray(rng.random((b.n, a.nrhs)))
+        X = B.copy(order="F"); plan.triangularsolve(X)
+        res = max(np.linalg.norm(A @ X[:, j] - B[:, j]) / np.linalg.norm(B[:, j]) for j in (0, a.nrhs // 2, a.nrhs - 1))
+    print(f"solve {r}: {plan.statf(3):.2f} ms ({a.nrhs} rhs), launches {plan.stat(1)}, residual {res:.2e}", flush=True)
