@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(TG * TG) k_diag_ldlt_reg(DevCtx c, const int32
 //   else : x_j =  a_j - sum_{k<j} x_k T[j,k]               (right solve with unit-lower L11^T / left solve with L11)
 template <bool UPPER>
 __device__ __forceinline__ double ts_coef(const double* __restrict__ Ts, int w, int k, int j) {
-    return UPPER ? Ts[k + j * w] : Ts[j + k * w];
+    return UPPER ? Ts[k + (size_t)j * w] : Ts[j + (size_t)k * w];      // w = leading dimension of the block
 }
 // x_j -= sum_{k in [k0,k1)} coef(k,j) x_k  for j in [j0,j1);  requires k1 <= j0
 template <bool UPPER>
@@ -344,14 +344,18 @@ __device__ __forceinline__ void ts_solve(double* x, const double* __restrict__ T
             if (cidx < nb) {
 #pragma unroll
                 for (int c2 = 0; c2 < 8; ++c2) if (c2 < cidx) acc[cidx] -= ts_coef<UPPER>(Ts, w, jb + c2, jb + cidx) * acc[c2];
-                if (UPPER) acc[cidx] = (1.0 / Ts[(jb + cidx) + (jb + cidx) * w]) * acc[cidx];
+                if (UPPER) acc[cidx] = (1.0 / Ts[(jb + cidx) + (size_t)(jb + cidx) * w]) * acc[cidx];
                 x[(jb + cidx) * PANEL_ROWS] = acc[cidx];
             }
         }
     }
 }
 
-inline size_t panel_smem_bytes(int w) { return ((size_t)w * w + (size_t)w * PANEL_ROWS) * sizeof(double); }
+// T is staged in shared memory next to the panel slice when both fit; wide steps keep T in global memory
+// (every thread reads the same entries, so they are L1 broadcasts).
+constexpr size_t PANEL_SMEM_LIMIT = 200 * 1024;
+inline bool panel_stage_T(int w) { return ((size_t)w * w + (size_t)w * PANEL_ROWS) * sizeof(double) <= PANEL_SMEM_LIMIT; }
+inline size_t panel_smem_bytes(int w) { return ((panel_stage_T(w) ? (size_t)w * w : 0) + (size_t)w * PANEL_ROWS) * sizeof(double); }
 
 template <bool LU>
 __global__ void __launch_bounds__(PANEL_ROWS) k_panel(DevCtx c, const int32_t* __restrict__ pslist,
@@ -366,9 +370,11 @@ __global__ void __launch_bounds__(PANEL_ROWS) k_panel(DevCtx c, const int32_t* _
     const int tid = threadIdx.x;
     double* Fm = c.F + ps.fofs;
     const double* __restrict__ T = Fm + (int64_t)ps.o + (int64_t)ps.o * ld;   // factored w x w block
-    double* Ts = psm;
-    double* Xs = psm + w * w;
-    block_g2s<PANEL_ROWS>(Ts, w, T, ld, w);
+    const bool stage = ((size_t)w * w + (size_t)w * PANEL_ROWS) * sizeof(double) <= PANEL_SMEM_LIMIT;
+    const double* Ts = stage ? psm : T;                 // Ts(i,j) = Ts[i + j * ldt]
+    const int ldt = stage ? w : ld;
+    double* Xs = psm + (stage ? w * w : 0);
+    if (stage) block_g2s<PANEL_ROWS>(psm, w, T, ld, w);
     const bool lside = lb < nb;
     const int i0 = (lside ? lb : lb - nb) * PANEL_ROWS;
     const int cnt = min(PANEL_ROWS, below - i0);
@@ -397,20 +403,20 @@ __global__ void __launch_bounds__(PANEL_ROWS) k_panel(DevCtx c, const int32_t* _
     if (tid < cnt) {
         double* x = Xs + tid;                                                  // x[k * PANEL_ROWS]
         if (lside) {
-            if (LU) ts_solve<true>(x, Ts, w, 0, w);                            // X = A21 * inv(U11)
-            else ts_solve<false>(x, Ts, w, 0, w);                              // X = A21 * inv(L11^T), kept UNSCALED here
+            if (LU) ts_solve<true>(x, Ts, ldt, 0, w);                          // X = A21 * inv(U11)
+            else ts_solve<false>(x, Ts, ldt, 0, w);                            // X = A21 * inv(L11^T), kept UNSCALED here
         } else if (LU) {
             const int32_t* ipiv = c.ipiv + ps.col0;
             const int32_t* subw = c.subw + ps.sub0;
             int s0 = 0;
             for (int b = 0; b < ps.nsub; ++b) {
                 const int s1 = s0 + subw[b];
-                ts_accum<false>(x, Ts, w, s0, s1, 0, s0);                      // contributions of earlier chunks (unswapped rows)
+                ts_accum<false>(x, Ts, ldt, s0, s1, 0, s0);                      // contributions of earlier chunks (unswapped rows)
                 for (int k = s0; k < s1; ++k) {                                // this chunk's interchanges
                     int ip = s0 + ipiv[k] - 1;
                     if (ip != k) { double tmp = x[k * PANEL_ROWS]; x[k * PANEL_ROWS] = x[ip * PANEL_ROWS]; x[ip * PANEL_ROWS] = tmp; }
                 }
-                ts_solve<false>(x, Ts, w, s0, s1);                             // unit-lower solve inside the chunk
+                ts_solve<false>(x, Ts, ldt, s0, s1);                             // unit-lower solve inside the chunk
                 s0 = s1;
             }
         }
@@ -423,7 +429,7 @@ __global__ void __launch_bounds__(PANEL_ROWS) k_panel(DevCtx c, const int32_t* _
         } else {
             // L21 = X / D (SpkLDLtFactor.jl:372-377); U12 = X^T = D * L21^T goes to the upper triangle of the
             // front, where the trailing-update kernel reads its B operand
-            for (int k = 0; k < w; ++k) if (tid < cnt) X0[tid + (size_t)k * ld] = Xs[k * PANEL_ROWS + tid] / Ts[k + k * w];
+            for (int k = 0; k < w; ++k) if (tid < cnt) X0[tid + (size_t)k * ld] = Xs[k * PANEL_ROWS + tid] / Ts[k + (size_t)k * ldt];
             double* Y0 = Fm + (int64_t)ps.o + (int64_t)(e0 + i0) * ld;
             for (int e = tid; e < w * cnt; e += PANEL_ROWS) { int col = e / w, k = e - col * w; Y0[k + (size_t)col * ld] = Xs[k * PANEL_ROWS + col]; }
         }

@@ -354,6 +354,7 @@ static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L, 
         else if (L.maxw <= 64 && !p->diag_smem_only && p->diag_tg == 8) k_diag_ldlt_reg<8, 8><<<L.count, 64, 0, st>>>(c, p->d_pslist + L.first);
         else if (L.maxw <= 64 && !p->diag_smem_only) k_diag_ldlt_reg<4, 16><<<L.count, 256, 0, st>>>(c, p->d_pslist + L.first);
         else if (L.maxw <= 96 && !p->diag_smem_only) k_diag_ldlt_reg<6, 16><<<L.count, 256, 0, st>>>(c, p->d_pslist + L.first);
+        else if (L.maxw <= 128 && !p->diag_smem_only) k_diag_ldlt_reg<8, 16><<<L.count, 256, 0, st>>>(c, p->d_pslist + L.first);
         else k_diag<false><<<L.count, 256, sm, st>>>(c, p->d_pslist + L.first, wl);
         break;
     }
