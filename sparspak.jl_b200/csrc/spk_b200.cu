@@ -179,7 +179,8 @@ static int64_t plan_upload(spk_plan* p) {
         CK(cudaFuncSetAttribute(k_diag<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
         CK(cudaFuncSetAttribute(k_diag<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
     }
-    p->panel_smem = panel_smem_bytes(P.maxpw);
+    p->panel_smem = 0;
+    for (int w = 1; w <= P.maxpw; ++w) p->panel_smem = std::max(p->panel_smem, panel_smem_bytes(w));   // not monotone in w (staging of T)
     if (p->panel_smem > 220 * 1024) { set_err("panel step too wide for shared memory (reduce maxblocksize)"); return -100; }
     if (p->panel_smem > 48 * 1024) {
         CK(cudaFuncSetAttribute(k_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->panel_smem));
@@ -359,7 +360,8 @@ static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L, 
         break;
     }
     case K_PANEL: {
-        size_t sm = panel_smem_bytes(L.maxw);
+        size_t sm = 0;                                   // tasks narrower than maxw may stage T: size for the worst case
+        for (int w = 1; w <= L.maxw; ++w) sm = std::max(sm, panel_smem_bytes(w));
         if (lu) k_panel<true><<<L.nblocks, PANEL_ROWS, sm, st>>>(c, p->d_pslist + L.first, pfx, L.count);
         else k_panel<false><<<L.nblocks, PANEL_ROWS, sm, st>>>(c, p->d_pslist + L.first, pfx, L.count);
         break;
