@@ -141,6 +141,18 @@ def measure_dgemm_peak(torch, n=8192, reps=5):
 
 
 def main():
+    # Libraries (NCCL prints its version banner) must not pollute stdout: the contract is ONE JSON line there.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    json_out = os.fdopen(json_fd, "w")
+    try:
+        _main(json_out)
+    finally:
+        json_out.flush()
+
+
+def _main(json_out):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -174,7 +186,7 @@ def main():
                "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": sample},
                "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                "gpu_launches": 0}
-        print(json.dumps(out))
+        print(json.dumps(out), file=json_out)
         return
 
     # ---------------------------------------------------------------- our arm
@@ -301,7 +313,7 @@ def main():
     value = n_rep * F / (factor_ms * 1e-3) / 1e9
     out = {
         "metric": metric, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
-        "ms_per_step": factor_ms + solve_ms, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+        "ms_per_step": wall * 1e3 / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload, "grid": args.grid, "n": int(b.n), "nnz_lnz": int(b.xlnz[-1]) - 1,
                    "structural_flops": F, "ordering": "geometric nested dissection (harness callback)",
@@ -328,7 +340,7 @@ def main():
         out["cpu_baseline"] = {"value": r["flops"] / r["factor_s"] / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": "port",
                                "sample": f"3D 7-point Laplacian {args.cpu_grid}^3 LDL^T factor, oracle restatement + OpenBLAS "
                                          f"({r['factor_s']:.2f} s factor, {r['solve_s']:.3f} s solve)"}
-    print(json.dumps(out))
+    print(json.dumps(out), file=json_out)
     if world > 1:
         dist.destroy_process_group()
 

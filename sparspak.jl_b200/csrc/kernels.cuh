@@ -359,7 +359,7 @@ inline size_t panel_smem_bytes(int w) { return ((panel_stage_T(w) ? (size_t)w * 
 
 template <bool LU>
 __global__ void __launch_bounds__(PANEL_ROWS) k_panel(DevCtx c, const int32_t* __restrict__ pslist,
-                                                      const int32_t* __restrict__ pfx, int count) {
+                                                      const int32_t* __restrict__ pfx, int count, int skip_lside) {
     extern __shared__ double psm[];
     int t = find_task(pfx, count, blockIdx.x);
     int lb = blockIdx.x - pfx[t];
@@ -376,6 +376,7 @@ __global__ void __launch_bounds__(PANEL_ROWS) k_panel(DevCtx c, const int32_t* _
     double* Xs = psm + (stage ? w * w : 0);
     if (stage) block_g2s<PANEL_ROWS>(psm, w, T, ld, w);
     const bool lside = lb < nb;
+    if (lside && skip_lside) return;                    // done by k_panel_reg
     const int i0 = (lside ? lb : lb - nb) * PANEL_ROWS;
     const int cnt = min(PANEL_ROWS, below - i0);
     if (lside) {
@@ -436,6 +437,69 @@ __global__ void __launch_bounds__(PANEL_ROWS) k_panel(DevCtx c, const int32_t* _
     } else if (LU) {
         double* Y0 = Fm + (int64_t)ps.o + (int64_t)(e0 + i0) * ld;
         for (int e = tid; e < w * cnt; e += PANEL_ROWS) { int col = e / w, k = e - col * w; Y0[k + (size_t)col * ld] = Xs[k * PANEL_ROWS + col]; }
+    }
+}
+
+// L-side panel of a panel step with w <= 64, one thread per row, the ROW IN REGISTERS (fully unrolled,
+// zero-padded to 64 columns) and the factored block T zero-padded in shared memory.  All 64 loads of a
+// row are in flight at once and the substitution runs as 8-wide independent FMA chains, which takes the
+// kernel off the latency floor of the shared-memory version (it sits on the critical path of every step).
+//   LU  : X = A21 * inv(U11);   LDLT: X = A21 * inv(L11^T), L21 = X / D written below, U12 = X^T above.
+template <bool LU>
+__global__ void __launch_bounds__(PANEL_ROWS) k_panel_reg(DevCtx c, const int32_t* __restrict__ pslist,
+                                                          const int32_t* __restrict__ pfx, int count) {
+    constexpr int WP = 64;
+    __shared__ double Ts[WP * WP];                      // Ts(i,j) = Ts[i + j*WP], zero outside the w x w block
+    int t = find_task(pfx, count, blockIdx.x);
+    int lb = blockIdx.x - pfx[t];
+    const PStep ps = c.psteps[pslist[t]];
+    const int w = ps.w, ld = ps.ld, e0 = ps.o + ps.w;
+    const int below = ps.R - e0;
+    const int nb = (below + PANEL_ROWS - 1) / PANEL_ROWS;
+    if (lb >= nb) return;                               // U-side blocks (LU) belong to k_panel
+    const int tid = threadIdx.x;
+    double* Fm = c.F + ps.fofs;
+    const double* __restrict__ T = Fm + (int64_t)ps.o + (int64_t)ps.o * ld;
+    for (int e0i = tid; e0i < WP * WP; e0i += 8 * PANEL_ROWS) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { int e = e0i + u * PANEL_ROWS; int j = e / WP, i = e - j * WP; v[u] = (e < WP * WP && i < w && j < w) ? __ldcg(T + i + (size_t)j * ld) : 0.0; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { int e = e0i + u * PANEL_ROWS; if (e < WP * WP) Ts[e] = v[u]; }
+    }
+    const int i = lb * PANEL_ROWS + tid;
+    const bool active = i < below;
+    double* X0 = Fm + (int64_t)(e0 + (active ? i : 0)) + (int64_t)ps.o * ld;
+    double x[WP];
+#pragma unroll
+    for (int k = 0; k < WP; ++k) x[k] = (active && k < w) ? __ldcs(X0 + (size_t)k * ld) : 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int jb = 0; jb < WP; jb += 8) {
+        double acc[8];
+#pragma unroll
+        for (int cidx = 0; cidx < 8; ++cidx) acc[cidx] = x[jb + cidx];
+#pragma unroll
+        for (int k = 0; k < jb; ++k) {
+#pragma unroll
+            for (int cidx = 0; cidx < 8; ++cidx) acc[cidx] -= (LU ? Ts[k + (jb + cidx) * WP] : Ts[(jb + cidx) + k * WP]) * x[k];
+        }
+#pragma unroll
+        for (int cidx = 0; cidx < 8; ++cidx) {
+#pragma unroll
+            for (int c2 = 0; c2 < cidx; ++c2) acc[cidx] -= (LU ? Ts[(jb + c2) + (jb + cidx) * WP] : Ts[(jb + cidx) + (jb + c2) * WP]) * acc[c2];
+            if (LU) { const double dj = Ts[(jb + cidx) + (jb + cidx) * WP]; acc[cidx] = dj != 0.0 ? (1.0 / dj) * acc[cidx] : 0.0; }
+            x[jb + cidx] = acc[cidx];
+        }
+    }
+    if (!active) return;
+    if (LU) {
+#pragma unroll
+        for (int k = 0; k < WP; ++k) if (k < w) X0[(size_t)k * ld] = x[k];
+    } else {
+        double* Y0 = Fm + (int64_t)ps.o + (int64_t)(e0 + i) * ld;             // U12 column of this row: w contiguous entries
+#pragma unroll
+        for (int k = 0; k < WP; ++k) if (k < w) { X0[(size_t)k * ld] = x[k] / Ts[k + k * WP]; Y0[k] = x[k]; }
     }
 }
 

@@ -55,6 +55,7 @@ struct spk_plan {
     cudaGraphExec_t sg_exec = nullptr; double* sg_rhs = nullptr; double* sg_w = nullptr;
     int64_t sg_nrhs = 0, sg_ld = 0, sg_launches = 0; int32_t sg_which = -1;
     int diag_tg = 16;                   // SPK_DIAG_TG: thread grid of the register LDL^T kernel (8 or 16)
+    bool panel_smem_only = false;       // SPK_PANEL_SMEM=1: always use the shared-memory panel kernel
     bool diag_smem_only = false;        // SPK_DIAG_SMEM=1: always use the shared-memory diagonal kernel
     int dmma_variant = 4;               // SPK_DMMA_VARIANT (see gemm_dmma.cuh)
     bool values_in_fronts = false;      // inmatrix scattered straight into the fronts
@@ -223,6 +224,7 @@ SPK_API spk_plan* spk_plan_create(int64_t n, int64_t nsuper, const int64_t* xsup
     if (const char* e = getenv("SPK_DIAG_SMEM")) p->diag_smem_only = e[0] == '1';
     if (const char* e = getenv("SPK_SOLVE_GRAPH")) p->solve_graphs = e[0] != '0';
     if (const char* e = getenv("SPK_DIAG_TG")) p->diag_tg = atoi(e);
+    if (const char* e = getenv("SPK_PANEL_SMEM")) p->panel_smem_only = e[0] == '1';
     build_schedule(p->P);
     if (device < 0) return p;                      // host-only plan: structure statistics without a GPU
     int ndev = 0;
@@ -362,8 +364,13 @@ static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L, 
     case K_PANEL: {
         size_t sm = 0;                                   // tasks narrower than maxw may stage T: size for the worst case
         for (int w = 1; w <= L.maxw; ++w) sm = std::max(sm, panel_smem_bytes(w));
-        if (lu) k_panel<true><<<L.nblocks, PANEL_ROWS, sm, st>>>(c, p->d_pslist + L.first, pfx, L.count);
-        else k_panel<false><<<L.nblocks, PANEL_ROWS, sm, st>>>(c, p->d_pslist + L.first, pfx, L.count);
+        const bool fast = L.maxw <= 64 && !p->panel_smem_only;
+        if (fast) {
+            if (lu) k_panel_reg<true><<<L.nblocks, PANEL_ROWS, 0, st>>>(c, p->d_pslist + L.first, pfx, L.count);
+            else k_panel_reg<false><<<L.nblocks, PANEL_ROWS, 0, st>>>(c, p->d_pslist + L.first, pfx, L.count);
+        }
+        if (lu) k_panel<true><<<L.nblocks, PANEL_ROWS, sm, st>>>(c, p->d_pslist + L.first, pfx, L.count, fast ? 1 : 0);
+        else if (!fast) k_panel<false><<<L.nblocks, PANEL_ROWS, sm, st>>>(c, p->d_pslist + L.first, pfx, L.count, 0);
         break;
     }
     case K_GEMM:
