@@ -291,6 +291,82 @@ __global__ void __launch_bounds__(TG * TG) k_diag_ldlt_reg(DevCtx c, const int32
         }
 }
 
+// 1/d without the IEEE slow path: hardware seed (>= 20 bits) + two Newton steps (relative error ~1e-16 for normal d).
+// The division sits on the dependent chain of every column of a diagonal block.
+__device__ __forceinline__ double fast_rcp(double d) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    double e = fma(-d, x, 1.0); x = fma(x, e, x);
+    e = fma(-d, x, 1.0); x = fma(x, e, x);
+    return x;
+}
+
+// LDL^T of a w x w diagonal block (w <= 64) held in registers, one row per DIAG_NS threads (thread NS*r+h owns
+// the column pairs P = h (mod NS) of row r).  Per column k the owners publish their still unscaled entries
+// a(r,k) (= d_k for r = k, = d_k l_rk below) through a double-buffered shared vector; after ONE barrier every
+// thread forms l_rk = a(r,k) / d_k from the published values and updates a(r,j) -= l_rk * (d_k l_jk) for its
+// own columns — the entry of column k+1 first, which is published at once; the global stores and the
+// zero-pivot flag stay off that dependent chain.  The code is a runtime loop over blocks of 8 columns (the
+// register row is shifted down after each block, so every register index is static): a fully unrolled
+// version is instruction-fetch bound (ncu: stall_no_instruction 8 cycles/issue), one thread per row is issue
+// bound, four threads per row pay for the wider barrier (tools/ubench_steps.cu: 17.9k / 25.4k / 27.6k clocks
+// for NS = 2 / 4 / 1 at w = 57) — the kernel runs once, on one SM, on the critical path of every panel step.
+// Entries right of the diagonal are computed without predicates and never stored (don't-care upper triangle).
+constexpr int DIAG_NS = 2;
+__global__ void __launch_bounds__(64 * DIAG_NS) k_diag_ldlt_row(DevCtx c, const int32_t* __restrict__ pslist) {
+    constexpr int WP = 64, NS = DIAG_NS, NE = WP / NS, PB = 8 / NS;   // entries per thread, entries per 8-column block
+    __shared__ __align__(16) double col[2][2 * WP];
+    const PStep ps = c.psteps[pslist[blockIdx.x]];
+    double* G = c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld;
+    const int w = ps.w, ld = ps.ld;
+    // slices by WARP: the coefficient loads below are then warp-uniform 128-bit broadcasts (2 clocks each; the
+    // same loads with 2-4 distinct addresses per warp cost 4 and made shared memory the bottleneck)
+    const int r = threadIdx.x & (WP - 1), h = threadIdx.x / WP;
+    double a[NE];
+#pragma unroll
+    for (int li = 0; li < NE; ++li) {
+        const int j = ((li >> 1) * NS + h) * 2 + (li & 1);
+        a[li] = (j <= r && r < w) ? __ldcg(G + r + (size_t)j * ld) : 0.0;
+    }
+    for (int i = threadIdx.x; i < 2 * WP; i += 64 * NS) col[i >> 6][WP + (i & 63)] = 0.0;
+    if (h == 0) col[0][r] = a[0];                       // column 0
+    bool bad = false;
+    double* gk = G + r;                                 // &G(r, k)
+#pragma unroll 1
+    for (int kb = 0; kb < w; kb += 8) {
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {
+            const int k = kb + cc;
+            if (k < w) {                                // uniform
+                const double* cb = col[k & 1];
+                double* cn = col[(k + 1) & 1];
+                __syncthreads();
+                const double d = cb[k];
+                const double ar = cb[r];
+                const double* cj = cb + kb + h * 2;
+                double u[NE];
+#pragma unroll
+                for (int li = 0; li < NE; ++li) u[li] = (kb + ((li >> 1) * NS + h) * 2 < w) ? cj[(li >> 1) * 2 * NS + (li & 1)] : 0.0;   // uniform: dead pairs cost no bandwidth
+                const double l = ar * fast_rcp(d);
+                const int cn1 = cc + 1;                 // column k+1: inside this block, or the first one of the next
+                const int ho = (cn1 >> 1) % NS, lcn = ((cn1 >> 1) / NS) * 2 + (cn1 & 1);
+                a[lcn] -= l * u[lcn];
+                if (h == ho && r > k) cn[r] = a[lcn];
+#pragma unroll
+                for (int li = 0; li < NE; ++li) if (li != lcn) a[li] -= l * u[li];
+                bad |= d == 0.0;
+                if (h == ((cc >> 1) % NS) && r >= k && r < w) __stcg(gk, r == k ? d : l);
+                gk += ld;
+            }
+        }
+#pragma unroll
+        for (int li = 0; li < NE - PB; ++li) a[li] = a[li + PB];
+#pragma unroll
+        for (int li = NE - PB; li < NE; ++li) a[li] = 0.0;
+    }
+    if (bad && threadIdx.x == 0) atomicExch(c.iflag, -1);
+}
+
 // ------------------------------------------------------------------------------------
 // Panels of a panel step.  One block = PANEL_ROWS front rows below the block (L side) or PANEL_ROWS
 // front columns to its right (U side); the factored w x w block T and the block's slice of the
@@ -440,16 +516,24 @@ __global__ void __launch_bounds__(PANEL_ROWS) k_panel(DevCtx c, const int32_t* _
     }
 }
 
-// L-side panel of a panel step with w <= 64, one thread per row, the ROW IN REGISTERS (fully unrolled,
-// zero-padded to 64 columns) and the factored block T zero-padded in shared memory.  All 64 loads of a
-// row are in flight at once and the substitution runs as 8-wide independent FMA chains, which takes the
-// kernel off the latency floor of the shared-memory version (it sits on the critical path of every step).
+// L-side panel of a panel step with w <= 64, one thread per row, the ROW IN REGISTERS and the factored
+// block T (transposed for LU, so that the coefficients of one elimination step are contiguous) zero-padded
+// in shared memory together with the reciprocals of its diagonal.  All loads of a row are in flight at once;
+// the substitution is right-looking (x_j -= t_jk x_k for all j > k: independent FMAs, no communication between
+// threads, coefficients fetched as warp-uniform 128-bit broadcasts), written as a runtime loop over blocks of
+// 8 columns with the register row shifted down by 8 after each block (a fully unrolled body is
+// instruction-fetch bound); coefficient pairs beyond the block's width are skipped.
+// Measured alternatives (tools/ubench_steps.cu): rows split over 4 lanes + shuffles cost 4 clocks per
+// coefficient load (4 distinct addresses) and twice the instructions; 4 rows x 16 columns per thread leaves
+// one warp per scheduler, issue bound.
 //   LU  : X = A21 * inv(U11);   LDLT: X = A21 * inv(L11^T), L21 = X / D written below, U12 = X^T above.
+constexpr int PANEL_REG_THREADS = PANEL_ROWS;
 template <bool LU>
-__global__ void __launch_bounds__(PANEL_ROWS) k_panel_reg(DevCtx c, const int32_t* __restrict__ pslist,
-                                                          const int32_t* __restrict__ pfx, int count) {
+__global__ void __launch_bounds__(PANEL_REG_THREADS) k_panel_reg(DevCtx c, const int32_t* __restrict__ pslist,
+                                                                 const int32_t* __restrict__ pfx, int count) {
     constexpr int WP = 64;
-    __shared__ double Ts[WP * WP];                      // Ts(i,j) = Ts[i + j*WP], zero outside the w x w block
+    __shared__ __align__(16) double Ts[WP * WP + WP];   // Ts[j + k*WP] = coefficient of x_k in unknown j (j > k)
+    __shared__ double rd[WP];                           // 1 / diagonal (0 where the diagonal is 0, as the LU reference does)
     int t = find_task(pfx, count, blockIdx.x);
     int lb = blockIdx.x - pfx[t];
     const PStep ps = c.psteps[pslist[t]];
@@ -460,46 +544,62 @@ __global__ void __launch_bounds__(PANEL_ROWS) k_panel_reg(DevCtx c, const int32_
     const int tid = threadIdx.x;
     double* Fm = c.F + ps.fofs;
     const double* __restrict__ T = Fm + (int64_t)ps.o + (int64_t)ps.o * ld;
-    for (int e0i = tid; e0i < WP * WP; e0i += 8 * PANEL_ROWS) {
-        double v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { int e = e0i + u * PANEL_ROWS; int j = e / WP, i = e - j * WP; v[u] = (e < WP * WP && i < w && j < w) ? __ldcg(T + i + (size_t)j * ld) : 0.0; }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { int e = e0i + u * PANEL_ROWS; if (e < WP * WP) Ts[e] = v[u]; }
-    }
     const int i = lb * PANEL_ROWS + tid;
     const bool active = i < below;
-    double* X0 = Fm + (int64_t)(e0 + (active ? i : 0)) + (int64_t)ps.o * ld;
+    double* xp = Fm + (int64_t)(e0 + (active ? i : 0)) + (int64_t)ps.o * ld;          // &X(i, k)
+    double* yp = Fm + (int64_t)ps.o + (int64_t)(e0 + (active ? i : 0)) * ld;          // LDLT: &U12(k, i)
     double x[WP];
 #pragma unroll
-    for (int k = 0; k < WP; ++k) x[k] = (active && k < w) ? __ldcs(X0 + (size_t)k * ld) : 0.0;
-    __syncthreads();
+    for (int k = 0; k < WP; ++k) x[k] = (active && k < w) ? __ldcs(xp + (size_t)k * ld) : 0.0;
+    for (int e0i = tid; e0i < WP * WP; e0i += 8 * PANEL_REG_THREADS) {
+        double v[8];
 #pragma unroll
-    for (int jb = 0; jb < WP; jb += 8) {
-        double acc[8];
-#pragma unroll
-        for (int cidx = 0; cidx < 8; ++cidx) acc[cidx] = x[jb + cidx];
-#pragma unroll
-        for (int k = 0; k < jb; ++k) {
-#pragma unroll
-            for (int cidx = 0; cidx < 8; ++cidx) acc[cidx] -= (LU ? Ts[k + (jb + cidx) * WP] : Ts[(jb + cidx) + k * WP]) * x[k];
+        for (int u = 0; u < 8; ++u) {
+            const int e = e0i + u * PANEL_REG_THREADS; const int k = e / WP, j = e - k * WP;       // smem slot (j,k)
+            const bool in = j < w && k < w && j > k;
+            v[u] = in ? __ldcg(LU ? T + k + (size_t)j * ld : T + j + (size_t)k * ld) : 0.0;
         }
 #pragma unroll
-        for (int cidx = 0; cidx < 8; ++cidx) {
-#pragma unroll
-            for (int c2 = 0; c2 < cidx; ++c2) acc[cidx] -= (LU ? Ts[(jb + c2) + (jb + cidx) * WP] : Ts[(jb + cidx) + (jb + c2) * WP]) * acc[c2];
-            if (LU) { const double dj = Ts[(jb + cidx) + (jb + cidx) * WP]; acc[cidx] = dj != 0.0 ? (1.0 / dj) * acc[cidx] : 0.0; }
-            x[jb + cidx] = acc[cidx];
-        }
+        for (int u = 0; u < 8; ++u) Ts[e0i + u * PANEL_REG_THREADS] = v[u];
     }
-    if (!active) return;
-    if (LU) {
+    static_assert((WP * WP) % (8 * PANEL_REG_THREADS) == 0, "whole batches");
+    if (tid < WP) {
+        Ts[WP * WP + tid] = 0.0;
+        const double dg = tid < w ? __ldcg(T + tid + (size_t)tid * ld) : 0.0; rd[tid] = dg != 0.0 ? 1.0 / dg : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int kb = 0; kb < w; kb += 8) {
+        const int live = w - kb;                        // unknowns kb .. w-1 are still open: local indices < live
 #pragma unroll
-        for (int k = 0; k < WP; ++k) if (k < w) X0[(size_t)k * ld] = x[k];
-    } else {
-        double* Y0 = Fm + (int64_t)ps.o + (int64_t)(e0 + i) * ld;             // U12 column of this row: w contiguous entries
+        for (int cc = 0; cc < 8; ++cc) {
+            const int k = kb + cc;
+            const double* tk = Ts + kb + k * WP;        // tk[jj] = coefficient for unknown kb + jj
+            double xk = x[cc];
+            if (LU) xk *= rd[k & (WP - 1)];
+            if (active && k < w) {
+                if (LU) *xp = xk;
+                else { *xp = xk * rd[k]; *yp = xk; }
+            }
+            xp += ld; ++yp;
 #pragma unroll
-        for (int k = 0; k < WP; ++k) if (k < w) { X0[(size_t)k * ld] = x[k] / Ts[k + k * WP]; Y0[k] = x[k]; }
+            for (int q0 = 0; q0 < WP; q0 += 16) {
+                if (q0 < live) {                        // uniform: dead quarters cost no shared-memory bandwidth
+#pragma unroll
+                    for (int jj = q0; jj < q0 + 16; jj += 2) {
+                        if (jj + 1 > cc) {              // static
+                            const double2 tt = *reinterpret_cast<const double2*>(tk + jj);
+                            if (jj > cc) x[jj] -= tt.x * xk;
+                            x[jj + 1] -= tt.y * xk;
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < WP - 8; ++j) x[j] = x[j + 8];
+#pragma unroll
+        for (int j = WP - 8; j < WP; ++j) x[j] = 0.0;
     }
 }
 

@@ -54,7 +54,7 @@ struct spk_plan {
     bool solve_graphs = true;           // SPK_SOLVE_GRAPH=0 disables CUDA-graph replay of the solve sweeps
     cudaGraphExec_t sg_exec = nullptr; double* sg_rhs = nullptr; double* sg_w = nullptr;
     int64_t sg_nrhs = 0, sg_ld = 0, sg_launches = 0; int32_t sg_which = -1;
-    int diag_tg = 16;                   // SPK_DIAG_TG: thread grid of the register LDL^T kernel (8 or 16)
+    int diag_tg = 1;                    // SPK_DIAG_TG: 1 = row kernel (4 threads per row), 8 / 16 = thread grid of the cyclic register kernel
     bool panel_smem_only = false;       // SPK_PANEL_SMEM=1: always use the shared-memory panel kernel
     bool diag_smem_only = false;        // SPK_DIAG_SMEM=1: always use the shared-memory diagonal kernel
     int dmma_variant = 4;               // SPK_DMMA_VARIANT (see gemm_dmma.cuh)
@@ -354,6 +354,7 @@ static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L, 
         int wl = std::min(L.maxw, p->diag_smem_nj);
         size_t sm = (size_t)wl * (wl | 1) * sizeof(double);
         if (lu) k_diag<true><<<L.count, 256, sm, st>>>(c, p->d_pslist + L.first, wl);
+        else if (L.maxw <= 64 && !p->diag_smem_only && p->diag_tg == 1) k_diag_ldlt_row<<<L.count, 64 * DIAG_NS, 0, st>>>(c, p->d_pslist + L.first);
         else if (L.maxw <= 64 && !p->diag_smem_only && p->diag_tg == 8) k_diag_ldlt_reg<8, 8><<<L.count, 64, 0, st>>>(c, p->d_pslist + L.first);
         else if (L.maxw <= 64 && !p->diag_smem_only) k_diag_ldlt_reg<4, 16><<<L.count, 256, 0, st>>>(c, p->d_pslist + L.first);
         else if (L.maxw <= 96 && !p->diag_smem_only) k_diag_ldlt_reg<6, 16><<<L.count, 256, 0, st>>>(c, p->d_pslist + L.first);
@@ -366,8 +367,8 @@ static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L, 
         for (int w = 1; w <= L.maxw; ++w) sm = std::max(sm, panel_smem_bytes(w));
         const bool fast = L.maxw <= 64 && !p->panel_smem_only;
         if (fast) {
-            if (lu) k_panel_reg<true><<<L.nblocks, PANEL_ROWS, 0, st>>>(c, p->d_pslist + L.first, pfx, L.count);
-            else k_panel_reg<false><<<L.nblocks, PANEL_ROWS, 0, st>>>(c, p->d_pslist + L.first, pfx, L.count);
+            if (lu) k_panel_reg<true><<<L.nblocks, PANEL_REG_THREADS, 0, st>>>(c, p->d_pslist + L.first, pfx, L.count);
+            else k_panel_reg<false><<<L.nblocks, PANEL_REG_THREADS, 0, st>>>(c, p->d_pslist + L.first, pfx, L.count);
         }
         if (lu) k_panel<true><<<L.nblocks, PANEL_ROWS, sm, st>>>(c, p->d_pslist + L.first, pfx, L.count, fast ? 1 : 0);
         else if (!fast) k_panel<false><<<L.nblocks, PANEL_ROWS, sm, st>>>(c, p->d_pslist + L.first, pfx, L.count, 0);
