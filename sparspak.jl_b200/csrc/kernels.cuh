@@ -527,15 +527,17 @@ __global__ void __launch_bounds__(PANEL_ROWS) k_panel(DevCtx c, const int32_t* _
 // coefficient load (4 distinct addresses) and twice the instructions; 4 rows x 16 columns per thread leaves
 // one warp per scheduler, issue bound.
 //   LU  : X = A21 * inv(U11);   LDLT: X = A21 * inv(L11^T), L21 = X / D written below, U12 = X^T above.
-constexpr int PANEL_REG_THREADS = PANEL_ROWS;
+constexpr int PANEL_REG_SPLIT = 1;                                    // launch blocks per PANEL_ROWS rows (more SMs on the few blocks of a top front)
+constexpr int PANEL_REG_THREADS = PANEL_ROWS / PANEL_REG_SPLIT;
 template <bool LU>
 __global__ void __launch_bounds__(PANEL_REG_THREADS) k_panel_reg(DevCtx c, const int32_t* __restrict__ pslist,
                                                                  const int32_t* __restrict__ pfx, int count) {
     constexpr int WP = 64;
     __shared__ __align__(16) double Ts[WP * WP + WP];   // Ts[j + k*WP] = coefficient of x_k in unknown j (j > k)
     __shared__ double rd[WP];                           // 1 / diagonal (0 where the diagonal is 0, as the LU reference does)
-    int t = find_task(pfx, count, blockIdx.x);
-    int lb = blockIdx.x - pfx[t];
+    const int bx = blockIdx.x / PANEL_REG_SPLIT, part = blockIdx.x % PANEL_REG_SPLIT;
+    int t = find_task(pfx, count, bx);
+    int lb = bx - pfx[t];
     const PStep ps = c.psteps[pslist[t]];
     const int w = ps.w, ld = ps.ld, e0 = ps.o + ps.w;
     const int below = ps.R - e0;
@@ -544,25 +546,27 @@ __global__ void __launch_bounds__(PANEL_REG_THREADS) k_panel_reg(DevCtx c, const
     const int tid = threadIdx.x;
     double* Fm = c.F + ps.fofs;
     const double* __restrict__ T = Fm + (int64_t)ps.o + (int64_t)ps.o * ld;
-    const int i = lb * PANEL_ROWS + tid;
+    const int i = lb * PANEL_ROWS + part * PANEL_REG_THREADS + tid;
+    if (i - tid >= below) return;                       // whole block beyond the panel
     const bool active = i < below;
     double* xp = Fm + (int64_t)(e0 + (active ? i : 0)) + (int64_t)ps.o * ld;          // &X(i, k)
     double* yp = Fm + (int64_t)ps.o + (int64_t)(e0 + (active ? i : 0)) * ld;          // LDLT: &U12(k, i)
     double x[WP];
 #pragma unroll
     for (int k = 0; k < WP; ++k) x[k] = (active && k < w) ? __ldcs(xp + (size_t)k * ld) : 0.0;
-    for (int e0i = tid; e0i < WP * WP; e0i += 8 * PANEL_REG_THREADS) {
-        double v[8];
+    constexpr int TB = 16;                              // loads in flight per thread while staging T
+    for (int e0i = tid; e0i < WP * WP; e0i += TB * PANEL_REG_THREADS) {
+        double v[TB];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < TB; ++u) {
             const int e = e0i + u * PANEL_REG_THREADS; const int k = e / WP, j = e - k * WP;       // smem slot (j,k)
             const bool in = j < w && k < w && j > k;
             v[u] = in ? __ldcg(LU ? T + k + (size_t)j * ld : T + j + (size_t)k * ld) : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) Ts[e0i + u * PANEL_REG_THREADS] = v[u];
+        for (int u = 0; u < TB; ++u) Ts[e0i + u * PANEL_REG_THREADS] = v[u];
     }
-    static_assert((WP * WP) % (8 * PANEL_REG_THREADS) == 0, "whole batches");
+    static_assert((WP * WP) % (TB * PANEL_REG_THREADS) == 0, "whole batches");
     if (tid < WP) {
         Ts[WP * WP + tid] = 0.0;
         const double dg = tid < w ? __ldcg(T + tid + (size_t)tid * ld) : 0.0; rd[tid] = dg != 0.0 ? 1.0 / dg : 0.0;

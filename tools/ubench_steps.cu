@@ -143,8 +143,9 @@ __global__ void __launch_bounds__(PANEL_REG_THREADS) k_panel_clk(DevCtx c, long 
     __shared__ __align__(16) double Ts[WP * WP + WP];   // Ts[j + k*WP] = coefficient of x_k in unknown j (j > k)
     __shared__ double rd[WP];                           // 1 / diagonal (0 where the diagonal is 0, as the LU reference does)
     long long t0 = clock64();
-    int t = find_task(pfx, count, blockIdx.x);
-    int lb = blockIdx.x - pfx[t];
+    const int bx = blockIdx.x / PANEL_REG_SPLIT, part = blockIdx.x % PANEL_REG_SPLIT;
+    int t = find_task(pfx, count, bx);
+    int lb = bx - pfx[t];
     const PStep ps = c.psteps[pslist[t]];
     const int w = ps.w, ld = ps.ld, e0 = ps.o + ps.w;
     const int below = ps.R - e0;
@@ -154,25 +155,27 @@ __global__ void __launch_bounds__(PANEL_REG_THREADS) k_panel_clk(DevCtx c, long 
     long long t1 = clock64();
     double* Fm = c.F + ps.fofs;
     const double* __restrict__ T = Fm + (int64_t)ps.o + (int64_t)ps.o * ld;
-    const int i = lb * PANEL_ROWS + tid;
+    const int i = lb * PANEL_ROWS + part * PANEL_REG_THREADS + tid;
+    if (i - tid >= below) return;                       // whole block beyond the panel
     const bool active = i < below;
     double* xp = Fm + (int64_t)(e0 + (active ? i : 0)) + (int64_t)ps.o * ld;          // &X(i, k)
     double* yp = Fm + (int64_t)ps.o + (int64_t)(e0 + (active ? i : 0)) * ld;          // LDLT: &U12(k, i)
     double x[WP];
 #pragma unroll
     for (int k = 0; k < WP; ++k) x[k] = (active && k < w) ? __ldcs(xp + (size_t)k * ld) : 0.0;
-    for (int e0i = tid; e0i < WP * WP; e0i += 8 * PANEL_REG_THREADS) {
-        double v[8];
+    constexpr int TB = 16;                              // loads in flight per thread while staging T
+    for (int e0i = tid; e0i < WP * WP; e0i += TB * PANEL_REG_THREADS) {
+        double v[TB];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < TB; ++u) {
             const int e = e0i + u * PANEL_REG_THREADS; const int k = e / WP, j = e - k * WP;       // smem slot (j,k)
             const bool in = j < w && k < w && j > k;
             v[u] = in ? __ldcg(LU ? T + k + (size_t)j * ld : T + j + (size_t)k * ld) : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) Ts[e0i + u * PANEL_REG_THREADS] = v[u];
+        for (int u = 0; u < TB; ++u) Ts[e0i + u * PANEL_REG_THREADS] = v[u];
     }
-    static_assert((WP * WP) % (8 * PANEL_REG_THREADS) == 0, "whole batches");
+    static_assert((WP * WP) % (TB * PANEL_REG_THREADS) == 0, "whole batches");
     if (tid < WP) {
         Ts[WP * WP + tid] = 0.0;
         const double dg = tid < w ? __ldcg(T + tid + (size_t)tid * ld) : 0.0; rd[tid] = dg != 0.0 ? 1.0 / dg : 0.0;
@@ -362,8 +365,8 @@ int main(int argc, char** argv) {
     timeit("diag NS=1 var0", [&] { k_diag_var<0, 1><<<1, 64>>>(c, dlist, dclk); });
     timeit("diag NS=1 var2 (no barrier)", [&] { k_diag_var<2, 1><<<1, 64>>>(c, dlist, dclk); });
     timeit("diag NS=1 var3 (no update)", [&] { k_diag_var<3, 1><<<1, 64>>>(c, dlist, dclk); });
-    timeit("panel clk (ps | issue loads | wait | compute)", [&] { k_panel_clk<false><<<nbp, PANEL_REG_THREADS>>>(c, dclk, dlist, dpfx, 1); });
-    timeit("panel_reg<ldlt>", [&] { k_panel_reg<false><<<nbp, PANEL_REG_THREADS>>>(c, dlist, dpfx, 1); });
+    timeit("panel clk (ps | issue loads | wait | compute)", [&] { k_panel_clk<false><<<nbp * PANEL_REG_SPLIT, PANEL_REG_THREADS>>>(c, dclk, dlist, dpfx, 1); });
+    timeit("panel_reg<ldlt>", [&] { k_panel_reg<false><<<nbp * PANEL_REG_SPLIT, PANEL_REG_THREADS>>>(c, dlist, dpfx, 1); });
     {
         size_t sm = 0; for (int ww = 1; ww <= w; ++ww) sm = std::max(sm, panel_smem_bytes(ww));
         CK(cudaFuncSetAttribute(k_panel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
