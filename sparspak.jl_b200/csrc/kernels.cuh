@@ -367,6 +367,113 @@ __global__ void __launch_bounds__(64 * DIAG_NS) k_diag_ldlt_row(DevCtx c, const 
     if (bad && threadIdx.x == 0) atomicExch(c.iflag, -1);
 }
 
+// LU with chunk-local partial pivoting of a w x w diagonal block (w <= 64) held in registers: thread (r, h) of
+// 64 x LU_NS owns the column pairs P = h (mod LU_NS) of ONE PHYSICAL ROW; slices are per warp, so coefficient
+// loads are warp-uniform.  Rows are never moved between threads: an interchange swaps the LOGICAL positions
+// `pos` of two threads.  Final values go to a shared image S of the block in logical layout: the pivot row
+// publishes its register slice in `prow` — the broadcast buffer of the update, copied to S(k, k..) off the
+// dependent chain — and every row below writes its multiplier to S(pos, k).  Interchanges reach back only to
+// the chunk's first column (_luswap!/dgetrf on the chunk's own rows, SpkLUFactor.jl:230-240): the already final
+// multipliers in S(k, s0..k-1) and S(kp, s0..k-1) are swapped in the image.  Per column: keys (column k by
+// logical row) -> barrier -> every warp finds the pivot redundantly (first maximum wins, ggetrf! / idamax;
+// three warp reductions on the bit pattern of |x|) -> pivot row published -> barrier -> multipliers (correctly
+// rounded reciprocal, as dgetf2) and update, next column's key first.  Predicated per-entry stores and loads
+// made a first version instruction bound (440 instructions per column): slices are moved whole.
+constexpr int LU_NS = 2;
+constexpr int LU_SLD = 66;                              // row stride of the shared image (16-byte aligned rows)
+__global__ void __launch_bounds__(64 * LU_NS) k_diag_lu_row(DevCtx c, const int32_t* __restrict__ pslist) {
+    constexpr int WP = 64, NS = LU_NS, NE = WP / NS, PB = 8 / NS;
+    __shared__ __align__(16) double S[WP * LU_SLD];
+    __shared__ __align__(16) double prow[2 * WP];       // the pivot row of the current column, by absolute column
+    __shared__ double keys[2][WP];
+    const PStep ps = c.psteps[pslist[blockIdx.x]];
+    double* G = c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld;
+    const int w = ps.w, ld = ps.ld;
+    int32_t* ipiv = c.ipiv + ps.col0;
+    const int32_t* subw = c.subw + ps.sub0;
+    const int r = threadIdx.x & (WP - 1), h = threadIdx.x / WP, lane = threadIdx.x & 31;
+    double a[NE];
+#pragma unroll
+    for (int li = 0; li < NE; ++li) {
+        const int j = ((li >> 1) * NS + h) * 2 + (li & 1);
+        a[li] = (j < w && r < w) ? __ldcg(G + r + (size_t)j * ld) : 0.0;
+    }
+    int pos = r;                                        // logical row of this thread's physical row
+    if (h == 0) { keys[0][r] = a[0]; prow[WP + r] = 0.0; }
+    bool bad = false;
+    int s0 = 0, s1 = subw[0], sb = 0;
+#pragma unroll 1
+    for (int kb = 0; kb < w; kb += 8) {
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {
+            const int k = kb + cc;
+            if (k < w) {                                // uniform
+                if (k == s1) { s0 = s1; s1 += subw[++sb]; }
+                const double* kc = keys[k & 1];
+                double* kn = keys[(k + 1) & 1];
+                __syncthreads();                        // keys of column k (by logical row) visible
+                // pivot search, every warp for itself: rows [k, s1).  |x| compares like its bit pattern, so
+                // three warp reductions (high word, low word, index) replace a 5-round shuffle tournament.
+                unsigned hi = 0, lo = 0; int bi = 0x7fffffff;
+                {
+                    const double v0 = fabs(kc[lane]), v1 = fabs(kc[lane + 32]);
+                    const bool c0 = lane >= k && lane < s1 && v0 == v0, c1 = lane + 32 >= k && lane + 32 < s1 && v1 == v1;
+                    const unsigned h0 = __double2hiint(v0), l0 = __double2loint(v0), h1 = __double2hiint(v1), l1 = __double2loint(v1);
+                    const bool take1 = c1 && (!c0 || h1 > h0 || (h1 == h0 && l1 > l0));
+                    if (c0 || c1) { hi = take1 ? h1 : h0; lo = take1 ? l1 : l0; bi = take1 ? lane + 32 : lane; }
+                    const unsigned cand = bi != 0x7fffffff;
+                    const unsigned mh = __reduce_max_sync(0xffffffffu, cand ? hi : 0u);
+                    const bool inh = cand && hi == mh;
+                    const unsigned ml = __reduce_max_sync(0xffffffffu, inh ? lo : 0u);
+                    const bool inl = inh && lo == ml;
+                    bi = (int)__reduce_min_sync(0xffffffffu, inl ? (unsigned)bi : 0x7fffffffu);
+                    if (bi == 0x7fffffff) bi = k;       // only NaNs: keep the diagonal
+                }
+                const int kp = bi;
+                const double pv = kc[kp];
+                const bool ok = pv != 0.0;
+                bad |= !ok;
+                const double rinv = ok ? __drcp_rn(pv) : 1.0;
+                const int oldpos = pos;
+                if (ok && kp != k) { if (pos == kp) pos = k; else if (pos == k) pos = kp; }
+                if (pos == k) {                         // the pivot row: publish its slice (entries left of k are dead values)
+                    double2* pw = reinterpret_cast<double2*>(prow + kb + h * 2);
+#pragma unroll
+                    for (int p2 = 0; p2 < NE / 2; ++p2) pw[p2 * NS] = make_double2(a[2 * p2], a[2 * p2 + 1]);
+                }
+                __syncthreads();                        // pivot row visible
+                if (threadIdx.x == 0) ipiv[k] = kp - s0 + 1;
+                if (h == NS - 1) {
+                    if (r >= k) S[k * LU_SLD + r] = prow[r];            // row k of U is final
+                    // multipliers of this chunk already in the image travel with their rows (nobody reads them here)
+                    else if (ok && kp != k && r >= s0) { const double t = S[k * LU_SLD + r]; S[k * LU_SLD + r] = S[kp * LU_SLD + r]; S[kp * LU_SLD + r] = t; }
+                }
+                const double l = kc[oldpos] * rinv;
+                const bool below = pos > k;
+                if (below && h == ((cc >> 1) % NS) && pos < w) S[pos * LU_SLD + k] = l;
+                const double lz = below ? l : 0.0;      // finished rows: keep the registers finite
+                const double* pj = prow + kb + h * 2;
+                double u[NE];
+#pragma unroll
+                for (int li = 0; li < NE; ++li) u[li] = pj[(li >> 1) * 2 * NS + (li & 1)];
+                const int cn1 = cc + 1;                 // column k+1: inside this block, or the first one of the next
+                const int ho = (cn1 >> 1) % NS, lcn = ((cn1 >> 1) / NS) * 2 + (cn1 & 1);
+                a[lcn] -= lz * u[lcn];
+                if (h == ho) kn[pos] = a[lcn];
+#pragma unroll
+                for (int li = 0; li < NE; ++li) if (li != lcn) a[li] -= lz * u[li];
+            }
+        }
+#pragma unroll
+        for (int li = 0; li < NE - PB; ++li) a[li] = a[li + PB];
+#pragma unroll
+        for (int li = NE - PB; li < NE; ++li) a[li] = 0.0;
+    }
+    if (bad && threadIdx.x == 0) atomicExch(c.iflag, -1);
+    __syncthreads();
+    for (int e = threadIdx.x; e < w * w; e += 64 * NS) { const int j = e / w, i = e - j * w; __stcg(G + i + (size_t)j * ld, S[i * LU_SLD + j]); }
+}
+
 // ------------------------------------------------------------------------------------
 // Panels of a panel step.  One block = PANEL_ROWS front rows below the block (L side) or PANEL_ROWS
 // front columns to its right (U side); the factored w x w block T and the block's slice of the

@@ -353,7 +353,8 @@ static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L, 
         // shared memory sized for the widest block of THIS launch (tiny fronts keep high occupancy)
         int wl = std::min(L.maxw, p->diag_smem_nj);
         size_t sm = (size_t)wl * (wl | 1) * sizeof(double);
-        if (lu) k_diag<true><<<L.count, 256, sm, st>>>(c, p->d_pslist + L.first, wl);
+        if (lu && L.maxw <= 64 && !p->diag_smem_only) k_diag_lu_row<<<L.count, 64 * LU_NS, 0, st>>>(c, p->d_pslist + L.first);
+        else if (lu) k_diag<true><<<L.count, 256, sm, st>>>(c, p->d_pslist + L.first, wl);
         else if (L.maxw <= 64 && !p->diag_smem_only && p->diag_tg == 1) k_diag_ldlt_row<<<L.count, 64 * DIAG_NS, 0, st>>>(c, p->d_pslist + L.first);
         else if (L.maxw <= 64 && !p->diag_smem_only && p->diag_tg == 8) k_diag_ldlt_reg<8, 8><<<L.count, 64, 0, st>>>(c, p->d_pslist + L.first);
         else if (L.maxw <= 64 && !p->diag_smem_only) k_diag_ldlt_reg<4, 16><<<L.count, 256, 0, st>>>(c, p->d_pslist + L.first);

@@ -220,6 +220,111 @@ __global__ void __launch_bounds__(PANEL_REG_THREADS) k_panel_clk(DevCtx c, long 
     if (blockIdx.x == 0 && tid == 0) { clk[0] = t1 - t0; clk[1] = t2 - t1; clk[2] = t3 - t2; clk[3] = t4 - t3; }
 }
 // PANELCLK-END
+// LUCLK-BEGIN
+__global__ void __launch_bounds__(64 * LU_NS) k_diag_lu_clk(DevCtx c, const int32_t* __restrict__ pslist, long long* clk) {
+    constexpr int WP = 64, NS = LU_NS, NE = WP / NS, PB = 8 / NS;
+    __shared__ __align__(16) double S[WP * LU_SLD + WP];
+    __shared__ double keys[2][WP];
+    const PStep ps = c.psteps[pslist[blockIdx.x]];
+    double* G = c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld;
+    const int w = ps.w, ld = ps.ld;
+    int32_t* ipiv = c.ipiv + ps.col0;
+    const int32_t* subw = c.subw + ps.sub0;
+    const int r = threadIdx.x & (WP - 1), h = threadIdx.x / WP, lane = threadIdx.x & 31;
+    double a[NE];
+#pragma unroll
+    for (int li = 0; li < NE; ++li) {
+        const int j = ((li >> 1) * NS + h) * 2 + (li & 1);
+        a[li] = (j < w && r < w) ? __ldcg(G + r + (size_t)j * ld) : 0.0;
+    }
+    long long T0 = clock64(), ta = 0, tb = 0, tc = 0, td = 0, te = 0, tf = 0;
+    int pos = r;                                        // logical row of this thread's physical row
+    if (h == 0) keys[0][r] = a[0];
+    bool bad = false;
+    int s0 = 0, s1 = subw[0], sb = 0;
+#pragma unroll 1
+    for (int kb = 0; kb < w; kb += 8) {
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {
+            const int k = kb + cc;
+            if (k < w) {                                // uniform
+                if (k == s1) { s0 = s1; s1 += subw[++sb]; }
+                const double* kc = keys[k & 1];
+                double* kn = keys[(k + 1) & 1];
+                if (k == 16) ta = clock64();
+                __syncthreads();                        // keys of column k (by logical row) visible
+                if (k == 16) tb = clock64();
+                // pivot search, every warp for itself: rows [k, s1).  |x| compares like its bit pattern, so
+                // three warp reductions (high word, low word, index) replace a 5-round shuffle tournament.
+                unsigned hi = 0, lo = 0; int bi = 0x7fffffff;
+                {
+                    const int i0 = lane, i1 = lane + 32;
+                    if (i0 >= k && i0 < s1) { const double v = fabs(kc[i0]); if (v == v) { hi = __double2hiint(v); lo = __double2loint(v); bi = i0; } }
+                    if (i1 >= k && i1 < s1) {
+                        const double v = fabs(kc[i1]);
+                        if (v == v) {
+                            const unsigned h1 = __double2hiint(v), l1 = __double2loint(v);
+                            if (bi == 0x7fffffff || h1 > hi || (h1 == hi && l1 > lo)) { hi = h1; lo = l1; bi = i1; }
+                        }
+                    }
+                    const unsigned cand = bi != 0x7fffffff;
+                    const unsigned mh = __reduce_max_sync(0xffffffffu, cand ? hi : 0u);
+                    const bool inh = cand && hi == mh;
+                    const unsigned ml = __reduce_max_sync(0xffffffffu, inh ? lo : 0u);
+                    const bool inl = inh && lo == ml;
+                    bi = (int)__reduce_min_sync(0xffffffffu, inl ? (unsigned)bi : 0x7fffffffu);
+                    if (bi == 0x7fffffff) bi = k;       // only NaNs: keep the diagonal
+                }
+                if (k == 16) tc = clock64();
+                const int kp = bi;
+                const double pv = kc[kp];
+                const bool ok = pv != 0.0;
+                bad |= !ok;
+                const double rinv = ok ? __drcp_rn(pv) : 1.0;
+                const int oldpos = pos;
+                if (ok && kp != k) { if (pos == kp) pos = k; else if (pos == k) pos = kp; }
+                if (pos == k) {                         // the pivot row: publish what is left of it
+#pragma unroll
+                    for (int li = 0; li < NE; ++li) {
+                        const int j = kb + ((li >> 1) * NS + h) * 2 + (li & 1);
+                        if (j >= k && j < WP) S[k * LU_SLD + j] = a[li];
+                    }
+                }
+                if (k == 16) td = clock64();
+                __syncthreads();                        // pivot row visible
+                if (k == 16) te = clock64();
+                if (threadIdx.x == 0) ipiv[k] = kp - s0 + 1;
+                // multipliers of this chunk already in the image travel with their rows (nobody reads them here)
+                if (ok && kp != k && h == NS - 1 && r >= s0 && r < k) { const double t = S[k * LU_SLD + r]; S[k * LU_SLD + r] = S[kp * LU_SLD + r]; S[kp * LU_SLD + r] = t; }
+                const double l = kc[oldpos] * rinv;
+                const bool below = pos > k;
+                if (below && h == ((cc >> 1) % NS) && pos < w) S[pos * LU_SLD + k] = l;
+                const double lz = below ? l : 0.0;      // finished rows: keep the registers finite
+                const double* pj = S + k * LU_SLD + kb + h * 2;
+                double u[NE];
+#pragma unroll
+                for (int li = 0; li < NE; ++li) u[li] = (kb + ((li >> 1) * NS + h) * 2 < w) ? pj[(li >> 1) * 2 * NS + (li & 1)] : 0.0;
+                const int cn1 = cc + 1;                 // column k+1: inside this block, or the first one of the next
+                const int ho = (cn1 >> 1) % NS, lcn = ((cn1 >> 1) / NS) * 2 + (cn1 & 1);
+                a[lcn] -= lz * u[lcn];
+                if (h == ho) kn[pos] = a[lcn];
+#pragma unroll
+                for (int li = 0; li < NE; ++li) if (li != lcn) a[li] -= lz * u[li];
+                if (k == 16) tf = clock64();
+            }
+        }
+#pragma unroll
+        for (int li = 0; li < NE - PB; ++li) a[li] = a[li + PB];
+#pragma unroll
+        for (int li = NE - PB; li < NE; ++li) a[li] = 0.0;
+    }
+    long long T1 = clock64();
+    if (bad && threadIdx.x == 0) atomicExch(c.iflag, -1);
+    __syncthreads();
+    for (int e = threadIdx.x; e < w * w; e += 64 * NS) { const int j = e / w, i = e - j * w; __stcg(G + i + (size_t)j * ld, S[i * LU_SLD + j]); }
+    if (threadIdx.x == 0 && clk) { clk[0] = 0; clk[1] = T1 - T0; clk[2] = tb - ta; clk[3] = tc - tb; clk[4] = td - tc; clk[5] = te - td; clk[6] = tf - te; }
+}
+// LUCLK-END
 // instruction latencies seen by ONE warp (dependent chains), in clocks per operation
 __global__ void k_lat(double* out, long long* clk, double seed) {
     __shared__ double sh[64];
@@ -306,13 +411,13 @@ int main(int argc, char** argv) {
     // first 64 columns: diagonally dominant block + small panel entries
     srand(1);
     for (int j = 0; j < 64; ++j) for (int i = 0; i < R; ++i) hF[i + (size_t)j * ld] = (i == j ? 100.0 : 0.01 * ((rand() % 200) - 100) / 100.0);
-    PStep ps{}; ps.fofs = 0; ps.col0 = 0; ps.ld = ld; ps.R = R; ps.o = 0; ps.w = w; ps.ob_end = w; ps.sub0 = 0; ps.nsub = 1; ps.front = 0;
+    PStep ps{}; ps.fofs = 0; ps.col0 = 0; ps.ld = ld; ps.R = R; ps.o = 0; ps.w = w; ps.ob_end = w; ps.sub0 = 0; ps.nsub = 2; ps.front = 0;
     PStep* dps; CK(cudaMalloc(&dps, sizeof(PStep))); CK(cudaMemcpy(dps, &ps, sizeof(PStep), cudaMemcpyHostToDevice));
     int32_t zero = 0, *dlist, *dpfx, *dflag, *dsubw; int32_t pf[2] = {0, (R - w + PANEL_ROWS - 1) / PANEL_ROWS};
     CK(cudaMalloc(&dlist, 4)); CK(cudaMemcpy(dlist, &zero, 4, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&dpfx, 8)); CK(cudaMemcpy(dpfx, pf, 8, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&dflag, 4)); CK(cudaMemset(dflag, 0, 4));
-    CK(cudaMalloc(&dsubw, 4)); CK(cudaMemcpy(dsubw, &w, 4, cudaMemcpyHostToDevice));
+    int32_t hsub[2] = {30, w - 30}; CK(cudaMalloc(&dsubw, 8)); CK(cudaMemcpy(dsubw, hsub, 8, cudaMemcpyHostToDevice));
     int32_t* dipiv; CK(cudaMalloc(&dipiv, 4 * 64));
     long long* dclk; CK(cudaMalloc(&dclk, 64)); CK(cudaMemset(dclk, 0, 64));
     DevCtx c{}; c.F = F; c.psteps = dps; c.iflag = dflag; c.subw = dsubw; c.ipiv = dipiv;
@@ -355,6 +460,8 @@ int main(int argc, char** argv) {
     timeit("empty-ish (k_perm_gather n=0)", [&] { k_ipiv_widen<<<1, 32>>>(0, dipiv, (int64_t*)dclk); });
     timeit("diag_ldlt_row (product)", [&] { k_diag_ldlt_row<<<1, 64 * DIAG_NS>>>(c, dlist); });
     timeit("diag_ldlt_reg<4,16>", [&] { k_diag_ldlt_reg<4, 16><<<1, 256>>>(c, dlist); });
+    timeit("diag LU row (bar1 | argmax | publish | bar2 | update)", [&] { k_diag_lu_clk<<<1, 64 * LU_NS>>>(c, dlist, dclk); });
+    timeit("diag LU row product", [&] { k_diag_lu_row<<<1, 64 * LU_NS>>>(c, dlist); });
     timeit("diag v2 NS=4", [&] { k_diag_v2<4><<<1, 256>>>(c, dlist, dclk); });
     timeit("diag v2 NS=2", [&] { k_diag_v2<2><<<1, 128>>>(c, dlist, dclk); });
     timeit("diag v2 NS=1", [&] { k_diag_v2<1><<<1, 64>>>(c, dlist, dclk); });
