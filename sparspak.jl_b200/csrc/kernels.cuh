@@ -642,6 +642,7 @@ __global__ void __launch_bounds__(PANEL_REG_THREADS) k_panel_reg(DevCtx c, const
     constexpr int WP = 64;
     __shared__ __align__(16) double Ts[WP * WP + WP];   // Ts[j + k*WP] = coefficient of x_k in unknown j (j > k)
     __shared__ double rd[WP];                           // 1 / diagonal (0 where the diagonal is 0, as the LU reference does)
+    __shared__ int32_t perm[WP], s0r[WP];               // U side: original row of each final row, first row of its chunk
     const int bx = blockIdx.x / PANEL_REG_SPLIT, part = blockIdx.x % PANEL_REG_SPLIT;
     int t = find_task(pfx, count, bx);
     int lb = bx - pfx[t];
@@ -649,18 +650,43 @@ __global__ void __launch_bounds__(PANEL_REG_THREADS) k_panel_reg(DevCtx c, const
     const int w = ps.w, ld = ps.ld, e0 = ps.o + ps.w;
     const int below = ps.R - e0;
     const int nb = (below + PANEL_ROWS - 1) / PANEL_ROWS;
-    if (lb >= nb) return;                               // U-side blocks (LU) belong to k_panel
+    // LU, U side (blocks nb .. 2nb-1): U12 = inv(L11) * P * A12 with P the chunk-local interchanges.  The rows of
+    // A12 are gathered through P up front and the multipliers a chunk inherits from earlier chunks (stored in
+    // pre-interchange row order, SpkLUFactor.jl:230-240) are gathered the same way, which leaves one plain
+    // unit-lower substitution — the same loop as the L side, one thread per column of U12.
+    const bool lside = !LU || lb < nb;
+    if (!lside) lb -= nb;
     const int tid = threadIdx.x;
     double* Fm = c.F + ps.fofs;
     const double* __restrict__ T = Fm + (int64_t)ps.o + (int64_t)ps.o * ld;
     const int i = lb * PANEL_ROWS + part * PANEL_REG_THREADS + tid;
     if (i - tid >= below) return;                       // whole block beyond the panel
     const bool active = i < below;
-    double* xp = Fm + (int64_t)(e0 + (active ? i : 0)) + (int64_t)ps.o * ld;          // &X(i, k)
-    double* yp = Fm + (int64_t)ps.o + (int64_t)(e0 + (active ? i : 0)) * ld;          // LDLT: &U12(k, i)
+    double* xp = Fm + (int64_t)(e0 + (active ? i : 0)) + (int64_t)ps.o * ld;          // L side: &X(i, k)
+    double* yp = Fm + (int64_t)ps.o + (int64_t)(e0 + (active ? i : 0)) * ld;          // LDLT: &U12(k, i); LU U side: &U12(k, i)
     double x[WP];
+    if (lside) {
 #pragma unroll
-    for (int k = 0; k < WP; ++k) x[k] = (active && k < w) ? __ldcs(xp + (size_t)k * ld) : 0.0;
+        for (int k = 0; k < WP; ++k) x[k] = (active && k < w) ? __ldcs(xp + (size_t)k * ld) : 0.0;
+    } else {
+        if (tid < WP) perm[tid] = tid;
+        __syncthreads();
+        if (tid < ps.nsub) {                            // one thread per chunk replays its interchanges
+            const int32_t* subw = c.subw + ps.sub0;
+            const int32_t* ipiv = c.ipiv + ps.col0;
+            int s0 = 0;
+            for (int b2 = 0; b2 < tid; ++b2) s0 += subw[b2];
+            const int s1 = s0 + subw[tid];
+            for (int k = s0; k < s1; ++k) {
+                const int kp = s0 + ipiv[k] - 1;
+                const int tp = perm[k]; perm[k] = perm[kp]; perm[kp] = tp;
+                s0r[k] = s0;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < WP; ++k) x[k] = (active && k < w) ? __ldcs(yp + perm[k]) : 0.0;
+    }
     constexpr int TB = 16;                              // loads in flight per thread while staging T
     for (int e0i = tid; e0i < WP * WP; e0i += TB * PANEL_REG_THREADS) {
         double v[TB];
@@ -668,7 +694,11 @@ __global__ void __launch_bounds__(PANEL_REG_THREADS) k_panel_reg(DevCtx c, const
         for (int u = 0; u < TB; ++u) {
             const int e = e0i + u * PANEL_REG_THREADS; const int k = e / WP, j = e - k * WP;       // smem slot (j,k)
             const bool in = j < w && k < w && j > k;
-            v[u] = in ? __ldcg(LU ? T + k + (size_t)j * ld : T + j + (size_t)k * ld) : 0.0;
+            const double* src;
+            if (!LU) src = T + j + (size_t)k * ld;
+            else if (lside) src = T + k + (size_t)j * ld;
+            else src = T + ((in && k < s0r[j]) ? perm[j] : j) + (size_t)k * ld;
+            v[u] = in ? __ldcg(src) : 0.0;
         }
 #pragma unroll
         for (int u = 0; u < TB; ++u) Ts[e0i + u * PANEL_REG_THREADS] = v[u];
@@ -676,7 +706,8 @@ __global__ void __launch_bounds__(PANEL_REG_THREADS) k_panel_reg(DevCtx c, const
     static_assert((WP * WP) % (TB * PANEL_REG_THREADS) == 0, "whole batches");
     if (tid < WP) {
         Ts[WP * WP + tid] = 0.0;
-        const double dg = tid < w ? __ldcg(T + tid + (size_t)tid * ld) : 0.0; rd[tid] = dg != 0.0 ? 1.0 / dg : 0.0;
+        const double dg = tid < w ? __ldcg(T + tid + (size_t)tid * ld) : 0.0;
+        rd[tid] = lside ? (dg != 0.0 ? 1.0 / dg : 0.0) : 1.0;
     }
     __syncthreads();
 #pragma unroll 1
@@ -689,7 +720,7 @@ __global__ void __launch_bounds__(PANEL_REG_THREADS) k_panel_reg(DevCtx c, const
             double xk = x[cc];
             if (LU) xk *= rd[k & (WP - 1)];
             if (active && k < w) {
-                if (LU) *xp = xk;
+                if (LU) { if (lside) *xp = xk; else *yp = xk; }
                 else { *xp = xk * rd[k]; *yp = xk; }
             }
             xp += ld; ++yp;

@@ -371,8 +371,8 @@ static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L, 
             if (lu) k_panel_reg<true><<<L.nblocks * PANEL_REG_SPLIT, PANEL_REG_THREADS, 0, st>>>(c, p->d_pslist + L.first, pfx, L.count);
             else k_panel_reg<false><<<L.nblocks * PANEL_REG_SPLIT, PANEL_REG_THREADS, 0, st>>>(c, p->d_pslist + L.first, pfx, L.count);
         }
-        if (lu) k_panel<true><<<L.nblocks, PANEL_ROWS, sm, st>>>(c, p->d_pslist + L.first, pfx, L.count, fast ? 1 : 0);
-        else if (!fast) k_panel<false><<<L.nblocks, PANEL_ROWS, sm, st>>>(c, p->d_pslist + L.first, pfx, L.count, 0);
+        else if (lu) k_panel<true><<<L.nblocks, PANEL_ROWS, sm, st>>>(c, p->d_pslist + L.first, pfx, L.count, 0);
+        else k_panel<false><<<L.nblocks, PANEL_ROWS, sm, st>>>(c, p->d_pslist + L.first, pfx, L.count, 0);
         break;
     }
     case K_GEMM:
