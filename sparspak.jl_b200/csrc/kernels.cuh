@@ -1118,6 +1118,19 @@ __device__ __forceinline__ void pb_diag_warp(const PStep& ps, const double* Ts, 
 __device__ __forceinline__ void pf_update_rows(const DevCtx& c, const PStep& ps, double* wf, const double* xs, int r0, int r1) {
     const double* __restrict__ Fm = c.F + ps.fofs + (int64_t)ps.o * ps.ld;
     const int w = ps.w;
+    if (w <= 64) {                                          // the whole row in flight: one round trip to memory
+        for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+            const double* __restrict__ row = Fm + r;
+            double v[64];
+#pragma unroll
+            for (int u = 0; u < 64; ++u) v[u] = __ldcs(row + (size_t)min(u, w - 1) * ps.ld);     // unconditional: all issued before the first use
+            double acc = 0.0;
+#pragma unroll
+            for (int u = 0; u < 64; ++u) if (u < w) acc += v[u] * xs[u];
+            wf[r] -= acc;
+        }
+        return;
+    }
     for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
         double acc = 0.0;
         const double* __restrict__ row = Fm + r;
@@ -1131,6 +1144,17 @@ __device__ __forceinline__ void pf_update_rows(const DevCtx& c, const PStep& ps,
         wf[r] -= acc;
     }
 }
+// asynchronous staging of a w x w block (column-major, leading dimension w in shared memory): issued early,
+// waited for with stage_wait() once the block is needed
+__device__ __forceinline__ void stage_block_async(double* S, const double* __restrict__ G, int ld, int w) {
+    for (int e = threadIdx.x; e < w * w; e += blockDim.x) {
+        const int j = e / w, i = e - j * w;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(S + e);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(G + i + (size_t)j * ld));
+    }
+    asm volatile("cp.async.commit_group;");
+}
+__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // partial sums over the front indices [r0, r1) beyond the step: out[k] = sum_r coef(r,k) * wf[r]
 //   LU: coef = U[o+k, r] (column r of the U panel: w contiguous entries);  LDL^T: coef = L[r, o+k]
 // red: shared scratch of (blockDim.x/32) * w doubles; the warps' sums are added in a fixed order.
@@ -1140,11 +1164,49 @@ __device__ __forceinline__ void pb_partial(const DevCtx& c, const PStep& ps, con
     const double* __restrict__ Fm = c.F + ps.fofs;
     for (int k = threadIdx.x; k < nw * w; k += blockDim.x) red[k] = 0.0;
     __syncthreads();
+    if (LU && w <= 64) {
+        // U panel: column r holds its w entries contiguously, so lane k reads U[o+k, r] (coalesced) for 32
+        // columns at a time — all 64 loads in flight — and sums over r in registers: no shuffle reduction
+        double acc0 = 0.0, acc1 = 0.0;
+        const double* __restrict__ U0 = Fm + (int64_t)ps.o + min(lane, w - 1);
+        const double* __restrict__ U1 = Fm + (int64_t)ps.o + min(lane + 32, w - 1);
+        for (int rb = r0 + warp * 32; rb < r1; rb += nw * 32) {
+            const double xl = rb + lane < r1 ? wf[rb + lane] : 0.0;
+            double a0[32], a1[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { const size_t cofs = (size_t)min(rb + j, r1 - 1) * ps.ld; a0[j] = __ldcs(U0 + cofs); a1[j] = __ldcs(U1 + cofs); }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { const double xj = __shfl_sync(0xffffffffu, xl, j); acc0 += a0[j] * xj; acc1 += a1[j] * xj; }
+        }
+        if (lane < w) red[warp * w + lane] = acc0;
+        if (lane + 32 < w) red[warp * w + lane + 32] = acc1;
+    } else
     for (int rb = r0 + warp * 32; rb < r1; rb += nw * 32) {
         const int r = rb + lane;
         const double xr = r < r1 ? wf[r] : 0.0;
         const double* __restrict__ col = LU ? Fm + (int64_t)ps.o + (int64_t)min(r, r1 - 1) * ps.ld
                                            : Fm + (int64_t)min(r, r1 - 1) + (int64_t)ps.o * ps.ld;
+        if (w <= 64) {                                      // the whole row / column in flight: one round trip to memory
+            double a[64];
+#pragma unroll
+            for (int u = 0; u < 64; ++u) { const int uu = min(u, w - 1); a[u] = __ldcs(LU ? col + uu : col + (size_t)uu * ps.ld); }   // unconditional
+#pragma unroll
+            for (int k0 = 0; k0 < 64; k0 += 8) {
+                if (k0 < w) {
+                    double v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = k0 + u < w ? a[k0 + u] * xr : 0.0;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) v[u] += __shfl_xor_sync(0xffffffffu, v[u], off);
+                    if (lane == 0)
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) if (k0 + u < w) red[warp * w + k0 + u] += v[u];
+                }
+            }
+            continue;
+        }
         for (int k0 = 0; k0 < w; k0 += 8) {
             double v[8];
 #pragma unroll
@@ -1250,15 +1312,21 @@ __global__ void __launch_bounds__(SV_ROWS) k_pf_step(DevCtx c, const int32_t* __
     const DFront F = c.fronts[ps.front];
     double* wf = c.w + (size_t)blockIdx.y * c.wlen + F.wofs;
     double* xs = ssm;                                           // x_j (w entries)
+    double* Ts = ssm + ((ps.w + 7) & ~7);                       // block 0: diagonal block of step j+1, staged while the update runs
+    const bool next = lb == 0 && pid + 1 < F.ps0 + F.nps;
+    PStep nx;
+    if (next) {
+        nx = c.psteps[pid + 1];
+        stage_block_async(Ts, c.F + nx.fofs + (int64_t)nx.o + (int64_t)nx.o * nx.ld, nx.ld, nx.w);
+    }
     for (int k = threadIdx.x; k < ps.w; k += blockDim.x) xs[k] = wf[ps.o + k];
     __syncthreads();
     const int e0 = ps.o + ps.w;
     pf_update_rows(c, ps, wf, xs, e0 + lb * SV_ROWS, min(ps.R, e0 + (lb + 1) * SV_ROWS));
-    if (lb == 0 && pid + 1 < F.ps0 + F.nps) {
-        __syncthreads();                                        // this block's rows (incl. step j+1's unknowns) are final
-        const PStep nx = c.psteps[pid + 1];
-        double* Ts = ssm; double* xn = ssm + nx.w * nx.w;
-        block_g2s<SV_ROWS>(Ts, nx.w, c.F + nx.fofs + (int64_t)nx.o + (int64_t)nx.o * nx.ld, nx.ld, nx.w);
+    if (next) {
+        stage_wait();
+        __syncthreads();                                        // this block's rows (incl. step j+1's unknowns) are final, T staged
+        double* xn = Ts + nx.w * nx.w;
         for (int k = threadIdx.x; k < nx.w; k += blockDim.x) xn[k] = wf[nx.o + k];
         __syncthreads();
         if (threadIdx.x < 32) pf_diag_warp<LU>(c, nx, Ts, xn);
@@ -1283,8 +1351,11 @@ __global__ void __launch_bounds__(SV_ROWS) k_pb_step(DevCtx c, const int32_t* __
     double* pb = c.pb + (size_t)blockIdx.y * c.pblen + F.pbofs;
     const int e0 = ps.o + ps.w, below = ps.R - e0;
     const int nblk = (below + SV_ROWS - 1) / SV_ROWS;
+    double* Ts = ssm; double* xs = ssm + ps.w * ps.w;
+    // every block stages the diagonal block while it forms its partial sums: the one that arrives last needs it at once
+    stage_block_async(Ts, c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld, ps.ld, ps.w);
     if (nblk > 0) {
-        pb_partial<LU>(c, ps, wf, e0 + lb * SV_ROWS, min(ps.R, e0 + (lb + 1) * SV_ROWS), ssm, pb + (size_t)lb * maxpw);
+        pb_partial<LU>(c, ps, wf, e0 + lb * SV_ROWS, min(ps.R, e0 + (lb + 1) * SV_ROWS), xs + ps.w, pb + (size_t)lb * maxpw);
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -1294,11 +1365,10 @@ __global__ void __launch_bounds__(SV_ROWS) k_pb_step(DevCtx c, const int32_t* __
             if (s_last) *cnt = 0;                                                    // ready for the next sweep
         }
         __syncthreads();
-        if (!s_last) return;
+        if (!s_last) { stage_wait(); return; }
         __threadfence();
     }
-    double* Ts = ssm; double* xs = ssm + ps.w * ps.w;
-    block_g2s<SV_ROWS>(Ts, ps.w, c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld, ps.ld, ps.w);
+    stage_wait();
     __syncthreads();
     for (int k = threadIdx.x; k < ps.w; k += blockDim.x) {
         double sum = 0.0;
