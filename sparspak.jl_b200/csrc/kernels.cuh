@@ -1155,6 +1155,15 @@ __device__ __forceinline__ void stage_block_async(double* S, const double* __res
     asm volatile("cp.async.commit_group;");
 }
 __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// Programmatic dependent launch: a kernel launched with the programmatic-serialization attribute may start
+// while its predecessor in the stream is still running.  pdl_trigger() lets the NEXT kernel start launching;
+// pdl_wait() blocks until the PREVIOUS kernel has completed and its writes are visible.  Everything that only
+// depends on the factors (task records, the diagonal block, the panel rows) is fetched before pdl_wait(), so
+// the launch gap and those round trips disappear from the chain of dependent panel steps.  Both are no-ops in
+// a kernel launched the ordinary way.  Every block calls pdl_wait() before it exits, which keeps completion
+// transitive along the chain.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 // partial sums over the front indices [r0, r1) beyond the step: out[k] = sum_r coef(r,k) * wf[r]
 //   LU: coef = U[o+k, r] (column r of the U panel: w contiguous entries);  LDL^T: coef = L[r, o+k]
 // red: shared scratch of (blockDim.x/32) * w doubles; the warps' sums are added in a fixed order.
@@ -1218,6 +1227,61 @@ __device__ __forceinline__ void pb_partial(const DevCtx& c, const PStep& ps, con
             if (lane == 0)
 #pragma unroll
                 for (int u = 0; u < 8; ++u) if (k0 + u < w) red[warp * w + k0 + u] += v[u];
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < w; k += blockDim.x) {
+        double s = 0.0;
+        for (int q = 0; q < nw; ++q) s += red[q * w + k];
+        out[k] = s;
+    }
+}
+
+// pb_partial for w <= 64 and one 32-row slab per warp (blockDim.x == SV_ROWS), split in two so that the loads
+// of the factor entries can be issued before the previous kernel's result is awaited (PDL, see pdl_wait):
+//   LDL^T: a[u] = L[r, o+u] for this lane's row r;  LU: a[j] / a[32+j] = U[o+lane, rb+j] / U[o+lane+32, rb+j]
+template <bool LU>
+__device__ __forceinline__ void pb_prefetch64(const DevCtx& c, const PStep& ps, int r0, int r1, double (&a)[64]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, w = ps.w;
+    const double* __restrict__ Fm = c.F + ps.fofs;
+    const int rb = r0 + warp * 32;
+    if (LU) {
+        const double* __restrict__ U0 = Fm + (int64_t)ps.o + min(lane, w - 1);
+        const double* __restrict__ U1 = Fm + (int64_t)ps.o + min(lane + 32, w - 1);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { const size_t cofs = (size_t)max(min(rb + j, r1 - 1), r0) * ps.ld; a[j] = __ldcs(U0 + cofs); a[32 + j] = __ldcs(U1 + cofs); }
+    } else {
+        const double* __restrict__ col = Fm + (int64_t)max(min(rb + lane, r1 - 1), r0) + (int64_t)ps.o * ps.ld;
+#pragma unroll
+        for (int u = 0; u < 64; ++u) a[u] = __ldcs(col + (size_t)min(u, w - 1) * ps.ld);
+    }
+}
+template <bool LU>
+__device__ __forceinline__ void pb_apply64(const PStep& ps, const double* wf, int r0, int r1, const double (&a)[64], double* red, double* out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, w = ps.w;
+    const int rb = r0 + warp * 32;
+    const double xl = rb + lane < r1 ? wf[rb + lane] : 0.0;
+    if (LU) {
+        double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { const double xj = __shfl_sync(0xffffffffu, xl, j); acc0 += a[j] * xj; acc1 += a[32 + j] * xj; }
+        if (lane < w) red[warp * w + lane] = acc0;
+        if (lane + 32 < w) red[warp * w + lane + 32] = acc1;
+    } else {
+#pragma unroll
+        for (int k0 = 0; k0 < 64; k0 += 8) {
+            if (k0 < w) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = k0 + u < w ? a[k0 + u] * xl : 0.0;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] += __shfl_xor_sync(0xffffffffu, v[u], off);
+                if (lane == 0)
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) if (k0 + u < w) red[warp * w + k0 + u] = v[u];
+            }
         }
     }
     __syncthreads();
@@ -1305,6 +1369,7 @@ template <bool LU>
 __global__ void __launch_bounds__(SV_ROWS) k_pf_step(DevCtx c, const int32_t* __restrict__ plist,
                                                      const int32_t* __restrict__ pfx, int count) {
     extern __shared__ double ssm[];
+    pdl_trigger();
     int ti = find_task(pfx, count, blockIdx.x);
     int lb = blockIdx.x - pfx[ti];
     const int pid = plist[ti];
@@ -1319,10 +1384,28 @@ __global__ void __launch_bounds__(SV_ROWS) k_pf_step(DevCtx c, const int32_t* __
         nx = c.psteps[pid + 1];
         stage_block_async(Ts, c.F + nx.fofs + (int64_t)nx.o + (int64_t)nx.o * nx.ld, nx.ld, nx.w);
     }
-    for (int k = threadIdx.x; k < ps.w; k += blockDim.x) xs[k] = wf[ps.o + k];
-    __syncthreads();
-    const int e0 = ps.o + ps.w;
-    pf_update_rows(c, ps, wf, xs, e0 + lb * SV_ROWS, min(ps.R, e0 + (lb + 1) * SV_ROWS));
+    const int e0 = ps.o + ps.w, w = ps.w;
+    const int r0 = e0 + lb * SV_ROWS, r1 = min(ps.R, e0 + (lb + 1) * SV_ROWS);
+    if (w <= 64) {
+        // one row per thread; the row of the panel is fetched BEFORE the previous step's result is awaited
+        const int r = r0 + threadIdx.x;
+        const double* __restrict__ row = c.F + ps.fofs + (int64_t)ps.o * ps.ld + min(r, r1 - 1);
+        double v[64];
+#pragma unroll
+        for (int u = 0; u < 64; ++u) v[u] = __ldcs(row + (size_t)min(u, w - 1) * ps.ld);
+        pdl_wait();
+        for (int k = threadIdx.x; k < w; k += blockDim.x) xs[k] = wf[ps.o + k];
+        __syncthreads();
+        double acc = 0.0;
+#pragma unroll
+        for (int u = 0; u < 64; ++u) if (u < w) acc += v[u] * xs[u];
+        if (r < r1) wf[r] -= acc;
+    } else {
+        pdl_wait();
+        for (int k = threadIdx.x; k < w; k += blockDim.x) xs[k] = wf[ps.o + k];
+        __syncthreads();
+        pf_update_rows(c, ps, wf, xs, r0, r1);
+    }
     if (next) {
         stage_wait();
         __syncthreads();                                        // this block's rows (incl. step j+1's unknowns) are final, T staged
@@ -1343,6 +1426,7 @@ __global__ void __launch_bounds__(SV_ROWS) k_pb_step(DevCtx c, const int32_t* __
                                                      double* __restrict__ rhs, int64_t ldrhs, int maxpw, int32_t* counters) {
     extern __shared__ double ssm[];
     __shared__ int s_last;
+    pdl_trigger();
     int ti = find_task(pfx, count, blockIdx.x);
     int lb = blockIdx.x - pfx[ti];
     const PStep ps = c.psteps[plist[ti]];
@@ -1355,7 +1439,16 @@ __global__ void __launch_bounds__(SV_ROWS) k_pb_step(DevCtx c, const int32_t* __
     // every block stages the diagonal block while it forms its partial sums: the one that arrives last needs it at once
     stage_block_async(Ts, c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld, ps.ld, ps.w);
     if (nblk > 0) {
-        pb_partial<LU>(c, ps, wf, e0 + lb * SV_ROWS, min(ps.R, e0 + (lb + 1) * SV_ROWS), xs + ps.w, pb + (size_t)lb * maxpw);
+        const int r0 = e0 + lb * SV_ROWS, r1 = min(ps.R, e0 + (lb + 1) * SV_ROWS);
+        if (ps.w <= 64) {
+            double a[64];
+            pb_prefetch64<LU>(c, ps, r0, r1, a);            // factor entries in flight before the previous step's x is awaited
+            pdl_wait();
+            pb_apply64<LU>(ps, wf, r0, r1, a, xs + ps.w, pb + (size_t)lb * maxpw);
+        } else {
+            pdl_wait();
+            pb_partial<LU>(c, ps, wf, r0, r1, xs + ps.w, pb + (size_t)lb * maxpw);
+        }
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -1367,7 +1460,7 @@ __global__ void __launch_bounds__(SV_ROWS) k_pb_step(DevCtx c, const int32_t* __
         __syncthreads();
         if (!s_last) { stage_wait(); return; }
         __threadfence();
-    }
+    } else pdl_wait();
     stage_wait();
     __syncthreads();
     for (int k = threadIdx.x; k < ps.w; k += blockDim.x) {

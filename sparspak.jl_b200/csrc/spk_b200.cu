@@ -55,6 +55,7 @@ struct spk_plan {
     cudaGraphExec_t sg_exec = nullptr; double* sg_rhs = nullptr; double* sg_w = nullptr;
     int64_t sg_nrhs = 0, sg_ld = 0, sg_launches = 0; int32_t sg_which = -1;
     int diag_tg = 1;                    // SPK_DIAG_TG: 1 = row kernel (4 threads per row), 8 / 16 = thread grid of the cyclic register kernel
+    bool pdl = true;                    // SPK_PDL=0: launch the solve steps without programmatic dependent launch
     bool panel_smem_only = false;       // SPK_PANEL_SMEM=1: always use the shared-memory panel kernel
     bool diag_smem_only = false;        // SPK_DIAG_SMEM=1: always use the shared-memory diagonal kernel
     int dmma_variant = 4;               // SPK_DMMA_VARIANT (see gemm_dmma.cuh)
@@ -70,6 +71,18 @@ struct spk_plan {
     double kind_ms[16] = {0}; int64_t kind_n[16] = {0};
     bool profile = false;
 };
+
+// Launch with (pdl) or without the programmatic-stream-serialization attribute (see pdl_wait in kernels.cuh).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 static DevCtx make_ctx(spk_plan* p) {
     DevCtx c{};
@@ -225,6 +238,7 @@ SPK_API spk_plan* spk_plan_create(int64_t n, int64_t nsuper, const int64_t* xsup
     if (const char* e = getenv("SPK_SOLVE_GRAPH")) p->solve_graphs = e[0] != '0';
     if (const char* e = getenv("SPK_DIAG_TG")) p->diag_tg = atoi(e);
     if (const char* e = getenv("SPK_PANEL_SMEM")) p->panel_smem_only = e[0] == '1';
+    if (const char* e = getenv("SPK_PDL")) p->pdl = e[0] != '0';
     build_schedule(p->P);
     if (device < 0) return p;                      // host-only plan: structure statistics without a GPU
     int ndev = 0;
@@ -539,14 +553,14 @@ static int64_t run_solve_launches(spk_plan* p, const DevCtx& c, const std::vecto
         case K_PF_UPDATE: k_pf_update<<<grid, SV_ROWS, 0, st>>>(c, list, pfx, L.count); break;
         case K_PF_STEP: {
             size_t sm = pstep_smem_bytes(L.maxw);
-            if (lu) k_pf_step<true><<<grid, SV_ROWS, sm, st>>>(c, list, pfx, L.count);
-            else k_pf_step<false><<<grid, SV_ROWS, sm, st>>>(c, list, pfx, L.count);
+            if (lu) CK(launch_pdl(k_pf_step<true>, grid, dim3(SV_ROWS), sm, st, p->pdl, c, list, pfx, (int)L.count));
+            else CK(launch_pdl(k_pf_step<false>, grid, dim3(SV_ROWS), sm, st, p->pdl, c, list, pfx, (int)L.count));
             break;
         }
         case K_PB_STEP: {
             size_t sm = pstep_smem_bytes(L.maxw);
-            if (lu) k_pb_step<true><<<grid, SV_ROWS, sm, st>>>(c, list, pfx, L.count, d_rhs, ldrhs, p->P.maxpw, p->d_counters);
-            else k_pb_step<false><<<grid, SV_ROWS, sm, st>>>(c, list, pfx, L.count, d_rhs, ldrhs, p->P.maxpw, p->d_counters);
+            if (lu) CK(launch_pdl(k_pb_step<true>, grid, dim3(SV_ROWS), sm, st, p->pdl, c, list, pfx, (int)L.count, d_rhs, (int64_t)ldrhs, (int)p->P.maxpw, p->d_counters));
+            else CK(launch_pdl(k_pb_step<false>, grid, dim3(SV_ROWS), sm, st, p->pdl, c, list, pfx, (int)L.count, d_rhs, (int64_t)ldrhs, (int)p->P.maxpw, p->d_counters));
             break;
         }
         case K_PB_UPDATE: {
