@@ -61,11 +61,13 @@ k_gemm_dmma(DevCtx c, const GemmTask* __restrict__ tasks, const int32_t* __restr
     static_assert(NT % TM == 0 && (TN * DM_TK) % NT == 0 && (TM * DM_TK) % NT == 0, "loader shapes");
     extern __shared__ double smem[];
 
+    pdl_trigger();
     int t = find_task(pfx, count, blockIdx.x);
     int lb = blockIdx.x - pfx[t];
     const GemmTask g = tasks[t];
     const int mt = (g.m + TM - 1) / TM;
     const int row0 = (lb % mt) * TM, col0 = (lb / mt) * TN;
+    pdl_wait();
     if (g.lower && row0 + TM - 1 + g.roff < col0) return;          // tile strictly above the diagonal
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;

@@ -32,6 +32,16 @@ struct DevCtx {
     int32_t lu;
 };
 
+// Programmatic dependent launch: a kernel launched with the programmatic-serialization attribute may start
+// while its predecessor in the stream is still running.  pdl_trigger() lets the NEXT kernel start launching;
+// pdl_wait() blocks until the PREVIOUS kernel has completed and its writes are visible.  Everything that only
+// depends on the factors (task records, the diagonal block, the panel rows) is fetched before pdl_wait(), so
+// the launch gap and those round trips disappear from the chain of dependent panel steps.  Both are no-ops in
+// a kernel launched the ordinary way.  Every block calls pdl_wait() before it exits, which keeps completion
+// transitive along the chain.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ int find_task(const int32_t* __restrict__ pfx, int count, int b) {
     int lo = 0, hi = count;
     while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (pfx[mid] <= b) lo = mid; else hi = mid; }
@@ -316,9 +326,11 @@ constexpr int DIAG_NS = 2;
 __global__ void __launch_bounds__(64 * DIAG_NS) k_diag_ldlt_row(DevCtx c, const int32_t* __restrict__ pslist) {
     constexpr int WP = 64, NS = DIAG_NS, NE = WP / NS, PB = 8 / NS;   // entries per thread, entries per 8-column block
     __shared__ __align__(16) double col[2][2 * WP];
+    pdl_trigger();
     const PStep ps = c.psteps[pslist[blockIdx.x]];
     double* G = c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld;
     const int w = ps.w, ld = ps.ld;
+    pdl_wait();
     // slices by WARP: the coefficient loads below are then warp-uniform 128-bit broadcasts (2 clocks each; the
     // same loads with 2-4 distinct addresses per warp cost 4 and made shared memory the bottleneck)
     const int r = threadIdx.x & (WP - 1), h = threadIdx.x / WP;
@@ -386,11 +398,13 @@ __global__ void __launch_bounds__(64 * LU_NS) k_diag_lu_row(DevCtx c, const int3
     __shared__ __align__(16) double S[WP * LU_SLD];
     __shared__ __align__(16) double prow[2 * WP];       // the pivot row of the current column, by absolute column
     __shared__ double keys[2][WP];
+    pdl_trigger();
     const PStep ps = c.psteps[pslist[blockIdx.x]];
     double* G = c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld;
     const int w = ps.w, ld = ps.ld;
     int32_t* ipiv = c.ipiv + ps.col0;
     const int32_t* subw = c.subw + ps.sub0;
+    pdl_wait();
     const int r = threadIdx.x & (WP - 1), h = threadIdx.x / WP, lane = threadIdx.x & 31;
     double a[NE];
 #pragma unroll
@@ -643,6 +657,7 @@ __global__ void __launch_bounds__(PANEL_REG_THREADS) k_panel_reg(DevCtx c, const
     __shared__ __align__(16) double Ts[WP * WP + WP];   // Ts[j + k*WP] = coefficient of x_k in unknown j (j > k)
     __shared__ double rd[WP];                           // 1 / diagonal (0 where the diagonal is 0, as the LU reference does)
     __shared__ int32_t perm[WP], s0r[WP];               // U side: original row of each final row, first row of its chunk
+    pdl_trigger();
     const int bx = blockIdx.x / PANEL_REG_SPLIT, part = blockIdx.x % PANEL_REG_SPLIT;
     int t = find_task(pfx, count, bx);
     int lb = bx - pfx[t];
@@ -650,6 +665,7 @@ __global__ void __launch_bounds__(PANEL_REG_THREADS) k_panel_reg(DevCtx c, const
     const int w = ps.w, ld = ps.ld, e0 = ps.o + ps.w;
     const int below = ps.R - e0;
     const int nb = (below + PANEL_ROWS - 1) / PANEL_ROWS;
+    pdl_wait();
     // LU, U side (blocks nb .. 2nb-1): U12 = inv(L11) * P * A12 with P the chunk-local interchanges.  The rows of
     // A12 are gathered through P up front and the multipliers a chunk inherits from earlier chunks (stored in
     // pre-interchange row order, SpkLUFactor.jl:230-240) are gathered the same way, which leaves one plain
@@ -1155,15 +1171,6 @@ __device__ __forceinline__ void stage_block_async(double* S, const double* __res
     asm volatile("cp.async.commit_group;");
 }
 __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-// Programmatic dependent launch: a kernel launched with the programmatic-serialization attribute may start
-// while its predecessor in the stream is still running.  pdl_trigger() lets the NEXT kernel start launching;
-// pdl_wait() blocks until the PREVIOUS kernel has completed and its writes are visible.  Everything that only
-// depends on the factors (task records, the diagonal block, the panel rows) is fetched before pdl_wait(), so
-// the launch gap and those round trips disappear from the chain of dependent panel steps.  Both are no-ops in
-// a kernel launched the ordinary way.  Every block calls pdl_wait() before it exits, which keeps completion
-// transitive along the chain.
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 // partial sums over the front indices [r0, r1) beyond the step: out[k] = sum_r coef(r,k) * wf[r]
 //   LU: coef = U[o+k, r] (column r of the U panel: w contiguous entries);  LDL^T: coef = L[r, o+k]
 // red: shared scratch of (blockDim.x/32) * w doubles; the warps' sums are added in a fixed order.

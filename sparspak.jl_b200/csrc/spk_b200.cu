@@ -56,6 +56,8 @@ struct spk_plan {
     int64_t sg_nrhs = 0, sg_ld = 0, sg_launches = 0; int32_t sg_which = -1;
     int diag_tg = 1;                    // SPK_DIAG_TG: 1 = row kernel (4 threads per row), 8 / 16 = thread grid of the cyclic register kernel
     bool pdl = true;                    // SPK_PDL=0: launch the solve steps without programmatic dependent launch
+    bool pdl_gemm = false;              // SPK_PDL_GEMM=1: also the DMMA kernels (measured slower: early blocks hold SM resources)
+    bool pdl_factor = false;            // SPK_PDL_FACTOR=1: same for the diagonal / panel kernels of the factorisation (measured: no gain)
     bool panel_smem_only = false;       // SPK_PANEL_SMEM=1: always use the shared-memory panel kernel
     bool diag_smem_only = false;        // SPK_DIAG_SMEM=1: always use the shared-memory diagonal kernel
     int dmma_variant = 4;               // SPK_DMMA_VARIANT (see gemm_dmma.cuh)
@@ -239,6 +241,8 @@ SPK_API spk_plan* spk_plan_create(int64_t n, int64_t nsuper, const int64_t* xsup
     if (const char* e = getenv("SPK_DIAG_TG")) p->diag_tg = atoi(e);
     if (const char* e = getenv("SPK_PANEL_SMEM")) p->panel_smem_only = e[0] == '1';
     if (const char* e = getenv("SPK_PDL")) p->pdl = e[0] != '0';
+    if (const char* e = getenv("SPK_PDL_FACTOR")) p->pdl_factor = e[0] != '0';
+    if (const char* e = getenv("SPK_PDL_GEMM")) p->pdl_gemm = e[0] == '1';
     build_schedule(p->P);
     if (device < 0) return p;                      // host-only plan: structure statistics without a GPU
     int ndev = 0;
@@ -367,9 +371,9 @@ static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L, 
         // shared memory sized for the widest block of THIS launch (tiny fronts keep high occupancy)
         int wl = std::min(L.maxw, p->diag_smem_nj);
         size_t sm = (size_t)wl * (wl | 1) * sizeof(double);
-        if (lu && L.maxw <= 64 && !p->diag_smem_only) k_diag_lu_row<<<L.count, 64 * LU_NS, 0, st>>>(c, p->d_pslist + L.first);
+        if (lu && L.maxw <= 64 && !p->diag_smem_only) CK(launch_pdl(k_diag_lu_row, dim3(L.count), dim3(64 * LU_NS), 0, st, p->pdl_factor, c, (const int32_t*)(p->d_pslist + L.first)));
         else if (lu) k_diag<true><<<L.count, 256, sm, st>>>(c, p->d_pslist + L.first, wl);
-        else if (L.maxw <= 64 && !p->diag_smem_only && p->diag_tg == 1) k_diag_ldlt_row<<<L.count, 64 * DIAG_NS, 0, st>>>(c, p->d_pslist + L.first);
+        else if (L.maxw <= 64 && !p->diag_smem_only && p->diag_tg == 1) CK(launch_pdl(k_diag_ldlt_row, dim3(L.count), dim3(64 * DIAG_NS), 0, st, p->pdl_factor, c, (const int32_t*)(p->d_pslist + L.first)));
         else if (L.maxw <= 64 && !p->diag_smem_only && p->diag_tg == 8) k_diag_ldlt_reg<8, 8><<<L.count, 64, 0, st>>>(c, p->d_pslist + L.first);
         else if (L.maxw <= 64 && !p->diag_smem_only) k_diag_ldlt_reg<4, 16><<<L.count, 256, 0, st>>>(c, p->d_pslist + L.first);
         else if (L.maxw <= 96 && !p->diag_smem_only) k_diag_ldlt_reg<6, 16><<<L.count, 256, 0, st>>>(c, p->d_pslist + L.first);
@@ -382,8 +386,8 @@ static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L, 
         for (int w = 1; w <= L.maxw; ++w) sm = std::max(sm, panel_smem_bytes(w));
         const bool fast = L.maxw <= 64 && !p->panel_smem_only;
         if (fast) {
-            if (lu) k_panel_reg<true><<<L.nblocks * PANEL_REG_SPLIT, PANEL_REG_THREADS, 0, st>>>(c, p->d_pslist + L.first, pfx, L.count);
-            else k_panel_reg<false><<<L.nblocks * PANEL_REG_SPLIT, PANEL_REG_THREADS, 0, st>>>(c, p->d_pslist + L.first, pfx, L.count);
+            if (lu) CK(launch_pdl(k_panel_reg<true>, dim3(L.nblocks * PANEL_REG_SPLIT), dim3(PANEL_REG_THREADS), 0, st, p->pdl_factor, c, (const int32_t*)(p->d_pslist + L.first), pfx, (int)L.count));
+            else CK(launch_pdl(k_panel_reg<false>, dim3(L.nblocks * PANEL_REG_SPLIT), dim3(PANEL_REG_THREADS), 0, st, p->pdl_factor, c, (const int32_t*)(p->d_pslist + L.first), pfx, (int)L.count));
         }
         else if (lu) k_panel<true><<<L.nblocks, PANEL_ROWS, sm, st>>>(c, p->d_pslist + L.first, pfx, L.count, 0);
         else k_panel<false><<<L.nblocks, PANEL_ROWS, sm, st>>>(c, p->d_pslist + L.first, pfx, L.count, 0);
@@ -394,7 +398,7 @@ static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L, 
     case K_GEMM_B64:
     case K_GEMM_B128: {
         GemmVariant v = gemm_dmma_variant(L.kind, p->dmma_variant);
-        v.fn<<<L.nblocks, v.threads, v.smem, st>>>(c, p->d_gemmt + L.first, pfx, L.count);
+        CK(launch_pdl(v.fn, dim3(L.nblocks), dim3(v.threads), v.smem, st, p->pdl_factor && p->pdl_gemm, c, (const GemmTask*)(p->d_gemmt + L.first), pfx, (int)L.count));
         break;
     }
     default:
