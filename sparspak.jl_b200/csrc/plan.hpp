@@ -144,6 +144,17 @@ struct Plan {
     struct Range { int32_t owner; int32_t f0, f1; int64_t lnz0, lnz1, unz0, unz1, col0, col1; };
     std::vector<Range> ranges;                 // contiguous front / storage ranges owned by one part
     std::vector<Launch> factor_local, factor_top, fwd_local, fwd_top, bwd_top, bwd_local;
+    // single GPU, TREE PIPELINES: the front tree is cut like the multi-GPU partition into `pipes` sets of
+    // subtrees plus a top set; the sets are factored CONCURRENTLY, each on its own (panel, update) stream
+    // pair, then the top set.  Within one pipeline a level ends in a latency-bound tail (the last outer
+    // blocks of its fronts: a chain of small dependent kernels with the update stream idle); the other
+    // pipelines' trailing updates fill it.  Same arithmetic per front, so the factors do not change.
+    // MEASURED (96^3, SPK_PIPES=2..4): no gain — a trace of the two-stream run (SPK_TRACE) shows the GPU busy
+    // with >= 148-block kernels for 214 of 232 ms, i.e. the factorisation is throughput-, not schedule-bound.
+    // Off by default (SPK_PIPES=1).
+    int32_t pipes = 1;
+    std::vector<std::vector<Launch>> factor_pipe;
+    std::vector<Launch> factor_ptop;
     std::string error;
 };
 
@@ -391,6 +402,7 @@ inline void plan_env_overrides(Plan& P) {        // test / tuning knobs
     if (const char* e = getenv("SPK_SOLVE_SMALL")) P.solve_small = atoll(e);
     if (const char* e = getenv("SPK_OB_STEPS")) P.ob_steps = std::max(1, atoi(e));
     if (const char* e = getenv("SPK_LOOKAHEAD")) P.lookahead = e[0] != '0';
+    if (const char* e = getenv("SPK_PIPES")) P.pipes = std::min(4, std::max(1, atoi(e)));
     if (const char* e = getenv("SPK_SOLVE_LNZ")) P.solve_on_fronts = e[0] != '1';
     if (const char* e = getenv("SPK_PS_WIDTH")) P.ps_width = std::max(1, atoi(e));
     if (const char* e = getenv("SPK_DMMA_VARIANT")) P.no_b128 = atoi(e) >= 2;
@@ -696,7 +708,31 @@ inline void build_schedule(Plan& P) {
     }
     partition(P);
     std::vector<uint8_t> sel(nf, 1);
-    if (P.nparts <= 1) { build_lists(P, sel, P.factor_launches, P.fwd_launches, P.bwd_launches); return; }
+    if (P.nparts <= 1) {
+        build_lists(P, sel, P.factor_launches, P.fwd_launches, P.bwd_launches);
+        P.factor_pipe.clear(); P.factor_ptop.clear();
+        if (P.pipes > 1 && P.lookahead && nf > 1) {
+            P.nparts = P.pipes;
+            partition(P);
+            const std::vector<int32_t> vowner = P.owner;
+            P.nparts = 1; P.owner.assign(nf, 0); P.xchg.clear(); P.ranges.clear();
+            bool any_top = false;
+            for (int32_t f = 0; f < nf; ++f) any_top |= vowner[f] == -1;
+            if (any_top) {
+                std::vector<Launch> unused_fwd, unused_bwd;
+                const bool sof = P.solve_on_fronts;
+                P.factor_pipe.resize(P.pipes);
+                for (int32_t v = 0; v < P.pipes; ++v) {
+                    for (int32_t f = 0; f < nf; ++f) sel[f] = vowner[f] == v;
+                    build_lists(P, sel, P.factor_pipe[v], unused_fwd, unused_bwd);
+                }
+                for (int32_t f = 0; f < nf; ++f) sel[f] = vowner[f] == -1;
+                build_lists(P, sel, P.factor_ptop, unused_fwd, unused_bwd);
+                P.solve_on_fronts = sof;
+            }
+        }
+        return;
+    }
     std::vector<Launch> unused_f;
     for (int32_t f = 0; f < nf; ++f) sel[f] = P.owner[f] == P.part;
     build_lists(P, sel, P.factor_local, P.fwd_local, P.bwd_local);

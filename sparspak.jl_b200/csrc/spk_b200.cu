@@ -40,6 +40,9 @@ struct spk_plan {
     int device = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;   // panel stream (high priority), trailing-update stream
     cudaEvent_t evs0 = nullptr, evs1 = nullptr;          // last record of each stream
+    // tree pipelines (Plan::pipes): stream / event pair per pipeline; pair 0 = (stream, stream2, evs0, evs1)
+    cudaStream_t pst[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+    cudaEvent_t pev[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evg0 = nullptr, evg1 = nullptr;
     // device state
     double *d_pb = nullptr, *d_F = nullptr, *d_lnz = nullptr, *d_unz = nullptr, *d_w = nullptr, *d_rhs = nullptr, *d_tmp = nullptr;
@@ -56,6 +59,7 @@ struct spk_plan {
     int64_t sg_nrhs = 0, sg_ld = 0, sg_launches = 0; int32_t sg_which = -1;
     int diag_tg = 1;                    // SPK_DIAG_TG: 1 = row kernel (4 threads per row), 8 / 16 = thread grid of the cyclic register kernel
     bool pdl = true;                    // SPK_PDL=0: launch the solve steps without programmatic dependent launch
+    bool use_pipes = true;              // SPK_PIPES=1 builds no pipelines; this switches them off at run time (tests)
     bool pdl_gemm = false;              // SPK_PDL_GEMM=1: also the DMMA kernels (measured slower: early blocks hold SM resources)
     bool pdl_factor = false;            // SPK_PDL_FACTOR=1: same for the diagonal / panel kernels of the factorisation (measured: no gain)
     bool panel_smem_only = false;       // SPK_PANEL_SMEM=1: always use the shared-memory panel kernel
@@ -123,6 +127,7 @@ SPK_API void spk_plan_destroy(spk_plan* p) {
         if (p->evs0) cudaEventDestroy(p->evs0);
         if (p->evs1) cudaEventDestroy(p->evs1);
         if (p->stream2) cudaStreamDestroy(p->stream2);
+        for (int v = 1; v < 4; ++v) for (int q = 0; q < 2; ++q) { if (p->pst[v][q]) cudaStreamDestroy(p->pst[v][q]); if (p->pev[v][q]) cudaEventDestroy(p->pev[v][q]); }
         if (p->stream) cudaStreamDestroy(p->stream);
     }
     delete p;
@@ -138,6 +143,13 @@ static int64_t plan_upload(spk_plan* p) {
         CK(cudaStreamCreateWithPriority(&p->stream2, cudaStreamNonBlocking, lo));
         CK(cudaEventCreateWithFlags(&p->evs0, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&p->evs1, cudaEventDisableTiming));
+        p->pst[0][0] = p->stream; p->pst[0][1] = p->stream2; p->pev[0][0] = p->evs0; p->pev[0][1] = p->evs1;
+        for (int v = 1; v < 4; ++v) {                 // panel streams share the top priority; update streams rank by pipeline
+            CK(cudaStreamCreateWithPriority(&p->pst[v][0], cudaStreamNonBlocking, hi));
+            CK(cudaStreamCreateWithPriority(&p->pst[v][1], cudaStreamNonBlocking, std::min(lo, hi + 1 + v)));
+            CK(cudaEventCreateWithFlags(&p->pev[v][0], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&p->pev[v][1], cudaEventDisableTiming));
+        }
     }
     CK(cudaEventCreate(&p->ev0)); CK(cudaEventCreate(&p->ev1));
     CK(cudaEventCreate(&p->evg0)); CK(cudaEventCreate(&p->evg1));
@@ -354,12 +366,12 @@ SPK_API int64_t spk_plan_reassemble(spk_plan* p) {
 }
 
 // ---- factor ---------------------------------------------------------------------------
-static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L, bool two_streams) {
+static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L, bool two_streams, int pair = 0) {
     const int32_t* pfx = p->d_blkpfx + L.pfx;
     cudaStream_t st = p->stream;
     if (two_streams) {
-        st = L.stream ? p->stream2 : p->stream;
-        if (L.wait_other) CK(cudaStreamWaitEvent(st, L.stream ? p->evs0 : p->evs1, 0));
+        st = p->pst[pair][L.stream ? 1 : 0];
+        if (L.wait_other) CK(cudaStreamWaitEvent(st, p->pev[pair][L.stream ? 0 : 1], 0));
     }
     const bool lu = p->P.lu;
     switch (L.kind) {
@@ -404,7 +416,7 @@ static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L, 
     default:
         set_err("bad launch kind"); return -100;
     }
-    if (two_streams && L.record) CK(cudaEventRecord(L.stream ? p->evs1 : p->evs0, st));
+    if (two_streams && L.record) CK(cudaEventRecord(p->pev[pair][L.stream ? 1 : 0], st));
     return 0;
 }
 
@@ -434,12 +446,49 @@ SPK_API int64_t spk_plan_factor_phase(spk_plan* p, int32_t phase) {
     size_t li = 0;
     const bool two = P.lookahead && !p->profile;      // per-launch timing needs the serial order on one stream
     if (two) { CK(cudaEventRecord(p->evs0, st)); CK(cudaEventRecord(p->evs1, p->stream2)); }
-    for (const Launch& L : Ls) {
+    const char* trace_path = getenv("SPK_TRACE");     // completion time of every launch in the real two-stream run
+    const bool trace = trace_path && two && phase < 0;
+    std::vector<cudaEvent_t> tev;
+    if (trace) { tev.resize(Ls.size() + 1); for (auto& e : tev) cudaEventCreate(&e); cudaEventRecord(tev[0], st); }
+    const bool piped = phase < 0 && two && p->use_pipes && !P.factor_pipe.empty() && !trace;
+    if (piped) {
+        // tree pipelines: every pipeline's streams start after the load on the main stream; launches are
+        // enqueued round-robin so that no pipeline waits for the CPU; the top set follows on pair 0
+        const int V = (int)P.factor_pipe.size();
+        for (int v = 0; v < V; ++v) for (int q = 0; q < 2; ++q) {
+            if (v == 0 && q == 0) continue;
+            CK(cudaStreamWaitEvent(p->pst[v][q], p->evs0, 0));
+            CK(cudaEventRecord(p->pev[v][q], p->pst[v][q]));
+        }
+        std::vector<size_t> at(V, 0);
+        for (bool more = true; more;) {
+            more = false;
+            for (int v = 0; v < V; ++v) {
+                if (at[v] >= P.factor_pipe[v].size()) continue;
+                const Launch& L = P.factor_pipe[v][at[v]++];
+                int64_t rc = run_factor_launch(p, c, L, true, v);
+                if (rc) return rc;
+                ++p->launches_factor;
+                if (L.kind == K_GEMM_B64 || L.kind == K_GEMM_B128) p->gemm_flops += L.flops;
+                more = true;
+            }
+        }
+        for (int v = 0; v < V; ++v) for (int q = 0; q < 2; ++q) {     // join on the main stream
+            if (v == 0 && q == 0) continue;
+            CK(cudaEventRecord(p->pev[v][q], p->pst[v][q]));
+            CK(cudaStreamWaitEvent(st, p->pev[v][q], 0));
+        }
+        CK(cudaEventRecord(p->evs0, st));
+        CK(cudaStreamWaitEvent(p->stream2, p->evs0, 0));
+        CK(cudaEventRecord(p->evs1, p->stream2));
+    }
+    for (const Launch& L : (piped ? P.factor_ptop : Ls)) {
         int64_t rc = run_factor_launch(p, c, L, two);
         if (rc) return rc;
         ++p->launches_factor;
         if (L.kind == K_GEMM_B64 || L.kind == K_GEMM_B128) p->gemm_flops += L.flops;
         if (p->profile) cudaEventRecord(evs[++li], st);
+        if (trace) cudaEventRecord(tev[++li], p->pst[0][L.stream ? 1 : 0]);
     }
     if (two) { CK(cudaEventRecord(p->evs1, p->stream2)); CK(cudaStreamWaitEvent(st, p->evs1, 0)); }
     if (phase != 0) {
@@ -451,6 +500,17 @@ SPK_API int64_t spk_plan_factor_phase(spk_plan* p, int32_t phase) {
     CK(cudaEventRecord(phase == 0 ? p->evg1 : p->ev1, st));
     CK(cudaStreamSynchronize(st));
     if (phase != 0) p->values_in_fronts = false;
+    if (trace) {
+        if (FILE* f = fopen(trace_path, "w")) {
+            fprintf(f, "idx,kind,level,step,stream,blocks,flops,wait_other,t_end_ms\n");
+            for (size_t i = 0; i < Ls.size(); ++i) {
+                float t = 0; cudaEventElapsedTime(&t, tev[0], tev[i + 1]);
+                fprintf(f, "%zu,%d,%d,%d,%d,%d,%.6g,%d,%.6f\n", i, Ls[i].kind, Ls[i].level, Ls[i].step, (int)Ls[i].stream, Ls[i].nblocks, Ls[i].flops, (int)Ls[i].wait_other, t);
+            }
+            fclose(f);
+        }
+        for (auto& e : tev) cudaEventDestroy(e);
+    }
     float ms = 0;
     if (phase < 0) { CK(cudaEventElapsedTime(&ms, p->ev0, p->ev1)); p->ms_factor = ms; }
     else if (phase == 0) { CK(cudaEventElapsedTime(&ms, p->ev0, p->evg1)); p->ms_factor = ms; p->ms_phase0 = ms; }
@@ -466,10 +526,10 @@ SPK_API int64_t spk_plan_factor_phase(spk_plan* p, int32_t phase) {
         for (auto& e : evs) cudaEventDestroy(e);
         if (const char* path = getenv("SPK_DUMP_LAUNCHES")) {       // per-launch CSV for profiles/
             if (FILE* f = fopen(path, "w")) {
-                fprintf(f, "idx,kind,level,step,tasks,blocks,maxw,flops,ms\n");
+                fprintf(f, "idx,kind,level,step,tasks,blocks,maxw,flops,ms,stream,wait_other,record\n");
                 for (size_t i = 0; i < Ls.size(); ++i) {
                     const Launch& L = Ls[i];
-                    fprintf(f, "%zu,%d,%d,%d,%d,%d,%d,%.6g,%.6f\n", i, L.kind, L.level, L.step, L.count, L.nblocks, L.maxw, L.flops, p->launch_ms[i]);
+                    fprintf(f, "%zu,%d,%d,%d,%d,%d,%d,%.6g,%.6f,%d,%d,%d\n", i, L.kind, L.level, L.step, L.count, L.nblocks, L.maxw, L.flops, p->launch_ms[i], (int)L.stream, (int)L.wait_other, (int)L.record);
                 }
                 fclose(f);
             }

@@ -239,7 +239,10 @@ API int64_t sim_xchg_info(void* h, int what, int64_t i, int64_t* out) {
 API int64_t sim_factor(void* h, double* lnz, double* unz, int64_t* ipvt) {
     Sim* s = (Sim*)h; Plan& P = s->P;
     sim_load(h, lnz, unz);
-    if (run_factor_list(s, P.factor_launches)) return -100;
+    if (!P.factor_pipe.empty()) {                       // the product's default order: tree pipelines, then the top set
+        for (auto& Lp : P.factor_pipe) if (run_factor_list(s, Lp)) return -100;
+        if (run_factor_list(s, P.factor_ptop)) return -100;
+    } else if (run_factor_list(s, P.factor_launches)) return -100;
     chunks_io(*s, true);
     std::copy(s->lnz.begin(), s->lnz.end(), lnz);
     if (P.lu) { std::copy(s->unz.begin(), s->unz.end(), unz); for (int64_t i = 0; i < P.n; ++i) ipvt[i] = s->ipiv[i]; }
