@@ -243,3 +243,40 @@ def test_large_front_solve_path(spd, monkeypatch):
     plan.triangularsolve(x)
     assert residual(A, x, bb) < RESID_TOL
     plan.destroy()
+
+
+VARIANTS = [
+    {"SPK_DIAG_SMEM": "1"},                     # shared-memory diagonal-block kernels instead of the register ones
+    {"SPK_PANEL_SMEM": "1"},                    # shared-memory panel kernel (both sides for LU)
+    {"SPK_DIAG_SMEM": "1", "SPK_PANEL_SMEM": "1", "SPK_PS_WIDTH": "100"},   # panel steps wider than 64 columns
+    {"SPK_PIPES": "2"},                         # tree pipelines: two subtree sets on their own stream pairs
+    {"SPK_LOOKAHEAD": "0"},                     # one stream
+    {"SPK_PDL": "0", "SPK_SOLVE_SMALL": "0"},   # solve steps without programmatic dependent launch
+    {"SPK_SOLVE_LNZ": "1"},                     # chunk-by-chunk solve on lnz / unz
+    {"SPK_SOLVE_GRAPH": "0", "SPK_SOLVE_SMALL": "0"},
+]
+
+
+@pytest.mark.parametrize("spd", [False, True])
+@pytest.mark.parametrize("env", VARIANTS, ids=["+".join(f"{k[4:]}={v}" for k, v in e.items()) for e in VARIANTS])
+def test_kernel_and_schedule_variants_agree(spd, env, monkeypatch):
+    """Every alternative kernel / schedule kept behind an environment knob reproduces the default path:
+    same pivot sequence, factors within the parity bar, residual within the bar."""
+    A = M.convdiff3d(14) if not spd else M.laplacian3d(14)
+    s = prepare(A, spd, spk.nd_grid_order(14, 14, 14))
+    b = s.slvr
+    lo, uo, po, _ = oracle_factor(b)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    plan, lg, ug, pg, fg = gpu_factor_plan(b)
+    assert fg == 0
+    assert rel_err(lg, lo, spd_mask(b)) < FACTOR_RTOL
+    if not spd:
+        assert np.array_equal(pg, po)
+        assert rel_err(ug, uo) < FACTOR_RTOL
+    bb = M.rhs_for(A)
+    x = bb.copy()
+    plan.set_perm(b.order.rperm, b.order.rinvp)
+    plan.triangularsolve(x)
+    assert residual(A, x, bb) < RESID_TOL
+    plan.destroy()
