@@ -64,6 +64,23 @@ SPK_API int64_t spk_ldltfactor_f64(int64_t n, int64_t nsuper, const int64_t* xsu
 SPK_API int64_t spk_ldltsolve_f64(int64_t nsuper, const int64_t* xsuper, const int64_t* xlindx,
                                   const int64_t* lindx, const int64_t* xlnz, const double* lnz, double* rhs);
 
+/* Float32 twins of the five drop-ins (the reference dispatches Float32 to sgemm/sgetrf/strsm,
+ * SpkSpdMMOps.jl:186-351; _factor!(s::_SparseBase{Int64,Float32}) binds these).  Values are widened on
+ * entry and narrowed on exit; the arithmetic is the FP64 engine's. */
+SPK_API int64_t spk_lufactor_f32(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* snode,
+                                 const int64_t* xlindx, const int64_t* lindx, const int64_t* xlnz, float* lnz,
+                                 const int64_t* xunz, float* unz, int64_t* ipvt);
+SPK_API int64_t spk_lulsolve_f32(int64_t nsuper, const int64_t* xsuper, const int64_t* xlindx,
+                                 const int64_t* lindx, const int64_t* xlnz, const float* lnz,
+                                 const int64_t* ipiv, float* rhs);
+SPK_API int64_t spk_luusolve_f32(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* xlindx,
+                                 const int64_t* lindx, const int64_t* xlnz, const float* lnz,
+                                 const int64_t* xunz, const float* unz, float* rhs);
+SPK_API int64_t spk_ldltfactor_f32(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* snode,
+                                   const int64_t* xlindx, const int64_t* lindx, const int64_t* xlnz, float* lnz);
+SPK_API int64_t spk_ldltsolve_f32(int64_t nsuper, const int64_t* xsuper, const int64_t* xlindx,
+                                  const int64_t* lindx, const int64_t* xlnz, const float* lnz, float* rhs);
+
 /* ---- stateful plan: structure + factors stay resident in HBM --------------------------
  * One plan per symbolic factorisation (rebuild when symbolicfactor! reruns,
  * SpkSparseSolver.jl:163-175).  Re-entrant per handle; every call is synchronous at return. */
@@ -109,6 +126,11 @@ SPK_API int64_t spk_plan_set_perm(spk_plan* p, const int64_t* rperm, const int64
 SPK_API int64_t spk_plan_triangularsolve(spk_plan* p, double* b, int64_t nrhs, int64_t ldb);
 
 /* ---- device-resident variants used by bench.py / multi-GPU drivers -------------------- */
+/* Float32 callers of a plan (the plan itself stays FP64) */
+SPK_API int64_t spk_plan_inmatrix_f32(spk_plan* p, int64_t nnz, const int64_t* dest_or_null, const float* nzval);
+SPK_API int64_t spk_plan_get_factors_f32(spk_plan* p, float* lnz, float* unz, int64_t* ipvt);
+SPK_API int64_t spk_plan_triangularsolve_f32(spk_plan* p, float* b, int64_t nrhs, int64_t ldb);
+
 SPK_API void*   spk_plan_device_ptr(spk_plan* p, int32_t what);   /* 0 lnz, 1 unz, 2 ipiv(int32), 5 frontal arena, 6 solve work vectors */
 SPK_API int64_t spk_plan_device_len(spk_plan* p, int32_t what);   /* element counts of the above */
 SPK_API int64_t spk_plan_factor_phase(spk_plan* p, int32_t phase); /* multi-GPU: 0 local subtrees, 1 top set + write-back */

@@ -15,6 +15,8 @@ F64P = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 
 SYMBOLS = [
     "spk_lufactor_f64", "spk_lulsolve_f64", "spk_luusolve_f64", "spk_ldltfactor_f64", "spk_ldltsolve_f64",
+    "spk_lufactor_f32", "spk_lulsolve_f32", "spk_luusolve_f32", "spk_ldltfactor_f32", "spk_ldltsolve_f32",
+    "spk_plan_inmatrix_f32", "spk_plan_get_factors_f32", "spk_plan_triangularsolve_f32",
     "spk_plan_create", "spk_plan_destroy", "spk_plan_inmatrix", "spk_plan_reassemble", "spk_plan_set_values", "spk_plan_factor",
     "spk_plan_get_factors", "spk_plan_set_factors", "spk_plan_solve", "spk_plan_set_perm",
     "spk_plan_triangularsolve", "spk_plan_device_ptr", "spk_plan_device_len", "spk_plan_factor_phase",
@@ -47,6 +49,23 @@ def lib():
     L.spk_ldltfactor_f64.restype = i64
     L.spk_ldltsolve_f64.argtypes = [i64, I64P, I64P, I64P, I64P, F64P, F64P]
     L.spk_ldltsolve_f64.restype = i64
+    F32P = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+    L.spk_lufactor_f32.argtypes = [i64, i64, I64P, I64P, I64P, I64P, I64P, F32P, I64P, F32P, I64P]
+    L.spk_lufactor_f32.restype = i64
+    L.spk_lulsolve_f32.argtypes = [i64, I64P, I64P, I64P, I64P, F32P, I64P, F32P]
+    L.spk_lulsolve_f32.restype = i64
+    L.spk_luusolve_f32.argtypes = [i64, i64, I64P, I64P, I64P, I64P, F32P, I64P, F32P, F32P]
+    L.spk_luusolve_f32.restype = i64
+    L.spk_ldltfactor_f32.argtypes = [i64, i64, I64P, I64P, I64P, I64P, I64P, F32P]
+    L.spk_ldltfactor_f32.restype = i64
+    L.spk_ldltsolve_f32.argtypes = [i64, I64P, I64P, I64P, I64P, F32P, F32P]
+    L.spk_ldltsolve_f32.restype = i64
+    L.spk_plan_inmatrix_f32.argtypes = [vp, i64, vp, F32P]
+    L.spk_plan_inmatrix_f32.restype = i64
+    L.spk_plan_get_factors_f32.argtypes = [vp, vp, vp, vp]
+    L.spk_plan_get_factors_f32.restype = i64
+    L.spk_plan_triangularsolve_f32.argtypes = [vp, F32P, i64, i64]
+    L.spk_plan_triangularsolve_f32.restype = i64
     L.spk_plan_create.argtypes = [i64, i64, I64P, I64P, I64P, I64P, I64P, vp, i32, i32, i32]
     L.spk_plan_create.restype = vp
     L.spk_plan_destroy.argtypes = [vp]

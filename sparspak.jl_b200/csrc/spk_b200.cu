@@ -945,4 +945,73 @@ SPK_API int64_t spk_ldltsolve_f64(int64_t nsuper, const int64_t* xsuper, const i
     return rc ? rc : 1;
 }
 
+// ---- Float32 twins ---------------------------------------------------------------------------
+// The reference routes Float32 problems to sgemm/sgetrf/strsm (SpkSpdMMOps.jl:186-351).  On B200 the FP64
+// tensor pipe is the fastest pipe this path can use (tcgen05 has no FP32-accumulate-FP32-input kind short of
+// TF32 rounding), so the _f32 entry points widen on entry, run the FP64 engine and narrow on exit: results are
+// at least as accurate as an FP32 computation; the pivot sequence is the FP64 one.
+static std::vector<double> widen(const float* a, int64_t len) { std::vector<double> v((size_t)std::max<int64_t>(len, 0)); for (int64_t i = 0; i < len; ++i) v[i] = a[i]; return v; }
+static void narrow(const std::vector<double>& v, float* a) { for (size_t i = 0; i < v.size(); ++i) a[i] = (float)v[i]; }
+
+SPK_API int64_t spk_lufactor_f32(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* snode,
+                                 const int64_t* xlindx, const int64_t* lindx, const int64_t* xlnz, float* lnz,
+                                 const int64_t* xunz, float* unz, int64_t* ipvt) {
+    std::vector<double> l = widen(lnz, xlnz[n] - 1), u = widen(unz, xunz[n] - 1);
+    int64_t rc = spk_lufactor_f64(n, nsuper, xsuper, snode, xlindx, lindx, xlnz, l.data(), xunz, u.data(), ipvt);
+    if (rc >= -1) { narrow(l, lnz); narrow(u, unz); }
+    return rc;
+}
+SPK_API int64_t spk_ldltfactor_f32(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* snode,
+                                   const int64_t* xlindx, const int64_t* lindx, const int64_t* xlnz, float* lnz) {
+    std::vector<double> l = widen(lnz, xlnz[n] - 1);
+    int64_t rc = spk_ldltfactor_f64(n, nsuper, xsuper, snode, xlindx, lindx, xlnz, l.data());
+    if (rc >= -1) narrow(l, lnz);
+    return rc;
+}
+SPK_API int64_t spk_lulsolve_f32(int64_t nsuper, const int64_t* xsuper, const int64_t* xlindx, const int64_t* lindx,
+                                 const int64_t* xlnz, const float* lnz, const int64_t* ipiv, float* rhs) {
+    const int64_t n = n_from_xsuper(nsuper, xsuper);
+    std::vector<double> l = widen(lnz, xlnz[n] - 1), r = widen(rhs, n);
+    int64_t rc = spk_lulsolve_f64(nsuper, xsuper, xlindx, lindx, xlnz, l.data(), ipiv, r.data());
+    if (rc == 1) narrow(r, rhs);
+    return rc;
+}
+SPK_API int64_t spk_luusolve_f32(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* xlindx,
+                                 const int64_t* lindx, const int64_t* xlnz, const float* lnz, const int64_t* xunz,
+                                 const float* unz, float* rhs) {
+    std::vector<double> l = widen(lnz, xlnz[n] - 1), u = widen(unz, xunz[n] - 1), r = widen(rhs, n);
+    int64_t rc = spk_luusolve_f64(n, nsuper, xsuper, xlindx, lindx, xlnz, l.data(), xunz, u.data(), r.data());
+    if (rc == 1) narrow(r, rhs);
+    return rc;
+}
+SPK_API int64_t spk_ldltsolve_f32(int64_t nsuper, const int64_t* xsuper, const int64_t* xlindx, const int64_t* lindx,
+                                  const int64_t* xlnz, const float* lnz, float* rhs) {
+    const int64_t n = n_from_xsuper(nsuper, xsuper);
+    std::vector<double> l = widen(lnz, xlnz[n] - 1), r = widen(rhs, n);
+    int64_t rc = spk_ldltsolve_f64(nsuper, xsuper, xlindx, lindx, xlnz, l.data(), r.data());
+    if (rc == 1) narrow(r, rhs);
+    return rc;
+}
+// plan twins: values / right-hand sides cross the boundary as Float32, the plan stays FP64
+SPK_API int64_t spk_plan_inmatrix_f32(spk_plan* p, int64_t nnz, const int64_t* dest_or_null, const float* nzval) {
+    std::vector<double> v = widen(nzval, nnz);
+    return spk_plan_inmatrix(p, nnz, dest_or_null, v.data());
+}
+SPK_API int64_t spk_plan_get_factors_f32(spk_plan* p, float* lnz, float* unz, int64_t* ipvt) {
+    NEED_DEV(p);
+    std::vector<double> l(lnz ? (size_t)p->P.nlnz : 0), u(unz ? (size_t)p->P.nunz : 0);
+    int64_t rc = spk_plan_get_factors(p, lnz ? l.data() : nullptr, unz ? u.data() : nullptr, ipvt);
+    if (!rc) { if (lnz) narrow(l, lnz); if (unz) narrow(u, unz); }
+    return rc;
+}
+SPK_API int64_t spk_plan_triangularsolve_f32(spk_plan* p, float* b, int64_t nrhs, int64_t ldb) {
+    NEED_DEV(p);
+    const int64_t n = p->P.n;
+    std::vector<double> r((size_t)n * std::max<int64_t>(nrhs, 0));
+    for (int64_t q = 0; q < nrhs; ++q) for (int64_t i = 0; i < n; ++i) r[(size_t)q * n + i] = b[(size_t)q * ldb + i];
+    int64_t rc = spk_plan_triangularsolve(p, r.data(), nrhs, n);
+    if (!rc) for (int64_t q = 0; q < nrhs; ++q) for (int64_t i = 0; i < n; ++i) b[(size_t)q * ldb + i] = (float)r[(size_t)q * n + i];
+    return rc;
+}
+
 } // extern "C"

@@ -280,3 +280,45 @@ def test_kernel_and_schedule_variants_agree(spd, env, monkeypatch):
     plan.triangularsolve(x)
     assert residual(A, x, bb) < RESID_TOL
     plan.destroy()
+
+
+@pytest.mark.parametrize("spd", [False, True])
+def test_float32_twins(spd):
+    """spk_*_f32: the Float32 methods of _factor! / _triangularsolve! (the reference sends Float32 to
+    sgetrf/sgemm/strsm, SpkSpdMMOps.jl:186-351).  Values cross the boundary as Float32, the arithmetic is the
+    FP64 engine's, so the result must match the FP64 oracle run on the same (Float32-representable) input to
+    Float32 rounding, with the same pivot sequence."""
+    A = (M.convdiff3d(9) if not spd else M.laplacian3d(9)).astype(np.float32).astype(np.float64)
+    s = prepare(A, spd, spk.nd_grid_order(9, 9, 9))
+    b = s.slvr
+    L = _cudalib.lib()
+    lo, uo, po, _ = oracle_factor(b)
+    lnz = b.lnz.astype(np.float32); unz = b.unz.astype(np.float32); ipiv = np.zeros(b.n, np.int64)
+    bb = M.rhs_for(A)
+    rhs = np.ascontiguousarray(bb[b.order.rperm - 1]).astype(np.float32)
+    eps32 = float(np.finfo(np.float32).eps)
+    if spd:
+        assert L.spk_ldltfactor_f32(b.n, b.nsuper, b.xsuper, b.snode, b.xlindx, b.lindx, b.xlnz, lnz) == 0
+        assert rel_err(lnz.astype(np.float64), lo, spd_mask(b)) < 4 * eps32
+        assert L.spk_ldltsolve_f32(b.nsuper, b.xsuper, b.xlindx, b.lindx, b.xlnz, lnz, rhs) == 1
+    else:
+        assert L.spk_lufactor_f32(b.n, b.nsuper, b.xsuper, b.snode, b.xlindx, b.lindx, b.xlnz, lnz, b.xunz, unz, ipiv) == 0
+        assert np.array_equal(ipiv, po)
+        assert rel_err(lnz.astype(np.float64), lo) < 4 * eps32 and rel_err(unz.astype(np.float64), uo) < 4 * eps32
+        assert L.spk_lulsolve_f32(b.nsuper, b.xsuper, b.xlindx, b.lindx, b.xlnz, lnz, ipiv, rhs) == 1
+        assert L.spk_luusolve_f32(b.n, b.nsuper, b.xsuper, b.xlindx, b.lindx, b.xlnz, lnz, b.xunz, unz, rhs) == 1
+    x = rhs.astype(np.float64)[b.order.rinvp - 1]
+    assert residual(A, x, bb) < 200 * eps32         # Float32 factors and right-hand side
+    # plan twins
+    plan = _cudalib.Plan(b)
+    dest, nzval = b._inmatrix_map(A)
+    assert L.spk_plan_inmatrix_f32(plan.h, nzval.size, dest.ctypes.data, nzval.astype(np.float32)) == 0
+    assert plan.factor() == 0
+    plan.set_perm(b.order.rperm, b.order.rinvp)
+    x32 = bb.astype(np.float32)
+    assert L.spk_plan_triangularsolve_f32(plan.h, x32, 1, b.n) == 0
+    assert residual(A, x32.astype(np.float64), bb) < 200 * eps32
+    l32 = np.zeros(b.lnz.size, np.float32)
+    assert L.spk_plan_get_factors_f32(plan.h, l32.ctypes.data, None, None) == 0
+    assert rel_err(l32.astype(np.float64), lo, spd_mask(b) if spd else None) < 4 * eps32
+    plan.destroy()
