@@ -62,7 +62,9 @@ __global__ void k_scatter_values(int64_t nnz, const int64_t* __restrict__ dest, 
 
 // reference layout -> fronts (values assembled by the host _inmatrix!) and back (factors)
 constexpr int CHUNK_EPB = 1024;      // entries per block
-template <bool STORE>
+// FILLU (load of FACTORS into LDL^T fronts): also write U = D L^T into the upper triangle, which is where the
+// factorisation leaves it and where the backward sweep reads it.
+template <bool STORE, bool FILLU = false>
 __global__ void __launch_bounds__(256) k_chunks(DevCtx c, const int32_t* __restrict__ pfx, int count) {
     int t = find_task(pfx, count, blockIdx.x);
     int lb = blockIdx.x - pfx[t];
@@ -78,6 +80,7 @@ __global__ void __launch_bounds__(256) k_chunks(DevCtx c, const int32_t* __restr
             int j = (int)(e / ch.jlen), i = (int)(e - (int64_t)j * ch.jlen);
             int64_t f = (int64_t)pos[i] + (int64_t)(ch.o + j) * ch.ld;
             if (STORE) c.lnz[ch.lofs + e] = F[f]; else F[f] = c.lnz[ch.lofs + e];
+            if (FILLU && !STORE && i > j) F[(int64_t)(ch.o + j) + (int64_t)pos[i] * ch.ld] = c.lnz[ch.lofs + (int64_t)j * ch.jlen + j] * c.lnz[ch.lofs + e];
         } else if (e - nl < nu) {
             int64_t eu = e - nl;
             int j = (int)(eu / ldu), i = (int)(eu - (int64_t)j * ldu);
@@ -1131,18 +1134,24 @@ __device__ __forceinline__ void pb_diag_warp(const PStep& ps, const double* Ts, 
 // rows [r0, r1) of the front below the step: wf[r] -= sum_k L[r, o+k] x[k]
 // (16 independent loads in flight per thread: the panel is streamed once from HBM, so the sweep is
 //  latency-bound unless every thread keeps many requests outstanding)
+template <int B = 64>
 __device__ __forceinline__ void pf_update_rows(const DevCtx& c, const PStep& ps, double* wf, const double* xs, int r0, int r1) {
     const double* __restrict__ Fm = c.F + ps.fofs + (int64_t)ps.o * ps.ld;
     const int w = ps.w;
-    if (w <= 64) {                                          // the whole row in flight: one round trip to memory
+    if (w <= 64) {                                          // B entries of the row in flight per pass (64: one round trip to memory)
         for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
             const double* __restrict__ row = Fm + r;
-            double v[64];
-#pragma unroll
-            for (int u = 0; u < 64; ++u) v[u] = __ldcs(row + (size_t)min(u, w - 1) * ps.ld);     // unconditional: all issued before the first use
             double acc = 0.0;
 #pragma unroll
-            for (int u = 0; u < 64; ++u) if (u < w) acc += v[u] * xs[u];
+            for (int h0 = 0; h0 < 64; h0 += B) {
+                if (h0 < w) {
+                    double v[B];
+#pragma unroll
+                    for (int u = 0; u < B; ++u) v[u] = __ldcs(row + (size_t)min(h0 + u, w - 1) * ps.ld);     // unconditional: all issued before the first use
+#pragma unroll
+                    for (int u = 0; u < B; ++u) if (h0 + u < w) acc += v[u] * xs[h0 + u];
+                }
+            }
             wf[r] -= acc;
         }
         return;
@@ -1180,9 +1189,10 @@ __device__ __forceinline__ void pb_partial(const DevCtx& c, const PStep& ps, con
     const double* __restrict__ Fm = c.F + ps.fofs;
     for (int k = threadIdx.x; k < nw * w; k += blockDim.x) red[k] = 0.0;
     __syncthreads();
-    if (LU && w <= 64) {
-        // U panel: column r holds its w entries contiguously, so lane k reads U[o+k, r] (coalesced) for 32
-        // columns at a time — all 64 loads in flight — and sums over r in registers: no shuffle reduction
+    if (w <= 64) {
+        // U panel (LDL^T fronts hold U = D L^T above the diagonal; the caller divides by D): column r holds its
+        // w entries contiguously, so lane k reads U[o+k, r] (coalesced) for 32 columns at a time — all 64 loads
+        // in flight — and sums over r in registers: no shuffle reduction
         double acc0 = 0.0, acc1 = 0.0;
         const double* __restrict__ U0 = Fm + (int64_t)ps.o + min(lane, w - 1);
         const double* __restrict__ U1 = Fm + (int64_t)ps.o + min(lane + 32, w - 1);
@@ -1245,51 +1255,31 @@ __device__ __forceinline__ void pb_partial(const DevCtx& c, const PStep& ps, con
 }
 
 // pb_partial for w <= 64 and one 32-row slab per warp (blockDim.x == SV_ROWS), split in two so that the loads
-// of the factor entries can be issued before the previous kernel's result is awaited (PDL, see pdl_wait):
-//   LDL^T: a[u] = L[r, o+u] for this lane's row r;  LU: a[j] / a[32+j] = U[o+lane, rb+j] / U[o+lane+32, rb+j]
+// of the factor entries can be issued before the previous kernel's result is awaited (PDL, see pdl_wait).
+// Both factorisations read the U panel (LDL^T fronts hold U = D L^T above the diagonal): column r holds its w
+// entries contiguously, lane k reads U[o+k, r] (coalesced) and sums over r in registers — no shuffle tree;
+// a[j] / a[32+j] = U[o+lane, rb+j] / U[o+lane+32, rb+j].  LDL^T divides the sums by D afterwards.
 template <bool LU>
 __device__ __forceinline__ void pb_prefetch64(const DevCtx& c, const PStep& ps, int r0, int r1, double (&a)[64]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, w = ps.w;
     const double* __restrict__ Fm = c.F + ps.fofs;
     const int rb = r0 + warp * 32;
-    if (LU) {
-        const double* __restrict__ U0 = Fm + (int64_t)ps.o + min(lane, w - 1);
-        const double* __restrict__ U1 = Fm + (int64_t)ps.o + min(lane + 32, w - 1);
+    const double* __restrict__ U0 = Fm + (int64_t)ps.o + min(lane, w - 1);
+    const double* __restrict__ U1 = Fm + (int64_t)ps.o + min(lane + 32, w - 1);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { const size_t cofs = (size_t)max(min(rb + j, r1 - 1), r0) * ps.ld; a[j] = __ldcs(U0 + cofs); a[32 + j] = __ldcs(U1 + cofs); }
-    } else {
-        const double* __restrict__ col = Fm + (int64_t)max(min(rb + lane, r1 - 1), r0) + (int64_t)ps.o * ps.ld;
-#pragma unroll
-        for (int u = 0; u < 64; ++u) a[u] = __ldcs(col + (size_t)min(u, w - 1) * ps.ld);
-    }
+    for (int j = 0; j < 32; ++j) { const size_t cofs = (size_t)max(min(rb + j, r1 - 1), r0) * ps.ld; a[j] = __ldcs(U0 + cofs); a[32 + j] = __ldcs(U1 + cofs); }
 }
 template <bool LU>
 __device__ __forceinline__ void pb_apply64(const PStep& ps, const double* wf, int r0, int r1, const double (&a)[64], double* red, double* out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, w = ps.w;
     const int rb = r0 + warp * 32;
     const double xl = rb + lane < r1 ? wf[rb + lane] : 0.0;
-    if (LU) {
+    {
         double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) { const double xj = __shfl_sync(0xffffffffu, xl, j); acc0 += a[j] * xj; acc1 += a[32 + j] * xj; }
         if (lane < w) red[warp * w + lane] = acc0;
         if (lane + 32 < w) red[warp * w + lane + 32] = acc1;
-    } else {
-#pragma unroll
-        for (int k0 = 0; k0 < 64; k0 += 8) {
-            if (k0 < w) {
-                double v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = k0 + u < w ? a[k0 + u] * xl : 0.0;
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) v[u] += __shfl_xor_sync(0xffffffffu, v[u], off);
-                if (lane == 0)
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) if (k0 + u < w) red[warp * w + k0 + u] = v[u];
-            }
-        }
     }
     __syncthreads();
     for (int k = threadIdx.x; k < w; k += blockDim.x) {
@@ -1300,6 +1290,13 @@ __device__ __forceinline__ void pb_apply64(const PStep& ps, const double* wf, in
 }
 
 inline size_t pstep_smem_bytes(int w) { return ((size_t)w * w + (size_t)w + 8 * (size_t)w) * sizeof(double); }
+// the fused step / front kernels with NR right-hand sides per block: T, NR x (padded) x, NR x next x or the
+// (NR x) 8 warps x w partial sums
+constexpr int SOLVE_NR = 8;                             // right-hand sides per block when nrhs > 1 (== warps per block)
+inline size_t pstep_smem_bytes_mr(int w, int nr, bool front) {
+    const size_t xst = w <= 64 ? 64 : (size_t)w;      // stride of one right-hand side's x (zero-padded to 64: unconditional FMAs)
+    return ((size_t)w * w + (size_t)(2 * nr) * xst + (size_t)(8 * (front ? nr : 1)) * (w + 8) + 8) * sizeof(double);
+}
 
 template <bool LU>
 __global__ void __launch_bounds__(128) k_pf_diag(DevCtx c, const int32_t* __restrict__ plist) {
@@ -1360,7 +1357,7 @@ __global__ void __launch_bounds__(128) k_pb_diag(DevCtx c, const int32_t* __rest
         double s = 0.0;
         for (int q = 0; q < nblk; ++q) s += pb[(size_t)q * maxpw + k];
         const double y = wf[ps.o + k];
-        xs[k] = LU ? y - s : y / Ts[k + k * ps.w] - s;
+        xs[k] = LU ? y - s : (ps.w <= 64 ? (y - s) / Ts[k + k * ps.w] : y / Ts[k + k * ps.w] - s);   // w <= 64: sums of U = D L^T entries
     }
     __syncthreads();
     if (threadIdx.x < 32) pb_diag_warp<LU>(ps, Ts, xs);
@@ -1372,9 +1369,9 @@ __global__ void __launch_bounds__(128) k_pb_diag(DevCtx c, const int32_t* __rest
 // Fused forward step: every block updates its rows beyond step j with x_j; block 0 (whose rows contain all
 // unknowns of step j+1) then also solves the diagonal block of step j+1, so a sweep needs one launch per
 // panel step instead of two.
-template <bool LU>
+template <bool LU, int NR>
 __global__ void __launch_bounds__(SV_ROWS) k_pf_step(DevCtx c, const int32_t* __restrict__ plist,
-                                                     const int32_t* __restrict__ pfx, int count) {
+                                                     const int32_t* __restrict__ pfx, int count, int nrhs) {
     extern __shared__ double ssm[];
     pdl_trigger();
     int ti = find_task(pfx, count, blockIdx.x);
@@ -1382,16 +1379,19 @@ __global__ void __launch_bounds__(SV_ROWS) k_pf_step(DevCtx c, const int32_t* __
     const int pid = plist[ti];
     const PStep ps = c.psteps[pid];
     const DFront F = c.fronts[ps.front];
-    double* wf = c.w + (size_t)blockIdx.y * c.wlen + F.wofs;
-    double* xs = ssm;                                           // x_j (w entries)
-    double* Ts = ssm + ((ps.w + 7) & ~7);                       // block 0: diagonal block of step j+1, staged while the update runs
+    // NR right-hand sides per block (blockIdx.y = group): the panel row of a thread is read ONCE for all of them
+    const int q0 = blockIdx.y * NR, nr = min(NR, nrhs - q0);
+    double* wf0 = c.w + (size_t)q0 * c.wlen + F.wofs;           // right-hand side q: wf0 + q * c.wlen
+    const int w = ps.w, wp = w <= 64 ? 64 : w;                 // x_j zero-padded to 64 entries: the FMAs below need no guard
+    double* xs = ssm;                                           // x_j: NR x wp
+    double* Ts = ssm + NR * wp;                                 // block 0: diagonal block of step j+1, staged while the update runs
     const bool next = lb == 0 && pid + 1 < F.ps0 + F.nps;
     PStep nx;
     if (next) {
         nx = c.psteps[pid + 1];
         stage_block_async(Ts, c.F + nx.fofs + (int64_t)nx.o + (int64_t)nx.o * nx.ld, nx.ld, nx.w);
     }
-    const int e0 = ps.o + ps.w, w = ps.w;
+    const int e0 = ps.o + ps.w;
     const int r0 = e0 + lb * SV_ROWS, r1 = min(ps.R, e0 + (lb + 1) * SV_ROWS);
     if (w <= 64) {
         // one row per thread; the row of the panel is fetched BEFORE the previous step's result is awaited
@@ -1401,36 +1401,49 @@ __global__ void __launch_bounds__(SV_ROWS) k_pf_step(DevCtx c, const int32_t* __
 #pragma unroll
         for (int u = 0; u < 64; ++u) v[u] = __ldcs(row + (size_t)min(u, w - 1) * ps.ld);
         pdl_wait();
-        for (int k = threadIdx.x; k < w; k += blockDim.x) xs[k] = wf[ps.o + k];
-        __syncthreads();
-        double acc = 0.0;
+        for (int e = threadIdx.x; e < nr * 64; e += blockDim.x) { const int q = e >> 6, k = e & 63; xs[e] = k < w ? wf0[(size_t)q * c.wlen + ps.o + k] : 0.0; }
+        double old[NR];                                         // all right-hand sides' entries of this row in flight together
 #pragma unroll
-        for (int u = 0; u < 64; ++u) if (u < w) acc += v[u] * xs[u];
-        if (r < r1) wf[r] -= acc;
+        for (int q = 0; q < NR; ++q) old[q] = (q < nr && r < r1) ? wf0[(size_t)q * c.wlen + r] : 0.0;
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < NR; ++q) {
+            if (q < nr) {
+                double acc = 0.0;
+#pragma unroll
+                for (int u = 0; u < 64; ++u) acc += v[u] * xs[q * 64 + u];
+                old[q] -= acc;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NR; ++q) if (q < nr && r < r1) wf0[(size_t)q * c.wlen + r] = old[q];
     } else {
         pdl_wait();
-        for (int k = threadIdx.x; k < w; k += blockDim.x) xs[k] = wf[ps.o + k];
-        __syncthreads();
-        pf_update_rows(c, ps, wf, xs, r0, r1);
+        for (int q = 0; q < nr; ++q) {
+            __syncthreads();
+            for (int k = threadIdx.x; k < w; k += blockDim.x) xs[k] = wf0[(size_t)q * c.wlen + ps.o + k];
+            __syncthreads();
+            pf_update_rows(c, ps, wf0 + (size_t)q * c.wlen, xs, r0, r1);
+        }
     }
     if (next) {
         stage_wait();
         __syncthreads();                                        // this block's rows (incl. step j+1's unknowns) are final, T staged
-        double* xn = Ts + nx.w * nx.w;
-        for (int k = threadIdx.x; k < nx.w; k += blockDim.x) xn[k] = wf[nx.o + k];
+        double* xn = Ts + nx.w * nx.w;                          // NR x nx.w
+        for (int e = threadIdx.x; e < nr * nx.w; e += blockDim.x) { const int q = e / nx.w, k = e - q * nx.w; xn[e] = wf0[(size_t)q * c.wlen + nx.o + k]; }
         __syncthreads();
-        if (threadIdx.x < 32) pf_diag_warp<LU>(c, nx, Ts, xn);
+        if ((threadIdx.x >> 5) < nr) pf_diag_warp<LU>(c, nx, Ts, xn + (threadIdx.x >> 5) * nx.w);   // one warp per right-hand side
         __syncthreads();
-        for (int k = threadIdx.x; k < nx.w; k += blockDim.x) wf[nx.o + k] = xn[k];
+        for (int e = threadIdx.x; e < nr * nx.w; e += blockDim.x) { const int q = e / nx.w, k = e - q * nx.w; wf0[(size_t)q * c.wlen + nx.o + k] = xn[e]; }
     }
 }
 
 // Fused backward step: every block writes the partial sums of its rows/columns beyond step j; the block that
 // arrives last (device-wide counter) adds the partials in a fixed order and solves the diagonal block of step j.
-template <bool LU>
+template <bool LU, int NR>
 __global__ void __launch_bounds__(SV_ROWS) k_pb_step(DevCtx c, const int32_t* __restrict__ plist,
                                                      const int32_t* __restrict__ pfx, int count,
-                                                     double* __restrict__ rhs, int64_t ldrhs, int maxpw, int32_t* counters) {
+                                                     double* __restrict__ rhs, int64_t ldrhs, int maxpw, int32_t* counters, int nrhs) {
     extern __shared__ double ssm[];
     __shared__ int s_last;
     pdl_trigger();
@@ -1438,28 +1451,36 @@ __global__ void __launch_bounds__(SV_ROWS) k_pb_step(DevCtx c, const int32_t* __
     int lb = blockIdx.x - pfx[ti];
     const PStep ps = c.psteps[plist[ti]];
     const DFront F = c.fronts[ps.front];
-    double* wf = c.w + (size_t)blockIdx.y * c.wlen + F.wofs;
-    double* pb = c.pb + (size_t)blockIdx.y * c.pblen + F.pbofs;
-    const int e0 = ps.o + ps.w, below = ps.R - e0;
+    const int q0 = blockIdx.y * NR, nr = min(NR, nrhs - q0);   // NR right-hand sides per block, factor entries read once
+    double* wf0 = c.w + (size_t)q0 * c.wlen + F.wofs;
+    double* pb0 = c.pb + (size_t)q0 * c.pblen + F.pbofs;
+    const int e0 = ps.o + ps.w, below = ps.R - e0, w = ps.w;
     const int nblk = (below + SV_ROWS - 1) / SV_ROWS;
-    double* Ts = ssm; double* xs = ssm + ps.w * ps.w;
+    double* Ts = ssm; double* xs = ssm + w * w;                // xs: NR x w, then 8 x w partial sums
+    double* red = xs + NR * w;
     // every block stages the diagonal block while it forms its partial sums: the one that arrives last needs it at once
-    stage_block_async(Ts, c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld, ps.ld, ps.w);
+    stage_block_async(Ts, c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld, ps.ld, w);
     if (nblk > 0) {
         const int r0 = e0 + lb * SV_ROWS, r1 = min(ps.R, e0 + (lb + 1) * SV_ROWS);
-        if (ps.w <= 64) {
+        if (w <= 64) {
             double a[64];
             pb_prefetch64<LU>(c, ps, r0, r1, a);            // factor entries in flight before the previous step's x is awaited
             pdl_wait();
-            pb_apply64<LU>(ps, wf, r0, r1, a, xs + ps.w, pb + (size_t)lb * maxpw);
+            for (int q = 0; q < nr; ++q) {
+                pb_apply64<LU>(ps, wf0 + (size_t)q * c.wlen, r0, r1, a, red, pb0 + (size_t)q * c.pblen + (size_t)lb * maxpw);
+                __syncthreads();
+            }
         } else {
             pdl_wait();
-            pb_partial<LU>(c, ps, wf, r0, r1, xs + ps.w, pb + (size_t)lb * maxpw);
+            for (int q = 0; q < nr; ++q) {
+                pb_partial<LU>(c, ps, wf0 + (size_t)q * c.wlen, r0, r1, red, pb0 + (size_t)q * c.pblen + (size_t)lb * maxpw);
+                __syncthreads();
+            }
         }
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) {
-            int32_t* cnt = counters + (size_t)blockIdx.y * gridDim.x + pfx[ti];      // one counter per (rhs, task)
+            int32_t* cnt = counters + (size_t)blockIdx.y * gridDim.x + pfx[ti];      // one counter per (rhs group, task)
             int prev = atomicAdd(cnt, 1);
             s_last = (prev == nblk - 1);
             if (s_last) *cnt = 0;                                                    // ready for the next sweep
@@ -1470,63 +1491,137 @@ __global__ void __launch_bounds__(SV_ROWS) k_pb_step(DevCtx c, const int32_t* __
     } else pdl_wait();
     stage_wait();
     __syncthreads();
-    for (int k = threadIdx.x; k < ps.w; k += blockDim.x) {
+    for (int e = threadIdx.x; e < nr * w; e += blockDim.x) {
+        const int q = e / w, k = e - q * w;
+        const double* pb = pb0 + (size_t)q * c.pblen;
         double sum = 0.0;
-        for (int q = 0; q < nblk; ++q) sum += __ldcg(pb + (size_t)q * maxpw + k);
-        const double y = wf[ps.o + k];
-        xs[k] = LU ? y - sum : y / Ts[k + k * ps.w] - sum;
+        for (int b2 = 0; b2 < nblk; ++b2) sum += __ldcg(pb + (size_t)b2 * maxpw + k);
+        const double y = wf0[(size_t)q * c.wlen + ps.o + k];
+        xs[e] = LU ? y - sum : (w <= 64 ? (y - sum) / Ts[k + k * w] : y / Ts[k + k * w] - sum);       // w <= 64: sums of U = D L^T entries
     }
     __syncthreads();
-    if (threadIdx.x < 32) pb_diag_warp<LU>(ps, Ts, xs);
+    if ((threadIdx.x >> 5) < nr) pb_diag_warp<LU>(ps, Ts, xs + (threadIdx.x >> 5) * w);              // one warp per right-hand side
     __syncthreads();
-    double* out = rhs + (size_t)blockIdx.y * ldrhs + ps.col0;
-    for (int k = threadIdx.x; k < ps.w; k += blockDim.x) { wf[ps.o + k] = xs[k]; out[k] = xs[k]; }
+    for (int e = threadIdx.x; e < nr * w; e += blockDim.x) {
+        const int q = e / w, k = e - q * w;
+        wf0[(size_t)q * c.wlen + ps.o + k] = xs[e];
+        rhs[(size_t)(q0 + q) * ldrhs + ps.col0 + k] = xs[e];
+    }
 }
 
-// small fronts: one block walks all panel steps of the front
-template <bool LU>
-__global__ void __launch_bounds__(256) k_pf_front(DevCtx c, const int32_t* __restrict__ flist) {
+// small fronts: one block walks all panel steps of the front, NR right-hand sides at a time (one warp per
+// right-hand side in the diagonal solves; every factor entry is read once per block)
+template <bool LU, int NR>
+__global__ void __launch_bounds__(256) k_pf_front(DevCtx c, const int32_t* __restrict__ flist, int nrhs) {
     extern __shared__ double ssm[];
     const DFront F = c.fronts[flist[blockIdx.x]];
-    double* wf = c.w + (size_t)blockIdx.y * c.wlen + F.wofs;
+    const int q0 = blockIdx.y * NR, nr = min(NR, nrhs - q0);
+    double* wf0 = c.w + (size_t)q0 * c.wlen + F.wofs;
+    const int warp = threadIdx.x >> 5;
     for (int j = 0; j < F.nps; ++j) {
         const PStep ps = c.psteps[F.ps0 + j];
-        double* Ts = ssm; double* xs = ssm + ps.w * ps.w;
-        block_g2s<256>(Ts, ps.w, c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld, ps.ld, ps.w);
-        for (int k = threadIdx.x; k < ps.w; k += blockDim.x) xs[k] = wf[ps.o + k];
+        const int w = ps.w;
+        const int xst = (NR > 1 && w <= 64) ? 64 : w;          // x of one right-hand side, zero-padded to 64 (unconditional FMAs)
+        double* Ts = ssm; double* xs = ssm + w * w;             // xs: NR x xst
+        block_g2s<256>(Ts, w, c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld, ps.ld, w);
+        for (int e = threadIdx.x; e < nr * xst; e += blockDim.x) { const int q = e / xst, k = e - q * xst; xs[e] = k < w ? wf0[(size_t)q * c.wlen + ps.o + k] : 0.0; }
         __syncthreads();
-        if (threadIdx.x < 32) pf_diag_warp<LU>(c, ps, Ts, xs);
+        if (warp < nr) pf_diag_warp<LU>(c, ps, Ts, xs + warp * xst);
         __syncthreads();
-        for (int k = threadIdx.x; k < ps.w; k += blockDim.x) wf[ps.o + k] = xs[k];
-        pf_update_rows(c, ps, wf, xs, ps.o + ps.w, ps.R);
+        for (int e = threadIdx.x; e < nr * xst; e += blockDim.x) { const int q = e / xst, k = e - q * xst; if (k < w) wf0[(size_t)q * c.wlen + ps.o + k] = xs[e]; }
+        if (NR == 1 || w > 64) {
+            for (int q = 0; q < nr; ++q) pf_update_rows<32>(c, ps, wf0 + (size_t)q * c.wlen, xs + q * xst, ps.o + w, ps.R);
+        } else {
+            const double* __restrict__ Fm = c.F + ps.fofs + (int64_t)ps.o * ps.ld;
+            for (int r = ps.o + w + threadIdx.x; r < ps.R; r += blockDim.x) {
+                double old[NR], acc[NR];
+#pragma unroll
+                for (int q = 0; q < NR; ++q) { old[q] = q < nr ? wf0[(size_t)q * c.wlen + r] : 0.0; acc[q] = 0.0; }
+#pragma unroll
+                for (int half = 0; half < 64; half += 32) {     // two passes of 32 entries keep the register count of this
+                    if (half < w) {                             // throughput-bound kernel low (several blocks per SM)
+                        double v[32];
+#pragma unroll
+                        for (int u = 0; u < 32; ++u) v[u] = __ldcs(Fm + r + (size_t)min(half + u, w - 1) * ps.ld);
+#pragma unroll
+                        for (int q = 0; q < NR; ++q)
+#pragma unroll
+                            for (int u = 0; u < 32; ++u) acc[q] += v[u] * xs[q * 64 + half + u];
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < NR; ++q) if (q < nr) wf0[(size_t)q * c.wlen + r] = old[q] - acc[q];
+            }
+        }
         __syncthreads();
     }
 }
 
-template <bool LU>
+template <bool LU, int NR>
 __global__ void __launch_bounds__(256) k_pb_front(DevCtx c, const int32_t* __restrict__ flist,
-                                                  double* __restrict__ rhs, int64_t ldrhs) {
+                                                  double* __restrict__ rhs, int64_t ldrhs, int nrhs) {
     extern __shared__ double ssm[];
     const DFront F = c.fronts[flist[blockIdx.x]];
-    double* wf = c.w + (size_t)blockIdx.y * c.wlen + F.wofs;
+    const int q0 = blockIdx.y * NR, nr = min(NR, nrhs - q0);
+    double* wf0 = c.w + (size_t)q0 * c.wlen + F.wofs;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int j = F.nps - 1; j >= 0; --j) {
         const PStep ps = c.psteps[F.ps0 + j];
-        double* Ts = ssm; double* xs = ssm + ps.w * ps.w; double* red = xs + ps.w;
-        block_g2s<256>(Ts, ps.w, c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld, ps.ld, ps.w);
-        pb_partial<LU>(c, ps, wf, ps.o + ps.w, ps.R, red, xs);      // xs[k] = sum over the rows/columns beyond the step
-        __syncthreads();
-        for (int k = threadIdx.x; k < ps.w; k += blockDim.x) {
-            const double y = wf[ps.o + k];
-            xs[k] = LU ? y - xs[k] : y / Ts[k + k * ps.w] - xs[k];
+        const int w = ps.w, e0 = ps.o + w;
+        double* Ts = ssm; double* xs = ssm + w * w; double* red = xs + NR * w;        // red: NR x 8 warps x w (NR == 1: 8 x w)
+        block_g2s<256>(Ts, w, c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld, ps.ld, w);
+        if (NR == 1 || w > 64) {
+            for (int q = 0; q < nr; ++q) { pb_partial<LU>(c, ps, wf0 + (size_t)q * c.wlen, e0, ps.R, red, xs + q * w); __syncthreads(); }
+        } else {
+            // 32-column slabs of the U panel beyond the step: entries fetched once, applied to every right-hand side
+            const double* __restrict__ Fm = c.F + ps.fofs;
+            double acc0[NR], acc1[NR];                          // LU: running sums over the slabs (same order as the single-RHS path)
+#pragma unroll
+            for (int q = 0; q < NR; ++q) { acc0[q] = 0.0; acc1[q] = 0.0; }
+            for (int rb = e0 + warp * 32; rb < ps.R; rb += 256) {
+                double a[64];
+                {
+                    const double* __restrict__ U0 = Fm + (int64_t)ps.o + min(lane, w - 1);
+                    const double* __restrict__ U1 = Fm + (int64_t)ps.o + min(lane + 32, w - 1);
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) { const size_t cofs = (size_t)min(rb + jj, ps.R - 1) * ps.ld; a[jj] = __ldcs(U0 + cofs); a[32 + jj] = __ldcs(U1 + cofs); }
+                }
+#pragma unroll
+                for (int q = 0; q < NR; ++q) {
+                    if (q >= nr) continue;
+                    const double xl = rb + lane < ps.R ? wf0[(size_t)q * c.wlen + rb + lane] : 0.0;
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) { const double xj = __shfl_sync(0xffffffffu, xl, jj); acc0[q] += a[jj] * xj; acc1[q] += a[32 + jj] * xj; }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < NR; ++q) {
+                if (q >= nr) continue;
+                double* rq = red + (size_t)(q * 8 + warp) * w;
+                if (lane < w) rq[lane] = acc0[q];
+                if (lane + 32 < w) rq[lane + 32] = acc1[q];
+            }
+            __syncthreads();
+            for (int e = threadIdx.x; e < nr * w; e += blockDim.x) {
+                const int q = e / w, k = e - q * w;
+                double sum = 0.0;
+                for (int wq = 0; wq < 8; ++wq) sum += red[(size_t)(q * 8 + wq) * w + k];
+                xs[e] = sum;
+            }
         }
         __syncthreads();
-        if (threadIdx.x < 32) pb_diag_warp<LU>(ps, Ts, xs);
+        for (int e = threadIdx.x; e < nr * w; e += blockDim.x) {
+            const int q = e / w, k = e - q * w;
+            const double y = wf0[(size_t)q * c.wlen + ps.o + k];
+            xs[e] = LU ? y - xs[e] : (w <= 64 ? (y - xs[e]) / Ts[k + k * w] : y / Ts[k + k * w] - xs[e]);   // w <= 64: sums of U = D L^T entries
+        }
         __syncthreads();
-        for (int k = threadIdx.x; k < ps.w; k += blockDim.x) wf[ps.o + k] = xs[k];
+        if (warp < nr) pb_diag_warp<LU>(ps, Ts, xs + warp * w);
+        __syncthreads();
+        for (int e = threadIdx.x; e < nr * w; e += blockDim.x) { const int q = e / w, k = e - q * w; wf0[(size_t)q * c.wlen + ps.o + k] = xs[e]; }
         __syncthreads();
     }
-    double* out = rhs + (size_t)blockIdx.y * ldrhs + F.F0;
-    for (int k = threadIdx.x; k < F.W; k += blockDim.x) out[k] = wf[k];
+    for (int e = threadIdx.x; e < nr * F.W; e += blockDim.x) { const int q = e / F.W, k = e - q * F.W; rhs[(size_t)(q0 + q) * ldrhs + F.F0 + k] = wf0[(size_t)q * c.wlen + k]; }
 }
 
 // forward-only result / backward-only input: copy between rhs and the front vectors

@@ -216,19 +216,33 @@ static int64_t plan_upload(spk_plan* p) {
     }
     {
         size_t sm = pstep_smem_bytes(P.maxpw);
+        {
+            {
+                const int s1f = (int)pstep_smem_bytes_mr(P.maxpw, 1, true), s8f = (int)pstep_smem_bytes_mr(P.maxpw, SOLVE_NR, true);
+                const int s1 = (int)pstep_smem_bytes_mr(P.maxpw, 1, false), s8 = (int)pstep_smem_bytes_mr(P.maxpw, SOLVE_NR, false);
+                CK(cudaFuncSetAttribute(k_pf_front<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1f));
+                CK(cudaFuncSetAttribute(k_pf_front<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1f));
+                CK(cudaFuncSetAttribute(k_pb_front<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1f));
+                CK(cudaFuncSetAttribute(k_pb_front<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1f));
+                CK(cudaFuncSetAttribute(k_pf_front<true, SOLVE_NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8f));
+                CK(cudaFuncSetAttribute(k_pf_front<false, SOLVE_NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8f));
+                CK(cudaFuncSetAttribute(k_pb_front<true, SOLVE_NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8f));
+                CK(cudaFuncSetAttribute(k_pb_front<false, SOLVE_NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8f));
+                CK(cudaFuncSetAttribute(k_pf_step<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
+                CK(cudaFuncSetAttribute(k_pf_step<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
+                CK(cudaFuncSetAttribute(k_pb_step<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
+                CK(cudaFuncSetAttribute(k_pb_step<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
+                CK(cudaFuncSetAttribute(k_pf_step<true, SOLVE_NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8));
+                CK(cudaFuncSetAttribute(k_pf_step<false, SOLVE_NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8));
+                CK(cudaFuncSetAttribute(k_pb_step<true, SOLVE_NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8));
+                CK(cudaFuncSetAttribute(k_pb_step<false, SOLVE_NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8));
+            }
+        }
         if (sm > 48 * 1024) {
-            CK(cudaFuncSetAttribute(k_pf_front<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            CK(cudaFuncSetAttribute(k_pf_front<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            CK(cudaFuncSetAttribute(k_pb_front<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            CK(cudaFuncSetAttribute(k_pb_front<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             CK(cudaFuncSetAttribute(k_pf_diag<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             CK(cudaFuncSetAttribute(k_pf_diag<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             CK(cudaFuncSetAttribute(k_pb_diag<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             CK(cudaFuncSetAttribute(k_pb_diag<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            CK(cudaFuncSetAttribute(k_pf_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            CK(cudaFuncSetAttribute(k_pf_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            CK(cudaFuncSetAttribute(k_pb_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            CK(cudaFuncSetAttribute(k_pb_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         }
     }
     CK(gemm_dmma_init());
@@ -295,7 +309,8 @@ SPK_API int64_t spk_plan_set_factors(spk_plan* p, const double* lnz, const doubl
     {   // the solve sweeps read the frontal matrices: rebuild them from the uploaded factors
         DevCtx c = make_ctx(p);
         CK(cudaMemsetAsync(p->d_F, 0, p->P.arena * sizeof(double), p->stream));
-        k_chunks<false><<<p->chunk_blocks, 256, 0, p->stream>>>(c, p->d_chunkpfx, (int)p->P.chunks.size());
+        if (p->P.lu) k_chunks<false><<<p->chunk_blocks, 256, 0, p->stream>>>(c, p->d_chunkpfx, (int)p->P.chunks.size());
+        else k_chunks<false, true><<<p->chunk_blocks, 256, 0, p->stream>>>(c, p->d_chunkpfx, (int)p->P.chunks.size());   // + U = D L^T
         CK(cudaStreamSynchronize(p->stream));
     }
     p->factored = true;
@@ -581,6 +596,7 @@ static int64_t run_solve_launches(spk_plan* p, const DevCtx& c, const std::vecto
         const int32_t* pfx = p->d_blkpfx + L.pfx;
         const int32_t* list = p->d_gathert + L.first;
         dim3 grid(L.nblocks, (unsigned)nrhs);
+        const unsigned ngrp = (unsigned)((nrhs + SOLVE_NR - 1) / SOLVE_NR);    // right-hand-side groups of the fused kernels
         switch (L.kind) {
         case K_FWD_GATHER: k_fwd_gather<<<dim3(L.count, (unsigned)nrhs), 256, 0, st>>>(c, list, d_rhs, ldrhs); break;
         case K_FWD_DIAG:
@@ -597,15 +613,27 @@ static int64_t run_solve_launches(spk_plan* p, const DevCtx& c, const std::vecto
             else k_bwd_front<false><<<dim3(L.count, (unsigned)nrhs), 256, 0, st>>>(c, list, d_rhs, ldrhs);
             break;
         case K_PF_FRONT: {
-            size_t sm = pstep_smem_bytes(L.maxw);
-            if (lu) k_pf_front<true><<<dim3(L.count, (unsigned)nrhs), 256, sm, st>>>(c, list);
-            else k_pf_front<false><<<dim3(L.count, (unsigned)nrhs), 256, sm, st>>>(c, list);
+            if (nrhs == 1) {
+                size_t sm = pstep_smem_bytes_mr(L.maxw, 1, true);
+                if (lu) k_pf_front<true, 1><<<dim3(L.count, 1), 256, sm, st>>>(c, list, (int)nrhs);
+                else k_pf_front<false, 1><<<dim3(L.count, 1), 256, sm, st>>>(c, list, (int)nrhs);
+            } else {
+                size_t sm = pstep_smem_bytes_mr(L.maxw, SOLVE_NR, true);
+                if (lu) k_pf_front<true, SOLVE_NR><<<dim3(L.count, ngrp), 256, sm, st>>>(c, list, (int)nrhs);
+                else k_pf_front<false, SOLVE_NR><<<dim3(L.count, ngrp), 256, sm, st>>>(c, list, (int)nrhs);
+            }
             break;
         }
         case K_PB_FRONT: {
-            size_t sm = pstep_smem_bytes(L.maxw);
-            if (lu) k_pb_front<true><<<dim3(L.count, (unsigned)nrhs), 256, sm, st>>>(c, list, d_rhs, ldrhs);
-            else k_pb_front<false><<<dim3(L.count, (unsigned)nrhs), 256, sm, st>>>(c, list, d_rhs, ldrhs);
+            if (nrhs == 1) {
+                size_t sm = pstep_smem_bytes_mr(L.maxw, 1, true);
+                if (lu) k_pb_front<true, 1><<<dim3(L.count, 1), 256, sm, st>>>(c, list, d_rhs, ldrhs, (int)nrhs);
+                else k_pb_front<false, 1><<<dim3(L.count, 1), 256, sm, st>>>(c, list, d_rhs, ldrhs, (int)nrhs);
+            } else {
+                size_t sm = pstep_smem_bytes_mr(L.maxw, SOLVE_NR, true);
+                if (lu) k_pb_front<true, SOLVE_NR><<<dim3(L.count, ngrp), 256, sm, st>>>(c, list, d_rhs, ldrhs, (int)nrhs);
+                else k_pb_front<false, SOLVE_NR><<<dim3(L.count, ngrp), 256, sm, st>>>(c, list, d_rhs, ldrhs, (int)nrhs);
+            }
             break;
         }
         case K_PF_DIAG: {
@@ -616,15 +644,27 @@ static int64_t run_solve_launches(spk_plan* p, const DevCtx& c, const std::vecto
         }
         case K_PF_UPDATE: k_pf_update<<<grid, SV_ROWS, 0, st>>>(c, list, pfx, L.count); break;
         case K_PF_STEP: {
-            size_t sm = pstep_smem_bytes(L.maxw);
-            if (lu) CK(launch_pdl(k_pf_step<true>, grid, dim3(SV_ROWS), sm, st, p->pdl, c, list, pfx, (int)L.count));
-            else CK(launch_pdl(k_pf_step<false>, grid, dim3(SV_ROWS), sm, st, p->pdl, c, list, pfx, (int)L.count));
+            if (nrhs == 1) {
+                size_t sm = pstep_smem_bytes_mr(L.maxw, 1, false);
+                if (lu) CK(launch_pdl(k_pf_step<true, 1>, dim3(L.nblocks, 1), dim3(SV_ROWS), sm, st, p->pdl, c, list, pfx, (int)L.count, (int)nrhs));
+                else CK(launch_pdl(k_pf_step<false, 1>, dim3(L.nblocks, 1), dim3(SV_ROWS), sm, st, p->pdl, c, list, pfx, (int)L.count, (int)nrhs));
+            } else {
+                size_t sm = pstep_smem_bytes_mr(L.maxw, SOLVE_NR, false);
+                if (lu) CK(launch_pdl(k_pf_step<true, SOLVE_NR>, dim3(L.nblocks, ngrp), dim3(SV_ROWS), sm, st, p->pdl, c, list, pfx, (int)L.count, (int)nrhs));
+                else CK(launch_pdl(k_pf_step<false, SOLVE_NR>, dim3(L.nblocks, ngrp), dim3(SV_ROWS), sm, st, p->pdl, c, list, pfx, (int)L.count, (int)nrhs));
+            }
             break;
         }
         case K_PB_STEP: {
-            size_t sm = pstep_smem_bytes(L.maxw);
-            if (lu) CK(launch_pdl(k_pb_step<true>, grid, dim3(SV_ROWS), sm, st, p->pdl, c, list, pfx, (int)L.count, d_rhs, (int64_t)ldrhs, (int)p->P.maxpw, p->d_counters));
-            else CK(launch_pdl(k_pb_step<false>, grid, dim3(SV_ROWS), sm, st, p->pdl, c, list, pfx, (int)L.count, d_rhs, (int64_t)ldrhs, (int)p->P.maxpw, p->d_counters));
+            if (nrhs == 1) {
+                size_t sm = pstep_smem_bytes_mr(L.maxw, 1, false);
+                if (lu) CK(launch_pdl(k_pb_step<true, 1>, dim3(L.nblocks, 1), dim3(SV_ROWS), sm, st, p->pdl, c, list, pfx, (int)L.count, d_rhs, (int64_t)ldrhs, (int)p->P.maxpw, p->d_counters, (int)nrhs));
+                else CK(launch_pdl(k_pb_step<false, 1>, dim3(L.nblocks, 1), dim3(SV_ROWS), sm, st, p->pdl, c, list, pfx, (int)L.count, d_rhs, (int64_t)ldrhs, (int)p->P.maxpw, p->d_counters, (int)nrhs));
+            } else {
+                size_t sm = pstep_smem_bytes_mr(L.maxw, SOLVE_NR, false);
+                if (lu) CK(launch_pdl(k_pb_step<true, SOLVE_NR>, dim3(L.nblocks, ngrp), dim3(SV_ROWS), sm, st, p->pdl, c, list, pfx, (int)L.count, d_rhs, (int64_t)ldrhs, (int)p->P.maxpw, p->d_counters, (int)nrhs));
+                else CK(launch_pdl(k_pb_step<false, SOLVE_NR>, dim3(L.nblocks, ngrp), dim3(SV_ROWS), sm, st, p->pdl, c, list, pfx, (int)L.count, d_rhs, (int64_t)ldrhs, (int)p->P.maxpw, p->d_counters, (int)nrhs));
+            }
             break;
         }
         case K_PB_UPDATE: {
