@@ -1512,7 +1512,7 @@ __global__ void __launch_bounds__(SV_ROWS) k_pb_step(DevCtx c, const int32_t* __
 // small fronts: one block walks all panel steps of the front, NR right-hand sides at a time (one warp per
 // right-hand side in the diagonal solves; every factor entry is read once per block)
 template <bool LU, int NR>
-__global__ void __launch_bounds__(256) k_pf_front(DevCtx c, const int32_t* __restrict__ flist, int nrhs) {
+__global__ void __launch_bounds__(256, 2) k_pf_front(DevCtx c, const int32_t* __restrict__ flist, int nrhs) {
     extern __shared__ double ssm[];
     const DFront F = c.fronts[flist[blockIdx.x]];
     const int q0 = blockIdx.y * NR, nr = min(NR, nrhs - q0);
@@ -1558,7 +1558,7 @@ __global__ void __launch_bounds__(256) k_pf_front(DevCtx c, const int32_t* __res
 }
 
 template <bool LU, int NR>
-__global__ void __launch_bounds__(256) k_pb_front(DevCtx c, const int32_t* __restrict__ flist,
+__global__ void __launch_bounds__(256, 2) k_pb_front(DevCtx c, const int32_t* __restrict__ flist,
                                                   double* __restrict__ rhs, int64_t ldrhs, int nrhs) {
     extern __shared__ double ssm[];
     const DFront F = c.fronts[flist[blockIdx.x]];
