@@ -653,8 +653,11 @@ __global__ void __launch_bounds__(PANEL_ROWS) k_panel(DevCtx c, const int32_t* _
 //   LU  : X = A21 * inv(U11);   LDLT: X = A21 * inv(L11^T), L21 = X / D written below, U12 = X^T above.
 constexpr int PANEL_REG_SPLIT = 1;                                    // launch blocks per PANEL_ROWS rows (more SMs on the few blocks of a top front)
 constexpr int PANEL_REG_THREADS = PANEL_ROWS / PANEL_REG_SPLIT;
+#ifndef PANEL_REG_MINB
+#define PANEL_REG_MINB 1      /* 3 blocks per SM (168 registers, spills) measured slower: 26 vs 21 ms of panel time at 96^3 */
+#endif
 template <bool LU>
-__global__ void __launch_bounds__(PANEL_REG_THREADS) k_panel_reg(DevCtx c, const int32_t* __restrict__ pslist,
+__global__ void __launch_bounds__(PANEL_REG_THREADS, PANEL_REG_MINB) k_panel_reg(DevCtx c, const int32_t* __restrict__ pslist,
                                                                  const int32_t* __restrict__ pfx, int count) {
     constexpr int WP = 64;
     __shared__ __align__(16) double Ts[WP * WP + WP];   // Ts[j + k*WP] = coefficient of x_k in unknown j (j > k)
