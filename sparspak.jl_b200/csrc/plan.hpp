@@ -126,6 +126,7 @@ struct Plan {
     int64_t solve_small = SOLVE_SMALL;
     int ob_width = OB_WIDTH, ps_width = PS_WIDTH, ob_steps = OB_STEPS;
     bool lookahead = true;
+    bool left_inblock = true;                  // SPK_LL=0: right-looking rank-w updates inside an outer block (LU always)
     bool no_b128 = true;                      // DMMA tasks all use 128x64 tiles, two blocks per SM (measured best)
     int relax_abs = RELAX_ABS; double relax_frac = RELAX_FRAC;
     // schedules
@@ -402,6 +403,7 @@ inline void plan_env_overrides(Plan& P) {        // test / tuning knobs
     if (const char* e = getenv("SPK_SOLVE_SMALL")) P.solve_small = atoll(e);
     if (const char* e = getenv("SPK_OB_STEPS")) P.ob_steps = std::max(1, atoi(e));
     if (const char* e = getenv("SPK_LOOKAHEAD")) P.lookahead = e[0] != '0';
+    if (const char* e = getenv("SPK_LL")) P.left_inblock = e[0] != '0';
     if (const char* e = getenv("SPK_PIPES")) P.pipes = std::min(4, std::max(1, atoi(e)));
     if (const char* e = getenv("SPK_SOLVE_LNZ")) P.solve_on_fronts = e[0] != '1';
     if (const char* e = getenv("SPK_PS_WIDTH")) P.ps_width = std::max(1, atoi(e));
@@ -441,6 +443,21 @@ inline void build_lists(Plan& P, const std::vector<uint8_t>& sel, std::vector<La
         }
         // ---- dense partial factorisation, panel step by panel step
         for (int32_t j = 0; j < maxnps; ++j) {
+            // LDL^T, inside an outer block: LEFT-looking — just before panel step j is factored its columns get the
+            // updates of all earlier steps of the block in ONE GEMM (k = 57..400) instead of one rank-57 update
+            // after every step (those ran at 11 TFLOP/s: 3.5 k-tiles between prologue and epilogue).
+            const bool ll = P.left_inblock && !lu;
+            if (ll && (j % P.ob_steps) != 0) {
+                GemmBatch gl;
+                for (int32_t f : fr) if (P.fronts[f].nps > j) {
+                    const Front& F = P.fronts[f];
+                    const PStep& ps = P.psteps[F.ps0 + j];
+                    const int32_t ob0 = P.psteps[F.ps0 + j - (j % P.ob_steps)].o;
+                    GemmTask g = front_gemm(P, F, ps.o, F.R - ps.o, ps.o, ps.w, ob0, ps.o - ob0);
+                    gl.add(P, g, gemm_flops(g));
+                }
+                gl.emit(P, fb, lev, j, 0, 0, 0);
+            }
             fb.begin(K_DIAG, (int32_t)P.pslist.size(), lev, j, 0, j == 0 ? 1 : 0, 1);
             for (int32_t f : fr) if (P.fronts[f].nps > j) { P.pslist.push_back(P.fronts[f].ps0 + j); fb.add(1, 0, P.psteps[P.fronts[f].ps0 + j].w); }
             fb.end();
@@ -468,6 +485,7 @@ inline void build_lists(Plan& P, const std::vector<uint8_t>& sel, std::vector<La
                 if (e >= F.R) continue;
                 const bool last = (F.nps == j + 1);
                 if (!boundary && !last) {
+                    if (ll) continue;                      // left-looking inside the block: nothing to do after the panel
                     GemmTask g = front_gemm(P, F, e, F.R - e, e, ps.ob_end - e, ps.o, ps.w);
                     gp.add(P, g, gemm_flops(g));
                     if (lu && ps.ob_end < F.R) {
