@@ -103,18 +103,38 @@ __device__ __forceinline__ void asm_entry(const DevCtx& c, const DFront& C, cons
     c.F[P.fofs + (int64_t)rel[i] + (int64_t)rel[j] * P.ld] += v;
 }
 
+// One block = ASM_TPB rows x ASM_COLS columns of the child's update matrix.  A thread owns one row: its ASM_COLS
+// child entries and the ASM_COLS parent entries they go to are all loaded before the first store (no index
+// division, 2 * ASM_COLS independent loads in flight per thread); rows are contiguous in the child and run-wise
+// contiguous in the parent.  LDL^T: tiles strictly above the diagonal exit at once.
 __global__ void __launch_bounds__(ASM_TPB) k_assemble(DevCtx c, const AsmTask* __restrict__ tasks,
                                                      const int32_t* __restrict__ pfx, int count) {
     int t = find_task(pfx, count, blockIdx.x);
     int lb = blockIdx.x - pfx[t];
     AsmTask a = tasks[t];
     const DFront C = c.fronts[a.child], P = c.fronts[a.parent];
-    const int32_t* rel = c.rel + C.relofs;
-    int64_t total = (int64_t)C.m * C.m;
-    int64_t e = (int64_t)lb * (ASM_TPB * ASM_EPT) + threadIdx.x;
+    const int32_t* __restrict__ rel = c.rel + C.relofs;
+    const int32_t m = C.m;
+    const int32_t nrt = (m + ASM_TPB - 1) / ASM_TPB;
+    const int32_t rt = lb % nrt, ct = lb / nrt;
+    const int32_t i = rt * ASM_TPB + threadIdx.x, j0 = ct * ASM_COLS;
+    if (!c.lu && rt * ASM_TPB + ASM_TPB - 1 < j0) return;           // whole tile above the diagonal
+    if (i >= m) return;
+    const double* __restrict__ src = c.F + C.fofs + (int64_t)(C.W + i) + (int64_t)(C.W + j0) * C.ld;
+    double* __restrict__ dst = c.F + P.fofs + (int64_t)rel[i];
+    double v[ASM_COLS], old[ASM_COLS];
+    int64_t pofs[ASM_COLS];
 #pragma unroll
-    for (int it = 0; it < ASM_EPT; ++it, e += ASM_TPB)
-        if (e < total) asm_entry(c, C, P, rel, e);
+    for (int cc = 0; cc < ASM_COLS; ++cc) {
+        const int32_t j = j0 + cc;
+        const bool on = j < m && (c.lu || i >= j);
+        pofs[cc] = on ? (int64_t)rel[j] * P.ld : -1;
+        v[cc] = on ? __ldcs(src + (int64_t)cc * C.ld) : 0.0;
+    }
+#pragma unroll
+    for (int cc = 0; cc < ASM_COLS; ++cc) old[cc] = pofs[cc] >= 0 ? dst[pofs[cc]] : 0.0;
+#pragma unroll
+    for (int cc = 0; cc < ASM_COLS; ++cc) if (pofs[cc] >= 0) dst[pofs[cc]] = old[cc] + v[cc];
 }
 
 // parents with more than ASM_ROUNDS children: one block walks the remaining children in order

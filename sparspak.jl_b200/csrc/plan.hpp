@@ -93,7 +93,7 @@ struct Launch {
 };
 
 constexpr int ASM_ROUNDS = 8;      // children handled by per-round launches; the rest by a tail kernel
-constexpr int ASM_TPB = 256, ASM_EPT = 4;
+constexpr int ASM_TPB = 256, ASM_EPT = 4, ASM_COLS = 8;   // extend-add: rows per block, (tail kernel) entries per thread, columns per block
 constexpr int PANEL_ROWS = 128;    // rows (L side) / columns (U side) per panel block
 constexpr int GEMM_TM = 64, GEMM_TN = 64;   // C tile of the small-tile kernel
 constexpr int BIG_TM = 128;                 // C tile rows of the DMMA kernels (TN = 64 or 128)
@@ -432,7 +432,7 @@ inline void build_lists(Plan& P, const std::vector<uint8_t>& sel, std::vector<La
                 int32_t c = P.childlist[F.child0 + r];
                 int64_t mc = P.fronts[c].m;
                 P.asmt.push_back(AsmTask{c, f});
-                fb.add(cdiv(mc * mc, ASM_TPB * ASM_EPT));
+                fb.add((int32_t)(cdiv(mc, ASM_TPB) * cdiv(mc, ASM_COLS)));
             }
             fb.end();
         }
