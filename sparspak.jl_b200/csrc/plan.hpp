@@ -140,6 +140,7 @@ struct Plan {
     // multi-GPU (elimination-subtree partition): owner[f] = part that factors front f, or -1 for the TOP SET
     // (the ancestors of all subtree roots), which every part factors redundantly after the exchange.
     int32_t part = 0, nparts = 1;
+    int32_t max_subtrees = 1 << 30;            // SPK_MAX_SUBTREES: cap on the number of subtrees (tests: parts left without one)
     std::vector<int32_t> owner;
     std::vector<int32_t> xchg;                 // subtree-root fronts (owner >= 0, parent in the top set)
     struct Range { int32_t owner; int32_t f0, f1; int64_t lnz0, lnz1, unz0, unz1, col0, col1; };
@@ -404,6 +405,7 @@ inline void plan_env_overrides(Plan& P) {        // test / tuning knobs
     if (const char* e = getenv("SPK_OB_STEPS")) P.ob_steps = std::max(1, atoi(e));
     if (const char* e = getenv("SPK_LOOKAHEAD")) P.lookahead = e[0] != '0';
     if (const char* e = getenv("SPK_LL")) P.left_inblock = e[0] != '0';
+    if (const char* e = getenv("SPK_MAX_SUBTREES")) P.max_subtrees = std::max(2, atoi(e));
     if (const char* e = getenv("SPK_PIPES")) P.pipes = std::min(4, std::max(1, atoi(e)));
     if (const char* e = getenv("SPK_SOLVE_LNZ")) P.solve_on_fronts = e[0] != '1';
     if (const char* e = getenv("SPK_PS_WIDTH")) P.ps_width = std::max(1, atoi(e));
@@ -657,21 +659,40 @@ inline void partition(Plan& P) {
     }
     std::vector<int32_t> roots;
     for (int32_t f = 0; f < nf; ++f) if (P.fronts[f].parent < 0) roots.push_back(f);
-    // Estimated time of a configuration = (replicated) top-set work + the largest part load under LPT.
-    // Keep splitting the largest splittable subtree (it joins the top set) and remember the best
-    // configuration seen: more subtrees balance better, but everything split off is replicated.
+    // Estimated time of a configuration = (replicated) top-set time + the slowest part under LPT.  A front costs
+    // its flops at the measured update rate, but never less than its chain of dependent panel steps (measured
+    // ~75 us per step): the top of the tree is latency-, not flop-bound, so splitting further stops paying even
+    // when flops still balance better (96^3 on 8 GPUs: 8 subtrees + 6 replicated top fronts ran slower than
+    // 4 subtrees + 2).  Keep splitting the largest splittable subtree (it joins the top set) and remember the
+    // best configuration seen; parts may stay without a subtree if that is faster.
+    const double rate = (P.lu ? 2.0 : 1.0) * 22e12 / 2.0;       // `own` counts multiply-adds of the LDL^T pattern
+    const double tstep = 75e-6;
     auto own = [&](int32_t f) { double W = P.fronts[f].W, m = P.fronts[f].m; return W * W * W / 3.0 + W * W * m + W * m * m + 1.0; };
+    std::vector<double> chain(nf, 0.0);                          // dependent panel steps below and including f, in seconds
+    for (int32_t f = 0; f < nf; ++f) {
+        double below = 0.0;
+        for (int32_t q = 0; q < P.fronts[f].nchild; ++q) below = std::max(below, chain[P.childlist[P.fronts[f].child0 + q]]);
+        chain[f] = below + P.fronts[f].nps * tstep;
+    }
+    auto sub_time = [&](int32_t r) { return std::max(work[r] / rate, chain[r]); };
     auto lpt_max = [&](std::vector<int32_t> rs) {
-        std::sort(rs.begin(), rs.end(), [&](int32_t a, int32_t b) { return work[a] != work[b] ? work[a] > work[b] : a < b; });
+        std::sort(rs.begin(), rs.end(), [&](int32_t a, int32_t b) { return sub_time(a) != sub_time(b) ? sub_time(a) > sub_time(b) : a < b; });
         std::vector<double> ld(P.nparts, 0.0);
-        for (int32_t r : rs) { int32_t t = 0; for (int32_t q = 1; q < P.nparts; ++q) if (ld[q] < ld[t]) t = q; ld[t] += work[r]; }
+        for (int32_t r : rs) { int32_t t = 0; for (int32_t q = 1; q < P.nparts; ++q) if (ld[q] < ld[t]) t = q; ld[t] += sub_time(r); }
         return *std::max_element(ld.begin(), ld.end());
     };
+    auto top_time = [&](const std::vector<int32_t>& tp) {       // fronts of one level share their launches
+        std::vector<double> fl(P.nlevels, 0.0), st(P.nlevels, 0.0);
+        for (int32_t f : tp) { int32_t l = P.fronts[f].level; fl[l] += own(f) / rate; st[l] = std::max(st[l], P.fronts[f].nps * tstep); }
+        double t = 0.0;
+        for (int32_t l = 0; l < P.nlevels; ++l) t += std::max(fl[l], st[l]);
+        return t;
+    };
     std::vector<int32_t> top, best_roots = roots, best_top;
-    double topwork = 0.0, best_cost = 1e300;
+    double best_cost = 1e300;
     for (int iter = 0; iter < 64; ++iter) {
-        if ((int32_t)roots.size() >= P.nparts) {
-            double cost = topwork + lpt_max(roots);
+        if ((roots.size() >= 2 && (int32_t)roots.size() <= P.max_subtrees) || P.nparts == 1) {
+            double cost = top_time(top) + lpt_max(roots);
             if (cost < best_cost) { best_cost = cost; best_roots = roots; best_top = top; }
         }
         int32_t pick = -1;
@@ -680,11 +701,11 @@ inline void partition(Plan& P) {
         if (pick < 0) break;
         int32_t f = roots[pick];
         roots.erase(roots.begin() + pick);
-        top.push_back(f); topwork += own(f);
+        top.push_back(f);
         for (int32_t q = 0; q < P.fronts[f].nchild; ++q) roots.push_back(P.childlist[P.fronts[f].child0 + q]);
-        if ((int32_t)roots.size() >= P.nparts && topwork > best_cost) break;   // cannot improve any more
+        if ((int32_t)roots.size() >= 4 * P.nparts && top_time(top) > best_cost) break;   // cannot improve any more
     }
-    if (best_cost >= 1e300) { best_roots = roots; best_top = top; }        // tree too thin to give every part a subtree
+    if (best_cost >= 1e300) { best_roots = roots; best_top = top; }        // tree too thin to split
     roots = best_roots;
     for (int32_t f : best_top) P.owner[f] = -1;
     std::sort(roots.begin(), roots.end(), [&](int32_t a, int32_t b) { return work[a] != work[b] ? work[a] > work[b] : a < b; });

@@ -69,9 +69,10 @@ class SimEngine:
         self.L.sim_solve_phase(self.h, rhs.numpy(), phase)
 
 
-def _worker(rank, world, port, spd, q):
+def _worker(rank, world, port, spd, q, env=None):
     for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
+    os.environ.update(env or {})
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -119,3 +120,20 @@ def test_subtree_partition_over_gloo(world, spd):
         assert flag == 0 and e_l < 1e-12 and e_u < 1e-12 and piv_ok and resid < 1e-13
         assert owners == list(range(world))       # every rank owns at least one subtree
         assert nx >= world                        # and at least that many subtree roots are exchanged
+
+
+def test_parts_without_a_subtree_over_gloo():
+    """The partition may leave parts without a subtree when splitting further does not pay (the top of the tree
+    is latency-bound): those ranks only take part in the exchanges and the replicated top set."""
+    world, spd = 4, True
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, spd, q, {"SPK_MAX_SUBTREES": "3"})) for r in range(world)]
+    for p in procs: p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs: p.join(timeout=60)
+    assert all(p.exitcode == 0 for p in procs)
+    for rank, flag, e_l, e_u, piv_ok, resid, owners, nx in res:
+        assert flag == 0 and e_l < 1e-12 and resid < 1e-13
+        assert len(owners) < world                # at least one rank has no subtree and idles in phase 0
