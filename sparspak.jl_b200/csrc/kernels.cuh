@@ -1534,8 +1534,10 @@ __global__ void __launch_bounds__(SV_ROWS) k_pb_step(DevCtx c, const int32_t* __
 
 // small fronts: one block walks all panel steps of the front, NR right-hand sides at a time (one warp per
 // right-hand side in the diagonal solves; every factor entry is read once per block)
-template <bool LU, int NR>
-__global__ void __launch_bounds__(256, 2) k_pf_front(DevCtx c, const int32_t* __restrict__ flist, int nrhs) {
+// NT = 256 threads, or 64 for the tiny fronts at the bottom of the tree: those blocks are pure latency (a chain of
+// dependent loads for a few hundred flops), so eight of them per SM instead of two is what helps.
+template <bool LU, int NR, int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 8) k_pf_front(DevCtx c, const int32_t* __restrict__ flist, int nrhs) {
     extern __shared__ double ssm[];
     const DFront F = c.fronts[flist[blockIdx.x]];
     const int q0 = blockIdx.y * NR, nr = min(NR, nrhs - q0);
@@ -1546,10 +1548,10 @@ __global__ void __launch_bounds__(256, 2) k_pf_front(DevCtx c, const int32_t* __
         const int w = ps.w;
         const int xst = (NR > 1 && w <= 64) ? 64 : w;          // x of one right-hand side, zero-padded to 64 (unconditional FMAs)
         double* Ts = ssm; double* xs = ssm + w * w;             // xs: NR x xst
-        block_g2s<256>(Ts, w, c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld, ps.ld, w);
+        block_g2s<NT>(Ts, w, c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld, ps.ld, w);
         for (int e = threadIdx.x; e < nr * xst; e += blockDim.x) { const int q = e / xst, k = e - q * xst; xs[e] = k < w ? wf0[(size_t)q * c.wlen + ps.o + k] : 0.0; }
         __syncthreads();
-        if (warp < nr) pf_diag_warp<LU>(c, ps, Ts, xs + warp * xst);
+        for (int q = warp; q < nr; q += NT / 32) pf_diag_warp<LU>(c, ps, Ts, xs + q * xst);
         __syncthreads();
         for (int e = threadIdx.x; e < nr * xst; e += blockDim.x) { const int q = e / xst, k = e - q * xst; if (k < w) wf0[(size_t)q * c.wlen + ps.o + k] = xs[e]; }
         if (NR == 1 || w > 64) {
@@ -1580,8 +1582,8 @@ __global__ void __launch_bounds__(256, 2) k_pf_front(DevCtx c, const int32_t* __
     }
 }
 
-template <bool LU, int NR>
-__global__ void __launch_bounds__(256, 2) k_pb_front(DevCtx c, const int32_t* __restrict__ flist,
+template <bool LU, int NR, int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 8) k_pb_front(DevCtx c, const int32_t* __restrict__ flist,
                                                   double* __restrict__ rhs, int64_t ldrhs, int nrhs) {
     extern __shared__ double ssm[];
     const DFront F = c.fronts[flist[blockIdx.x]];
@@ -1592,7 +1594,7 @@ __global__ void __launch_bounds__(256, 2) k_pb_front(DevCtx c, const int32_t* __
         const PStep ps = c.psteps[F.ps0 + j];
         const int w = ps.w, e0 = ps.o + w;
         double* Ts = ssm; double* xs = ssm + w * w; double* red = xs + NR * w;        // red: NR x 8 warps x w (NR == 1: 8 x w)
-        block_g2s<256>(Ts, w, c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld, ps.ld, w);
+        block_g2s<NT>(Ts, w, c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld, ps.ld, w);
         if (NR == 1 || w > 64) {
             for (int q = 0; q < nr; ++q) { pb_partial<LU>(c, ps, wf0 + (size_t)q * c.wlen, e0, ps.R, red, xs + q * w); __syncthreads(); }
         } else {
@@ -1601,7 +1603,7 @@ __global__ void __launch_bounds__(256, 2) k_pb_front(DevCtx c, const int32_t* __
             double acc0[NR], acc1[NR];                          // LU: running sums over the slabs (same order as the single-RHS path)
 #pragma unroll
             for (int q = 0; q < NR; ++q) { acc0[q] = 0.0; acc1[q] = 0.0; }
-            for (int rb = e0 + warp * 32; rb < ps.R; rb += 256) {
+            for (int rb = e0 + warp * 32; rb < ps.R; rb += NT) {
                 double a[64];
                 {
                     const double* __restrict__ U0 = Fm + (int64_t)ps.o + min(lane, w - 1);
@@ -1620,7 +1622,7 @@ __global__ void __launch_bounds__(256, 2) k_pb_front(DevCtx c, const int32_t* __
 #pragma unroll
             for (int q = 0; q < NR; ++q) {
                 if (q >= nr) continue;
-                double* rq = red + (size_t)(q * 8 + warp) * w;
+                double* rq = red + (size_t)(q * (NT / 32) + warp) * w;
                 if (lane < w) rq[lane] = acc0[q];
                 if (lane + 32 < w) rq[lane + 32] = acc1[q];
             }
@@ -1628,7 +1630,7 @@ __global__ void __launch_bounds__(256, 2) k_pb_front(DevCtx c, const int32_t* __
             for (int e = threadIdx.x; e < nr * w; e += blockDim.x) {
                 const int q = e / w, k = e - q * w;
                 double sum = 0.0;
-                for (int wq = 0; wq < 8; ++wq) sum += red[(size_t)(q * 8 + wq) * w + k];
+                for (int wq = 0; wq < NT / 32; ++wq) sum += red[(size_t)(q * (NT / 32) + wq) * w + k];
                 xs[e] = sum;
             }
         }
@@ -1639,7 +1641,7 @@ __global__ void __launch_bounds__(256, 2) k_pb_front(DevCtx c, const int32_t* __
             xs[e] = LU ? y - xs[e] : (w <= 64 ? (y - xs[e]) / Ts[k + k * w] : y / Ts[k + k * w] - xs[e]);   // w <= 64: sums of U = D L^T entries
         }
         __syncthreads();
-        if (warp < nr) pb_diag_warp<LU>(ps, Ts, xs + warp * w);
+        for (int q = warp; q < nr; q += NT / 32) pb_diag_warp<LU>(ps, Ts, xs + q * w);
         __syncthreads();
         for (int e = threadIdx.x; e < nr * w; e += blockDim.x) { const int q = e / w, k = e - q * w; wf0[(size_t)q * c.wlen + ps.o + k] = xs[e]; }
         __syncthreads();

@@ -220,14 +220,22 @@ static int64_t plan_upload(spk_plan* p) {
             {
                 const int s1f = (int)pstep_smem_bytes_mr(P.maxpw, 1, true), s8f = (int)pstep_smem_bytes_mr(P.maxpw, SOLVE_NR, true);
                 const int s1 = (int)pstep_smem_bytes_mr(P.maxpw, 1, false), s8 = (int)pstep_smem_bytes_mr(P.maxpw, SOLVE_NR, false);
-                CK(cudaFuncSetAttribute(k_pf_front<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1f));
-                CK(cudaFuncSetAttribute(k_pf_front<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1f));
-                CK(cudaFuncSetAttribute(k_pb_front<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1f));
-                CK(cudaFuncSetAttribute(k_pb_front<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1f));
-                CK(cudaFuncSetAttribute(k_pf_front<true, SOLVE_NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8f));
-                CK(cudaFuncSetAttribute(k_pf_front<false, SOLVE_NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8f));
-                CK(cudaFuncSetAttribute(k_pb_front<true, SOLVE_NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8f));
-                CK(cudaFuncSetAttribute(k_pb_front<false, SOLVE_NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8f));
+                CK(cudaFuncSetAttribute(k_pf_front<true, 1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1f));
+                CK(cudaFuncSetAttribute(k_pf_front<true, 1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1f));
+                CK(cudaFuncSetAttribute(k_pf_front<false, 1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1f));
+                CK(cudaFuncSetAttribute(k_pf_front<false, 1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1f));
+                CK(cudaFuncSetAttribute(k_pb_front<true, 1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1f));
+                CK(cudaFuncSetAttribute(k_pb_front<true, 1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1f));
+                CK(cudaFuncSetAttribute(k_pb_front<false, 1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1f));
+                CK(cudaFuncSetAttribute(k_pb_front<false, 1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1f));
+                CK(cudaFuncSetAttribute(k_pf_front<true, SOLVE_NR, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8f));
+                CK(cudaFuncSetAttribute(k_pf_front<true, SOLVE_NR, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8f));
+                CK(cudaFuncSetAttribute(k_pf_front<false, SOLVE_NR, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8f));
+                CK(cudaFuncSetAttribute(k_pf_front<false, SOLVE_NR, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8f));
+                CK(cudaFuncSetAttribute(k_pb_front<true, SOLVE_NR, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8f));
+                CK(cudaFuncSetAttribute(k_pb_front<true, SOLVE_NR, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8f));
+                CK(cudaFuncSetAttribute(k_pb_front<false, SOLVE_NR, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8f));
+                CK(cudaFuncSetAttribute(k_pb_front<false, SOLVE_NR, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8f));
                 CK(cudaFuncSetAttribute(k_pf_step<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
                 CK(cudaFuncSetAttribute(k_pf_step<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
                 CK(cudaFuncSetAttribute(k_pb_step<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
@@ -613,26 +621,28 @@ static int64_t run_solve_launches(spk_plan* p, const DevCtx& c, const std::vecto
             else k_bwd_front<false><<<dim3(L.count, (unsigned)nrhs), 256, 0, st>>>(c, list, d_rhs, ldrhs);
             break;
         case K_PF_FRONT: {
+            const bool tiny = L.maxw <= 32;                  // bottom of the tree: 64-thread blocks, 8 per SM
+            const size_t sm = pstep_smem_bytes_mr(L.maxw, nrhs == 1 ? 1 : SOLVE_NR, true);
+            const dim3 g(L.count, nrhs == 1 ? 1 : ngrp);
             if (nrhs == 1) {
-                size_t sm = pstep_smem_bytes_mr(L.maxw, 1, true);
-                if (lu) k_pf_front<true, 1><<<dim3(L.count, 1), 256, sm, st>>>(c, list, (int)nrhs);
-                else k_pf_front<false, 1><<<dim3(L.count, 1), 256, sm, st>>>(c, list, (int)nrhs);
+                if (tiny) { if (lu) k_pf_front<true, 1, 64><<<g, 64, sm, st>>>(c, list, (int)nrhs); else k_pf_front<false, 1, 64><<<g, 64, sm, st>>>(c, list, (int)nrhs); }
+                else { if (lu) k_pf_front<true, 1, 256><<<g, 256, sm, st>>>(c, list, (int)nrhs); else k_pf_front<false, 1, 256><<<g, 256, sm, st>>>(c, list, (int)nrhs); }
             } else {
-                size_t sm = pstep_smem_bytes_mr(L.maxw, SOLVE_NR, true);
-                if (lu) k_pf_front<true, SOLVE_NR><<<dim3(L.count, ngrp), 256, sm, st>>>(c, list, (int)nrhs);
-                else k_pf_front<false, SOLVE_NR><<<dim3(L.count, ngrp), 256, sm, st>>>(c, list, (int)nrhs);
+                if (tiny) { if (lu) k_pf_front<true, SOLVE_NR, 64><<<g, 64, sm, st>>>(c, list, (int)nrhs); else k_pf_front<false, SOLVE_NR, 64><<<g, 64, sm, st>>>(c, list, (int)nrhs); }
+                else { if (lu) k_pf_front<true, SOLVE_NR, 256><<<g, 256, sm, st>>>(c, list, (int)nrhs); else k_pf_front<false, SOLVE_NR, 256><<<g, 256, sm, st>>>(c, list, (int)nrhs); }
             }
             break;
         }
         case K_PB_FRONT: {
+            const bool tiny = L.maxw <= 32;
+            const size_t sm = pstep_smem_bytes_mr(L.maxw, nrhs == 1 ? 1 : SOLVE_NR, true);
+            const dim3 g(L.count, nrhs == 1 ? 1 : ngrp);
             if (nrhs == 1) {
-                size_t sm = pstep_smem_bytes_mr(L.maxw, 1, true);
-                if (lu) k_pb_front<true, 1><<<dim3(L.count, 1), 256, sm, st>>>(c, list, d_rhs, ldrhs, (int)nrhs);
-                else k_pb_front<false, 1><<<dim3(L.count, 1), 256, sm, st>>>(c, list, d_rhs, ldrhs, (int)nrhs);
+                if (tiny) { if (lu) k_pb_front<true, 1, 64><<<g, 64, sm, st>>>(c, list, d_rhs, ldrhs, (int)nrhs); else k_pb_front<false, 1, 64><<<g, 64, sm, st>>>(c, list, d_rhs, ldrhs, (int)nrhs); }
+                else { if (lu) k_pb_front<true, 1, 256><<<g, 256, sm, st>>>(c, list, d_rhs, ldrhs, (int)nrhs); else k_pb_front<false, 1, 256><<<g, 256, sm, st>>>(c, list, d_rhs, ldrhs, (int)nrhs); }
             } else {
-                size_t sm = pstep_smem_bytes_mr(L.maxw, SOLVE_NR, true);
-                if (lu) k_pb_front<true, SOLVE_NR><<<dim3(L.count, ngrp), 256, sm, st>>>(c, list, d_rhs, ldrhs, (int)nrhs);
-                else k_pb_front<false, SOLVE_NR><<<dim3(L.count, ngrp), 256, sm, st>>>(c, list, d_rhs, ldrhs, (int)nrhs);
+                if (tiny) { if (lu) k_pb_front<true, SOLVE_NR, 64><<<g, 64, sm, st>>>(c, list, d_rhs, ldrhs, (int)nrhs); else k_pb_front<false, SOLVE_NR, 64><<<g, 64, sm, st>>>(c, list, d_rhs, ldrhs, (int)nrhs); }
+                else { if (lu) k_pb_front<true, SOLVE_NR, 256><<<g, 256, sm, st>>>(c, list, d_rhs, ldrhs, (int)nrhs); else k_pb_front<false, SOLVE_NR, 256><<<g, 256, sm, st>>>(c, list, d_rhs, ldrhs, (int)nrhs); }
             }
             break;
         }
