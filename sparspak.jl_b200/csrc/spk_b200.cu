@@ -62,6 +62,7 @@ struct spk_plan {
     bool use_pipes = true;              // SPK_PIPES=1 builds no pipelines; this switches them off at run time (tests)
     bool pdl_gemm = false;              // SPK_PDL_GEMM=1: also the DMMA kernels (measured slower: early blocks hold SM resources)
     bool pdl_factor = false;            // SPK_PDL_FACTOR=1: same for the diagonal / panel kernels of the factorisation (measured: no gain)
+    int panel_reg_minw = 32;            // SPK_PANEL_REG_MINW
     bool panel_smem_only = false;       // SPK_PANEL_SMEM=1: always use the shared-memory panel kernel
     bool diag_smem_only = false;        // SPK_DIAG_SMEM=1: always use the shared-memory diagonal kernel
     int dmma_variant = 4;               // SPK_DMMA_VARIANT (see gemm_dmma.cuh)
@@ -274,6 +275,7 @@ SPK_API spk_plan* spk_plan_create(int64_t n, int64_t nsuper, const int64_t* xsup
     if (const char* e = getenv("SPK_SOLVE_GRAPH")) p->solve_graphs = e[0] != '0';
     if (const char* e = getenv("SPK_DIAG_TG")) p->diag_tg = atoi(e);
     if (const char* e = getenv("SPK_PANEL_SMEM")) p->panel_smem_only = e[0] == '1';
+    if (const char* e = getenv("SPK_PANEL_REG_MINW")) p->panel_reg_minw = atoi(e);
     if (const char* e = getenv("SPK_PDL")) p->pdl = e[0] != '0';
     if (const char* e = getenv("SPK_PDL_FACTOR")) p->pdl_factor = e[0] != '0';
     if (const char* e = getenv("SPK_PDL_GEMM")) p->pdl_gemm = e[0] == '1';
@@ -419,7 +421,9 @@ static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L, 
     case K_PANEL: {
         size_t sm = 0;                                   // tasks narrower than maxw may stage T: size for the worst case
         for (int w = 1; w <= L.maxw; ++w) sm = std::max(sm, panel_smem_bytes(w));
-        const bool fast = L.maxw <= 64 && !p->panel_smem_only;
+        // register kernel for 32 < w <= 64; narrower steps (the tiny fronts at the bottom of the tree: tens of thousands
+        // of blocks of a few rows) keep the shared-memory kernel, whose footprint scales with w (measured per level)
+        const bool fast = L.maxw <= 64 && L.maxw > p->panel_reg_minw && !p->panel_smem_only;
         if (fast) {
             if (lu) CK(launch_pdl(k_panel_reg<true>, dim3(L.nblocks * PANEL_REG_SPLIT), dim3(PANEL_REG_THREADS), 0, st, p->pdl_factor, c, (const int32_t*)(p->d_pslist + L.first), pfx, (int)L.count));
             else CK(launch_pdl(k_panel_reg<false>, dim3(L.nblocks * PANEL_REG_SPLIT), dim3(PANEL_REG_THREADS), 0, st, p->pdl_factor, c, (const int32_t*)(p->d_pslist + L.first), pfx, (int)L.count));
