@@ -787,6 +787,27 @@ __global__ void __launch_bounds__(PANEL_REG_THREADS, PANEL_REG_MINB) k_panel_reg
     }
 }
 
+// C -= A * B for the tiny fronts at the bottom of the tree (every task of the launch has m, n <= GEMM_TINY, so
+// one block per task): element-wise dot products straight from global memory, 128-thread blocks, many per SM —
+// tens of thousands of such tasks per level are launch-slot bound in a tiled kernel.  Same summation order over k
+// as the tiled kernel.
+constexpr int GEMM_TINY = 48;
+__global__ void __launch_bounds__(128) k_gemm_tiny(DevCtx c, const GemmTask* __restrict__ tasks, int count) {
+    if ((int)blockIdx.x >= count) return;
+    const GemmTask g = tasks[blockIdx.x];
+    const double* __restrict__ A = c.F + g.a0;
+    const double* __restrict__ B = c.F + g.b0;
+    double* __restrict__ C = c.F + g.c0;
+    const int ld = g.ld, tot = g.m * g.n;
+    for (int e = threadIdx.x; e < tot; e += blockDim.x) {
+        const int j = e / g.m, i = e - j * g.m;
+        if (g.lower && i + g.roff < j) continue;
+        double acc = 0.0;
+        for (int k = 0; k < g.k; ++k) acc += A[(size_t)i + (size_t)k * ld] * B[(size_t)k + (size_t)j * ld];
+        C[(size_t)i + (size_t)j * ld] -= acc;
+    }
+}
+
 // ------------------------------------------------------------------------------------
 // C -= A * B inside a frontal matrix (small-tile DFMA kernel; 64x64 tile, 4x4 per thread).
 // The big-tile DMMA kernels live in gemm_dmma.cuh.

@@ -367,7 +367,7 @@ struct GemmBatch {
         auto one = [&](std::vector<Item>& v, int32_t kind, int tm, int tn) {
             if (v.empty()) return;
             fb.begin(kind, (int32_t)P.gemmt.size(), lev, step, stream, wait_other, record);
-            for (const Item& it : v) { P.gemmt.push_back(it.t); fb.add(gemm_blocks(it.t, tm, tn), it.flops); }
+            for (const Item& it : v) { P.gemmt.push_back(it.t); fb.add(gemm_blocks(it.t, tm, tn), it.flops, std::max(it.t.m, it.t.n)); }   // maxw = largest C dimension of the launch
             fb.end();
             v.clear();
         };

@@ -433,7 +433,9 @@ static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L, 
         break;
     }
     case K_GEMM:
-        k_gemm_small<<<L.nblocks, 256, 0, st>>>(c, p->d_gemmt + L.first, pfx, L.count); break;
+        if (L.maxw > 0 && L.maxw <= GEMM_TINY && L.nblocks == L.count) k_gemm_tiny<<<L.count, 128, 0, st>>>(c, p->d_gemmt + L.first, L.count);
+        else k_gemm_small<<<L.nblocks, 256, 0, st>>>(c, p->d_gemmt + L.first, pfx, L.count);
+        break;
     case K_GEMM_B64:
     case K_GEMM_B128: {
         GemmVariant v = gemm_dmma_variant(L.kind, p->dmma_variant);
