@@ -64,11 +64,8 @@ __global__ void k_scatter_values(int64_t nnz, const int64_t* __restrict__ dest, 
 constexpr int CHUNK_EPB = 1024;      // entries per block
 // FILLU (load of FACTORS into LDL^T fronts): also write U = D L^T into the upper triangle, which is where the
 // factorisation leaves it and where the backward sweep reads it.
-template <bool STORE, bool FILLU = false>
-__global__ void __launch_bounds__(256) k_chunks(DevCtx c, const int32_t* __restrict__ pfx, int count) {
-    int t = find_task(pfx, count, blockIdx.x);
-    int lb = blockIdx.x - pfx[t];
-    const DChunk ch = c.chunks[t];
+template <bool STORE, bool FILLU>
+__device__ __forceinline__ void chunk_io(const DevCtx& c, const DChunk& ch, int lb) {
     const int32_t* __restrict__ pos = c.pos + ch.posofs;
     double* __restrict__ F = c.F + ch.fofs;
     const int64_t nl = (int64_t)ch.jlen * ch.nj;
@@ -88,6 +85,18 @@ __global__ void __launch_bounds__(256) k_chunks(DevCtx c, const int32_t* __restr
             if (STORE) c.unz[ch.uofs + eu] = F[f]; else F[f] = c.unz[ch.uofs + eu];
         }
     }
+}
+template <bool STORE, bool FILLU = false>
+__global__ void __launch_bounds__(256) k_chunks(DevCtx c, const int32_t* __restrict__ pfx, int count) {
+    int t = find_task(pfx, count, blockIdx.x);
+    chunk_io<STORE, FILLU>(c, c.chunks[t], blockIdx.x - pfx[t]);
+}
+// the chunks of ONE LEVEL of the front tree (list of chunk ids): the factors of a level are written back to
+// lnz / unz on a third stream while the next levels are being factored (HBM-bound copy under tensor-bound GEMMs)
+__global__ void __launch_bounds__(256) k_chunks_store_list(DevCtx c, const int32_t* __restrict__ list,
+                                                           const int32_t* __restrict__ pfx, int count) {
+    int t = find_task(pfx, count, blockIdx.x);
+    chunk_io<true, false>(c, c.chunks[list[t]], blockIdx.x - pfx[t]);
 }
 
 // ------------------------------------------------------------------------------------

@@ -54,6 +54,11 @@ struct spk_plan {
     double* d_nzval = nullptr; int64_t nzcap = 0, nz_last = 0;
     AsmTask* d_asmt = nullptr; GemmTask* d_gemmt = nullptr; SolveTask* d_solvet = nullptr;
     int32_t chunk_blocks = 0;
+    int32_t *d_stlist = nullptr, *d_stpfx = nullptr;    // chunk ids / block prefixes by level (overlapped factor write-back)
+    std::vector<int32_t> st_list0, st_pfx0, st_count, st_blocks;
+    cudaStream_t stream3 = nullptr;                     // write-back stream (lowest priority)
+    cudaEvent_t ev3a = nullptr, ev3b = nullptr, ev3c = nullptr;
+    bool store_overlap = true;                          // SPK_STORE_OVERLAP=0: one write-back kernel after the factorisation
     bool solve_graphs = true;           // SPK_SOLVE_GRAPH=0 disables CUDA-graph replay of the solve sweeps
     cudaGraphExec_t sg_exec = nullptr; double* sg_rhs = nullptr; double* sg_w = nullptr;
     int64_t sg_nrhs = 0, sg_ld = 0, sg_launches = 0; int32_t sg_which = -1;
@@ -128,6 +133,12 @@ SPK_API void spk_plan_destroy(spk_plan* p) {
         if (p->evs0) cudaEventDestroy(p->evs0);
         if (p->evs1) cudaEventDestroy(p->evs1);
         if (p->stream2) cudaStreamDestroy(p->stream2);
+        if (p->stream3) cudaStreamDestroy(p->stream3);
+        if (p->ev3a) cudaEventDestroy(p->ev3a);
+        if (p->ev3b) cudaEventDestroy(p->ev3b);
+        if (p->ev3c) cudaEventDestroy(p->ev3c);
+        if (p->d_stlist) cudaFree(p->d_stlist);
+        if (p->d_stpfx) cudaFree(p->d_stpfx);
         for (int v = 1; v < 4; ++v) for (int q = 0; q < 2; ++q) { if (p->pst[v][q]) cudaStreamDestroy(p->pst[v][q]); if (p->pev[v][q]) cudaEventDestroy(p->pev[v][q]); }
         if (p->stream) cudaStreamDestroy(p->stream);
     }
@@ -145,6 +156,10 @@ static int64_t plan_upload(spk_plan* p) {
         CK(cudaEventCreateWithFlags(&p->evs0, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&p->evs1, cudaEventDisableTiming));
         p->pst[0][0] = p->stream; p->pst[0][1] = p->stream2; p->pev[0][0] = p->evs0; p->pev[0][1] = p->evs1;
+        CK(cudaStreamCreateWithPriority(&p->stream3, cudaStreamNonBlocking, lo));
+        CK(cudaEventCreateWithFlags(&p->ev3a, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&p->ev3b, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&p->ev3c, cudaEventDisableTiming));
         for (int v = 1; v < 4; ++v) {                 // panel streams share the top priority; update streams rank by pipeline
             CK(cudaStreamCreateWithPriority(&p->pst[v][0], cudaStreamNonBlocking, hi));
             CK(cudaStreamCreateWithPriority(&p->pst[v][1], cudaStreamNonBlocking, std::min(lo, hi + 1 + v)));
@@ -168,6 +183,20 @@ static int64_t plan_upload(spk_plan* p) {
         cpfx[i + 1] = cpfx[i] + cdiv(ne, CHUNK_EPB);
     }
     p->chunk_blocks = cpfx.back();
+    {   // chunk lists by level of the front tree (overlapped write-back of the factors, see k_chunks_store_list)
+        std::vector<std::vector<int32_t>> byl(std::max(P.nlevels, 1));
+        for (size_t i = 0; i < dc.size(); ++i) byl[P.fronts[P.chunks[i].front].level].push_back((int32_t)i);
+        std::vector<int32_t> slist, spfx;
+        p->st_list0.assign(byl.size(), 0); p->st_pfx0.assign(byl.size(), 0); p->st_count.assign(byl.size(), 0); p->st_blocks.assign(byl.size(), 0);
+        for (size_t l = 0; l < byl.size(); ++l) {
+            p->st_list0[l] = (int32_t)slist.size(); p->st_pfx0[l] = (int32_t)spfx.size(); p->st_count[l] = (int32_t)byl[l].size();
+            int32_t acc = 0; spfx.push_back(0);
+            for (int32_t ci : byl[l]) { slist.push_back(ci); acc += cpfx[ci + 1] - cpfx[ci]; spfx.push_back(acc); }
+            p->st_blocks[l] = acc;
+        }
+        CK(upload(&p->d_stlist, slist));
+        CK(upload(&p->d_stpfx, spfx));
+    }
     CK(upload(&p->d_fronts, df));
     CK(upload(&p->d_chunks, dc));
     CK(upload(&p->d_chunkpfx, cpfx));
@@ -276,6 +305,7 @@ SPK_API spk_plan* spk_plan_create(int64_t n, int64_t nsuper, const int64_t* xsup
     if (const char* e = getenv("SPK_DIAG_TG")) p->diag_tg = atoi(e);
     if (const char* e = getenv("SPK_PANEL_SMEM")) p->panel_smem_only = e[0] == '1';
     if (const char* e = getenv("SPK_PANEL_REG_MINW")) p->panel_reg_minw = atoi(e);
+    if (const char* e = getenv("SPK_STORE_OVERLAP")) p->store_overlap = e[0] != '0';
     if (const char* e = getenv("SPK_PDL")) p->pdl = e[0] != '0';
     if (const char* e = getenv("SPK_PDL_FACTOR")) p->pdl_factor = e[0] != '0';
     if (const char* e = getenv("SPK_PDL_GEMM")) p->pdl_gemm = e[0] == '1';
@@ -511,7 +541,22 @@ SPK_API int64_t spk_plan_factor_phase(spk_plan* p, int32_t phase) {
         CK(cudaStreamWaitEvent(p->stream2, p->evs0, 0));
         CK(cudaEventRecord(p->evs1, p->stream2));
     }
+    // write-back of a finished level on the third stream, under the factorisation of the next levels
+    const bool ovl = two && phase < 0 && !piped && !trace && p->store_overlap && !Ls.empty();
+    auto store_level = [&](int lev, cudaStream_t s3) -> int64_t {
+        if (lev < 0 || lev >= (int)p->st_count.size() || p->st_blocks[lev] == 0) return 0;
+        k_chunks_store_list<<<p->st_blocks[lev], 256, 0, s3>>>(c, p->d_stlist + p->st_list0[lev], p->d_stpfx + p->st_pfx0[lev], p->st_count[lev]);
+        ++p->launches_factor;
+        return 0;
+    };
+    int cur_level = Ls.empty() ? 0 : Ls[0].level;
     for (const Launch& L : (piped ? P.factor_ptop : Ls)) {
+        if (ovl && L.level != cur_level) {
+            CK(cudaEventRecord(p->ev3a, p->stream)); CK(cudaEventRecord(p->ev3b, p->stream2));
+            CK(cudaStreamWaitEvent(p->stream3, p->ev3a, 0)); CK(cudaStreamWaitEvent(p->stream3, p->ev3b, 0));
+            for (int lv = cur_level; lv < L.level; ++lv) store_level(lv, p->stream3);
+            cur_level = L.level;
+        }
         int64_t rc = run_factor_launch(p, c, L, two);
         if (rc) return rc;
         ++p->launches_factor;
@@ -520,7 +565,11 @@ SPK_API int64_t spk_plan_factor_phase(spk_plan* p, int32_t phase) {
         if (trace) cudaEventRecord(tev[++li], p->pst[0][L.stream ? 1 : 0]);
     }
     if (two) { CK(cudaEventRecord(p->evs1, p->stream2)); CK(cudaStreamWaitEvent(st, p->evs1, 0)); }
-    if (phase != 0) {
+    if (phase != 0 && ovl) {
+        for (int lv = cur_level; lv < (int)p->st_count.size(); ++lv) store_level(lv, st);     // the last level(s), then join
+        CK(cudaEventRecord(p->ev3c, p->stream3));
+        CK(cudaStreamWaitEvent(st, p->ev3c, 0));
+    } else if (phase != 0) {
         // scatter the factors back into the reference layout (lnz / unz)
         k_chunks<true><<<p->chunk_blocks, 256, 0, st>>>(c, p->d_chunkpfx, (int)P.chunks.size());
         ++p->launches_factor;
