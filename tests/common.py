@@ -139,4 +139,7 @@ CASES = [
     ("pivot-4x4", lambda: M.pivoting_stress(4, 0.3, 3), False, None, None),
     ("single-1x1", lambda: sp.csc_matrix(np.array([[3.0]])), False, None, None),
     ("diag-5-spd", lambda: sp.diags([np.arange(1.0, 6.0)], [0], format="csc"), True, None, None),
+    # one dense front: a single fundamental supernode split into several chunks (widths around maxblocksize)
+    ("dense-70-lu", lambda: sp.csc_matrix(np.random.default_rng(5).standard_normal((70, 70)) + 0.5 * np.eye(70)), False, None, None),
+    ("dense-130-spd", lambda: sp.csc_matrix((lambda G: G @ G.T + 130.0 * np.eye(130))(np.random.default_rng(6).standard_normal((130, 130)))), True, None, None),
 ]
