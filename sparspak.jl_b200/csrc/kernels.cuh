@@ -1494,7 +1494,7 @@ __global__ void __launch_bounds__(SV_ROWS) k_pf_step(DevCtx c, const int32_t* __
 // Fused backward step: every block writes the partial sums of its rows/columns beyond step j; the block that
 // arrives last (device-wide counter) adds the partials in a fixed order and solves the diagonal block of step j.
 template <bool LU, int NR>
-__global__ void __launch_bounds__(SV_ROWS) k_pb_step(DevCtx c, const int32_t* __restrict__ plist,
+__global__ void __launch_bounds__(SV_ROWS, 1) k_pb_step(DevCtx c, const int32_t* __restrict__ plist,
                                                      const int32_t* __restrict__ pfx, int count,
                                                      double* __restrict__ rhs, int64_t ldrhs, int maxpw, int32_t* counters, int nrhs) {
     extern __shared__ double ssm[];
