@@ -55,7 +55,7 @@ struct spk_plan {
     AsmTask* d_asmt = nullptr; GemmTask* d_gemmt = nullptr; SolveTask* d_solvet = nullptr;
     int32_t chunk_blocks = 0;
     int32_t *d_stlist = nullptr, *d_stpfx = nullptr;    // chunk ids / block prefixes by level (overlapped factor write-back)
-    std::vector<int32_t> st_list0, st_pfx0, st_count, st_blocks;
+    std::vector<int32_t> st_list0[2], st_pfx0[2], st_count[2], st_blocks[2];   // [0] phase-0 / all fronts, [1] top set
     cudaStream_t stream3 = nullptr;                     // write-back stream (lowest priority)
     cudaEvent_t ev3a = nullptr, ev3b = nullptr, ev3c = nullptr;
     bool store_overlap = true;                          // SPK_STORE_OVERLAP=0: one write-back kernel after the factorisation
@@ -183,16 +183,25 @@ static int64_t plan_upload(spk_plan* p) {
         cpfx[i + 1] = cpfx[i] + cdiv(ne, CHUNK_EPB);
     }
     p->chunk_blocks = cpfx.back();
-    {   // chunk lists by level of the front tree (overlapped write-back of the factors, see k_chunks_store_list)
-        std::vector<std::vector<int32_t>> byl(std::max(P.nlevels, 1));
-        for (size_t i = 0; i < dc.size(); ++i) byl[P.fronts[P.chunks[i].front].level].push_back((int32_t)i);
+    {   // chunk lists by level of the front tree (overlapped write-back of the factors, see k_chunks_store_list).
+        // Class 0 = the fronts this part factors in phase 0 (all fronts of a single-part plan), class 1 = the top set.
+        const int nl = std::max(P.nlevels, 1);
         std::vector<int32_t> slist, spfx;
-        p->st_list0.assign(byl.size(), 0); p->st_pfx0.assign(byl.size(), 0); p->st_count.assign(byl.size(), 0); p->st_blocks.assign(byl.size(), 0);
-        for (size_t l = 0; l < byl.size(); ++l) {
-            p->st_list0[l] = (int32_t)slist.size(); p->st_pfx0[l] = (int32_t)spfx.size(); p->st_count[l] = (int32_t)byl[l].size();
-            int32_t acc = 0; spfx.push_back(0);
-            for (int32_t ci : byl[l]) { slist.push_back(ci); acc += cpfx[ci + 1] - cpfx[ci]; spfx.push_back(acc); }
-            p->st_blocks[l] = acc;
+        for (int cls = 0; cls < 2; ++cls) {
+            std::vector<std::vector<int32_t>> byl(nl);
+            for (size_t i = 0; i < dc.size(); ++i) {
+                const int32_t f = P.chunks[i].front;
+                const int32_t ow = P.nparts > 1 ? P.owner[f] : 0;
+                const bool in = cls == 0 ? (P.nparts > 1 ? ow == P.part : true) : (P.nparts > 1 && ow == -1);
+                if (in) byl[P.fronts[f].level].push_back((int32_t)i);
+            }
+            p->st_list0[cls].assign(nl, 0); p->st_pfx0[cls].assign(nl, 0); p->st_count[cls].assign(nl, 0); p->st_blocks[cls].assign(nl, 0);
+            for (int l = 0; l < nl; ++l) {
+                p->st_list0[cls][l] = (int32_t)slist.size(); p->st_pfx0[cls][l] = (int32_t)spfx.size(); p->st_count[cls][l] = (int32_t)byl[l].size();
+                int32_t acc = 0; spfx.push_back(0);
+                for (int32_t ci : byl[l]) { slist.push_back(ci); acc += cpfx[ci + 1] - cpfx[ci]; spfx.push_back(acc); }
+                p->st_blocks[cls][l] = acc;
+            }
         }
         CK(upload(&p->d_stlist, slist));
         CK(upload(&p->d_stpfx, spfx));
@@ -542,10 +551,12 @@ SPK_API int64_t spk_plan_factor_phase(spk_plan* p, int32_t phase) {
         CK(cudaEventRecord(p->evs1, p->stream2));
     }
     // write-back of a finished level on the third stream, under the factorisation of the next levels
-    const bool ovl = two && phase < 0 && !piped && !trace && p->store_overlap && !Ls.empty();
+    // (multi-part plans: phase 0 writes back the part's own subtrees, phase 1 the top set — not the other parts' chunks)
+    const bool ovl = two && !piped && !trace && p->store_overlap && !Ls.empty();
+    const int scls = phase == 1 ? 1 : 0;
     auto store_level = [&](int lev, cudaStream_t s3) -> int64_t {
-        if (lev < 0 || lev >= (int)p->st_count.size() || p->st_blocks[lev] == 0) return 0;
-        k_chunks_store_list<<<p->st_blocks[lev], 256, 0, s3>>>(c, p->d_stlist + p->st_list0[lev], p->d_stpfx + p->st_pfx0[lev], p->st_count[lev]);
+        if (lev < 0 || lev >= (int)p->st_count[scls].size() || p->st_blocks[scls][lev] == 0) return 0;
+        k_chunks_store_list<<<p->st_blocks[scls][lev], 256, 0, s3>>>(c, p->d_stlist + p->st_list0[scls][lev], p->d_stpfx + p->st_pfx0[scls][lev], p->st_count[scls][lev]);
         ++p->launches_factor;
         return 0;
     };
@@ -565,8 +576,8 @@ SPK_API int64_t spk_plan_factor_phase(spk_plan* p, int32_t phase) {
         if (trace) cudaEventRecord(tev[++li], p->pst[0][L.stream ? 1 : 0]);
     }
     if (two) { CK(cudaEventRecord(p->evs1, p->stream2)); CK(cudaStreamWaitEvent(st, p->evs1, 0)); }
-    if (phase != 0 && ovl) {
-        for (int lv = cur_level; lv < (int)p->st_count.size(); ++lv) store_level(lv, st);     // the last level(s), then join
+    if (ovl) {
+        for (int lv = cur_level; lv < (int)p->st_count[scls].size(); ++lv) store_level(lv, st);     // the last level(s), then join
         CK(cudaEventRecord(p->ev3c, p->stream3));
         CK(cudaStreamWaitEvent(st, p->ev3c, 0));
     } else if (phase != 0) {
