@@ -254,6 +254,8 @@ VARIANTS = [
     {"SPK_PDL": "0", "SPK_SOLVE_SMALL": "0"},   # solve steps without programmatic dependent launch
     {"SPK_SOLVE_LNZ": "1"},                     # chunk-by-chunk solve on lnz / unz
     {"SPK_SOLVE_GRAPH": "0", "SPK_SOLVE_SMALL": "0"},
+    {"SPK_STORE_OVERLAP": "0", "SPK_LL": "0"},  # one write-back kernel at the end; right-looking in-block updates (LDLt)
+    {"SPK_PANEL_REG_MINW": "0", "SPK_PDL_FACTOR": "1"},   # register panel kernel for every width <= 64; PDL in the factorisation
 ]
 
 
