@@ -321,6 +321,9 @@ def _main(json_out):
         "config": {"workload": workload, "grid": args.grid, "n": int(b.n), "nnz_lnz": int(b.xlnz[-1]) - 1,
                    "structural_flops": F, "ordering": "geometric nested dissection (harness callback)",
                    "l2": "working set (frontal arena + factors, tens of GB) far exceeds the 126 MB L2; no flush needed",
+                   "step": "arena clear + device scatter of A's values + numeric factorisation + one triangular solve; "
+                           "value = structural factor flops / factor_s (BASELINE metric: factor GFLOP/s), "
+                           "ms_per_step = the whole step, solve_s reported separately",
                    "parallelism": (f"{world} elimination subtrees -> GPUs, NCCL broadcast of subtree-root fronts, replicated top set"
                                    if world > 1 else "single GPU")},
         "factor_s": factor_ms * 1e-3, "solve_s": solve_ms * 1e-3, "residual": resid,
