@@ -9,8 +9,13 @@ import sparspak_jl_b200 as spk
 import oracle
 from common import maketridiagproblem, prepare, oracle_factor, residual, M
 
-FIG313_I = [1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5, 5, 5, 6, 6, 6]
-FIG313_J = [1, 2, 6, 1, 2, 3, 4, 2, 3, 5, 2, 4, 3, 5, 6, 1, 5, 6]
+import json
+import os
+
+# fixtures: tests/golden/reference_goldens.json (each entry cites the reference test file:line it was copied from)
+GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_goldens.json")))
+FIG313_I = GOLD["graph_fig313"]["I"]
+FIG313_J = GOLD["graph_fig313"]["J"]
 
 
 def test_graph_goldens():
@@ -18,8 +23,8 @@ def test_graph_goldens():
     p = spk.Problem(6, 6)
     spk.insparse(p, FIG313_I, FIG313_J, [1.0] * 18)
     g = spk.Graph(p)
-    assert g.xadj.tolist() == [1, 3, 6, 8, 9, 11, 13]
-    assert g.adj.tolist() == [2, 6, 1, 3, 4, 2, 5, 2, 3, 6, 1, 5]
+    assert g.xadj.tolist() == GOLD["graph_fig313"]["xadj"]
+    assert g.adj.tolist() == GOLD["graph_fig313"]["adj"]
     assert spk.isstructuresymmetric(g)
 
 
@@ -42,8 +47,8 @@ def test_mmd_ordering_golden():
     s = spk.SparseSolver(maketridiagproblem(11))
     spk.findorder(s)
     o = s.slvr.order
-    assert o.rperm.tolist() == [11, 1, 10, 2, 9, 3, 8, 4, 7, 5, 6]
-    assert o.rinvp.tolist() == [2, 4, 6, 8, 10, 11, 9, 7, 5, 3, 1]
+    assert o.rperm.tolist() == GOLD["tridiag11_mmd"]["rperm"]
+    assert o.rinvp.tolist() == GOLD["tridiag11_mmd"]["rinvp"]
     assert o.cperm.tolist() == o.rperm.tolist() and o.cinvp.tolist() == o.rinvp.tolist()
 
 
@@ -52,25 +57,22 @@ def test_symbolic_structure_golden():
     s = spk.SparseSolver(maketridiagproblem(11))
     spk.findorder(s); spk.symbolicfactor(s)
     b = s.slvr
-    assert b.xlnz.tolist() == [1, 3, 5, 7, 9, 11, 13, 15, 17, 19, 21, 23]
-    assert b.xunz.tolist() == [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 10, 10]
-    assert b.xlindx.tolist() == [1, 3, 5, 7, 9, 11, 13, 15, 17, 19, 21]
-    assert b.lindx.tolist() == [1, 2, 2, 3, 3, 4, 4, 5, 5, 11, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11]
+    G = GOLD["tridiag11_symbolic"]
+    assert b.xlnz.tolist() == G["xlnz"]
+    assert b.xunz.tolist() == G["xunz"]
+    assert b.xlindx.tolist() == G["xlindx"]
+    assert b.lindx.tolist() == G["lindx"]
 
 
 def test_inmatrix_golden():
     # test/test_sparse_method.jl:172-175
     s = spk.SparseSolver(maketridiagproblem(11))
     spk.findorder(s); spk.symbolicfactor(s); spk.inmatrix(s)
-    assert s.slvr.unz.tolist() == [-1.0] * 9
-    assert s.slvr.lnz.tolist() == [4.0, -1.0] * 10 + [-1.0, 4.0]
+    assert s.slvr.unz.tolist() == GOLD["tridiag11_inmatrix"]["unz"]
+    assert s.slvr.lnz.tolist() == GOLD["tridiag11_inmatrix"]["lnz"]
 
 
-GOLD_LNZ = [4.0, -0.25000000000000000, 3.7500000000000000, -0.26666666666666666, 3.7333333333333334,
-            -0.26785714285714285, 3.7321428571428572, -0.26794258373205743, 3.7320574162679425,
-            -0.26794871794871794, 4.0, -0.25000000000000000, 3.7500000000000000, -0.26666666666666666,
-            3.7333333333333334, -0.26785714285714285, 3.7321428571428572, -0.26794258373205743,
-            3.7320574162679425, -0.26794871794871794, -1.0000000000000000, 3.4641025641025642]
+GOLD_LNZ = GOLD["tridiag11_lufactor"]["lnz"]
 
 
 def test_oracle_lufactor_golden():
@@ -81,8 +83,8 @@ def test_oracle_lufactor_golden():
     assert fl == 0
     g = np.array(GOLD_LNZ)
     assert np.linalg.norm(lnz - g) / np.linalg.norm(g) < 1e-15
-    assert np.abs(unz + 1.0).max() == 0.0
-    assert ipiv.tolist() == [1] * 10 + [2]          # block-local LAPACK pivots (SURVEY.md §8a')
+    assert unz.tolist() == GOLD["tridiag11_lufactor"]["unz"]
+    assert ipiv.tolist() == GOLD["tridiag11_lufactor"]["ipiv"]          # block-local LAPACK pivots (SURVEY.md §8a')
 
 
 def test_oracle_worked_example_3x3_grid():
