@@ -126,6 +126,16 @@ SPK_API int64_t spk_plan_set_perm(spk_plan* p, const int64_t* rperm, const int64
 SPK_API int64_t spk_plan_triangularsolve(spk_plan* p, double* b, int64_t nrhs, int64_t ldb);
 
 /* ---- device-resident variants used by bench.py / multi-GPU drivers -------------------- */
+/* Residual and iterative refinement on the device (computeresidual SpkProblem.jl:448-496, the
+ * refinement the reference only keeps as commented-out Fortran, SpkSparseSpdSolver.jl:267-459).
+ * spk_plan_set_matrix: A as SparseMatrixCSC (colptr[n+1], rowval[nnz], nzval[nnz], 1-based, ORIGINAL ordering).
+ * spk_plan_residual:   res = b - A x (res may be NULL), relnorm[q] = ||res_q||_2 / ||b_q||_2.
+ * spk_plan_refine:     x += inv(A)(b - A x) with the resident factors until max relnorm <= tol or maxit
+ *                      corrections; returns the number of corrections (>= 0) or an error code (<= -100). */
+SPK_API int64_t spk_plan_set_matrix(spk_plan* p, int64_t nnz, const int64_t* colptr, const int64_t* rowval, const double* nzval);
+SPK_API int64_t spk_plan_residual(spk_plan* p, const double* b, const double* x, int64_t nrhs, int64_t ld, double* res_or_null, double* relnorm);
+SPK_API int64_t spk_plan_refine(spk_plan* p, const double* b, double* x, int64_t nrhs, int64_t ld, int32_t maxit, double tol, double* relnorm);
+
 /* Float32 callers of a plan (the plan itself stays FP64) */
 SPK_API int64_t spk_plan_inmatrix_f32(spk_plan* p, int64_t nnz, const int64_t* dest_or_null, const float* nzval);
 SPK_API int64_t spk_plan_get_factors_f32(spk_plan* p, float* lnz, float* unz, int64_t* ipvt);

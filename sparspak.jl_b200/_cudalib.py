@@ -17,6 +17,7 @@ SYMBOLS = [
     "spk_lufactor_f64", "spk_lulsolve_f64", "spk_luusolve_f64", "spk_ldltfactor_f64", "spk_ldltsolve_f64",
     "spk_lufactor_f32", "spk_lulsolve_f32", "spk_luusolve_f32", "spk_ldltfactor_f32", "spk_ldltsolve_f32",
     "spk_plan_inmatrix_f32", "spk_plan_get_factors_f32", "spk_plan_triangularsolve_f32",
+    "spk_plan_set_matrix", "spk_plan_residual", "spk_plan_refine",
     "spk_plan_create", "spk_plan_destroy", "spk_plan_inmatrix", "spk_plan_reassemble", "spk_plan_set_values", "spk_plan_factor",
     "spk_plan_get_factors", "spk_plan_set_factors", "spk_plan_solve", "spk_plan_set_perm",
     "spk_plan_triangularsolve", "spk_plan_device_ptr", "spk_plan_device_len", "spk_plan_factor_phase",
@@ -66,6 +67,12 @@ def lib():
     L.spk_plan_get_factors_f32.restype = i64
     L.spk_plan_triangularsolve_f32.argtypes = [vp, F32P, i64, i64]
     L.spk_plan_triangularsolve_f32.restype = i64
+    L.spk_plan_set_matrix.argtypes = [vp, i64, I64P, I64P, F64P]
+    L.spk_plan_set_matrix.restype = i64
+    L.spk_plan_residual.argtypes = [vp, vp, vp, i64, i64, vp, vp]
+    L.spk_plan_residual.restype = i64
+    L.spk_plan_refine.argtypes = [vp, vp, vp, i64, i64, i32, dbl, vp]
+    L.spk_plan_refine.restype = i64
     L.spk_plan_create.argtypes = [i64, i64, I64P, I64P, I64P, I64P, I64P, vp, i32, i32, i32]
     L.spk_plan_create.restype = vp
     L.spk_plan_destroy.argtypes = [vp]
@@ -154,6 +161,32 @@ class Plan:
         if dest is not None:
             dest = np.ascontiguousarray(dest, dtype=np.int64)
         self._ck(self.L.spk_plan_inmatrix(self.h, nzval.size, _ptr(dest), nzval), "spk_plan_inmatrix")
+
+    def set_matrix(self, A):
+        """A: scipy.sparse matrix in the original ordering (kept on the device as CSR for residual / refine)."""
+        A = A.tocsc(); A.sort_indices()
+        colptr = np.ascontiguousarray(A.indptr, dtype=np.int64) + 1
+        rowval = np.ascontiguousarray(A.indices, dtype=np.int64) + 1
+        self._ck(self.L.spk_plan_set_matrix(self.h, A.nnz, colptr, rowval, np.ascontiguousarray(A.data, dtype=np.float64)), "spk_plan_set_matrix")
+
+    def residual(self, b, x):
+        """(res, relnorm): res = b - A x on the device, relnorm[q] = ||res_q|| / ||b_q||."""
+        b = np.asfortranarray(b, dtype=np.float64); x = np.asfortranarray(x, dtype=np.float64)
+        nrhs = 1 if b.ndim == 1 else b.shape[1]
+        res = np.zeros_like(b, order="F"); rel = np.zeros(nrhs)
+        self._ck(self.L.spk_plan_residual(self.h, b.ctypes.data, x.ctypes.data, nrhs, b.shape[0], res.ctypes.data, rel.ctypes.data), "spk_plan_residual")
+        return res, rel
+
+    def refine(self, b, x, maxit=3, tol=1e-15):
+        """Iterative refinement of x in place with the resident factors; returns (corrections, relnorm)."""
+        assert x.flags.f_contiguous or x.ndim == 1
+        b = np.asfortranarray(b, dtype=np.float64)
+        nrhs = 1 if b.ndim == 1 else b.shape[1]
+        rel = np.zeros(nrhs)
+        rc = self.L.spk_plan_refine(self.h, b.ctypes.data, x.ctypes.data, nrhs, b.shape[0], maxit, tol, rel.ctypes.data)
+        if rc < 0:
+            self._ck(rc, "spk_plan_refine")
+        return int(rc), rel
 
     def reassemble(self):
         self._ck(self.L.spk_plan_reassemble(self.h), "spk_plan_reassemble")

@@ -1689,6 +1689,37 @@ __global__ void k_copy_front_x(DevCtx c, int nfronts, double* __restrict__ rhs, 
     for (int i = threadIdx.x; i < F.W; i += blockDim.x) { if (to_rhs) b[i] = w[i]; else w[i] = b[i]; }
 }
 
+// ------------------------------------------------------------------------------------
+// Residual / iterative refinement on the device (computeresidual, SpkProblem.jl:448-496; the refinement of
+// SpkSparseSpdSolver.jl:267-459 exists only as commented-out Fortran in the reference).
+// r = b - A x for a CSR copy of A in the ORIGINAL ordering: one thread per row, terms subtracted in storage order.
+__global__ void k_csr_residual(int64_t n, const int64_t* __restrict__ rp, const int32_t* __restrict__ ci,
+                               const double* __restrict__ av, const double* __restrict__ b, const double* __restrict__ x,
+                               double* __restrict__ r, int64_t ld) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* xq = x + (size_t)blockIdx.y * ld;
+    double acc = b[(size_t)blockIdx.y * ld + i];
+    for (int64_t k = rp[i]; k < rp[i + 1]; ++k) acc -= av[k] * xq[ci[k]];
+    r[(size_t)blockIdx.y * ld + i] = acc;
+}
+// sums of squares, one partial per block, fixed summation order (the host adds the partials in order)
+__global__ void __launch_bounds__(256) k_sumsq_partial(int64_t n, const double* __restrict__ v, int64_t ld, double* __restrict__ part) {
+    __shared__ double sh[256];
+    const double* vq = v + (size_t)blockIdx.y * ld;
+    const int64_t i0 = (int64_t)blockIdx.x * 4096;
+    double acc = 0.0;
+    for (int k = 0; k < 16; ++k) { const int64_t i = i0 + threadIdx.x + 256 * k; if (i < n) acc += vq[i] * vq[i]; }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) { if ((int)threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off]; __syncthreads(); }
+    if (threadIdx.x == 0) part[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = sh[0];
+}
+__global__ void k_add_inplace(int64_t n, double* __restrict__ x, const double* __restrict__ d, int64_t ld) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[(size_t)blockIdx.y * ld + i] += d[(size_t)blockIdx.y * ld + i];
+}
+
 // rhs permutation gathers of _triangularsolve! (SpkSparseBase.jl:406-413): out[i] = in[idx[i]-1]
 __global__ void k_perm_gather(int64_t n, const int64_t* __restrict__ idx, const double* __restrict__ in,
                               double* __restrict__ out, int64_t ldin, int64_t ldout) {

@@ -54,6 +54,9 @@ struct spk_plan {
     double* d_nzval = nullptr; int64_t nzcap = 0, nz_last = 0;
     AsmTask* d_asmt = nullptr; GemmTask* d_gemmt = nullptr; SolveTask* d_solvet = nullptr;
     int32_t chunk_blocks = 0;
+    // CSR copy of A in the original ordering + work vectors (spk_plan_set_matrix / residual / refine)
+    int64_t* d_arp = nullptr; int32_t* d_aci = nullptr; double* d_av = nullptr; int64_t annz = -1;
+    double *d_rb = nullptr, *d_rx = nullptr, *d_rr = nullptr, *d_rpart = nullptr; int64_t rcap = 0;
     int32_t *d_stlist = nullptr, *d_stpfx = nullptr;    // chunk ids / block prefixes by level (overlapped factor write-back)
     std::vector<int32_t> st_list0[2], st_pfx0[2], st_count[2], st_blocks[2];   // [0] phase-0 / all fronts, [1] top set
     cudaStream_t stream3 = nullptr;                     // write-back stream (lowest priority)
@@ -137,6 +140,7 @@ SPK_API void spk_plan_destroy(spk_plan* p) {
         if (p->ev3a) cudaEventDestroy(p->ev3a);
         if (p->ev3b) cudaEventDestroy(p->ev3b);
         if (p->ev3c) cudaEventDestroy(p->ev3c);
+        for (void* q : {(void*)p->d_arp, (void*)p->d_aci, (void*)p->d_av, (void*)p->d_rb, (void*)p->d_rx, (void*)p->d_rr, (void*)p->d_rpart}) if (q) cudaFree(q);
         if (p->d_stlist) cudaFree(p->d_stlist);
         if (p->d_stpfx) cudaFree(p->d_stpfx);
         for (int v = 1; v < 4; ++v) for (int q = 0; q < 2; ++q) { if (p->pst[v][q]) cudaStreamDestroy(p->pst[v][q]); if (p->pev[v][q]) cudaEventDestroy(p->pev[v][q]); }
@@ -1059,6 +1063,108 @@ SPK_API int64_t spk_ldltsolve_f64(int64_t nsuper, const int64_t* xsuper, const i
     if (!rc) rc = spk_plan_solve(p, rhs, 1, n, 0);
     spk_plan_destroy(p);
     return rc ? rc : 1;
+}
+
+// ---- residual and iterative refinement on the device --------------------
+// A as the reference holds it: SparseMatrixCSC colptr / rowval / nzval, 1-based, ORIGINAL ordering.
+SPK_API int64_t spk_plan_set_matrix(spk_plan* p, int64_t nnz, const int64_t* colptr, const int64_t* rowval, const double* nzval) {
+    NEED_DEV(p);
+    const int64_t n = p->P.n;
+    if (nnz < 0 || colptr[n] - 1 != nnz) { set_err("spk_plan_set_matrix: colptr[n+1]-1 != nnz"); return -100; }
+    std::vector<int64_t> rp(n + 1, 0);
+    for (int64_t k = 0; k < nnz; ++k) { const int64_t i = rowval[k] - 1; if (i < 0 || i >= n) { set_err("spk_plan_set_matrix: row index out of range"); return -100; } rp[i + 1]++; }
+    for (int64_t i = 0; i < n; ++i) rp[i + 1] += rp[i];
+    std::vector<int32_t> ci((size_t)nnz); std::vector<double> av((size_t)nnz);
+    std::vector<int64_t> at(rp.begin(), rp.end() - 1);
+    for (int64_t j = 0; j < n; ++j)                       // columns ascending => every row's entries end up sorted by column
+        for (int64_t k = colptr[j] - 1; k < colptr[j + 1] - 1; ++k) { const int64_t q = at[rowval[k] - 1]++; ci[q] = (int32_t)j; av[q] = nzval[k]; }
+    for (void* q : {(void*)p->d_arp, (void*)p->d_aci, (void*)p->d_av}) if (q) cudaFree(q);
+    p->d_arp = nullptr; p->d_aci = nullptr; p->d_av = nullptr; p->annz = -1;
+    CK(upload(&p->d_arp, rp)); CK(upload(&p->d_aci, ci)); CK(upload(&p->d_av, av));
+    p->annz = nnz;
+    return 0;
+}
+
+static int64_t ensure_refine(spk_plan* p, int64_t nrhs) {
+    const int64_t need = p->P.n * nrhs;
+    if (need > p->rcap) {
+        for (void* q : {(void*)p->d_rb, (void*)p->d_rx, (void*)p->d_rr, (void*)p->d_rpart}) if (q) cudaFree(q);
+        p->d_rb = p->d_rx = p->d_rr = p->d_rpart = nullptr; p->rcap = 0;
+        CK(cudaMalloc((void**)&p->d_rb, need * sizeof(double)));
+        CK(cudaMalloc((void**)&p->d_rx, need * sizeof(double)));
+        CK(cudaMalloc((void**)&p->d_rr, need * sizeof(double)));
+        CK(cudaMalloc((void**)&p->d_rpart, (size_t)(cdiv(p->P.n, 4096) + 1) * nrhs * sizeof(double)));
+        p->rcap = need;
+    }
+    return 0;
+}
+// ||v_q||_2 for q < nrhs (device vector, leading dimension n)
+static int64_t dev_norms(spk_plan* p, const double* d_v, int64_t nrhs, double* out) {
+    const int64_t n = p->P.n; const int nb = (int)cdiv(n, 4096);
+    k_sumsq_partial<<<dim3(nb, (unsigned)nrhs), 256, 0, p->stream>>>(n, d_v, n, p->d_rpart);
+    std::vector<double> part((size_t)nb * nrhs);
+    CK(cudaMemcpyAsync(part.data(), p->d_rpart, part.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    for (int64_t q = 0; q < nrhs; ++q) { double s2 = 0.0; for (int b2 = 0; b2 < nb; ++b2) s2 += part[(size_t)q * nb + b2]; out[q] = std::sqrt(s2); }
+    return 0;
+}
+static int64_t refine_chunk(spk_plan* p, const double* b, double* x, int64_t nrhs, int64_t ld, int32_t maxit, double tol,
+                            double* res_or_null, double* relnorm, bool correct) {
+    const int64_t n = p->P.n;
+    cudaStream_t st = p->stream;
+    int64_t rc = ensure_refine(p, nrhs); if (rc) return rc;
+    CK(cudaMemcpy2DAsync(p->d_rb, n * sizeof(double), b, ld * sizeof(double), n * sizeof(double), nrhs, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpy2DAsync(p->d_rx, n * sizeof(double), x, ld * sizeof(double), n * sizeof(double), nrhs, cudaMemcpyHostToDevice, st));
+    std::vector<double> nb(nrhs), nr(nrhs);
+    rc = dev_norms(p, p->d_rb, nrhs, nb.data()); if (rc) return rc;
+    int64_t steps = 0;
+    for (int32_t it = 0;; ++it) {
+        k_csr_residual<<<dim3((unsigned)cdiv(n, 256), (unsigned)nrhs), 256, 0, st>>>(n, p->d_arp, p->d_aci, p->d_av, p->d_rb, p->d_rx, p->d_rr, n);
+        rc = dev_norms(p, p->d_rr, nrhs, nr.data()); if (rc) return rc;
+        double worst = 0.0;
+        for (int64_t q = 0; q < nrhs; ++q) { relnorm[q] = nb[q] > 0.0 ? nr[q] / nb[q] : nr[q]; worst = std::max(worst, relnorm[q]); }
+        if (!correct || it >= maxit || worst <= tol) break;
+        // d = A^{-1} r with the resident factors (permute, sweeps, un-permute), x += d
+        rc = ensure_rhs(p, nrhs); if (rc) return rc;
+        k_perm_gather<<<dim3(cdiv(n, 256), (unsigned)nrhs), 256, 0, st>>>(n, p->d_rperm, p->d_rr, p->d_rhs, n, n);
+        rc = spk_plan_solve_device(p, p->d_rhs, nrhs, n, 0); if (rc) return rc;
+        k_perm_gather<<<dim3(cdiv(n, 256), (unsigned)nrhs), 256, 0, st>>>(n, p->d_rinvp, p->d_rhs, p->d_tmp, n, n);
+        k_add_inplace<<<dim3((unsigned)cdiv(n, 256), (unsigned)nrhs), 256, 0, st>>>(n, p->d_rx, p->d_tmp, n);
+        ++steps;
+    }
+    if (res_or_null) CK(cudaMemcpy2DAsync(res_or_null, ld * sizeof(double), p->d_rr, n * sizeof(double), n * sizeof(double), nrhs, cudaMemcpyDeviceToHost, st));
+    if (correct) CK(cudaMemcpy2DAsync(x, ld * sizeof(double), p->d_rx, n * sizeof(double), n * sizeof(double), nrhs, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    return steps;
+}
+// res = b - A x (res may be NULL), relnorm[q] = ||res_q|| / ||b_q||
+SPK_API int64_t spk_plan_residual(spk_plan* p, const double* b, const double* x, int64_t nrhs, int64_t ld, double* res_or_null, double* relnorm) {
+    NEED_DEV(p);
+    if (p->annz < 0) { set_err("spk_plan_set_matrix not called"); return -100; }
+    for (int64_t q0 = 0; q0 < nrhs; q0 += 32) {
+        const int64_t nq = std::min<int64_t>(32, nrhs - q0);
+        int64_t rc = refine_chunk(p, b + (size_t)q0 * ld, const_cast<double*>(x) + (size_t)q0 * ld, nq, ld, 0, 0.0,
+                                  res_or_null ? res_or_null + (size_t)q0 * ld : nullptr, relnorm + q0, false);
+        if (rc < 0) return rc;
+    }
+    return 0;
+}
+// iterative refinement in FP64: x += A^{-1}(b - A x) until max_q relnorm[q] <= tol or maxit corrections; returns
+// the largest number of corrections applied to a block of right-hand sides (>= 0) or an error code (<= -100)
+SPK_API int64_t spk_plan_refine(spk_plan* p, const double* b, double* x, int64_t nrhs, int64_t ld, int32_t maxit, double tol, double* relnorm) {
+    NEED_DEV(p);
+    if (p->annz < 0) { set_err("spk_plan_set_matrix not called"); return -100; }
+    if (!p->have_perm) { set_err("spk_plan_set_perm not called"); return -100; }
+    if (!p->factored) { set_err("spk_plan_refine: no factors"); return -100; }
+    int64_t most = 0;
+    for (int64_t q0 = 0; q0 < nrhs; q0 += 32) {
+        const int64_t nq = std::min<int64_t>(32, nrhs - q0);
+        int64_t rc = refine_chunk(p, b + (size_t)q0 * ld, x + (size_t)q0 * ld, nq, ld, maxit, tol, nullptr, relnorm + q0, true);
+        if (rc < 0) return rc;
+        most = std::max(most, rc);
+    }
+    return most;
 }
 
 // ---- Float32 twins ---------------------------------------------------------------------------

@@ -324,3 +324,33 @@ def test_float32_twins(spd):
     assert L.spk_plan_get_factors_f32(plan.h, l32.ctypes.data, None, None) == 0
     assert rel_err(l32.astype(np.float64), lo, spd_mask(b) if spd else None) < 4 * eps32
     plan.destroy()
+
+
+@pytest.mark.parametrize("spd", [False, True])
+def test_device_residual_and_refinement(spd):
+    """computeresidual (SpkProblem.jl:448-496) and iterative refinement on the device.
+    A deliberately poor start (the solution rounded to Float32) must be refined to the FP64 residual bar."""
+    A = M.convdiff3d(10) if not spd else M.laplacian3d(10)
+    s = prepare(A, spd, spk.nd_grid_order(10, 10, 10))
+    b = s.slvr
+    plan = _cudalib.Plan(b)
+    plan.set_values(b.lnz, None if spd else b.unz); assert plan.factor() == 0
+    plan.set_perm(b.order.rperm, b.order.rinvp)
+    plan.set_matrix(A)
+    rng = np.random.default_rng(2024)
+    B = np.asfortranarray(rng.standard_normal((b.n, 3)))
+    X = B.copy(order="F"); plan.triangularsolve(X)
+    X0 = np.asfortranarray(X.astype(np.float32).astype(np.float64))
+    res, rel = plan.residual(B, X0)
+    ref = B - A @ X0
+    assert np.abs(res - ref).max() <= 1e-13 * np.abs(B).max()    # both sides cancel ~7 digits: compare on the scale of b
+    assert np.allclose(rel, np.linalg.norm(ref, axis=0) / np.linalg.norm(B, axis=0), rtol=1e-5)
+    assert rel.max() > 1e-9                                     # Float32 rounding of x is visible
+    steps, rel2 = plan.refine(B, X0, maxit=4, tol=1e-14)
+    assert 1 <= steps <= 4 and rel2.max() <= 1e-14
+    for j in range(3):
+        assert residual(A, X0[:, j], B[:, j]) < RESID_TOL
+    # a converged start needs no correction
+    steps, rel3 = plan.refine(B, X0, maxit=4, tol=1e-12)
+    assert steps == 0 and rel3.max() <= 1e-12
+    plan.destroy()
