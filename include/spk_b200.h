@@ -96,9 +96,12 @@ SPK_API spk_plan* spk_plan_create(int64_t n, int64_t nsuper, const int64_t* xsup
                                   const int64_t* xunz_or_null, int32_t device, int32_t part, int32_t nparts);
 SPK_API void spk_plan_destroy(spk_plan* p);
 
-/* _inmatrix! on the device (SpkSparseBase.jl:302-372 / SpkSparseSpdBase.jl:234-311): zero lnz/unz,
- * then lnz[dest[k]-1] += nzval[k] (dest>0) or unz[-dest[k]-1] += nzval[k] (dest<0); dest==0 skipped.
- * dest is uploaded once per plan (pass NULL afterwards to reuse it). */
+/* _inmatrix! on the device (SpkSparseBase.jl:302-372 / SpkSparseSpdBase.jl:234-311).  dest[k] names the slot
+ * of the reference layout that nzval[k] is added to: lnz[dest[k]-1] (dest>0), unz[-dest[k]-1] (dest<0), none
+ * (dest==0); duplicates accumulate.  The values are scattered STRAIGHT INTO THE ZEROED FRONTAL MATRICES the
+ * factorisation works on; the device copies of lnz/unz (and spk_plan_get_factors) are only meaningful again
+ * after the next spk_plan_factor.  The map is translated and uploaded once (pass NULL afterwards to reuse it;
+ * nnz must then equal the nnz the map was built for). */
 SPK_API int64_t spk_plan_inmatrix(spk_plan* p, int64_t nnz, const int64_t* dest_or_null, const double* nzval);
 
 /* the same with the values already resident from the last spk_plan_inmatrix (no host traffic; asynchronous) */

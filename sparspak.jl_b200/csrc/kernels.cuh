@@ -51,13 +51,14 @@ __device__ __forceinline__ int find_task(const int32_t* __restrict__ pfx, int co
 // ------------------------------------------------------------------------------------
 // inmatrix on the device (SpkSparseBase.jl:302-372): scatter A's values
 // straight into the frontal matrices through a destination map built once per pattern.
-// A duplicate-free CSC gives unique destinations, so no atomics are needed.
+// Duplicate (i,j) entries of a CSC accumulate, as in the reference's `lnz[..] += nzval[k]`: atomicAdd (native
+// FP64 red on sm_100a; with unique destinations — every sorted, summed CSC — the result is order-independent).
 __global__ void k_scatter_values(int64_t nnz, const int64_t* __restrict__ dest, const double* __restrict__ v,
                                  double* __restrict__ F) {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nnz) return;
     int64_t d = dest[k];
-    if (d >= 0) F[d] += v[k];
+    if (d >= 0) atomicAdd(F + d, v[k]);
 }
 
 // reference layout -> fronts (values assembled by the host _inmatrix!) and back (factors)

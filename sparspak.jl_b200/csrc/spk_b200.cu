@@ -51,7 +51,7 @@ struct spk_plan {
     int32_t *d_subw = nullptr, *d_childlist = nullptr, *d_rel = nullptr, *d_pos = nullptr, *d_blkpfx = nullptr,
             *d_gathert = nullptr, *d_pslist = nullptr, *d_chunkpfx = nullptr;
     int64_t *d_dest = nullptr, *d_rperm = nullptr, *d_rinvp = nullptr;
-    double* d_nzval = nullptr; int64_t nzcap = 0, nz_last = 0;
+    double* d_nzval = nullptr; int64_t nzcap = 0, nz_last = 0, map_nnz = -1;   // map_nnz: the nnz the destination map was built for
     AsmTask* d_asmt = nullptr; GemmTask* d_gemmt = nullptr; SolveTask* d_solvet = nullptr;
     int32_t chunk_blocks = 0;
     // CSR copy of A in the original ordering + work vectors (spk_plan_set_matrix / residual / refine)
@@ -107,6 +107,40 @@ static DevCtx make_ctx(spk_plan* p) {
     c.childlist = p->d_childlist; c.rel = p->d_rel; c.pos = p->d_pos;
     c.solvet = p->d_solvet; c.wlen = p->P.wlen; c.lu = p->P.lu ? 1 : 0;
     return c;
+}
+
+// Dynamic shared-memory limits are a property of (function, device), not of a plan: every kernel that may need
+// more than 48 KB gets the device's opt-in maximum (minus its static shared memory) ONCE per device, so plans of
+// different panel widths can live side by side (a per-plan value would lower the limit under an older plan).
+template <class K>
+static cudaError_t set_max_dyn_smem(K kern, int optin) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+}
+static int64_t init_kernel_attributes(int device) {
+    static std::mutex mu;
+    static bool done[64] = {false};
+    std::lock_guard<std::mutex> lk(mu);
+    if (device < 0 || device >= 64) { set_err("device index out of range"); return -100; }
+    if (done[device]) return 0;
+    int optin = 0;
+    CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+#define SPK_SMEM(k) CK(set_max_dyn_smem(k, optin))
+    SPK_SMEM(k_diag<true>); SPK_SMEM(k_diag<false>); SPK_SMEM(k_panel<true>); SPK_SMEM(k_panel<false>);
+    SPK_SMEM((k_pf_front<true, 1, 256>)); SPK_SMEM((k_pf_front<true, 1, 64>)); SPK_SMEM((k_pf_front<false, 1, 256>)); SPK_SMEM((k_pf_front<false, 1, 64>));
+    SPK_SMEM((k_pb_front<true, 1, 256>)); SPK_SMEM((k_pb_front<true, 1, 64>)); SPK_SMEM((k_pb_front<false, 1, 256>)); SPK_SMEM((k_pb_front<false, 1, 64>));
+    SPK_SMEM((k_pf_front<true, SOLVE_NR, 256>)); SPK_SMEM((k_pf_front<true, SOLVE_NR, 64>)); SPK_SMEM((k_pf_front<false, SOLVE_NR, 256>)); SPK_SMEM((k_pf_front<false, SOLVE_NR, 64>));
+    SPK_SMEM((k_pb_front<true, SOLVE_NR, 256>)); SPK_SMEM((k_pb_front<true, SOLVE_NR, 64>)); SPK_SMEM((k_pb_front<false, SOLVE_NR, 256>)); SPK_SMEM((k_pb_front<false, SOLVE_NR, 64>));
+    SPK_SMEM((k_pf_step<true, 1>)); SPK_SMEM((k_pf_step<false, 1>)); SPK_SMEM((k_pb_step<true, 1>)); SPK_SMEM((k_pb_step<false, 1>));
+    SPK_SMEM((k_pf_step<true, SOLVE_NR>)); SPK_SMEM((k_pf_step<false, SOLVE_NR>)); SPK_SMEM((k_pb_step<true, SOLVE_NR>)); SPK_SMEM((k_pb_step<false, SOLVE_NR>));
+    SPK_SMEM(k_pf_diag<true>); SPK_SMEM(k_pf_diag<false>); SPK_SMEM(k_pb_diag<true>); SPK_SMEM(k_pb_diag<false>);
+    SPK_SMEM(k_pb_update<true>); SPK_SMEM(k_pb_update<false>);
+#undef SPK_SMEM
+    CK(gemm_dmma_init());
+    done[device] = true;
+    return 0;
 }
 
 extern "C" {
@@ -246,57 +280,18 @@ static int64_t plan_upload(spk_plan* p) {
     if (need > cap) { int q = 1; while ((size_t)(q + 1) * ((q + 1) | 1) * 8 <= cap) ++q; p->diag_smem_nj = q; need = (size_t)q * (q | 1) * 8; }
     else p->diag_smem_nj = maxnj;
     p->diag_smem_bytes = need;
-    if (need > 48 * 1024) {
-        CK(cudaFuncSetAttribute(k_diag<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-        CK(cudaFuncSetAttribute(k_diag<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-    }
     p->panel_smem = 0;
     for (int w = 1; w <= P.maxpw; ++w) p->panel_smem = std::max(p->panel_smem, panel_smem_bytes(w));   // not monotone in w (staging of T)
     if (p->panel_smem > 220 * 1024) { set_err("panel step too wide for shared memory (reduce maxblocksize)"); return -100; }
-    if (p->panel_smem > 48 * 1024) {
-        CK(cudaFuncSetAttribute(k_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->panel_smem));
-        CK(cudaFuncSetAttribute(k_panel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->panel_smem));
-    }
     {
-        size_t sm = pstep_smem_bytes(P.maxpw);
-        {
-            {
-                const int s1f = (int)pstep_smem_bytes_mr(P.maxpw, 1, true), s8f = (int)pstep_smem_bytes_mr(P.maxpw, SOLVE_NR, true);
-                const int s1 = (int)pstep_smem_bytes_mr(P.maxpw, 1, false), s8 = (int)pstep_smem_bytes_mr(P.maxpw, SOLVE_NR, false);
-                CK(cudaFuncSetAttribute(k_pf_front<true, 1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1f));
-                CK(cudaFuncSetAttribute(k_pf_front<true, 1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1f));
-                CK(cudaFuncSetAttribute(k_pf_front<false, 1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1f));
-                CK(cudaFuncSetAttribute(k_pf_front<false, 1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1f));
-                CK(cudaFuncSetAttribute(k_pb_front<true, 1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1f));
-                CK(cudaFuncSetAttribute(k_pb_front<true, 1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1f));
-                CK(cudaFuncSetAttribute(k_pb_front<false, 1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1f));
-                CK(cudaFuncSetAttribute(k_pb_front<false, 1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1f));
-                CK(cudaFuncSetAttribute(k_pf_front<true, SOLVE_NR, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8f));
-                CK(cudaFuncSetAttribute(k_pf_front<true, SOLVE_NR, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8f));
-                CK(cudaFuncSetAttribute(k_pf_front<false, SOLVE_NR, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8f));
-                CK(cudaFuncSetAttribute(k_pf_front<false, SOLVE_NR, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8f));
-                CK(cudaFuncSetAttribute(k_pb_front<true, SOLVE_NR, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8f));
-                CK(cudaFuncSetAttribute(k_pb_front<true, SOLVE_NR, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8f));
-                CK(cudaFuncSetAttribute(k_pb_front<false, SOLVE_NR, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8f));
-                CK(cudaFuncSetAttribute(k_pb_front<false, SOLVE_NR, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8f));
-                CK(cudaFuncSetAttribute(k_pf_step<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
-                CK(cudaFuncSetAttribute(k_pf_step<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
-                CK(cudaFuncSetAttribute(k_pb_step<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
-                CK(cudaFuncSetAttribute(k_pb_step<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1));
-                CK(cudaFuncSetAttribute(k_pf_step<true, SOLVE_NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8));
-                CK(cudaFuncSetAttribute(k_pf_step<false, SOLVE_NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8));
-                CK(cudaFuncSetAttribute(k_pb_step<true, SOLVE_NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8));
-                CK(cudaFuncSetAttribute(k_pb_step<false, SOLVE_NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, s8));
-            }
-        }
-        if (sm > 48 * 1024) {
-            CK(cudaFuncSetAttribute(k_pf_diag<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            CK(cudaFuncSetAttribute(k_pf_diag<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            CK(cudaFuncSetAttribute(k_pb_diag<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            CK(cudaFuncSetAttribute(k_pb_diag<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        }
+        int64_t rc = init_kernel_attributes(p->device);
+        if (rc) return rc;
+        int optin = 0;
+        CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device));
+        const size_t worst = std::max({need, p->panel_smem, pstep_smem_bytes(P.maxpw), pstep_smem_bytes_mr(P.maxpw, SOLVE_NR, true),
+                                       pstep_smem_bytes_mr(P.maxpw, SOLVE_NR, false)});
+        if (worst + 1024 > (size_t)optin) { set_err("panel step too wide for shared memory (reduce maxblocksize)"); return -100; }
     }
-    CK(gemm_dmma_init());
     return 0;
 }
 
@@ -354,10 +349,10 @@ SPK_API int64_t spk_plan_set_factors(spk_plan* p, const double* lnz, const doubl
     if (p->P.lu && ipvt) {
         int64_t* tmp = nullptr;
         CK(cudaMalloc((void**)&tmp, p->P.n * sizeof(int64_t)));
-        CK(cudaMemcpy(tmp, ipvt, p->P.n * sizeof(int64_t), cudaMemcpyHostToDevice));
-        k_ipiv_narrow<<<cdiv(p->P.n, 256), 256, 0, p->stream>>>(p->P.n, tmp, p->d_ipiv);
-        CK(cudaStreamSynchronize(p->stream));
-        CK(cudaFree(tmp));
+        cudaError_t e = cudaMemcpy(tmp, ipvt, p->P.n * sizeof(int64_t), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) { k_ipiv_narrow<<<cdiv(p->P.n, 256), 256, 0, p->stream>>>(p->P.n, tmp, p->d_ipiv); e = cudaStreamSynchronize(p->stream); }
+        cudaFree(tmp);
+        CK(e);
     }
     {   // the solve sweeps read the frontal matrices: rebuild them from the uploaded factors
         DevCtx c = make_ctx(p);
@@ -396,22 +391,28 @@ static int64_t slot_to_arena(const Plan& P, int64_t d) {
 
 SPK_API int64_t spk_plan_inmatrix(spk_plan* p, int64_t nnz, const int64_t* dest, const double* nzval) {
     NEED_DEV(p);
-    if (nnz > p->nzcap || !p->d_dest) {
-        if (p->d_nzval) cudaFree(p->d_nzval);
-        if (p->d_dest) cudaFree(p->d_dest);
-        p->d_nzval = nullptr; p->d_dest = nullptr; p->nzcap = 0;
-        if (!dest) { set_err("destination map required on first inmatrix"); return -100; }
-        CK(cudaMalloc((void**)&p->d_nzval, std::max<int64_t>(nnz, 1) * sizeof(double)));
-        CK(cudaMalloc((void**)&p->d_dest, std::max<int64_t>(nnz, 1) * sizeof(int64_t)));
-        p->nzcap = nnz;
+    if (nnz < 0) { set_err("inmatrix: nnz < 0"); return -100; }
+    if (!dest && (!p->d_dest || nnz != p->map_nnz)) {
+        set_err("inmatrix: no destination map for this nnz (pass dest on the first call and whenever the pattern changes)");
+        return -100;
     }
     if (dest) {
-        std::vector<int64_t> ad(nnz);
+        std::vector<int64_t> ad((size_t)nnz);
         for (int64_t k = 0; k < nnz; ++k) {
             ad[k] = slot_to_arena(p->P, dest[k]);
-            if (ad[k] == -2) { set_err("inmatrix: destination outside the factor structure"); return -100; }
+            if (ad[k] == -2) { set_err("inmatrix: destination outside the factor structure"); return -100; }   // the old map (if any) stays valid
         }
+        if (nnz > p->nzcap || !p->d_dest) {
+            if (p->d_nzval) cudaFree(p->d_nzval);
+            if (p->d_dest) cudaFree(p->d_dest);
+            p->d_nzval = nullptr; p->d_dest = nullptr; p->nzcap = 0; p->map_nnz = -1;
+            CK(cudaMalloc((void**)&p->d_nzval, std::max<int64_t>(nnz, 1) * sizeof(double)));
+            CK(cudaMalloc((void**)&p->d_dest, std::max<int64_t>(nnz, 1) * sizeof(int64_t)));
+            p->nzcap = nnz;
+        }
+        p->map_nnz = -1;
         CK(cudaMemcpy(p->d_dest, ad.data(), nnz * sizeof(int64_t), cudaMemcpyHostToDevice));
+        p->map_nnz = nnz;
     }
     CK(cudaMemcpyAsync(p->d_nzval, nzval, nnz * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     CK(cudaMemsetAsync(p->d_F, 0, p->P.arena * sizeof(double), p->stream));
@@ -644,9 +645,10 @@ SPK_API int64_t spk_plan_get_factors(spk_plan* p, double* lnz, double* unz, int6
         int64_t* tmp = nullptr;
         CK(cudaMalloc((void**)&tmp, p->P.n * sizeof(int64_t)));
         k_ipiv_widen<<<cdiv(p->P.n, 256), 256, 0, p->stream>>>(p->P.n, p->d_ipiv, tmp);
-        CK(cudaMemcpyAsync(ipvt, tmp, p->P.n * sizeof(int64_t), cudaMemcpyDeviceToHost, p->stream));
-        CK(cudaStreamSynchronize(p->stream));
-        CK(cudaFree(tmp));
+        cudaError_t e = cudaMemcpyAsync(ipvt, tmp, p->P.n * sizeof(int64_t), cudaMemcpyDeviceToHost, p->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+        cudaFree(tmp);
+        CK(e);
     }
     CK(cudaStreamSynchronize(p->stream));
     return 0;
@@ -799,6 +801,7 @@ static int64_t enqueue_solve(spk_plan* p, double* d_rhs, int64_t nrhs, int64_t l
 SPK_API int64_t spk_plan_solve_device(spk_plan* p, double* d_rhs, int64_t nrhs, int64_t ldrhs, int32_t which) {
     NEED_DEV(p);
     if (nrhs <= 0) return 0;
+    if (!p->factored) { set_err("solve: the plan holds no factors (call spk_plan_factor or spk_plan_set_factors first)"); return -100; }
     cudaStream_t st = p->stream;
     int64_t rc = ensure_w(p, std::min<int64_t>(nrhs, 32)); if (rc) return rc;
     const bool use_graph = p->solve_graphs;
@@ -886,6 +889,7 @@ SPK_API int64_t spk_plan_triangularsolve(spk_plan* p, double* b, int64_t nrhs, i
 SPK_API int64_t spk_plan_solve_phase(spk_plan* p, double* d_rhs, int64_t nrhs, int64_t ldrhs, int32_t phase) {
     NEED_DEV(p);
     if (p->P.nparts <= 1) { set_err("single-part plan"); return -100; }
+    if (!p->factored) { set_err("solve: the plan holds no factors"); return -100; }
     if (nrhs > 32) { set_err("multi-part solve: at most 32 right-hand sides per call"); return -100; }
     int64_t rc = ensure_w(p, 32); if (rc) return rc;
     DevCtx c = make_ctx(p);
@@ -950,6 +954,7 @@ SPK_API int64_t spk_plan_stat(spk_plan* p, int32_t what) {
     case 11: return p->P.maxR;
     case 12: return p->P.nparts;
     case 13: { int64_t k = 0; for (int32_t o : p->P.owner) if (o == -1) ++k; return k; }
+    case 14: { int64_t k = 0; for (const Front& f : p->P.fronts) k = std::max<int64_t>(k, (f.nps + p->P.ob_steps - 1) / p->P.ob_steps); return k; }   // outer blocks of the widest front
     case 100: p->profile = true; return 0;
     case 101: p->profile = false; return 0;
     default: return 0;
@@ -1037,7 +1042,7 @@ SPK_API int64_t spk_lulsolve_f64(int64_t nsuper, const int64_t* xsuper, const in
         if (!rc && cudaMemset(p->d_F, 0, p->P.arena * sizeof(double)) != cudaSuccess) rc = -100;
         if (!rc) { k_chunks<false><<<p->chunk_blocks, 256, 0, p->stream>>>(c, p->d_chunkpfx, (int)p->P.chunks.size()); if (cudaStreamSynchronize(p->stream) != cudaSuccess) rc = -100; }
     }
-    if (!rc) rc = spk_plan_solve(p, rhs, 1, n, 1);
+    if (!rc) { p->factored = true; rc = spk_plan_solve(p, rhs, 1, n, 1); }
     spk_plan_destroy(p);
     return rc ? rc : 1;
 }

@@ -16,6 +16,7 @@ from .problem import Problem, Graph, Ordering, ETree, makestructuresymmetric, mm
 
 def _csc_1based(m):
     m = sp.csc_matrix(m)
+    m.sum_duplicates()               # one entry per (i, j), as SparseMatrixCSC guarantees
     m.sort_indices()
     return m.indptr.astype(np.int64) + 1, m.indices.astype(np.int64) + 1, np.ascontiguousarray(m.data, dtype=np.float64)
 
@@ -40,6 +41,7 @@ class _Base:
         self.lnz = np.zeros(0); self.unz = np.zeros(0)
         self._plan = None           # device plan (rebuilt by _symbolicfactor)
         self._dest = None           # inmatrix index map, built once per pattern
+        self._dest_key = None
         self._factors_on_host = False
 
     # -- step 1 -------------------------------------------------------------
@@ -99,7 +101,8 @@ class _Base:
     # -- step 3 -------------------------------------------------------------
     def _inmatrix_map(self, p):
         colptr, rowval, nzval = _csc_1based(p.csc() if isinstance(p, Problem) else p)
-        if self._dest is None or self._dest.size != rowval.size:
+        key = (rowval.size, hash(colptr.tobytes()), hash(rowval.tobytes()))     # the map belongs to ONE pattern
+        if self._dest is None or self._dest_key != key:
             H = _hostlib.lib()
             dest = np.zeros(rowval.size, np.int64)
             o = self.order
@@ -112,7 +115,7 @@ class _Base:
             if bad:
                 i = int(rowval[bad - 1]); j = int(np.searchsorted(colptr, bad, side="right"))
                 raise RuntimeError(f"No space for matrix element ({o.rinvp[i - 1]}, {o.cinvp[j - 1]}).")
-            self._dest = dest
+            self._dest = dest; self._dest_key = key
         return self._dest, nzval
 
     def _inmatrix(self, p):

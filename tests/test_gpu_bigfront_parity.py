@@ -1,0 +1,134 @@
+"""GPU-vs-oracle ENTRYWISE parity on fronts with MANY outer blocks (VERDICT r1 "What's weak" #1).
+
+The 16^3 cases of test_gpu_parity.py have fronts of at most one outer block (<= 512 columns).  The code
+that produces 97 % of the flops of the headline benchmark only runs on wider fronts: delayed rank-(~456)
+updates, strip / rest split, two-stream look-ahead (wait_other / record events), LU row strips, per-level
+overlapped write-back.  These tests pin that code to the north_star bar — factor entries to a relative
+1e-11, pivot sequence bit-exact — against the oracle (with its dense call sites on OpenBLAS, which
+tests/test_oracle_golden.py proves equal to the generic arithmetic), at 32^3 / 40^3 / 48^3 / 64^3 (config 2)
+and on a config-5-shaped 3-dof problem; plus small problems that force the same schedule with tiny outer
+blocks (SPK_OB_STEPS / SPK_PS_WIDTH), look-ahead on and off."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import sparspak_jl_b200 as spk
+from sparspak_jl_b200 import _cudalib
+import oracle
+from common import prepare, oracle_factor, spd_mask, rel_err, residual, M, FACTOR_RTOL, RESID_TOL
+
+pytestmark = pytest.mark.gpu
+
+
+def pivot3d(g, seed):
+    """7-point pattern with random values, |offdiag| <= 1, diagonal in [1, 2]: NOT diagonally dominant, so
+    the in-supernode partial pivoting really exchanges rows inside the big separator fronts."""
+    A = M.laplacian3d(g).tocoo()
+    rng = np.random.default_rng(seed)
+    v = rng.uniform(-1, 1, A.nnz)
+    d = A.row == A.col
+    v[d] = rng.uniform(1.0, 2.0, int(d.sum()))
+    return sp.csc_matrix((v, (A.row, A.col)), shape=A.shape)
+
+
+def _gpu(b):
+    plan = _cudalib.Plan(b)
+    plan.set_values(b.lnz, None if b.spd else b.unz)
+    fl = plan.factor()
+    lnz = np.zeros(b.lnz.size); unz = np.zeros(b.unz.size); ipiv = np.zeros(b.n, np.int64)
+    plan.get_factors(lnz, None if b.spd else unz, None if b.spd else ipiv)
+    return plan, lnz, unz, ipiv, fl
+
+
+def _check(A, b, spd, tol=FACTOR_RTOL, blas=True, min_outer_blocks=2):
+    oracle.use_openblas(blas)
+    try:
+        lo, uo, po, fo = oracle_factor(b)
+    finally:
+        oracle.use_openblas(False)
+    plan, lg, ug, pg, fg = _gpu(b)
+    assert fg == fo == 0
+    # the point of the test: some front spans several outer blocks
+    maxW = max(int(plan.stat(14)), 1)
+    assert maxW >= min_outer_blocks, f"widest front has only {maxW} outer block(s)"
+    e_l = rel_err(lg, lo, spd_mask(b))
+    assert e_l < tol, f"lnz differs from the oracle: {e_l:.2e}"
+    if not spd:
+        assert np.array_equal(pg, po), "pivot sequence differs from the reference rule"
+        e_u = rel_err(ug, uo)
+        assert e_u < tol, f"unz differs from the oracle: {e_u:.2e}"
+    bb = M.rhs_for(A)
+    x = bb.copy()
+    plan.set_perm(b.order.rperm, b.order.rinvp)
+    plan.triangularsolve(x)
+    xo = oracle.triangularsolve(b, lo, uo, po, bb)
+    return plan, x, xo, bb
+
+
+BIG = [
+    ("lap3d-32-spd", lambda: M.laplacian3d(32), True, 32, 1),
+    ("convdiff-32-lu", lambda: M.convdiff3d(32), False, 32, 1),
+    ("lap3d-40-spd", lambda: M.laplacian3d(40), True, 40, 1),
+    ("convdiff-40-lu", lambda: M.convdiff3d(40), False, 40, 1),
+    ("lap3d-48-spd", lambda: M.laplacian3d(48), True, 48, 1),
+    ("elasticity-24-spd-dof3", lambda: M.elasticity27(24), True, 24, 3),     # config-5 shape
+    ("cfg2-lap3d-64-spd", lambda: M.laplacian3d(64), True, 64, 1),           # config 2 at its real size
+]
+
+
+@pytest.mark.parametrize("name,build,spd,g,dof", BIG, ids=[c[0] for c in BIG])
+def test_bigfront_factors_match_oracle_entrywise(name, build, spd, g, dof):
+    A = build()
+    s = prepare(A, spd, spk.nd_grid_order(g, g, g, dof) if dof > 1 else spk.nd_grid_order(g, g, g))
+    plan, x, xo, bb = _check(A, s.slvr, spd)
+    assert residual(A, x, bb) < RESID_TOL
+    assert np.linalg.norm(x - xo) / np.linalg.norm(xo) < 1e-10
+    plan.destroy()
+
+
+@pytest.mark.parametrize("g,seed", [(20, 11), (24, 12)])
+def test_bigfront_real_pivoting_bit_exact(g, seed):
+    """Row exchanges inside separator fronts of several outer blocks: the pivot sequence must be the oracle's
+    bit for bit.  Restricted pivoting lets |L| grow to ~1e3, so two correct arithmetic orders differ by ~1e-10
+    in the factors (generic vs OpenBLAS oracle: 3.7e-10 at 24^3): entries are held to 1e-8 here."""
+    A = pivot3d(g, seed)
+    s = prepare(A, False, spk.nd_grid_order(g, g, g))
+    b = s.slvr
+    plan, x, xo, bb = _check(A, b, False, tol=1e-8, blas=False, min_outer_blocks=1)
+    ipiv = np.zeros(b.n, np.int64); plan.get_factors(None, None, ipiv)
+    local = np.arange(b.n) - (b.xsuper[b.snode - 1] - 1) + 1
+    assert int((ipiv != local).sum()) > 100                          # it really pivots
+    assert np.linalg.norm(x - xo) / np.linalg.norm(xo) < 1e-7
+    plan.destroy()
+
+
+SCHED = [
+    {"SPK_OB_STEPS": "1", "SPK_PS_WIDTH": "8"},
+    {"SPK_OB_STEPS": "2", "SPK_PS_WIDTH": "16"},
+    {"SPK_OB_STEPS": "2", "SPK_PS_WIDTH": "8", "SPK_LOOKAHEAD": "0"},
+    {"SPK_OB_STEPS": "1", "SPK_PS_WIDTH": "16", "SPK_STORE_OVERLAP": "0"},
+    {"SPK_OB_STEPS": "3", "SPK_PS_WIDTH": "24", "SPK_LL": "0"},
+]
+
+
+@pytest.mark.parametrize("spd", [False, True])
+@pytest.mark.parametrize("env", SCHED, ids=["+".join(f"{k[4:]}={v}" for k, v in e.items()) for e in SCHED])
+def test_forced_small_outer_blocks(spd, env, monkeypatch):
+    """16^3 with outer blocks of 8..72 columns: the 256-column root front runs 4..32 outer blocks, i.e. the
+    delayed-update / strip / rest / look-ahead schedule of the big fronts, against the generic oracle."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    g = 16
+    A = M.convdiff3d(g) if not spd else M.laplacian3d(g)
+    s = prepare(A, spd, spk.nd_grid_order(g, g, g))
+    plan, x, xo, bb = _check(A, s.slvr, spd, blas=False, min_outer_blocks=3)
+    assert residual(A, x, bb) < RESID_TOL
+    plan.destroy()
+
+
+def test_forced_small_outer_blocks_with_pivoting(monkeypatch):
+    monkeypatch.setenv("SPK_OB_STEPS", "2"); monkeypatch.setenv("SPK_PS_WIDTH", "12")
+    A = pivot3d(14, 5)
+    s = prepare(A, False, spk.nd_grid_order(14, 14, 14))
+    plan, x, xo, bb = _check(A, s.slvr, False, tol=1e-9, blas=False, min_outer_blocks=3)
+    plan.destroy()

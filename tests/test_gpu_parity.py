@@ -354,3 +354,62 @@ def test_device_residual_and_refinement(spd):
     steps, rel3 = plan.refine(B, X0, maxit=4, tol=1e-12)
     assert steps == 0 and rel3.max() <= 1e-12
     plan.destroy()
+
+
+def test_two_live_plans_of_different_panel_width():
+    """Dynamic shared-memory limits are per (kernel, device), not per plan: a plan with narrow
+    panel steps created AFTER one with wide steps must not lower the limits under the older plan.  Interleaves
+    factor, solve and multi-RHS solve of both."""
+    rng = np.random.default_rng(77)
+    G = rng.standard_normal((150, 150))
+    Awide = sp.csc_matrix(G @ G.T + 150.0 * np.eye(150))         # one dense front, chunks ~75 wide -> wide panel steps
+    s1 = prepare(Awide, True, maxblocksize=100)
+    A2 = M.convdiff3d(8)
+    s2 = prepare(A2, False, spk.nd_grid_order(8, 8, 8), 6)          # narrow panel steps
+    p1 = _cudalib.Plan(s1.slvr)
+    w1 = p1.stat(10)
+    p2 = _cudalib.Plan(s2.slvr)
+    assert w1 > 64 and p2.stat(10) < w1
+    for plan, s in ((p1, s1), (p2, s2)):
+        b = s.slvr
+        plan.set_values(b.lnz, None if b.spd else b.unz)
+        plan.set_perm(b.order.rperm, b.order.rinvp)
+    assert p1.factor() == 0 and p2.factor() == 0
+    for rep in range(2):
+        for plan, A in ((p1, Awide), (p2, A2), (p1, Awide)):
+            B = np.asfortranarray(rng.random((A.shape[0], 9)))
+            X = B.copy(order="F"); plan.triangularsolve(X)              # multi-RHS kernels (largest shared memory)
+            x = B[:, 0].copy(); plan.triangularsolve(x)
+            assert residual(A, x, B[:, 0]) < RESID_TOL
+            assert max(residual(A, X[:, j], B[:, j]) for j in range(9)) < RESID_TOL
+        assert p1.factor() == 0
+    lo, _, _, _ = oracle_factor(s1.slvr)
+    lg = np.zeros(s1.slvr.lnz.size); p1.get_factors(lg)
+    assert rel_err(lg, lo, spd_mask(s1.slvr)) < FACTOR_RTOL
+    p1.destroy(); p2.destroy()
+
+
+def test_solve_without_factors_is_an_error_and_inmatrix_map_guards():
+    A = M.laplacian3d(6)
+    s = prepare(A, True, spk.nd_grid_order(6, 6, 6))
+    b = s.slvr
+    plan = _cudalib.Plan(b)
+    plan.set_perm(b.order.rperm, b.order.rinvp)
+    with pytest.raises(RuntimeError):
+        plan.triangularsolve(M.rhs_for(A))                          # no factors yet
+    dest, nzval = b._inmatrix_map(A)
+    with pytest.raises(RuntimeError):
+        plan.inmatrix(nzval)                                        # no map yet
+    plan.inmatrix(nzval, dest)
+    with pytest.raises(RuntimeError):
+        plan.inmatrix(nzval[:-1])                                   # map was built for another nnz
+    # duplicate (i, j) entries accumulate like the reference's `+=`
+    dd = np.concatenate([dest, dest[:5]]); vv = np.concatenate([nzval, nzval[:5]])
+    plan.inmatrix(vv, dd)
+    assert plan.factor() == 0
+    Ac = sp.csc_matrix(A); Ac.sort_indices()
+    cols = np.repeat(np.arange(Ac.shape[1]), np.diff(Ac.indptr))
+    bump = sp.csc_matrix((nzval[:5], (Ac.indices[:5], cols[:5])), shape=A.shape)
+    x = M.rhs_for(A); plan.triangularsolve(x)
+    assert residual(sp.csc_matrix(A + bump), x, M.rhs_for(A)) < RESID_TOL
+    plan.destroy()
