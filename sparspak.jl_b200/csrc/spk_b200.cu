@@ -79,6 +79,7 @@ struct spk_plan {
     size_t dev_bytes = 0;
     int diag_smem_nj = 0; size_t diag_smem_bytes = 0, panel_smem = 0;
     bool have_perm = false, factored = false;
+    bool ev0_armed = false;             // spk_plan_reassemble recorded ev0: the next factorisation's time starts there
     // stats
     int64_t launches_factor = 0, launches_solve = 0;
     double ms_factor = 0, ms_solve = 0, gemm_flops = 0, gemm_ms = 0, ms_phase0 = 0, ms_phase1 = 0;
@@ -427,6 +428,8 @@ SPK_API int64_t spk_plan_inmatrix(spk_plan* p, int64_t nnz, const int64_t* dest,
 SPK_API int64_t spk_plan_reassemble(spk_plan* p) {
     NEED_DEV(p);
     if (!p->d_dest || p->nz_last <= 0) { set_err("spk_plan_inmatrix has not been called"); return -100; }
+    CK(cudaEventRecord(p->ev0, p->stream));            // the factor time reported by the next spk_plan_factor includes this clear + scatter
+    p->ev0_armed = true;
     CK(cudaMemsetAsync(p->d_F, 0, p->P.arena * sizeof(double), p->stream));
     k_scatter_values<<<cdiv(p->nz_last, 256), 256, 0, p->stream>>>(p->nz_last, p->d_dest, p->d_nzval, p->d_F);
     CK(cudaGetLastError());
@@ -503,7 +506,9 @@ SPK_API int64_t spk_plan_factor_phase(spk_plan* p, int32_t phase) {
     const std::vector<Launch>& Ls = phase < 0 ? P.factor_launches : (phase == 0 ? P.factor_local : P.factor_top);
     DevCtx c = make_ctx(p);
     cudaStream_t st = p->stream;
-    CK(cudaEventRecord(phase == 1 ? p->evg0 : p->ev0, st));
+    if (phase == 1) CK(cudaEventRecord(p->evg0, st));
+    else if (!p->ev0_armed) CK(cudaEventRecord(p->ev0, st));
+    p->ev0_armed = false;
     if (phase <= 0) {
         CK(cudaMemsetAsync(p->d_iflag, 0, sizeof(int32_t), st));
         p->launches_factor = 0; p->gemm_flops = 0; p->gemm_ms = 0;
@@ -954,6 +959,7 @@ SPK_API int64_t spk_plan_stat(spk_plan* p, int32_t what) {
     case 11: return p->P.maxR;
     case 12: return p->P.nparts;
     case 13: { int64_t k = 0; for (int32_t o : p->P.owner) if (o == -1) ++k; return k; }
+    case 15: return (int64_t)p->P.ranges.size();                 // elimination subtrees dealt to the parts
     case 14: { int64_t k = 0; for (const Front& f : p->P.fronts) k = std::max<int64_t>(k, (f.nps + p->P.ob_steps - 1) / p->P.ob_steps); return k; }   // outer blocks of the widest front
     case 100: p->profile = true; return 0;
     case 101: p->profile = false; return 0;
