@@ -390,8 +390,8 @@ def test_two_live_plans_of_different_panel_width():
 
 
 def test_solve_without_factors_is_an_error_and_inmatrix_map_guards():
-    A = M.laplacian3d(6)
-    s = prepare(A, True, spk.nd_grid_order(6, 6, 6))
+    A = M.convdiff3d(6)                                             # LU: every entry of A has a destination
+    s = prepare(A, False, spk.nd_grid_order(6, 6, 6))
     b = s.slvr
     plan = _cudalib.Plan(b)
     plan.set_perm(b.order.rperm, b.order.rinvp)
