@@ -154,6 +154,35 @@ SPK_API int64_t spk_plan_solve_phase(spk_plan* p, double* d_rhs, int64_t nrhs, i
 SPK_API int64_t spk_plan_xchg_info(spk_plan* p, int32_t what, int64_t i, int64_t* out);
 SPK_API int64_t spk_plan_solve_device(spk_plan* p, double* d_rhs, int64_t nrhs, int64_t ldrhs, int32_t which);
 
+/* ---- multi-GPU: one plan per GPU (part r of nparts on device d_r), elimination subtrees dealt to
+ * the parts, NCCL over NVLink / NVSwitch for the exchanges.  The library owns the communicator:
+ *   one process per GPU:  id from ONE call of spk_nccl_unique_id (128 bytes), carried to every process by the
+ *                         host application (MPI / torch.distributed / a file), then spk_plan_comm_init on each.
+ *   one process, N GPUs:  spk_multi_create below.
+ * spk_plan_factor_multi = own subtrees -> exchange of the subtree roots' update matrices -> top set (LDL^T:
+ * distributed by column blocks with one panel broadcast per outer block; LU: replicated) -> write-back, enqueued
+ * in one go.  spk_plan_solve_multi: d_rhs on the device in permuted order, full solution on every part at return. */
+SPK_API int64_t spk_nccl_unique_id(void* out128);
+SPK_API int64_t spk_plan_comm_init(spk_plan* p, const void* id128);
+SPK_API int64_t spk_plan_factor_multi(spk_plan* p);
+SPK_API int64_t spk_plan_solve_multi(spk_plan* p, double* d_rhs, int64_t nrhs, int64_t ldrhs);
+
+/* One process, N GPUs (devices 0..ngpus-1): a single ccall-able handle that owns the per-GPU plans and the NCCL
+ * communicators; every call fans out to one host thread per GPU and joins before returning.  Same semantics as
+ * the spk_plan_* calls of the same name (host pointers; lnz/unz/ipvt/b overwritten in place). */
+typedef struct spk_multi spk_multi;
+SPK_API spk_multi* spk_multi_create(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* snode,
+                                    const int64_t* xlindx, const int64_t* lindx, const int64_t* xlnz,
+                                    const int64_t* xunz_or_null, int32_t ngpus);
+SPK_API void      spk_multi_destroy(spk_multi* m);
+SPK_API spk_plan* spk_multi_plan(spk_multi* m, int32_t r);          /* part r's plan (introspection) */
+SPK_API int64_t   spk_multi_inmatrix(spk_multi* m, int64_t nnz, const int64_t* dest_or_null, const double* nzval);
+SPK_API int64_t   spk_multi_set_values(spk_multi* m, const double* lnz, const double* unz_or_null);
+SPK_API int64_t   spk_multi_factor(spk_multi* m);
+SPK_API int64_t   spk_multi_get_factors(spk_multi* m, double* lnz, double* unz, int64_t* ipvt);
+SPK_API int64_t   spk_multi_set_perm(spk_multi* m, const int64_t* rperm, const int64_t* rinvp);
+SPK_API int64_t   spk_multi_triangularsolve(spk_multi* m, double* b, int64_t nrhs, int64_t ldb);
+
 /* ---- introspection --------------------------------------------------------------------- */
 /* what: 0 kernel launches of the last factor, 1 of the last solve, 2 #fronts, 3 #levels,
  *       4 device bytes held, 5 #big fronts, 6 update-matrix (S) doubles */

@@ -21,7 +21,9 @@ SYMBOLS = [
     "spk_plan_create", "spk_plan_destroy", "spk_plan_inmatrix", "spk_plan_reassemble", "spk_plan_set_values", "spk_plan_factor",
     "spk_plan_get_factors", "spk_plan_set_factors", "spk_plan_solve", "spk_plan_set_perm",
     "spk_plan_triangularsolve", "spk_plan_device_ptr", "spk_plan_device_len", "spk_plan_factor_phase",
-    "spk_plan_solve_device", "spk_plan_solve_phase", "spk_plan_xchg_info", "spk_plan_stat", "spk_plan_statf", "spk_last_error", "spk_device_count", "spk_version",
+    "spk_plan_solve_device", "spk_plan_solve_phase", "spk_nccl_unique_id", "spk_plan_comm_init", "spk_plan_factor_multi", "spk_plan_solve_multi",
+    "spk_multi_create", "spk_multi_destroy", "spk_multi_plan", "spk_multi_inmatrix", "spk_multi_set_values", "spk_multi_factor",
+    "spk_multi_get_factors", "spk_multi_set_perm", "spk_multi_triangularsolve", "spk_plan_xchg_info", "spk_plan_stat", "spk_plan_statf", "spk_last_error", "spk_device_count", "spk_version",
 ]
 
 
@@ -105,6 +107,32 @@ def lib():
     L.spk_plan_solve_device.restype = i64
     L.spk_plan_solve_phase.argtypes = [vp, vp, i64, i64, i32]
     L.spk_plan_solve_phase.restype = i64
+    L.spk_nccl_unique_id.argtypes = [vp]
+    L.spk_nccl_unique_id.restype = i64
+    L.spk_plan_comm_init.argtypes = [vp, vp]
+    L.spk_plan_comm_init.restype = i64
+    L.spk_plan_factor_multi.argtypes = [vp]
+    L.spk_plan_factor_multi.restype = i64
+    L.spk_plan_solve_multi.argtypes = [vp, vp, i64, i64]
+    L.spk_plan_solve_multi.restype = i64
+    L.spk_multi_create.argtypes = [i64, i64, I64P, I64P, I64P, I64P, I64P, vp, i32]
+    L.spk_multi_create.restype = vp
+    L.spk_multi_destroy.argtypes = [vp]
+    L.spk_multi_destroy.restype = None
+    L.spk_multi_plan.argtypes = [vp, i32]
+    L.spk_multi_plan.restype = vp
+    L.spk_multi_inmatrix.argtypes = [vp, i64, vp, F64P]
+    L.spk_multi_inmatrix.restype = i64
+    L.spk_multi_set_values.argtypes = [vp, F64P, vp]
+    L.spk_multi_set_values.restype = i64
+    L.spk_multi_factor.argtypes = [vp]
+    L.spk_multi_factor.restype = i64
+    L.spk_multi_get_factors.argtypes = [vp, vp, vp, vp]
+    L.spk_multi_get_factors.restype = i64
+    L.spk_multi_set_perm.argtypes = [vp, I64P, I64P]
+    L.spk_multi_set_perm.restype = i64
+    L.spk_multi_triangularsolve.argtypes = [vp, F64P, i64, i64]
+    L.spk_multi_triangularsolve.restype = i64
     L.spk_plan_xchg_info.argtypes = [vp, i32, i64, vp]
     L.spk_plan_xchg_info.restype = i64
     L.spk_plan_stat.argtypes = [vp, i32]
@@ -242,6 +270,21 @@ class Plan:
     def solve_phase(self, d_ptr, nrhs, ld, phase):
         self._ck(self.L.spk_plan_solve_phase(self.h, d_ptr, nrhs, ld, phase), "spk_plan_solve_phase")
 
+    def nccl_unique_id(self):
+        ident = np.zeros(128, np.uint8)
+        self._ck(self.L.spk_nccl_unique_id(ident.ctypes.data), "spk_nccl_unique_id")
+        return ident
+
+    def comm_init(self, ident):
+        ident = np.ascontiguousarray(ident, dtype=np.uint8)
+        self._ck(self.L.spk_plan_comm_init(self.h, ident.ctypes.data), "spk_plan_comm_init")
+
+    def factor_multi(self):
+        return int(self._ck(self.L.spk_plan_factor_multi(self.h), "spk_plan_factor_multi"))
+
+    def solve_multi(self, d_ptr, nrhs, ld):
+        self._ck(self.L.spk_plan_solve_multi(self.h, d_ptr, nrhs, ld), "spk_plan_solve_multi")
+
     def xchg_list(self, what):
         n = int(self.L.spk_plan_xchg_info(self.h, what, 0, None))
         out = []
@@ -259,3 +302,64 @@ class Plan:
 
     def statf(self, what):
         return float(self.L.spk_plan_statf(self.h, what))
+
+
+class MultiPlan:
+    """`spk_multi`: one process, `ngpus` GPUs (devices 0..ngpus-1); same verbs as `Plan`."""
+
+    def __init__(self, base, ngpus):
+        L = lib()
+        self.L = L
+        self.spd = bool(base.spd)
+        self.n = int(base.n)
+        self.ngpus = int(ngpus)
+        xunz = None if self.spd else base.xunz.ctypes.data
+        self.h = L.spk_multi_create(base.n, base.nsuper, base.xsuper, base.snode, base.xlindx, base.lindx, base.xlnz, xunz, ngpus)
+        if not self.h:
+            raise SpkError("spk_multi_create failed: " + last_error())
+
+    def _ck(self, rc, what):
+        if rc <= -100:
+            raise SpkError(f"{what} failed ({rc}): {last_error()}")
+        return rc
+
+    def destroy(self):
+        if getattr(self, "h", None):
+            self.L.spk_multi_destroy(self.h)
+            self.h = None
+
+    __del__ = destroy
+
+    def inmatrix(self, nzval, dest=None):
+        nzval = np.ascontiguousarray(nzval, dtype=np.float64)
+        if dest is not None:
+            dest = np.ascontiguousarray(dest, dtype=np.int64)
+        self._ck(self.L.spk_multi_inmatrix(self.h, nzval.size, _ptr(dest), nzval), "spk_multi_inmatrix")
+
+    def set_values(self, lnz, unz=None):
+        self._ck(self.L.spk_multi_set_values(self.h, lnz, _ptr(unz)), "spk_multi_set_values")
+
+    def factor(self):
+        return int(self._ck(self.L.spk_multi_factor(self.h), "spk_multi_factor"))
+
+    def get_factors(self, lnz=None, unz=None, ipiv=None):
+        self._ck(self.L.spk_multi_get_factors(self.h, _ptr(lnz), _ptr(unz), _ptr(ipiv)), "spk_multi_get_factors")
+
+    def set_perm(self, rperm, rinvp):
+        self._ck(self.L.spk_multi_set_perm(self.h, np.ascontiguousarray(rperm, np.int64), np.ascontiguousarray(rinvp, np.int64)), "spk_multi_set_perm")
+
+    def triangularsolve(self, b):
+        assert b.dtype == np.float64
+        if b.ndim == 1:
+            nrhs, ld = 1, b.shape[0]
+        else:
+            assert b.flags.f_contiguous
+            nrhs, ld = b.shape[1], b.shape[0]
+        self._ck(self.L.spk_multi_triangularsolve(self.h, b.reshape(-1, order="A"), nrhs, ld), "spk_multi_triangularsolve")
+        return b
+
+    def part_stat(self, r, what):
+        return int(self.L.spk_plan_stat(self.L.spk_multi_plan(self.h, r), what))
+
+    def part_statf(self, r, what):
+        return float(self.L.spk_plan_statf(self.L.spk_multi_plan(self.h, r), what))

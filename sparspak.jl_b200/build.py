@@ -55,7 +55,7 @@ def build_cuda(force=False, verbose=False):
         return LIB_CUDA
     if shutil.which(NVCC) is None and not os.path.exists(NVCC):
         raise RuntimeError("nvcc not found; cannot build libspkb200.so")
-    cmd = [NVCC] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC, "-shared", "-o", LIB_CUDA] + srcs + ["-lcudart"]
+    cmd = [NVCC] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC, "-shared", "-o", LIB_CUDA] + srcs + ["-lcudart", "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     out = _run(cmd)

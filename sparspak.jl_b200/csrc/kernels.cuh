@@ -14,7 +14,8 @@ namespace spk {
 
 struct DFront {
     int64_t fofs, relofs, wofs, F0, pbofs;
-    int32_t W, R, m, ld, parent, child0, nchild, c0, nch, ps0, nps, pad;
+    int32_t W, R, m, ld, parent, child0, nchild, c0, nch, ps0, nps;
+    int32_t ownofs;                  // distributed top-set front: offset of its column-owner array in DevCtx::fown, else -1
 };
 struct DChunk {
     int64_t lofs, uofs, posofs, fofs;
@@ -30,6 +31,8 @@ struct DevCtx {
     const SolveTask* solvet;
     int64_t wlen, pblen;
     int32_t lu;
+    int32_t me;                      // this part (multi-GPU)
+    const int8_t* fown;              // column owners of the distributed top-set fronts
 };
 
 // Programmatic dependent launch: a kernel launched with the programmatic-serialization attribute may start
@@ -67,6 +70,7 @@ constexpr int CHUNK_EPB = 1024;      // entries per block
 // factorisation leaves it and where the backward sweep reads it.
 template <bool STORE, bool FILLU>
 __device__ __forceinline__ void chunk_io(const DevCtx& c, const DChunk& ch, int lb) {
+    if (ch.fofs < 0) return;                          // a front this part holds no storage for (multi-GPU)
     const int32_t* __restrict__ pos = c.pos + ch.posofs;
     double* __restrict__ F = c.F + ch.fofs;
     const int64_t nl = (int64_t)ch.jlen * ch.nj;
@@ -109,6 +113,7 @@ __device__ __forceinline__ void asm_entry(const DevCtx& c, const DFront& C, cons
     const int32_t m = C.m;
     const int32_t j = (int32_t)(e / m), i = (int32_t)(e - (int64_t)j * m);
     if (!c.lu && i < j) return;                       // LDL^T: lower triangle only
+    if (P.ownofs >= 0 && c.fown[P.ownofs + rel[j]] != c.me) return;   // distributed parent: only the columns this part owns
     const double v = c.F[C.fofs + (int64_t)(C.W + i) + (int64_t)(C.W + j) * C.ld];
     c.F[P.fofs + (int64_t)rel[i] + (int64_t)rel[j] * P.ld] += v;
 }
@@ -137,7 +142,8 @@ __global__ void __launch_bounds__(ASM_TPB) k_assemble(DevCtx c, const AsmTask* _
 #pragma unroll
     for (int cc = 0; cc < ASM_COLS; ++cc) {
         const int32_t j = j0 + cc;
-        const bool on = j < m && (c.lu || i >= j);
+        bool on = j < m && (c.lu || i >= j);
+        if (on && P.ownofs >= 0) on = c.fown[P.ownofs + rel[j]] == c.me;     // distributed parent: only the columns this part owns
         pofs[cc] = on ? (int64_t)rel[j] * P.ld : -1;
         v[cc] = on ? __ldcs(src + (int64_t)cc * C.ld) : 0.0;
     }
@@ -157,6 +163,29 @@ __global__ void __launch_bounds__(256) k_assemble_tail(DevCtx c, const AsmTask* 
         int64_t total = (int64_t)C.m * C.m;
         for (int64_t e = threadIdx.x; e < total; e += blockDim.x) asm_entry(c, C, P, rel, e);
         __syncthreads();
+    }
+}
+
+// Distributed top set: U[ob0 + k, c] = D_k * L[c, ob0 + k] (k < e - ob0, e <= c < R) rebuilt from a panel that
+// arrived by broadcast — the upper triangle is where the update kernel reads its B operand and where the
+// backward sweep reads U.  32 x 32 tiles transposed through shared memory (coalesced on both sides).
+__global__ void __launch_bounds__(256) k_fill_u(DevCtx c, const FillTask* __restrict__ tasks, const int32_t* __restrict__ pfx, int count) {
+    __shared__ double tile[32][33];
+    const int t = find_task(pfx, count, blockIdx.x);
+    const int lb = blockIdx.x - pfx[t];
+    const FillTask ft = tasks[t];
+    const int nct = (ft.R - ft.e + 31) / 32;
+    const int c0 = ft.e + (lb % nct) * 32, k0 = ft.ob0 + (lb / nct) * 32;
+    double* __restrict__ Fm = c.F + ft.fofs;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int kk = ty; kk < 32; kk += 8) {                          // L[c0 + tx, k0 + kk] scaled by D
+        const int cc = c0 + tx, k = k0 + kk;
+        if (cc < ft.R && k < ft.e) tile[kk][tx] = Fm[(int64_t)k + (int64_t)k * ft.ld] * Fm[(int64_t)cc + (int64_t)k * ft.ld];
+    }
+    __syncthreads();
+    for (int cl = ty; cl < 32; cl += 8) {                          // U[k0 + tx, c0 + cl]
+        const int cc = c0 + cl, k = k0 + tx;
+        if (cc < ft.R && k < ft.e) Fm[(int64_t)k + (int64_t)cc * ft.ld] = tile[tx][cl];
     }
 }
 

@@ -77,7 +77,9 @@ enum Kind : int32_t {
     K_FWD_GATHER, K_FWD_DIAG, K_FWD_UPDATE, K_BWD_GATHER, K_BWD_UPDATE, K_BWD_DIAG, K_FWD_FRONT, K_BWD_FRONT,
     // solve on the frontal matrices, one step per PANEL STEP (dense, uniformly strided panels)
     K_PF_FRONT, K_PF_DIAG, K_PF_UPDATE, K_PB_FRONT, K_PB_UPDATE, K_PB_DIAG,
-    K_PF_STEP, K_PB_STEP      // fused: update + next diagonal block (forward), partial sums + diagonal block (backward)
+    K_PF_STEP, K_PB_STEP,     // fused: update + next diagonal block (forward), partial sums + diagonal block (backward)
+    // distributed top set (multi-GPU LDL^T): broadcast of a column slab from its owner; U = D L^T rebuilt from a received panel
+    K_BCAST, K_FILLU
 };
 struct Launch {
     int32_t kind;
@@ -89,8 +91,12 @@ struct Launch {
     int32_t maxw;             // widest panel step in a DIAG / PANEL launch (sizes its shared memory)
     // look-ahead: stream 0 = panel stream (diag / panel / in-block updates / next-block strip),
     // stream 1 = trailing-update stream (the bulk GEMMs).  Listed order is always a valid serial order.
-    uint8_t stream, wait_other, record, pad;   // wait_other: wait for the other stream's last record first
+    uint8_t stream, wait_other, record, wait_mask;   // wait_other: wait for the other stream's last record first
+    // distributed lists use three streams (0 panel, 1 trailing update, 2 communication) and wait_mask: bit s = wait
+    // for the last record of stream s before launching
 };
+struct Bcast { int64_t ofs, len; int32_t root, front; };          // in-place broadcast of F[ofs, ofs+len) from part `root`
+struct FillTask { int64_t fofs; int32_t ld, R, ob0, e; };          // U[ob0+k, c] = D_k * L[c, ob0+k] for k < e-ob0, e <= c < R
 
 constexpr int ASM_ROUNDS = 8;      // children handled by per-round launches; the rest by a tail kernel
 constexpr int ASM_TPB = 256, ASM_EPT = 4, ASM_COLS = 8;   // extend-add: rows per block, (tail kernel) entries per thread, columns per block
@@ -146,6 +152,18 @@ struct Plan {
     struct Range { int32_t owner; int32_t f0, f1; int64_t lnz0, lnz1, unz0, unz1, col0, col1; };
     std::vector<Range> ranges;                 // contiguous front / storage ranges owned by one part
     std::vector<Launch> factor_local, factor_top, fwd_local, fwd_top, bwd_top, bwd_local;
+    // DISTRIBUTED TOP SET (LDL^T, nparts > 1): the columns of every top-set front are dealt to the parts by OUTER
+    // BLOCK (block q of front f -> part (q + shift_f) mod nparts); the ownership of a front's update-matrix columns
+    // follows the ancestor column they are added to, so extend-adds between top-set fronts stay local.  Only the
+    // owner factors a block's panel; the factored column slab is broadcast in place (every part keeps a full copy
+    // of the top-set FACTORS, so the solve and the write-back stay as they are) and every part applies the
+    // delayed rank-(block width) update to the column blocks it owns.
+    bool dist_top = false; int dist_top_env = -1;      // SPK_DIST_TOP=0/1 overrides the default (on for LDL^T with nparts > 1)
+    std::vector<int8_t> fown;                  // owner of every front column, all top-set fronts (DFront::ownofs)
+    std::vector<int32_t> ownofs;               // per front: offset into fown, or -1 (not a distributed front)
+    std::vector<Bcast> bcasts;
+    std::vector<FillTask> fillt;
+    std::vector<uint8_t> held;                 // fronts this part keeps storage for (its subtrees, the top set, the exchanged subtree roots)
     // single GPU, TREE PIPELINES: the front tree is cut like the multi-GPU partition into `pipes` sets of
     // subtrees plus a top set; the sets are factored CONCURRENTLY, each on its own (panel, update) stream
     // pair, then the top set.  Within one pipeline a level ends in a latency-bound tail (the last outer
@@ -410,6 +428,7 @@ inline void plan_env_overrides(Plan& P) {        // test / tuning knobs
     if (const char* e = getenv("SPK_SOLVE_LNZ")) P.solve_on_fronts = e[0] != '1';
     if (const char* e = getenv("SPK_PS_WIDTH")) P.ps_width = std::max(1, atoi(e));
     if (const char* e = getenv("SPK_DMMA_VARIANT")) P.no_b128 = atoi(e) >= 2;
+    if (const char* e = getenv("SPK_DIST_TOP")) P.dist_top_env = e[0] != '0';
 }
 
 // Launch lists for the fronts selected by `sel` (all of them, one part's subtrees, or the top set).
@@ -634,6 +653,181 @@ inline void build_lists(Plan& P, const std::vector<uint8_t>& sel, std::vector<La
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Distributed top set: ownership of the front columns, storage held by this part, and the factor launch list.
+inline void assign_ownership(Plan& P) {
+    const int32_t nf = (int32_t)P.fronts.size();
+    P.ownofs.assign(nf, -1); P.fown.clear();
+    if (!P.dist_top) return;
+    std::vector<int32_t> shift(nf, 0), cnt(P.nlevels, 0);
+    for (int32_t f = 0; f < nf; ++f) if (P.owner[f] == -1) shift[f] = cnt[P.fronts[f].level]++;
+    for (int32_t f = nf - 1; f >= 0; --f) {                    // parents before children
+        if (P.owner[f] != -1) continue;
+        const Front& F = P.fronts[f];
+        P.ownofs[f] = (int32_t)P.fown.size();
+        P.fown.resize(P.fown.size() + F.R, 0);
+        int8_t* own = P.fown.data() + P.ownofs[f];
+        for (int32_t j = 0; j < F.nps; ++j) {
+            const PStep& ps = P.psteps[F.ps0 + j];
+            const int8_t o = (int8_t)((j / P.ob_steps + shift[f]) % P.nparts);
+            for (int32_t c = ps.o; c < ps.o + ps.w; ++c) own[c] = o;
+        }
+        if (F.m > 0) {
+            const int8_t* pown = P.fown.data() + P.ownofs[F.parent];     // the parent of a top-set front is in the top set
+            for (int32_t i = 0; i < F.m; ++i) own[F.W + i] = pown[P.rel[F.relofs + i]];
+        }
+    }
+}
+
+// Storage: a part of a multi-part plan keeps frontal matrices only for its own subtrees, the top set and the
+// subtree roots whose update matrices it receives; everything else gets no arena space (fofs = -1).
+inline void assign_storage(Plan& P) {
+    const int32_t nf = (int32_t)P.fronts.size();
+    P.held.assign(nf, 1);
+    if (P.nparts <= 1) return;
+    for (int32_t f = 0; f < nf; ++f) P.held[f] = (P.owner[f] == P.part || P.owner[f] == -1);
+    for (int32_t f : P.xchg) P.held[f] = 1;
+    int64_t fofs = 0;
+    for (int32_t f = 0; f < nf; ++f) {
+        Front& F = P.fronts[f];
+        if (P.held[f]) { F.fofs = fofs; fofs += (int64_t)F.ld * F.R; fofs = (fofs + 1) & ~(int64_t)1; }
+        else F.fofs = -1;
+        for (int32_t t = 0; t < F.nch; ++t) P.chunks[F.c0 + t].fofs = F.fofs;
+        for (int32_t j = 0; j < F.nps; ++j) P.psteps[F.ps0 + j].fofs = F.fofs;
+    }
+    P.arena = fofs;
+}
+
+inline void build_lists_dist(Plan& P, std::vector<Launch>& out) {
+    const int32_t nf = (int32_t)P.fronts.size(), me = P.part;
+    std::vector<std::vector<int32_t>> bylevel(P.nlevels);
+    for (int32_t f = 0; f < nf; ++f) if (P.owner[f] == -1) bylevel[P.fronts[f].level].push_back(f);
+    LaunchBuilder fb(P, out);
+    auto begin = [&](int32_t kind, int32_t first, int32_t lev, int32_t step, int stream, int wait_mask) {
+        fb.begin(kind, first, lev, step, stream, 0, 1); fb.cur.wait_mask = (uint8_t)wait_mask;
+    };
+    auto emit = [&](GemmBatch& g, int32_t lev, int32_t step, int stream, int wait_mask) {
+        const size_t n0 = out.size();
+        g.emit(P, fb, lev, step, stream, 0, 1);
+        for (size_t i = n0; i < out.size(); ++i) out[i].wait_mask = (uint8_t)wait_mask;
+    };
+    // the one exchange: update-matrix column slabs of the subtree roots, from their owners to everybody
+    begin(K_BCAST, (int32_t)P.bcasts.size(), 0, 0, 2, 1 | 2);
+    for (int32_t f : P.xchg) {
+        const Front& F = P.fronts[f];
+        if (F.m <= 0) continue;
+        P.bcasts.push_back(Bcast{F.fofs + (int64_t)F.W * F.ld, (int64_t)F.ld * F.m, P.owner[f], f});
+        fb.add(1);
+    }
+    fb.end();
+    for (int32_t lev = 0; lev < P.nlevels; ++lev) {
+        const std::vector<int32_t>& fr = bylevel[lev];
+        if (fr.empty()) continue;
+        int32_t maxch = 0, maxnps = 0;
+        for (int32_t f : fr) { maxch = std::max(maxch, P.fronts[f].nchild); maxnps = std::max(maxnps, P.fronts[f].nps); }
+        // extend-add into the columns this part owns (k_assemble filters by DFront::ownofs)
+        for (int32_t r = 0; r < std::min(maxch, ASM_ROUNDS); ++r) {
+            begin(K_ASM, (int32_t)P.asmt.size(), lev, r, 0, 2 | 4);
+            for (int32_t f : fr) {
+                const Front& F = P.fronts[f];
+                if (F.nchild <= r) continue;
+                int32_t c = P.childlist[F.child0 + r];
+                int64_t mc = P.fronts[c].m;
+                P.asmt.push_back(AsmTask{c, f});
+                fb.add((int32_t)(cdiv(mc, ASM_TPB) * cdiv(mc, ASM_COLS)));
+            }
+            fb.end();
+        }
+        if (maxch > ASM_ROUNDS) {
+            begin(K_ASM_TAIL, (int32_t)P.asmt.size(), lev, ASM_ROUNDS, 0, 2 | 4);
+            for (int32_t f : fr) if (P.fronts[f].nchild > ASM_ROUNDS) { P.asmt.push_back(AsmTask{-1, f}); fb.add(1); }
+            fb.end();
+        }
+        for (int32_t j = 0; j < maxnps; ++j) {
+            auto mine = [&](int32_t f, int32_t step) {
+                const Front& F = P.fronts[f];
+                return P.fown[P.ownofs[f] + P.psteps[F.ps0 + step].o] == me;
+            };
+            // ---- the owner's chain: left-looking in-block update, diagonal block, panel
+            if ((j % P.ob_steps) != 0) {
+                GemmBatch gl;
+                for (int32_t f : fr) if (P.fronts[f].nps > j && mine(f, j)) {
+                    const Front& F = P.fronts[f];
+                    const PStep& ps = P.psteps[F.ps0 + j];
+                    const int32_t ob0 = P.psteps[F.ps0 + j - (j % P.ob_steps)].o;
+                    GemmTask g = front_gemm(P, F, ps.o, F.R - ps.o, ps.o, ps.w, ob0, ps.o - ob0);
+                    gl.add(P, g, gemm_flops(g));
+                }
+                emit(gl, lev, j, 0, 0);
+            }
+            begin(K_DIAG, (int32_t)P.pslist.size(), lev, j, 0, j == 0 ? 2 : 0);
+            for (int32_t f : fr) if (P.fronts[f].nps > j && mine(f, j)) { P.pslist.push_back(P.fronts[f].ps0 + j); fb.add(1, 0, P.psteps[P.fronts[f].ps0 + j].w); }
+            fb.end();
+            begin(K_PANEL, (int32_t)P.pslist.size(), lev, j, 0, 0);
+            for (int32_t f : fr) if (P.fronts[f].nps > j && mine(f, j)) {
+                const PStep& ps = P.psteps[P.fronts[f].ps0 + j];
+                int32_t below = ps.R - ps.o - ps.w;
+                if (below <= 0) continue;
+                P.pslist.push_back(P.fronts[f].ps0 + j);
+                fb.add(cdiv(below, PANEL_ROWS), 0, ps.w);
+            }
+            fb.end();
+            // ---- end of an outer block: broadcast the factored column slab, rebuild U = D L^T from it, delayed updates
+            const bool boundary = ((j + 1) % P.ob_steps) == 0;
+            struct End { int32_t f, ob0, e, e2; bool last; };
+            std::vector<End> ends;
+            for (int32_t f : fr) if (P.fronts[f].nps > j) {
+                const Front& F = P.fronts[f];
+                const PStep& ps = P.psteps[F.ps0 + j];
+                const bool last = (F.nps == j + 1);
+                if (!boundary && !last) continue;
+                int32_t ob0 = ps.o;
+                for (int32_t q = j; q >= 0 && P.psteps[F.ps0 + q].ob_end == ps.ob_end; --q) ob0 = P.psteps[F.ps0 + q].o;
+                const int32_t e = ps.o + ps.w;
+                ends.push_back(End{f, ob0, e, last ? e : P.psteps[F.ps0 + j + 1].ob_end, last});
+            }
+            if (ends.empty()) continue;
+            begin(K_BCAST, (int32_t)P.bcasts.size(), lev, j, 2, 1 | 2);
+            for (const End& E : ends) {
+                const Front& F = P.fronts[E.f];
+                P.bcasts.push_back(Bcast{F.fofs + (int64_t)E.ob0 * F.ld, (int64_t)F.ld * (E.e - E.ob0), P.fown[P.ownofs[E.f] + E.ob0], E.f});
+                fb.add(1);
+            }
+            fb.end();
+            begin(K_FILLU, (int32_t)P.fillt.size(), lev, j, 0, 4);
+            for (const End& E : ends) {
+                const Front& F = P.fronts[E.f];
+                if (E.e >= F.R) continue;
+                P.fillt.push_back(FillTask{F.fofs, F.ld, F.R, E.ob0, E.e});
+                fb.add(cdiv(F.R - E.e, 32) * cdiv(E.e - E.ob0, 32));
+            }
+            fb.end();
+            GemmBatch gp, gg;
+            for (const End& E : ends) {
+                const Front& F = P.fronts[E.f];
+                if (E.e >= F.R) continue;
+                const int8_t* own = P.fown.data() + P.ownofs[E.f];
+                const int32_t kb = E.e - E.ob0;
+                if (!E.last && own[E.e] == me) {             // the strip the next block's owner needs first
+                    GemmTask g = front_gemm(P, F, E.e, F.R - E.e, E.e, E.e2 - E.e, E.ob0, kb);
+                    gp.add(P, g, gemm_flops(g));
+                }
+                for (int32_t c0 = E.e2; c0 < F.R;) {         // the rest, by runs of columns this part owns
+                    if (own[c0] != me) { ++c0; continue; }
+                    int32_t c1 = c0;
+                    while (c1 < F.R && own[c1] == me) ++c1;
+                    GemmTask r = front_gemm(P, F, c0, F.R - c0, c0, c1 - c0, E.ob0, kb);
+                    gg.add(P, r, gemm_flops(r));
+                    c0 = c1;
+                }
+            }
+            emit(gp, lev, j, 0, 2);                           // after the previous block's rest (same target region)
+            emit(gg, lev, j, 1, 1);                           // after this block's U is in place
+        }
+    }
+}
+
 // Elimination-subtree partition: split the front tree from the root until there are at
 // least `nparts` subtrees, biggest first; the fronts split off form the top set; subtrees are dealt to
 // parts by decreasing work (LPT).  Subtrees are contiguous front ranges because the reference post-orders
@@ -685,7 +879,8 @@ inline void partition(Plan& P) {
         std::vector<double> fl(P.nlevels, 0.0), st(P.nlevels, 0.0);
         for (int32_t f : tp) { int32_t l = P.fronts[f].level; fl[l] += own(f) / rate; st[l] = std::max(st[l], P.fronts[f].nps * tstep); }
         double t = 0.0;
-        for (int32_t l = 0; l < P.nlevels; ++l) t += std::max(fl[l], st[l]);
+        // distributed top set: the trailing updates of a level are shared by all parts, the chain of panel steps is not
+        for (int32_t l = 0; l < P.nlevels; ++l) t += std::max(P.dist_top ? fl[l] / P.nparts : fl[l], st[l]);
         return t;
     };
     std::vector<int32_t> top, best_roots = roots, best_top;
@@ -745,6 +940,7 @@ inline void build_schedule(Plan& P) {
         F.pbofs = P.pblen;
         if ((int64_t)F.R * F.W > P.solve_small) P.pblen += (int64_t)cdiv(F.R, SV_ROWS) * P.maxpw;
     }
+    P.dist_top = P.nparts > 1 && !P.lu && P.dist_top_env != 0;
     partition(P);
     std::vector<uint8_t> sel(nf, 1);
     if (P.nparts <= 1) {
@@ -772,11 +968,23 @@ inline void build_schedule(Plan& P) {
         }
         return;
     }
-    std::vector<Launch> unused_f;
+    assign_ownership(P);
+    assign_storage(P);
     for (int32_t f = 0; f < nf; ++f) sel[f] = P.owner[f] == P.part;
     build_lists(P, sel, P.factor_local, P.fwd_local, P.bwd_local);
     for (int32_t f = 0; f < nf; ++f) sel[f] = P.owner[f] == -1;
     build_lists(P, sel, P.factor_top, P.fwd_top, P.bwd_top);
+    if (P.dist_top) { P.factor_top.clear(); build_lists_dist(P, P.factor_top); }
+    else {
+        // replicated top set: the exchange = the whole subtree-root fronts, then the ordinary two-stream lists
+        std::vector<Launch> top;
+        LaunchBuilder fb(P, top);
+        fb.begin(K_BCAST, (int32_t)P.bcasts.size(), 0, 0, 2, 0, 1); fb.cur.wait_mask = 1 | 2;
+        for (int32_t f : P.xchg) { const Front& F = P.fronts[f]; P.bcasts.push_back(Bcast{F.fofs, (int64_t)F.ld * F.R, P.owner[f], f}); fb.add(1); }
+        fb.end();
+        top.insert(top.end(), P.factor_top.begin(), P.factor_top.end());
+        P.factor_top.swap(top);
+    }
 }
 
 } // namespace spk

@@ -6,6 +6,8 @@
 #include <vector>
 #include <mutex>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 #include "spk_b200.h"
 #include "plan.hpp"
 #include "kernels.cuh"
@@ -40,6 +42,10 @@ struct spk_plan {
     int device = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;   // panel stream (high priority), trailing-update stream
     cudaEvent_t evs0 = nullptr, evs1 = nullptr;          // last record of each stream
+    cudaStream_t stream_c = nullptr; cudaEvent_t evsc = nullptr;   // communication stream of a multi-part plan (NCCL broadcasts)
+    ncclComm_t comm = nullptr; bool comm_owned = false;  // communicator over the parts (spk_plan_comm_init / spk_multi_create)
+    int8_t* d_fown = nullptr; FillTask* d_fillt = nullptr;
+    double ms_xchg = 0;
     // tree pipelines (Plan::pipes): stream / event pair per pipeline; pair 0 = (stream, stream2, evs0, evs1)
     cudaStream_t pst[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
     cudaEvent_t pev[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
@@ -79,6 +85,7 @@ struct spk_plan {
     size_t dev_bytes = 0;
     int diag_smem_nj = 0; size_t diag_smem_bytes = 0, panel_smem = 0;
     bool have_perm = false, factored = false;
+    bool phase0_async = false;          // phase 0 returns without synchronising (the top set is enqueued right behind it)
     bool ev0_armed = false;             // spk_plan_reassemble recorded ev0: the next factorisation's time starts there
     // stats
     int64_t launches_factor = 0, launches_solve = 0;
@@ -107,6 +114,7 @@ static DevCtx make_ctx(spk_plan* p) {
     c.fronts = p->d_fronts; c.chunks = p->d_chunks; c.psteps = p->d_psteps; c.subw = p->d_subw;
     c.childlist = p->d_childlist; c.rel = p->d_rel; c.pos = p->d_pos;
     c.solvet = p->d_solvet; c.wlen = p->P.wlen; c.lu = p->P.lu ? 1 : 0;
+    c.me = p->P.part; c.fown = p->d_fown;
     return c;
 }
 
@@ -144,6 +152,46 @@ static int64_t init_kernel_attributes(int device) {
     return 0;
 }
 
+// ---- NCCL, resolved at run time (the library has no link-time dependency on it; a process that already
+// loaded libnccl.so.2 — e.g. through torch.distributed — shares that copy) -------------------------------
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi* nccl_api() {
+    static NcclApi api; static std::once_flag once; static bool ok = false;
+    std::call_once(once, [] {
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) { api.h = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (api.h) break; }
+        if (!api.h) return;
+        auto sym = [&](const char* n) { return dlsym(api.h, n); };
+        api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+        api.CommInitAll = (decltype(api.CommInitAll))sym("ncclCommInitAll");
+        api.Broadcast = (decltype(api.Broadcast))sym("ncclBroadcast");
+        api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+        api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+        api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+        api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+        ok = api.GetUniqueId && api.CommInitRank && api.CommInitAll && api.Broadcast && api.GroupStart && api.GroupEnd && api.CommDestroy && api.GetErrorString;
+    });
+    return ok ? &api : nullptr;
+}
+#define NK(call)                                                                              \
+    do {                                                                                      \
+        ncclResult_t r_ = (call);                                                             \
+        if (r_ != ncclSuccess) {                                                              \
+            set_err(std::string(#call) + ": " + nccl_api()->GetErrorString(r_));              \
+            return -300 - (int64_t)r_;                                                        \
+        }                                                                                     \
+    } while (0)
+
 extern "C" {
 
 SPK_API const char* spk_last_error(void) { return g_err.c_str(); }
@@ -170,6 +218,11 @@ SPK_API void spk_plan_destroy(spk_plan* p) {
         if (p->sg_exec) cudaGraphExecDestroy(p->sg_exec);
         if (p->evs0) cudaEventDestroy(p->evs0);
         if (p->evs1) cudaEventDestroy(p->evs1);
+        if (p->comm && p->comm_owned && nccl_api()) nccl_api()->CommDestroy(p->comm);
+        if (p->d_fown) cudaFree(p->d_fown);
+        if (p->d_fillt) cudaFree(p->d_fillt);
+        if (p->evsc) cudaEventDestroy(p->evsc);
+        if (p->stream_c) cudaStreamDestroy(p->stream_c);
         if (p->stream2) cudaStreamDestroy(p->stream2);
         if (p->stream3) cudaStreamDestroy(p->stream3);
         if (p->ev3a) cudaEventDestroy(p->ev3a);
@@ -196,6 +249,8 @@ static int64_t plan_upload(spk_plan* p) {
         CK(cudaEventCreateWithFlags(&p->evs1, cudaEventDisableTiming));
         p->pst[0][0] = p->stream; p->pst[0][1] = p->stream2; p->pev[0][0] = p->evs0; p->pev[0][1] = p->evs1;
         CK(cudaStreamCreateWithPriority(&p->stream3, cudaStreamNonBlocking, lo));
+        CK(cudaStreamCreateWithPriority(&p->stream_c, cudaStreamNonBlocking, hi));
+        CK(cudaEventCreateWithFlags(&p->evsc, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&p->ev3a, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&p->ev3b, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&p->ev3c, cudaEventDisableTiming));
@@ -211,7 +266,7 @@ static int64_t plan_upload(spk_plan* p) {
     std::vector<DFront> df(P.fronts.size());
     for (size_t i = 0; i < df.size(); ++i) {
         const Front& F = P.fronts[i];
-        df[i] = DFront{F.fofs, F.relofs, F.wofs, F.F0, F.pbofs, F.W, F.R, F.m, F.ld, F.parent, F.child0, F.nchild, F.c0, F.nch, F.ps0, F.nps, 0};
+        df[i] = DFront{F.fofs, F.relofs, F.wofs, F.F0, F.pbofs, F.W, F.R, F.m, F.ld, F.parent, F.child0, F.nchild, F.c0, F.nch, F.ps0, F.nps, P.ownofs.empty() ? -1 : P.ownofs[i]};
     }
     std::vector<DChunk> dc(P.chunks.size());
     std::vector<int32_t> cpfx(P.chunks.size() + 1, 0);
@@ -259,6 +314,8 @@ static int64_t plan_upload(spk_plan* p) {
     CK(upload(&p->d_asmt, P.asmt));
     CK(upload(&p->d_gemmt, P.gemmt));
     CK(upload(&p->d_solvet, P.solvet));
+    CK(upload(&p->d_fown, P.fown));
+    CK(upload(&p->d_fillt, P.fillt));
     CK(cudaMalloc((void**)&p->d_F, std::max<int64_t>(P.arena, 1) * sizeof(double)));
     CK(cudaMalloc((void**)&p->d_lnz, std::max<int64_t>(P.nlnz, 1) * sizeof(double)));
     CK(cudaMalloc((void**)&p->d_unz, std::max<int64_t>(P.nunz, 1) * sizeof(double)));
@@ -377,6 +434,7 @@ static int64_t slot_to_arena(const Plan& P, int64_t d) {
         int64_t e = slot - c.lofs;
         int64_t j = e / c.jlen, i = e - j * c.jlen;
         if (j >= c.nj) return -2;
+        if (c.fofs < 0) return -1;                      // a front this part holds no storage for
         return c.fofs + P.pos[c.posofs + i] + (int64_t)(c.o + j) * c.ld;
     }
     int64_t slot = -d - 1;
@@ -387,6 +445,7 @@ static int64_t slot_to_arena(const Plan& P, int64_t d) {
     if (ldu <= 0) return -2;
     int64_t j = e / ldu, i = e - j * ldu;
     if (j >= c.nj) return -2;
+    if (c.fofs < 0) return -1;
     return c.fofs + (int64_t)(c.o + j) + (int64_t)P.pos[c.posofs + c.nj + i] * c.ld;
 }
 
@@ -438,10 +497,11 @@ SPK_API int64_t spk_plan_reassemble(spk_plan* p) {
 }
 
 // ---- factor ---------------------------------------------------------------------------
-static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L, bool two_streams, int pair = 0) {
+static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L, bool two_streams, int pair = 0, cudaStream_t force = nullptr) {
     const int32_t* pfx = p->d_blkpfx + L.pfx;
     cudaStream_t st = p->stream;
-    if (two_streams) {
+    if (force) { st = force; two_streams = false; }     // the caller handles waits / records (lists with broadcasts)
+    else if (two_streams) {
         st = p->pst[pair][L.stream ? 1 : 0];
         if (L.wait_other) CK(cudaStreamWaitEvent(st, p->pev[pair][L.stream ? 0 : 1], 0));
     }
@@ -489,10 +549,50 @@ static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L, 
         CK(launch_pdl(v.fn, dim3(L.nblocks), dim3(v.threads), v.smem, st, p->pdl_factor && p->pdl_gemm, c, (const GemmTask*)(p->d_gemmt + L.first), pfx, (int)L.count));
         break;
     }
+    case K_FILLU:
+        k_fill_u<<<L.nblocks, 256, 0, st>>>(c, p->d_fillt + L.first, pfx, L.count); break;
     default:
         set_err("bad launch kind"); return -100;
     }
     if (two_streams && L.record) CK(cudaEventRecord(p->pev[pair][L.stream ? 1 : 0], st));
+    return 0;
+}
+
+// Launch list of the top set of a multi-part plan: three streams (0 panel, 1 trailing update, 2 communication),
+// K_BCAST launches = in-place NCCL broadcasts of column slabs on the communication stream.  Every part enqueues
+// the broadcasts in the same (static) order, so no host-side coordination is needed while the list runs.
+static int64_t run_top_list(spk_plan* p, const DevCtx& c, const std::vector<Launch>& Ls) {
+    Plan& P = p->P;
+    NcclApi* N = nccl_api();
+    cudaStream_t S[3] = {p->stream, p->stream2, p->stream_c};
+    cudaEvent_t E[3] = {p->evs0, p->evs1, p->evsc};
+    for (int q = 0; q < 3; ++q) CK(cudaEventRecord(E[q], S[q]));
+    for (const Launch& L : Ls) {
+        const int sid = L.stream < 3 ? L.stream : 0;
+        cudaStream_t st = S[sid];
+        if (L.wait_other && sid < 2) CK(cudaStreamWaitEvent(st, E[1 - sid], 0));              // replicated lists (two-stream look-ahead)
+        for (int q = 0; q < 3; ++q) if (((L.wait_mask >> q) & 1) && q != sid) CK(cudaStreamWaitEvent(st, E[q], 0));
+        if (L.kind == K_BCAST) {
+            if (!p->comm || !N) { set_err("multi-part plan without a communicator (spk_plan_comm_init)"); return -100; }
+            NK(N->GroupStart());
+            for (int32_t i = 0; i < L.count; ++i) {
+                const Bcast& b = P.bcasts[L.first + i];
+                NK(N->Broadcast(p->d_F + b.ofs, p->d_F + b.ofs, (size_t)b.len, ncclDouble, b.root, p->comm, st));
+            }
+            NK(N->GroupEnd());
+            CK(cudaEventRecord(E[sid], st));
+            if (!P.dist_top) { CK(cudaStreamWaitEvent(S[0], E[2], 0)); CK(cudaStreamWaitEvent(S[1], E[2], 0)); }   // replicated top set: everything waits for the exchange
+        } else {
+            int64_t rc = run_factor_launch(p, c, L, false, 0, st);
+            if (rc) return rc;
+            if (L.record) CK(cudaEventRecord(E[sid], st));
+            if (!p->profile && (L.kind == K_GEMM_B64 || L.kind == K_GEMM_B128)) p->gemm_flops += L.flops;   // profiling mode times phase 0 only
+        }
+        ++p->launches_factor;
+    }
+    // join on the main stream
+    CK(cudaEventRecord(E[1], S[1])); CK(cudaStreamWaitEvent(S[0], E[1], 0));
+    CK(cudaEventRecord(E[2], S[2])); CK(cudaStreamWaitEvent(S[0], E[2], 0));
     return 0;
 }
 
@@ -509,6 +609,27 @@ SPK_API int64_t spk_plan_factor_phase(spk_plan* p, int32_t phase) {
     if (phase == 1) CK(cudaEventRecord(p->evg0, st));
     else if (!p->ev0_armed) CK(cudaEventRecord(p->ev0, st));
     p->ev0_armed = false;
+    if (phase == 1) {
+        // top set of a multi-part plan: exchange + (distributed or replicated) factorisation, then the write-back
+        int64_t rc = run_top_list(p, c, Ls);
+        if (rc) return rc;
+        for (int lv = 0; lv < (int)p->st_count[1].size(); ++lv)
+            if (p->st_blocks[1][lv] > 0) {
+                k_chunks_store_list<<<p->st_blocks[1][lv], 256, 0, st>>>(c, p->d_stlist + p->st_list0[1][lv], p->d_stpfx + p->st_pfx0[1][lv], p->st_count[1][lv]);
+                ++p->launches_factor;
+            }
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(p->ev1, st));
+        CK(cudaStreamSynchronize(st));
+        p->values_in_fronts = false;
+        float ms1 = 0; CK(cudaEventElapsedTime(&ms1, p->evg0, p->ev1)); p->ms_phase1 = ms1;
+        if (p->phase0_async) { float ms0 = 0; CK(cudaEventElapsedTime(&ms0, p->ev0, p->evg1)); p->ms_phase0 = ms0; p->phase0_async = false; }
+        p->ms_factor = p->ms_phase0 + ms1;
+        int32_t flag1 = 0;
+        CK(cudaMemcpy(&flag1, p->d_iflag, sizeof(int32_t), cudaMemcpyDeviceToHost));
+        p->factored = true;
+        return flag1;
+    }
     if (phase <= 0) {
         CK(cudaMemsetAsync(p->d_iflag, 0, sizeof(int32_t), st));
         p->launches_factor = 0; p->gemm_flops = 0; p->gemm_ms = 0;
@@ -597,6 +718,7 @@ SPK_API int64_t spk_plan_factor_phase(spk_plan* p, int32_t phase) {
     }
     CK(cudaGetLastError());
     CK(cudaEventRecord(phase == 0 ? p->evg1 : p->ev1, st));
+    if (phase == 0 && p->phase0_async) return 0;        // spk_plan_factor_multi: phase 1 follows without a host synchronisation
     CK(cudaStreamSynchronize(st));
     if (phase != 0) p->values_in_fronts = false;
     if (trace) {
@@ -641,6 +763,38 @@ SPK_API int64_t spk_plan_factor_phase(spk_plan* p, int32_t phase) {
 }
 
 SPK_API int64_t spk_plan_factor(spk_plan* p) { return spk_plan_factor_phase(p, -1); }
+
+// ---- multi-part plans: communicator + whole-factorisation / whole-solve entry points --------------------------
+SPK_API int64_t spk_nccl_unique_id(void* out128) {
+    NcclApi* N = nccl_api();
+    if (!N) { set_err("libnccl.so.2 not found"); return -100; }
+    ncclUniqueId id;
+    NK(N->GetUniqueId(&id));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    memcpy(out128, &id, 128);
+    return 0;
+}
+// every part calls this with the id produced by ONE call of spk_nccl_unique_id (collective, blocks until all joined)
+SPK_API int64_t spk_plan_comm_init(spk_plan* p, const void* id128) {
+    NEED_DEV(p);
+    NcclApi* N = nccl_api();
+    if (!N) { set_err("libnccl.so.2 not found"); return -100; }
+    if (p->comm) { set_err("communicator already set"); return -100; }
+    ncclUniqueId id; memcpy(&id, id128, 128);
+    NK(N->CommInitRank(&p->comm, p->P.nparts, id, p->P.part));
+    p->comm_owned = true;
+    return 0;
+}
+// phase 0 (own subtrees), exchange, top set, write-back: one call, no host synchronisation in between
+SPK_API int64_t spk_plan_factor_multi(spk_plan* p) {
+    NEED_DEV(p);
+    if (p->P.nparts <= 1) return spk_plan_factor_phase(p, -1);
+    if (!p->comm) { set_err("multi-part plan without a communicator (spk_plan_comm_init)"); return -100; }
+    p->phase0_async = !p->profile;                  // per-launch timing reads its events at the end of phase 0
+    int64_t rc = spk_plan_factor_phase(p, 0);
+    if (rc < 0) { p->phase0_async = false; return rc; }
+    return spk_plan_factor_phase(p, 1);
+}
 
 SPK_API int64_t spk_plan_get_factors(spk_plan* p, double* lnz, double* unz, int64_t* ipvt) {
     NEED_DEV(p);
@@ -912,6 +1066,46 @@ SPK_API int64_t spk_plan_solve_phase(spk_plan* p, double* d_rhs, int64_t nrhs, i
     return 0;
 }
 
+// whole multi-part solve in one call: forward over the own subtrees, broadcast of the subtree-root work vectors,
+// top set (replicated), backward over the own subtrees, broadcast of the owned pieces of x.  d_rhs: device,
+// permuted order; on return every part holds the full solution.
+SPK_API int64_t spk_plan_solve_multi(spk_plan* p, double* d_rhs, int64_t nrhs, int64_t ldrhs) {
+    NEED_DEV(p);
+    Plan& P = p->P;
+    if (P.nparts <= 1) return spk_plan_solve_device(p, d_rhs, nrhs, ldrhs, 0);
+    if (!p->comm) { set_err("multi-part plan without a communicator (spk_plan_comm_init)"); return -100; }
+    if (!p->factored) { set_err("solve: the plan holds no factors"); return -100; }
+    NcclApi* N = nccl_api();
+    cudaStream_t st = p->stream;
+    CK(cudaEventRecord(p->ev0, st));
+    p->launches_solve = 0;
+    for (int64_t r0 = 0; r0 < nrhs; r0 += 32) {
+        const int64_t nb = std::min<int64_t>(32, nrhs - r0);
+        int64_t rc = ensure_w(p, 32); if (rc) return rc;
+        DevCtx c = make_ctx(p);
+        double* b = d_rhs + (size_t)r0 * ldrhs;
+        rc = run_solve_launches(p, c, P.fwd_local, b, nb, ldrhs); if (rc) return rc;
+        NK(N->GroupStart());
+        for (int32_t f : P.xchg) {
+            const Front& F = P.fronts[f];
+            for (int64_t q = 0; q < nb; ++q) { double* w = p->d_w + (size_t)q * P.wlen + F.wofs; NK(N->Broadcast(w, w, (size_t)F.R, ncclDouble, P.owner[f], p->comm, st)); }
+        }
+        NK(N->GroupEnd());
+        rc = run_solve_launches(p, c, P.fwd_top, b, nb, ldrhs); if (rc) return rc;
+        rc = run_solve_launches(p, c, P.bwd_top, b, nb, ldrhs); if (rc) return rc;
+        rc = run_solve_launches(p, c, P.bwd_local, b, nb, ldrhs); if (rc) return rc;
+        NK(N->GroupStart());
+        for (const Plan::Range& g : P.ranges)
+            for (int64_t q = 0; q < nb; ++q) { double* x = b + (size_t)q * ldrhs + g.col0; NK(N->Broadcast(x, x, (size_t)(g.col1 - g.col0), ncclDouble, g.owner, p->comm, st)); }
+        NK(N->GroupEnd());
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(p->ev1, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, p->ev0, p->ev1)); p->ms_solve = ms;
+    return 0;
+}
+
 // exchange lists of a multi-part plan.  what = 0: subtree-root fronts, out = {owner, F offset, F length,
 // w offset, w length (per right-hand side), front id};  what = 1: storage ranges owned by one part,
 // out = {owner, lnz offset, lnz length, unz offset, unz length, first column, #columns}.  Returns the count
@@ -931,6 +1125,119 @@ SPK_API int64_t spk_plan_xchg_info(spk_plan* p, int32_t what, int64_t i, int64_t
     const Plan::Range& g = P.ranges[i];
     out[0] = g.owner; out[1] = g.lnz0; out[2] = g.lnz1 - g.lnz0; out[3] = g.unz0; out[4] = g.unz1 - g.unz0; out[5] = g.col0; out[6] = g.col1 - g.col0;
     return 0;
+}
+
+
+// ---- one process, N GPUs -----------------------------------------------------------------------------------
+// spk_multi owns one plan per GPU (part r on device r) and the NCCL communicators (ncclCommInitAll); every call
+// fans out to one host thread per GPU (the parts enqueue their launch lists and their side of the broadcasts
+// concurrently) and joins before it returns, so a single ccall from the host application scales over the box.
+struct spk_multi {
+    std::vector<spk_plan*> plans;
+    std::vector<ncclComm_t> comms;
+    std::vector<double*> d_b;           // per device: right-hand sides (original order)
+    int64_t bcap = 0;
+};
+} // extern "C"
+#include <thread>
+template <class Fn>
+static int64_t multi_run(spk_multi* m, Fn fn) {
+    const int N = (int)m->plans.size();
+    std::vector<int64_t> rc(N, 0); std::vector<std::string> err(N);
+    std::vector<std::thread> th;
+    for (int r = 0; r < N; ++r) th.emplace_back([&, r] { rc[r] = fn(r, m->plans[r]); if (rc[r] <= -100) err[r] = g_err; });
+    for (auto& t : th) t.join();
+    int64_t worst = 0;
+    for (int r = 0; r < N; ++r) if (rc[r] <= -100) { set_err("device " + std::to_string(r) + ": " + err[r]); return rc[r]; } else worst = std::min(worst, rc[r]);
+    return worst;
+}
+extern "C" {
+SPK_API void spk_multi_destroy(spk_multi* m) {
+    if (!m) return;
+    for (size_t r = 0; r < m->plans.size(); ++r) {
+        if (m->plans[r]) { cudaSetDevice(m->plans[r]->device); if (r < m->d_b.size() && m->d_b[r]) cudaFree(m->d_b[r]); }
+        if (r < m->comms.size() && m->comms[r] && nccl_api()) nccl_api()->CommDestroy(m->comms[r]);
+        if (m->plans[r]) { m->plans[r]->comm = nullptr; spk_plan_destroy(m->plans[r]); }
+    }
+    delete m;
+}
+SPK_API spk_multi* spk_multi_create(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* snode,
+                                    const int64_t* xlindx, const int64_t* lindx, const int64_t* xlnz,
+                                    const int64_t* xunz_or_null, int32_t ngpus) {
+    if (ngpus < 1 || ngpus > spk_device_count()) { set_err("spk_multi_create: ngpus out of range"); return nullptr; }
+    spk_multi* m = new spk_multi();
+    m->plans.assign(ngpus, nullptr); m->comms.assign(ngpus, nullptr); m->d_b.assign(ngpus, nullptr);
+    int64_t rc = multi_run(m, [&](int r, spk_plan*) -> int64_t {
+        m->plans[r] = spk_plan_create(n, nsuper, xsuper, snode, xlindx, lindx, xlnz, xunz_or_null, r, r, ngpus);
+        return m->plans[r] ? 0 : -100;
+    });
+    if (rc) { spk_multi_destroy(m); return nullptr; }
+    if (ngpus > 1) {
+        NcclApi* N = nccl_api();
+        std::vector<int> devs(ngpus);
+        for (int r = 0; r < ngpus; ++r) devs[r] = r;
+        if (!N) { set_err("libnccl.so.2 not found"); spk_multi_destroy(m); return nullptr; }
+        ncclResult_t e = N->CommInitAll(m->comms.data(), ngpus, devs.data());
+        if (e != ncclSuccess) { set_err(std::string("ncclCommInitAll: ") + N->GetErrorString(e)); spk_multi_destroy(m); return nullptr; }
+        for (int r = 0; r < ngpus; ++r) { m->plans[r]->comm = m->comms[r]; m->plans[r]->comm_owned = false; }
+    }
+    return m;
+}
+SPK_API spk_plan* spk_multi_plan(spk_multi* m, int32_t r) { return (m && r >= 0 && r < (int)m->plans.size()) ? m->plans[r] : nullptr; }
+SPK_API int64_t spk_multi_inmatrix(spk_multi* m, int64_t nnz, const int64_t* dest_or_null, const double* nzval) {
+    return multi_run(m, [&](int, spk_plan* p) { return spk_plan_inmatrix(p, nnz, dest_or_null, nzval); });
+}
+SPK_API int64_t spk_multi_set_values(spk_multi* m, const double* lnz, const double* unz_or_null) {
+    return multi_run(m, [&](int, spk_plan* p) { return spk_plan_set_values(p, lnz, unz_or_null); });
+}
+SPK_API int64_t spk_multi_factor(spk_multi* m) {
+    return multi_run(m, [&](int, spk_plan* p) { return spk_plan_factor_multi(p); });
+}
+// factors in the reference layout: every subtree's storage range from its owner, the top set from part 0
+SPK_API int64_t spk_multi_get_factors(spk_multi* m, double* lnz, double* unz, int64_t* ipvt) {
+    spk_plan* p0 = m->plans[0];
+    if (m->plans.size() == 1) return spk_plan_get_factors(p0, lnz, unz, ipvt);
+    int64_t rc = spk_plan_get_factors(p0, lnz, unz, ipvt);            // top set + part 0's subtrees (+ stale ranges, overwritten below)
+    if (rc) return rc;
+    const Plan& P = p0->P;
+    std::vector<int64_t> ip;
+    for (const Plan::Range& g : P.ranges) {
+        if (g.owner == 0) continue;
+        spk_plan* q = m->plans[g.owner];
+        CK(cudaSetDevice(q->device));
+        if (lnz) CK(cudaMemcpy(lnz + g.lnz0, q->d_lnz + g.lnz0, (g.lnz1 - g.lnz0) * sizeof(double), cudaMemcpyDeviceToHost));
+        if (unz && P.lu && g.unz1 > g.unz0) CK(cudaMemcpy(unz + g.unz0, q->d_unz + g.unz0, (g.unz1 - g.unz0) * sizeof(double), cudaMemcpyDeviceToHost));
+        if (ipvt && P.lu) {
+            std::vector<int32_t> t((size_t)(g.col1 - g.col0));
+            CK(cudaMemcpy(t.data(), q->d_ipiv + g.col0, t.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < t.size(); ++i) ipvt[g.col0 + (int64_t)i] = t[i];
+        }
+    }
+    return 0;
+}
+SPK_API int64_t spk_multi_set_perm(spk_multi* m, const int64_t* rperm, const int64_t* rinvp) {
+    return multi_run(m, [&](int, spk_plan* p) { return spk_plan_set_perm(p, rperm, rinvp); });
+}
+// _triangularsolve! over all GPUs: b (host, original order, ld = ldb) in place
+SPK_API int64_t spk_multi_triangularsolve(spk_multi* m, double* b, int64_t nrhs, int64_t ldb) {
+    if (m->plans.size() == 1) return spk_plan_triangularsolve(m->plans[0], b, nrhs, ldb);
+    if (nrhs <= 0) return 0;
+    return multi_run(m, [&](int r, spk_plan* p) -> int64_t {
+        NEED_DEV(p);
+        if (!p->have_perm) { set_err("spk_multi_set_perm not called"); return -100; }
+        const int64_t n = p->P.n;
+        int64_t rc = ensure_rhs(p, nrhs); if (rc) return rc;
+        cudaStream_t st = p->stream;
+        CK(cudaMemcpy2DAsync(p->d_tmp, n * sizeof(double), b, ldb * sizeof(double), n * sizeof(double), nrhs, cudaMemcpyHostToDevice, st));
+        k_perm_gather<<<dim3(cdiv(n, 256), (unsigned)nrhs), 256, 0, st>>>(n, p->d_rperm, p->d_tmp, p->d_rhs, n, n);
+        rc = spk_plan_solve_multi(p, p->d_rhs, nrhs, n); if (rc) return rc;
+        if (r == 0) {
+            k_perm_gather<<<dim3(cdiv(n, 256), (unsigned)nrhs), 256, 0, st>>>(n, p->d_rinvp, p->d_rhs, p->d_tmp, n, n);
+            CK(cudaMemcpy2DAsync(b, ldb * sizeof(double), p->d_tmp, n * sizeof(double), n * sizeof(double), nrhs, cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaStreamSynchronize(st));
+        return 0;
+    });
 }
 
 // ---- introspection ----------------------------------------------------------------------

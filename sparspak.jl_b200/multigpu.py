@@ -1,15 +1,16 @@
 """Multi-GPU numeric factor / solve: one process per GPU, elimination-subtree partition.
 
-Each rank holds a full plan (same structure, `part = rank`): it factors the fronts of its own
-subtrees (phase 0), the subtree-ROOT frontal matrices are then broadcast from their owners
-(the only exchange of the factorisation: NCCL over NVLink / NVSwitch in production, gloo in the
-CPU tests), and every rank factors the small top set of the tree redundantly (phase 1) — bitwise
-identical on every rank, so the pivot sequence does not depend on the GPU count.  The solve
-mirrors it: forward over the subtrees, broadcast of the subtree-root work vectors, top set,
-backward over the subtrees, broadcast of the owned pieces of x.
-
-The orchestration is engine-agnostic: `CudaEngine` drives the CUDA C-ABI plan, the CPU tests
-drive the host simulator of the schedule with the same code (tests/test_multigpu_gloo.py)."""
+Each rank holds a plan for `part = rank`: frontal storage for its own subtrees, the top set of the tree and the
+subtree roots it receives.  Phase 0 factors the own subtrees; the update matrices of the subtree roots are then
+exchanged, and the TOP SET is factored
+  * LDL^T: DISTRIBUTED — the columns of every top-set front are dealt to the ranks by outer block; only the owner
+    factors a block's panel, broadcasts the factored column slab, and every rank applies the delayed update to
+    the column blocks it owns (plan.hpp: build_lists_dist);
+  * LU: replicated on every rank (bitwise identical, so the pivot sequence does not depend on the GPU count).
+The CUDA engine does all of this inside the C library (`spk_plan_factor_multi` / `spk_plan_solve_multi`, NCCL
+broadcasts on the plan's own streams, no host synchronisation between the phases); Python only hands over the
+NCCL unique id.  The CPU tests drive the host simulator of the same launch lists over gloo
+(tests/test_multigpu_gloo.py): the simulator stops at every broadcast and `DistributedSolver` performs it."""
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -35,6 +36,16 @@ class CudaEngine:
         from . import _cudalib
         self.plan = _cudalib.Plan(base, device=device, part=rank, nparts=world)
         self.device = device
+        self.native_comm = False
+        if world > 1 and dist.is_available() and dist.is_initialized():
+            # the library owns its NCCL communicator; torch.distributed only carries the 128-byte unique id
+            ident = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                ident = torch.from_numpy(self.plan.nccl_unique_id().copy())
+            ident = ident.to(f"cuda:{device}") if dist.get_backend() == "nccl" else ident
+            dist.broadcast(ident, src=0)
+            self.plan.comm_init(ident.cpu().numpy())
+            self.native_comm = True
         self.lu = not base.spd
         self.n = int(base.n)
         self._w = None
@@ -63,6 +74,13 @@ class CudaEngine:
     def factor_phase(self, phase):
         return self.plan.factor_phase(phase)
 
+    def factor_multi(self):
+        return self.plan.factor_multi()
+
+    def solve_multi(self, rhs):
+        nrhs, ld = (1, rhs.numel()) if rhs.dim() == 1 else (rhs.shape[0], rhs.shape[1])     # (nrhs, n) rows = column-major n x nrhs
+        self.plan.solve_multi(rhs.data_ptr(), nrhs, ld)
+
     def solve_phase(self, rhs, phase):
         self.plan.solve_phase(rhs.data_ptr(), 1, rhs.numel(), phase)
 
@@ -76,14 +94,14 @@ class DistributedSolver:
         self.rng = engine.ranges()            # rows: owner, lnz off, lnz len, unz off, unz len, col0, ncols
 
     def factor(self):
-        flag = self.e.factor_phase(0)
-        F = self.e.F()
-        for r in self.fronts:                 # the one exchange step of the factorisation
-            dist.broadcast(F[int(r[1]): int(r[1] + r[2])], src=int(r[0]))
-        if F.is_cuda:
-            torch.cuda.synchronize()
-        flag = min(flag, self.e.factor_phase(1))
-        t = torch.tensor([flag], dtype=torch.int64, device=F.device)
+        if getattr(self.e, "native_comm", False):
+            flag = self.e.factor_multi()              # phases + exchanges inside the library
+        else:
+            flag = self.e.factor_phase(0)
+            F = self.e.F()
+            # the engine runs the top-set list and hands every broadcast (arena offset, length, root) back
+            flag = min(flag, self.e.factor_top(lambda ofs, n, root: dist.broadcast(F[ofs: ofs + n], src=root)))
+        t = torch.tensor([flag], dtype=torch.int64, device=self.e.F().device)
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         return int(t.item())
 
@@ -100,6 +118,9 @@ class DistributedSolver:
 
     def solve(self, rhs):
         """rhs: 1-D tensor (permuted order) on the engine's device; overwritten with the solution on every rank."""
+        if getattr(self.e, "native_comm", False):
+            self.e.solve_multi(rhs)
+            return rhs
         self.e.solve_phase(rhs, 0)
         w = self.e.w()
         for r in self.fronts:

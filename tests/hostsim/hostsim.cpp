@@ -21,6 +21,7 @@ struct Sim {
 static void chunks_io(Sim& s, bool store) {
     Plan& P = s.P;
     for (const Chunk& c : P.chunks) {
+        if (c.fofs < 0) continue;                           // a front this part holds no storage for
         const int32_t* pos = P.pos.data() + c.posofs;
         double* F = s.F.data() + c.fofs;
         for (int j = 0; j < c.nj; ++j)
@@ -44,9 +45,12 @@ static void chunks_io(Sim& s, bool store) {
 static void assemble(Sim& s, const Front& C, const Front& Pa) {
     Plan& P = s.P;
     const int32_t* rel = P.rel.data() + C.relofs;
+    const int32_t pf = (int32_t)(&Pa - P.fronts.data());
+    const int8_t* own = (!P.ownofs.empty() && P.ownofs[pf] >= 0) ? P.fown.data() + P.ownofs[pf] : nullptr;
     for (int j = 0; j < C.m; ++j)
         for (int i = 0; i < C.m; ++i) {
             if (!P.lu && i < j) continue;
+            if (own && own[rel[j]] != P.part) continue;     // distributed parent: only the columns this part owns
             s.F[Pa.fofs + (int64_t)rel[i] + (int64_t)rel[j] * Pa.ld] += s.F[C.fofs + (int64_t)(C.W + i) + (int64_t)(C.W + j) * C.ld];
         }
 }
@@ -169,6 +173,8 @@ API int64_t sim_stat(void* h, int what) {
     case 10: { int64_t k = 0; for (auto& L : P.factor_launches) k += L.nblocks; return k; }
     case 11: return (int64_t)P.psteps.size();
     case 12: { int64_t k = 0; for (auto& f : P.fronts) k += (int64_t)f.m * f.m; return k; }
+    case 13: return P.dist_top ? 1 : 0;
+    case 14: { int64_t k = 0; for (int32_t o : P.owner) if (o == -1) ++k; return k; }
     default: return 0; }
 }
 API double sim_statf(void* h, int what) {
@@ -193,6 +199,13 @@ static int64_t run_factor_list(Sim* s, const std::vector<Launch>& Ls) {
         case K_DIAG: for (int t = 0; t < L.count; ++t) diag(*s, P.psteps[P.pslist[L.first + t]]); break;
         case K_PANEL: for (int t = 0; t < L.count; ++t) panel(*s, P.psteps[P.pslist[L.first + t]]); break;
         case K_GEMM: case K_GEMM_B64: case K_GEMM_B128: for (int t = 0; t < L.count; ++t) gemm(*s, P.gemmt[L.first + t]); break;
+        case K_FILLU:
+            for (int t = 0; t < L.count; ++t) {
+                const FillTask& ft = P.fillt[L.first + t];
+                double* Fm = s->F.data() + ft.fofs;
+                for (int c = ft.e; c < ft.R; ++c) for (int k = ft.ob0; k < ft.e; ++k) Fm[(int64_t)k + (int64_t)c * ft.ld] = Fm[(int64_t)k + (int64_t)k * ft.ld] * Fm[(int64_t)c + (int64_t)k * ft.ld];
+            } break;
+        case K_BCAST: return -101;                          // the caller drives the exchanges (sim_top_next)
         default: return -100;
         }
     }
@@ -214,6 +227,27 @@ API int64_t sim_factor_list(void* h, int which) {
     int64_t rc = run_factor_list(s, which == 0 ? P.factor_launches : (which == 1 ? P.factor_local : P.factor_top));
     return rc ? rc : s->iflag;
 }
+// Top-set list of a multi-part plan: runs the launches [from, ...) up to the next K_BCAST launch and returns its
+// index (the caller performs its broadcasts, then continues at index + 1), or -1 when the list is done.
+API int64_t sim_top_next(void* h, int64_t from) {
+    Sim* s = (Sim*)h; Plan& P = s->P;
+    for (int64_t i = from; i < (int64_t)P.factor_top.size(); ++i) {
+        if (P.factor_top[i].kind == K_BCAST) return i;
+        std::vector<Launch> one(1, P.factor_top[i]);
+        if (run_factor_list(s, one)) return -100;
+    }
+    return -1;
+}
+// broadcasts of launch `li` of the top-set list: count when out == NULL, else out = {arena offset, length, root}
+API int64_t sim_bcast_info(void* h, int64_t li, int64_t i, int64_t* out) {
+    Sim* s = (Sim*)h; Plan& P = s->P;
+    const Launch& L = P.factor_top[li];
+    if (!out) return L.count;
+    const Bcast& b = P.bcasts[L.first + i];
+    out[0] = b.ofs; out[1] = b.len; out[2] = b.root;
+    return 0;
+}
+API int64_t sim_iflag(void* h) { return ((Sim*)h)->iflag; }
 API void* sim_ptr(void* h, int what) {
     Sim* s = (Sim*)h;
     switch (what) { case 0: return s->lnz.data(); case 1: return s->unz.data(); case 2: return s->ipiv.data(); case 5: return s->F.data(); case 6: return s->w.data(); default: return nullptr; }

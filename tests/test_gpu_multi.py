@@ -1,5 +1,8 @@
-"""Multi-GPU parity (needs >= 2 CUDA devices; skipped otherwise): CUDA plans, one process per GPU,
-NCCL exchange of the subtree-root fronts, against the CPU oracle."""
+"""Multi-GPU parity (needs >= 2 CUDA devices; skipped otherwise) against the CPU oracle:
+  * one process per GPU (torch.distributed only carries the NCCL unique id; the library owns the communicator):
+    elimination-subtree partition, exchange of the subtree roots' update matrices, top set DISTRIBUTED by column
+    blocks for LDL^T (one panel broadcast per outer block) / replicated for LU;
+  * one process, N GPUs through the single ccall-able handle `spk_multi_*`."""
 import os
 import socket
 import sys
@@ -14,25 +17,28 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, spd, q):
+def _worker(rank, world, port, spd, g, env, q):
     for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
+    os.environ.update(env or {})
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         import sparspak_jl_b200 as spk
+        import oracle
         from sparspak_jl_b200.multigpu import CudaEngine, DistributedSolver
         from common import prepare, oracle_factor, spd_mask, rel_err, residual, M
-        g = 14
         A = M.laplacian3d(g) if spd else M.convdiff3d(g)
         s = prepare(A, spd, spk.nd_grid_order(g, g, g))
         b = s.slvr
         eng = CudaEngine(b, rank, world, rank)
+        assert eng.native_comm
         eng.plan.set_values(b.lnz, None if spd else b.unz)
         ds = DistributedSolver(eng, rank, world)
         flag = ds.factor()
         ds.gather_factors()
+        oracle.use_openblas(g > 16)
         lo, uo, po, _ = oracle_factor(b)
         lg = np.zeros(b.lnz.size); ug = np.zeros(b.unz.size); pg = np.zeros(b.n, np.int64)
         eng.plan.get_factors(lg, None if spd else ug, None if spd else pg)
@@ -42,21 +48,82 @@ def _worker(rank, world, port, spd, q):
         rhs = torch.from_numpy(np.ascontiguousarray(bb[b.order.rperm - 1])).cuda()
         ds.solve(rhs)
         x = rhs.cpu().numpy()[b.order.rinvp - 1]
-        q.put((rank, flag, e_l, e_u, piv_ok, residual(A, x, bb)))
+        # refactor (same plan, values re-uploaded): the exchange / broadcast machinery must be re-entrant
+        eng.plan.set_values(b.lnz, None if spd else b.unz)
+        flag2 = ds.factor()
+        l2 = np.zeros(b.lnz.size); eng.plan.get_factors(l2)
+        own = np.zeros(b.lnz.size, bool)
+        for r in ds.rng:
+            if int(r[0]) == rank:
+                own[int(r[1]): int(r[1] + r[2])] = True
+        top = np.ones(b.lnz.size, bool)
+        for r in ds.rng:
+            top[int(r[1]): int(r[1] + r[2])] = False
+        same = bool(np.array_equal(l2[own | top], lg[own | top]))
+        q.put((rank, min(flag, flag2), e_l, e_u, piv_ok, residual(A, x, bb), same, eng.plan.stat(13), eng.plan.stat(6)))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("spd", [True, False])
-def test_two_gpu_subtree_partition(spd):
-    if torch.cuda.device_count() < 2:
+CASES = [
+    (True, 14, {}),
+    (False, 14, {}),
+    (True, 16, {"SPK_OB_STEPS": "1", "SPK_PS_WIDTH": "8"}),      # top-set fronts of many outer blocks: real block-cyclic ownership
+    (True, 16, {"SPK_OB_STEPS": "2", "SPK_PS_WIDTH": "16"}),
+    (True, 32, {}),                                              # root front of several default-size outer blocks
+    (False, 24, {}),
+]
+
+
+@pytest.mark.parametrize("spd,g,env", CASES, ids=[f"{'spd' if c[0] else 'lu'}-{c[1]}" + "".join(f"-{k[4:]}{v}" for k, v in c[2].items()) for c in CASES])
+def test_multi_gpu_one_process_per_gpu(spd, g, env):
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
         pytest.skip("needs 2 GPUs")
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, spd, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, spd, g, env, q)) for r in range(world)]
     for p in procs: p.start()
-    res = [q.get(timeout=300) for _ in range(2)]
+    res = [q.get(timeout=600) for _ in range(world)]
     for p in procs: p.join(timeout=60)
-    for rank, flag, e_l, e_u, piv_ok, resid in res:
+    for rank, flag, e_l, e_u, piv_ok, resid, same, ntop, arena in res:
         assert flag == 0 and e_l < 1e-11 and e_u < 1e-11 and piv_ok and resid < 1e-12
+        assert same, "refactorisation is not bitwise reproducible"
+        assert ntop >= 1
+
+
+@pytest.mark.parametrize("spd", [True, False])
+def test_multi_gpu_single_process_handle(spd):
+    """spk_multi_*: one handle, one host thread per GPU inside the library."""
+    ngpus = min(torch.cuda.device_count(), 4)
+    if ngpus < 2:
+        pytest.skip("needs 2 GPUs")
+    import sparspak_jl_b200 as spk
+    from sparspak_jl_b200 import _cudalib
+    from common import prepare, oracle_factor, spd_mask, rel_err, residual, M
+    g = 20
+    A = M.laplacian3d(g) if spd else M.convdiff3d(g)
+    s = prepare(A, spd, spk.nd_grid_order(g, g, g))
+    b = s.slvr
+    mp_ = _cudalib.MultiPlan(b, ngpus)
+    dest, nzval = b._inmatrix_map(A)
+    mp_.inmatrix(nzval, dest)
+    assert mp_.factor() == 0
+    lg = np.zeros(b.lnz.size); ug = np.zeros(b.unz.size); pg = np.zeros(b.n, np.int64)
+    mp_.get_factors(lg, None if spd else ug, None if spd else pg)
+    lo, uo, po, _ = oracle_factor(b)
+    assert rel_err(lg, lo, spd_mask(b)) < 1e-11
+    if not spd:
+        assert np.array_equal(pg, po) and rel_err(ug, uo) < 1e-11
+    mp_.set_perm(b.order.rperm, b.order.rinvp)
+    bb = M.rhs_for(A)
+    x = bb.copy(); mp_.triangularsolve(x)
+    assert residual(A, x, bb) < 1e-12
+    B = np.asfortranarray(np.random.default_rng(3).random((b.n, 5)))
+    X = B.copy(order="F"); mp_.triangularsolve(X)
+    assert max(residual(A, X[:, j], B[:, j]) for j in range(5)) < 1e-12
+    # every part holds only its own subtrees + the top set
+    single = _cudalib.Plan(b, host_only=True).stat(6)
+    assert max(mp_.part_stat(r, 6) for r in range(ngpus)) < 0.85 * single
+    mp_.destroy()

@@ -28,7 +28,12 @@ class SimEngine:
         L.sim_ptr.argtypes = [C.c_void_p, C.c_int]; L.sim_ptr.restype = C.c_void_p
         L.sim_len.argtypes = [C.c_void_p, C.c_int]; L.sim_len.restype = C.c_int64
         L.sim_xchg_info.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p]; L.sim_xchg_info.restype = C.c_int64
+        L.sim_top_next.argtypes = [C.c_void_p, C.c_int64]; L.sim_top_next.restype = C.c_int64
+        L.sim_bcast_info.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]; L.sim_bcast_info.restype = C.c_int64
+        L.sim_iflag.argtypes = [C.c_void_p]; L.sim_iflag.restype = C.c_int64
+        L.sim_stat.argtypes = [C.c_void_p, C.c_int]; L.sim_stat.restype = C.c_int64
         self.L, self.b, self.lu = L, b, not b.spd
+        self.nbcast = 0
         self.h = L.sim_create2(b.n, b.nsuper, b.xsuper, b.snode, b.xlindx, b.lindx, b.xlnz,
                                None if b.spd else b.xunz.ctypes.data, 1, 4, 0.02, 1, rank, world)
         assert self.h
@@ -60,10 +65,26 @@ class SimEngine:
     def ranges(self): return self._list(1)
 
     def factor_phase(self, phase):
-        fl = int(self.L.sim_factor_list(self.h, 1 if phase == 0 else 2))
-        if phase == 1:
-            self.L.sim_store(self.h)
-        return fl
+        assert phase == 0
+        return int(self.L.sim_factor_list(self.h, 1))
+
+    def factor_top(self, bcast):
+        """Top-set launch list (exchange + distributed / replicated factorisation): the simulator stops at every
+        K_BCAST launch, `bcast(offset, length, root)` performs it on the arena view, then the list continues."""
+        cur = 0
+        buf = np.zeros(3, np.int64)
+        while True:
+            li = int(self.L.sim_top_next(self.h, cur))
+            assert li >= -1
+            if li < 0:
+                break
+            for i in range(int(self.L.sim_bcast_info(self.h, li, 0, None))):
+                self.L.sim_bcast_info(self.h, li, i, buf.ctypes.data)
+                bcast(int(buf[0]), int(buf[1]), int(buf[2]))
+                self.nbcast += 1
+            cur = li + 1
+        self.L.sim_store(self.h)
+        return int(self.L.sim_iflag(self.h))
 
     def solve_phase(self, rhs, phase):
         self.L.sim_solve_phase(self.h, rhs.numpy(), phase)
@@ -79,7 +100,7 @@ def _worker(rank, world, port, spd, q, env=None):
         import sparspak_jl_b200 as spk
         from sparspak_jl_b200.multigpu import DistributedSolver
         from common import prepare, oracle_factor, spd_mask, rel_err, residual, M
-        g = 10
+        g = int(os.environ.get("TEST_GRID", "10"))
         A = M.laplacian3d(g) if spd else M.convdiff3d(g)
         s = prepare(A, spd, spk.nd_grid_order(g, g, g), 8)
         b = s.slvr
@@ -97,7 +118,7 @@ def _worker(rank, world, port, spd, q, env=None):
         rhs = torch.from_numpy(np.ascontiguousarray(bb[b.order.rperm - 1]))
         ds.solve(rhs)
         x = rhs.numpy()[b.order.rinvp - 1]
-        q.put((rank, flag, e_l, e_u, piv_ok, residual(A, x, bb), owners, len(ds.fronts)))
+        q.put((rank, flag, e_l, e_u, piv_ok, residual(A, x, bb), owners, len(ds.fronts), int(eng.L.sim_stat(eng.h, 13)), eng.nbcast, int(eng.L.sim_len(eng.h, 5))))
     finally:
         dist.destroy_process_group()
 
@@ -116,10 +137,12 @@ def test_subtree_partition_over_gloo(world, spd):
     res = [q.get(timeout=180) for _ in range(world)]
     for p in procs: p.join(timeout=60)
     assert all(p.exitcode == 0 for p in procs)
-    for rank, flag, e_l, e_u, piv_ok, resid, owners, nx in res:
+    for rank, flag, e_l, e_u, piv_ok, resid, owners, nx, dist_top, nbcast, arena in res:
         assert flag == 0 and e_l < 1e-12 and e_u < 1e-12 and piv_ok and resid < 1e-13
         assert owners == list(range(world))       # every rank owns at least one subtree
         assert nx >= world                        # and at least that many subtree roots are exchanged
+        assert dist_top == (1 if spd else 0)      # LDL^T: distributed top set; LU: replicated
+        assert nbcast >= (nx + 1 if spd else nx)  # the exchange + one broadcast per outer block of the top set
 
 
 def test_parts_without_a_subtree_over_gloo():
@@ -134,6 +157,41 @@ def test_parts_without_a_subtree_over_gloo():
     res = [q.get(timeout=180) for _ in range(world)]
     for p in procs: p.join(timeout=60)
     assert all(p.exitcode == 0 for p in procs)
-    for rank, flag, e_l, e_u, piv_ok, resid, owners, nx in res:
+    for rank, flag, e_l, e_u, piv_ok, resid, owners, nx, dist_top, nbcast, arena in res:
         assert flag == 0 and e_l < 1e-12 and resid < 1e-13
         assert len(owners) < world                # at least one rank has no subtree and idles in phase 0
+
+
+@pytest.mark.parametrize("world,env", [
+    (2, {"SPK_OB_STEPS": "1", "SPK_PS_WIDTH": "8", "TEST_GRID": "12"}),
+    (4, {"SPK_OB_STEPS": "2", "SPK_PS_WIDTH": "8", "TEST_GRID": "12"}),
+    (3, {"SPK_OB_STEPS": "1", "SPK_PS_WIDTH": "16", "TEST_GRID": "11"}),
+    (8, {"SPK_OB_STEPS": "1", "SPK_PS_WIDTH": "8", "TEST_GRID": "12"}),
+])
+def test_distributed_top_set_many_outer_blocks_over_gloo(world, env):
+    """Tiny outer blocks: every top-set front spans many blocks, so the block-cyclic ownership, the panel
+    broadcasts, the U rebuild and the owner-filtered extend-adds between top-set fronts are all exercised."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, True, q, env)) for r in range(world)]
+    for p in procs: p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs: p.join(timeout=60)
+    assert all(p.exitcode == 0 for p in procs)
+    arenas = []
+    for rank, flag, e_l, e_u, piv_ok, resid, owners, nx, dist_top, nbcast, arena in res:
+        assert flag == 0 and e_l < 1e-12 and resid < 1e-13
+        assert dist_top == 1 and nbcast >= nx + 8          # many panel broadcasts
+        arenas.append(arena)
+    # every rank holds storage for its own subtrees + the top set only: well below the single-part arena
+    import sparspak_jl_b200 as spk
+    from common import prepare, HostSim, M
+    g = int(env["TEST_GRID"])
+    os.environ.update({k: v for k, v in env.items() if k.startswith("SPK_")})
+    try:
+        full = HostSim(prepare(M.laplacian3d(g), True, spk.nd_grid_order(g, g, g), 8).slvr, alloc=False).stat(2)
+    finally:
+        for k in env:
+            os.environ.pop(k, None)
+    assert max(arenas) < 0.9 * full
