@@ -788,14 +788,18 @@ inline void build_lists_dist(Plan& P, std::vector<Launch>& out) {
                 ends.push_back(End{f, ob0, e, last ? e : P.psteps[F.ps0 + j + 1].ob_end, last});
             }
             if (ends.empty()) continue;
-            begin(K_BCAST, (int32_t)P.bcasts.size(), lev, j, 2, 1 | 2);
+            // the slab is final once the owner's chain is done (stream 0); on the receivers only the U rebuild of the
+            // previous block (stream 0) touches these columns — the trailing updates (stream 1) never do
+            begin(K_BCAST, (int32_t)P.bcasts.size(), lev, j, 2, 1);
+            bool all_mine = true;
             for (const End& E : ends) {
+                all_mine = all_mine && P.fown[P.ownofs[E.f] + E.ob0] == me;
                 const Front& F = P.fronts[E.f];
                 P.bcasts.push_back(Bcast{F.fofs + (int64_t)E.ob0 * F.ld, (int64_t)F.ld * (E.e - E.ob0), P.fown[P.ownofs[E.f] + E.ob0], E.f});
                 fb.add(1);
             }
             fb.end();
-            begin(K_FILLU, (int32_t)P.fillt.size(), lev, j, 0, 4);
+            begin(K_FILLU, (int32_t)P.fillt.size(), lev, j, 0, all_mine ? 0 : 4);      // the owner already holds the panel
             for (const End& E : ends) {
                 const Front& F = P.fronts[E.f];
                 if (E.e >= F.R) continue;
@@ -861,6 +865,8 @@ inline void partition(Plan& P) {
     // best configuration seen; parts may stay without a subtree if that is faster.
     const double rate = (P.lu ? 2.0 : 1.0) * 22e12 / 2.0;       // `own` counts multiply-adds of the LDL^T pattern
     const double tstep = 75e-6;
+    // distributed top set: + one broadcast, one U rebuild and one strip update per outer block on the chain
+    const double tstep_top = P.dist_top ? 110e-6 : tstep;
     auto own = [&](int32_t f) { double W = P.fronts[f].W, m = P.fronts[f].m; return W * W * W / 3.0 + W * W * m + W * m * m + 1.0; };
     std::vector<double> chain(nf, 0.0);                          // dependent panel steps below and including f, in seconds
     for (int32_t f = 0; f < nf; ++f) {
@@ -877,7 +883,7 @@ inline void partition(Plan& P) {
     };
     auto top_time = [&](const std::vector<int32_t>& tp) {       // fronts of one level share their launches
         std::vector<double> fl(P.nlevels, 0.0), st(P.nlevels, 0.0);
-        for (int32_t f : tp) { int32_t l = P.fronts[f].level; fl[l] += own(f) / rate; st[l] = std::max(st[l], P.fronts[f].nps * tstep); }
+        for (int32_t f : tp) { int32_t l = P.fronts[f].level; fl[l] += own(f) / rate; st[l] = std::max(st[l], P.fronts[f].nps * tstep_top); }
         double t = 0.0;
         // distributed top set: the trailing updates of a level are shared by all parts, the chain of panel steps is not
         for (int32_t l = 0; l < P.nlevels; ++l) t += std::max(P.dist_top ? fl[l] / P.nparts : fl[l], st[l]);

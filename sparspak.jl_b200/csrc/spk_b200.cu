@@ -567,6 +567,10 @@ static int64_t run_top_list(spk_plan* p, const DevCtx& c, const std::vector<Laun
     cudaStream_t S[3] = {p->stream, p->stream2, p->stream_c};
     cudaEvent_t E[3] = {p->evs0, p->evs1, p->evsc};
     for (int q = 0; q < 3; ++q) CK(cudaEventRecord(E[q], S[q]));
+    const char* trace_path = getenv("SPK_TRACE_TOP");   // completion time of every launch of the top-set list (profiling only)
+    std::vector<cudaEvent_t> tev;
+    if (trace_path) { tev.resize(Ls.size() + 1); for (auto& e : tev) cudaEventCreate(&e); cudaEventRecord(tev[0], S[0]); }
+    size_t li = 0;
     for (const Launch& L : Ls) {
         const int sid = L.stream < 3 ? L.stream : 0;
         cudaStream_t st = S[sid];
@@ -589,10 +593,24 @@ static int64_t run_top_list(spk_plan* p, const DevCtx& c, const std::vector<Laun
             if (!p->profile && (L.kind == K_GEMM_B64 || L.kind == K_GEMM_B128)) p->gemm_flops += L.flops;   // profiling mode times phase 0 only
         }
         ++p->launches_factor;
+        if (trace_path) cudaEventRecord(tev[++li], st);
     }
     // join on the main stream
     CK(cudaEventRecord(E[1], S[1])); CK(cudaStreamWaitEvent(S[0], E[1], 0));
     CK(cudaEventRecord(E[2], S[2])); CK(cudaStreamWaitEvent(S[0], E[2], 0));
+    if (trace_path) {
+        CK(cudaStreamSynchronize(S[0]));
+        std::string path = std::string(trace_path) + "." + std::to_string(P.part);
+        if (FILE* f = fopen(path.c_str(), "w")) {
+            fprintf(f, "idx,kind,level,step,stream,tasks,blocks,flops,wait_mask,t_end_ms\n");
+            for (size_t i = 0; i < Ls.size(); ++i) {
+                float t = 0; cudaEventElapsedTime(&t, tev[0], tev[i + 1]);
+                fprintf(f, "%zu,%d,%d,%d,%d,%d,%d,%.6g,%d,%.6f\n", i, Ls[i].kind, Ls[i].level, Ls[i].step, (int)Ls[i].stream, Ls[i].count, Ls[i].nblocks, Ls[i].flops, (int)Ls[i].wait_mask, t);
+            }
+            fclose(f);
+        }
+        for (auto& e : tev) cudaEventDestroy(e);
+    }
     return 0;
 }
 
