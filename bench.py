@@ -379,7 +379,7 @@ def _main(json_out):
     else:
         ds.factor()
     gemm_flops, gemm_ms = plan.statf(4), plan.statf(5)
-    kinds = ["asm", "asm_tail", "diag", "panel", "gemm_small", "gemm_dmma64", "gemm_dmma128"]
+    kinds = ["asm", "asm_tail", "diag", "panel", "gemm_small", "gemm_dmma_128x64", "gemm_dmma_64x64"]
     breakdown = {k: {"ms": plan.statf(10 + i), "launches": int(plan.statf(30 + i))} for i, k in enumerate(kinds)}
     prof_total = plan.statf(2)
     plan.stat(101)
@@ -390,7 +390,7 @@ def _main(json_out):
     phase_ms = (plan.statf(6), plan.statf(7)) if ds is not None else None
     dev_bytes = plan.stat(4)
     n_sub = plan.stat(15) if world > 1 else 1
-    n_dmma_launches = breakdown["gemm_dmma64"]["launches"] + breakdown["gemm_dmma128"]["launches"]
+    n_dmma_launches = breakdown["gemm_dmma_128x64"]["launches"] + breakdown["gemm_dmma_64x64"]["launches"]
     plan.destroy()
     if ds is not None:
         del ds, eng

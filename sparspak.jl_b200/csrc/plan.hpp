@@ -66,6 +66,7 @@ struct GemmTask {         // C -= A * B   inside one frontal matrix (offsets rel
     uint8_t lower;        // only entries on/below the front's diagonal are needed / written (LDL^T)
     uint8_t pad0, pad1, pad2;
 };
+struct GemmTile { int32_t task; uint16_t ti, tj; };   // one C tile of a DMMA launch: task (relative to the launch), tile row / column
 struct AsmTask { int32_t child, parent; };
 struct SolveTask {        // one chunk of a triangular sweep (values read from lnz / unz)
     int64_t lofs, uofs, col0, wofs, posofs;
@@ -73,7 +74,7 @@ struct SolveTask {        // one chunk of a triangular sweep (values read from l
 };
 
 enum Kind : int32_t {
-    K_ASM = 0, K_ASM_TAIL, K_DIAG, K_PANEL, K_GEMM, K_GEMM_B64, K_GEMM_B128,
+    K_ASM = 0, K_ASM_TAIL, K_DIAG, K_PANEL, K_GEMM, K_GEMM_B64 /* DMMA, 128 x 64 tiles */, K_GEMM_T64 /* DMMA, 64 x 64 tiles */,
     K_FWD_GATHER, K_FWD_DIAG, K_FWD_UPDATE, K_BWD_GATHER, K_BWD_UPDATE, K_BWD_DIAG, K_FWD_FRONT, K_BWD_FRONT,
     // solve on the frontal matrices, one step per PANEL STEP (dense, uniformly strided panels)
     K_PF_FRONT, K_PF_DIAG, K_PF_UPDATE, K_PB_FRONT, K_PB_UPDATE, K_PB_DIAG,
@@ -91,6 +92,10 @@ struct Launch {
     int32_t maxw;             // widest panel step in a DIAG / PANEL launch (sizes its shared memory)
     // look-ahead: stream 0 = panel stream (diag / panel / in-block updates / next-block strip),
     // stream 1 = trailing-update stream (the bulk GEMMs).  Listed order is always a valid serial order.
+    // DMMA launches (persistent kernel over a tile list): tiles [tile0, tile0 + ntiles) of Plan::tiles, atomic tile
+    // counter `ctr`, and `reserve`: leave that many block slots of the machine free (trailing updates that run beside
+    // the latency-critical diagonal / panel chain of the next outer block)
+    int64_t tile0; int32_t ntiles, ctr; int32_t reserve;
     uint8_t stream, wait_other, record, wait_mask;   // wait_other: wait for the other stream's last record first
     // distributed lists use three streams (0 panel, 1 trailing update, 2 communication) and wait_mask: bit s = wait
     // for the last record of stream s before launching
@@ -102,7 +107,8 @@ constexpr int ASM_ROUNDS = 8;      // children handled by per-round launches; th
 constexpr int ASM_TPB = 256, ASM_EPT = 4, ASM_COLS = 8;   // extend-add: rows per block, (tail kernel) entries per thread, columns per block
 constexpr int PANEL_ROWS = 128;    // rows (L side) / columns (U side) per panel block
 constexpr int GEMM_TM = 64, GEMM_TN = 64;   // C tile of the small-tile kernel
-constexpr int BIG_TM = 128;                 // C tile rows of the DMMA kernels (TN = 64 or 128)
+constexpr int BIG_TM = 128;                 // C tile rows of the big DMMA kernel (128 x 64 tiles; the small one: 64 x 64)
+constexpr int DMMA_FILL = 296;              // a launch with fewer 128-row tiles than this (2 blocks x 148 SMs) uses 64-row tiles
 constexpr int UPD_ROWS = 256;      // rows per block in the forward-solve update
 constexpr int SV_ROWS = 256;       // rows / columns per block in the panel-step solve kernels
 constexpr int BWD_COLS = 1;        // columns per block in the backward-solve update (one block reduces one column)
@@ -133,11 +139,13 @@ struct Plan {
     int ob_width = OB_WIDTH, ps_width = PS_WIDTH, ob_steps = OB_STEPS;
     bool lookahead = true;
     bool left_inblock = true;                  // SPK_LL=0: right-looking rank-w updates inside an outer block (LU always)
-    bool no_b128 = true;                      // DMMA tasks all use 128x64 tiles, two blocks per SM (measured best)
     int relax_abs = RELAX_ABS; double relax_frac = RELAX_FRAC;
     // schedules
     std::vector<AsmTask> asmt;
     std::vector<GemmTask> gemmt;
+    std::vector<GemmTile> tiles;              // tile lists of the DMMA launches
+    int32_t nctr = 0;                         // atomic tile counters (one per DMMA launch)
+    int32_t gemm_reserve = 32;                // SPK_GEMM_RESERVE
     std::vector<int32_t> pslist;              // panel-step ids, grouped per DIAG/PANEL launch
     std::vector<SolveTask> solvet;            // one per chunk
     std::vector<int32_t> gathert;
@@ -370,28 +378,55 @@ struct LaunchBuilder {
 
 inline int32_t gemm_blocks(const GemmTask& t, int tm, int tn) { return cdiv(t.m, tm) * cdiv(t.n, tn); }
 
+// Tiles of a DMMA task that have work.  The kernel moves a task's origin to the previous even row (sa): tile rows
+// are counted from there.  LDL^T updates skip the tiles strictly above the diagonal.
+inline void dmma_tiles(const GemmTask& t, int tm, int tn, int32_t task_rel, std::vector<GemmTile>* out, int64_t* count) {
+    const int sa = (int)(t.a0 & 1);
+    const int mp = t.m + sa, roffp = t.roff - sa;
+    const int mt = cdiv(mp, tm), nt = cdiv(t.n, tn);
+    for (int tj = 0; tj < nt; ++tj)
+        for (int ti = 0; ti < mt; ++ti) {
+            if (t.lower && ti * tm + tm - 1 + roffp < tj * tn) continue;
+            if (out) out->push_back(GemmTile{task_rel, (uint16_t)ti, (uint16_t)tj});
+            if (count) ++*count;
+        }
+}
+
 struct GemmBatch {
     struct Item { GemmTask t; double flops; };
-    std::vector<Item> small, b64, b128;
+    std::vector<Item> small, dmma;
     void add(const Plan& P, const GemmTask& t, double flops) {
         if (t.m <= 0 || t.n <= 0 || t.k <= 0) return;
-        if (P.use_dmma && !P.no_b128 && t.m >= 128 && t.n > 64) b128.push_back({t, flops});
-        else if (P.use_dmma && t.m >= 128 && t.n > 16) b64.push_back({t, flops});
+        if (P.use_dmma && t.m >= 64 && t.n > 16) dmma.push_back({t, flops});
         else small.push_back({t, flops});
     }
-    bool empty() const { return small.empty() && b64.empty() && b128.empty(); }
+    bool empty() const { return small.empty() && dmma.empty(); }
     // every launch of the batch waits for the other stream (cheap) and records its own completion
-    void emit(Plan& P, LaunchBuilder& fb, int32_t lev, int32_t step, int stream = 0, int wait_other = 0, int record = 0) {
-        auto one = [&](std::vector<Item>& v, int32_t kind, int tm, int tn) {
-            if (v.empty()) return;
-            fb.begin(kind, (int32_t)P.gemmt.size(), lev, step, stream, wait_other, record);
-            for (const Item& it : v) { P.gemmt.push_back(it.t); fb.add(gemm_blocks(it.t, tm, tn), it.flops, std::max(it.t.m, it.t.n)); }   // maxw = largest C dimension of the launch
+    void emit(Plan& P, LaunchBuilder& fb, int32_t lev, int32_t step, int stream = 0, int wait_other = 0, int record = 0, int reserve = 0) {
+        if (!small.empty()) {
+            fb.begin(K_GEMM, (int32_t)P.gemmt.size(), lev, step, stream, wait_other, record);
+            for (const Item& it : small) { P.gemmt.push_back(it.t); fb.add(gemm_blocks(it.t, GEMM_TM, GEMM_TN), it.flops, std::max(it.t.m, it.t.n)); }   // maxw = largest C dimension of the launch
             fb.end();
-            v.clear();
-        };
-        one(small, K_GEMM, GEMM_TM, GEMM_TN);
-        one(b64, K_GEMM_B64, BIG_TM, 64);
-        one(b128, K_GEMM_B128, BIG_TM, 128);
+            small.clear();
+        }
+        if (!dmma.empty()) {
+            int64_t big = 0;
+            for (const Item& it : dmma) dmma_tiles(it.t, BIG_TM, 64, 0, nullptr, &big);
+            const bool t64 = big < DMMA_FILL;                       // 128-row tiles would leave SMs idle
+            const int tm = t64 ? 64 : BIG_TM;
+            fb.begin(t64 ? K_GEMM_T64 : K_GEMM_B64, (int32_t)P.gemmt.size(), lev, step, stream, wait_other, record);
+            fb.cur.tile0 = (int64_t)P.tiles.size(); fb.cur.ctr = P.nctr++; fb.cur.reserve = reserve;
+            int32_t rel = 0;
+            for (const Item& it : dmma) {
+                P.gemmt.push_back(it.t);
+                const size_t n0 = P.tiles.size();
+                dmma_tiles(it.t, tm, 64, rel++, &P.tiles, nullptr);
+                fb.add((int32_t)(P.tiles.size() - n0), it.flops, std::max(it.t.m, it.t.n));
+            }
+            fb.cur.ntiles = (int32_t)(P.tiles.size() - (size_t)fb.cur.tile0);
+            fb.end();
+            dmma.clear();
+        }
     }
 };
 
@@ -427,7 +462,7 @@ inline void plan_env_overrides(Plan& P) {        // test / tuning knobs
     if (const char* e = getenv("SPK_PIPES")) P.pipes = std::min(4, std::max(1, atoi(e)));
     if (const char* e = getenv("SPK_SOLVE_LNZ")) P.solve_on_fronts = e[0] != '1';
     if (const char* e = getenv("SPK_PS_WIDTH")) P.ps_width = std::max(1, atoi(e));
-    if (const char* e = getenv("SPK_DMMA_VARIANT")) P.no_b128 = atoi(e) >= 2;
+    if (const char* e = getenv("SPK_GEMM_RESERVE")) P.gemm_reserve = std::max(0, atoi(e));
     if (const char* e = getenv("SPK_DIST_TOP")) P.dist_top_env = e[0] != '0';
 }
 
@@ -537,7 +572,8 @@ inline void build_lists(Plan& P, const std::vector<uint8_t>& sel, std::vector<La
             }
             // strips must wait for the previous block's REST (same target region); rests wait for this step's panels
             gp.emit(P, fb, lev, j, 0, boundary ? 1 : 0, 1);
-            gg.emit(P, fb, lev, j, 1, 1, 1);
+            // the bulk update runs beside the next block's diagonal / panel chain: leave that chain some block slots
+            gg.emit(P, fb, lev, j, 1, 1, 1, (j + 1 < maxnps) ? P.gemm_reserve : 0);
         }
     }
 
@@ -707,9 +743,9 @@ inline void build_lists_dist(Plan& P, std::vector<Launch>& out) {
     auto begin = [&](int32_t kind, int32_t first, int32_t lev, int32_t step, int stream, int wait_mask) {
         fb.begin(kind, first, lev, step, stream, 0, 1); fb.cur.wait_mask = (uint8_t)wait_mask;
     };
-    auto emit = [&](GemmBatch& g, int32_t lev, int32_t step, int stream, int wait_mask) {
+    auto emit = [&](GemmBatch& g, int32_t lev, int32_t step, int stream, int wait_mask, int reserve = 0) {
         const size_t n0 = out.size();
-        g.emit(P, fb, lev, step, stream, 0, 1);
+        g.emit(P, fb, lev, step, stream, 0, 1, reserve);
         for (size_t i = n0; i < out.size(); ++i) out[i].wait_mask = (uint8_t)wait_mask;
     };
     // the one exchange: update-matrix column slabs of the subtree roots, from their owners to everybody
@@ -827,7 +863,7 @@ inline void build_lists_dist(Plan& P, std::vector<Launch>& out) {
                 }
             }
             emit(gp, lev, j, 0, 2);                           // after the previous block's rest (same target region)
-            emit(gg, lev, j, 1, 1);                           // after this block's U is in place
+            emit(gg, lev, j, 1, 1, (j + 1 < maxnps) ? P.gemm_reserve : 0);   // after this block's U is in place; beside the next chain
         }
     }
 }

@@ -45,6 +45,7 @@ struct spk_plan {
     cudaStream_t stream_c = nullptr; cudaEvent_t evsc = nullptr;   // communication stream of a multi-part plan (NCCL broadcasts)
     ncclComm_t comm = nullptr; bool comm_owned = false;  // communicator over the parts (spk_plan_comm_init / spk_multi_create)
     int8_t* d_fown = nullptr; FillTask* d_fillt = nullptr;
+    GemmTile* d_tiles = nullptr; int32_t* d_tilectr = nullptr; int num_sms = 148;
     double ms_xchg = 0;
     // tree pipelines (Plan::pipes): stream / event pair per pipeline; pair 0 = (stream, stream2, evs0, evs1)
     cudaStream_t pst[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
@@ -219,6 +220,8 @@ SPK_API void spk_plan_destroy(spk_plan* p) {
         if (p->evs0) cudaEventDestroy(p->evs0);
         if (p->evs1) cudaEventDestroy(p->evs1);
         if (p->comm && p->comm_owned && nccl_api()) nccl_api()->CommDestroy(p->comm);
+        if (p->d_tiles) cudaFree(p->d_tiles);
+        if (p->d_tilectr) cudaFree(p->d_tilectr);
         if (p->d_fown) cudaFree(p->d_fown);
         if (p->d_fillt) cudaFree(p->d_fillt);
         if (p->evsc) cudaEventDestroy(p->evsc);
@@ -314,6 +317,9 @@ static int64_t plan_upload(spk_plan* p) {
     CK(upload(&p->d_asmt, P.asmt));
     CK(upload(&p->d_gemmt, P.gemmt));
     CK(upload(&p->d_solvet, P.solvet));
+    CK(upload(&p->d_tiles, P.tiles));
+    CK(cudaMalloc((void**)&p->d_tilectr, (size_t)std::max(P.nctr, 1) * sizeof(int32_t)));
+    CK(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, p->device));
     CK(upload(&p->d_fown, P.fown));
     CK(upload(&p->d_fillt, P.fillt));
     CK(cudaMalloc((void**)&p->d_F, std::max<int64_t>(P.arena, 1) * sizeof(double)));
@@ -544,9 +550,13 @@ static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L, 
         else k_gemm_small<<<L.nblocks, 256, 0, st>>>(c, p->d_gemmt + L.first, pfx, L.count);
         break;
     case K_GEMM_B64:
-    case K_GEMM_B128: {
+    case K_GEMM_T64: {
         GemmVariant v = gemm_dmma_variant(L.kind, p->dmma_variant);
-        CK(launch_pdl(v.fn, dim3(L.nblocks), dim3(v.threads), v.smem, st, p->pdl_factor && p->pdl_gemm, c, (const GemmTask*)(p->d_gemmt + L.first), pfx, (int)L.count));
+        int cap = v.blocks_per_sm * p->num_sms - (L.reserve > 0 ? L.reserve * v.blocks_per_sm / 2 : 0);
+        if (cap < p->num_sms) cap = p->num_sms;
+        const int grid = std::min<int>(L.ntiles, cap);
+        CK(launch_pdl(v.fn, dim3(grid), dim3(v.threads), v.smem, st, p->pdl_factor && p->pdl_gemm, c, (const GemmTask*)(p->d_gemmt + L.first),
+                      (const GemmTile*)(p->d_tiles + L.tile0), (int)L.ntiles, (int32_t*)(p->d_tilectr + L.ctr)));
         break;
     }
     case K_FILLU:
@@ -590,7 +600,7 @@ static int64_t run_top_list(spk_plan* p, const DevCtx& c, const std::vector<Laun
             int64_t rc = run_factor_launch(p, c, L, false, 0, st);
             if (rc) return rc;
             if (L.record) CK(cudaEventRecord(E[sid], st));
-            if (!p->profile && (L.kind == K_GEMM_B64 || L.kind == K_GEMM_B128)) p->gemm_flops += L.flops;   // profiling mode times phase 0 only
+            if (!p->profile && (L.kind == K_GEMM_B64 || L.kind == K_GEMM_T64)) p->gemm_flops += L.flops;   // profiling mode times phase 0 only
         }
         ++p->launches_factor;
         if (trace_path) cudaEventRecord(tev[++li], st);
@@ -650,6 +660,7 @@ SPK_API int64_t spk_plan_factor_phase(spk_plan* p, int32_t phase) {
     }
     if (phase <= 0) {
         CK(cudaMemsetAsync(p->d_iflag, 0, sizeof(int32_t), st));
+        CK(cudaMemsetAsync(p->d_tilectr, 0, (size_t)std::max(P.nctr, 1) * sizeof(int32_t), st));    // tile counters of the persistent DMMA launches
         p->launches_factor = 0; p->gemm_flops = 0; p->gemm_ms = 0;
         if (!p->values_in_fronts) {
             // gather the assembled matrix (reference layout) into the zeroed frontal matrices
@@ -686,7 +697,7 @@ SPK_API int64_t spk_plan_factor_phase(spk_plan* p, int32_t phase) {
                 int64_t rc = run_factor_launch(p, c, L, true, v);
                 if (rc) return rc;
                 ++p->launches_factor;
-                if (L.kind == K_GEMM_B64 || L.kind == K_GEMM_B128) p->gemm_flops += L.flops;
+                if (L.kind == K_GEMM_B64 || L.kind == K_GEMM_T64) p->gemm_flops += L.flops;
                 more = true;
             }
         }
@@ -720,7 +731,7 @@ SPK_API int64_t spk_plan_factor_phase(spk_plan* p, int32_t phase) {
         int64_t rc = run_factor_launch(p, c, L, two);
         if (rc) return rc;
         ++p->launches_factor;
-        if (L.kind == K_GEMM_B64 || L.kind == K_GEMM_B128) p->gemm_flops += L.flops;
+        if (L.kind == K_GEMM_B64 || L.kind == K_GEMM_T64) p->gemm_flops += L.flops;
         if (p->profile) cudaEventRecord(evs[++li], st);
         if (trace) cudaEventRecord(tev[++li], p->pst[0][L.stream ? 1 : 0]);
     }
@@ -760,7 +771,7 @@ SPK_API int64_t spk_plan_factor_phase(spk_plan* p, int32_t phase) {
         for (size_t i = 0; i < Ls.size(); ++i) {
             cudaEventElapsedTime(&p->launch_ms[i], evs[i], evs[i + 1]);
             p->kind_ms[Ls[i].kind & 15] += p->launch_ms[i]; p->kind_n[Ls[i].kind & 15]++;
-            if (Ls[i].kind == K_GEMM_B64 || Ls[i].kind == K_GEMM_B128) p->gemm_ms += p->launch_ms[i];
+            if (Ls[i].kind == K_GEMM_B64 || Ls[i].kind == K_GEMM_T64) p->gemm_ms += p->launch_ms[i];
         }
         for (auto& e : evs) cudaEventDestroy(e);
         if (const char* path = getenv("SPK_DUMP_LAUNCHES")) {       // per-launch CSV for profiles/

@@ -136,6 +136,22 @@ static void gemm(Sim& s, const GemmTask& g) {
     for (int j = 0; j < g.n; ++j) for (int i = 0; i < g.m; ++i) if (!(g.lower && i + g.roff < j)) C[i + (size_t)j * g.ld] -= acc[i + (size_t)j * g.m];
 }
 
+// one C tile of a DMMA launch, with the kernel's conventions: origin moved to the previous even row (sa),
+// rows in front of the origin and entries above the diagonal (lower) masked
+static void gemm_tile(Sim& s, const GemmTask& g, const GemmTile& tl, int tm, int tn) {
+    const int sa = (int)(g.a0 & 1);
+    const int mp = g.m + sa, roffp = g.roff - sa;
+    const double* A = s.F.data() + (g.a0 - sa); const double* B = s.F.data() + g.b0;
+    double* C = s.F.data() + (g.c0 - sa);
+    for (int j = tl.tj * tn; j < std::min<int>(g.n, (tl.tj + 1) * tn); ++j)
+        for (int i = std::max<int>(tl.ti * tm, sa); i < std::min<int>(mp, (tl.ti + 1) * tm); ++i) {
+            if (g.lower && i + roffp < j) continue;
+            double acc = 0.0;
+            for (int k = 0; k < g.k; ++k) acc += A[i + (size_t)k * g.ld] * B[(size_t)k + (size_t)j * g.ld];
+            C[i + (size_t)j * g.ld] -= acc;
+        }
+}
+
 API void* sim_create2(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* snode, const int64_t* xlindx,
                       const int64_t* lindx, const int64_t* xlnz, const int64_t* xunz, int use_dmma_buckets,
                       int relax_abs, double relax_frac, int alloc, int part, int nparts);
@@ -181,7 +197,7 @@ API double sim_statf(void* h, int what) {
     Sim* s = (Sim*)h; Plan& P = s->P;
     if (what == 0) return P.flops_struct; if (what == 1) return P.nnzL;
     if (what == 2) { double f = 0; for (auto& L : P.factor_launches) f += L.flops; return f; }
-    if (what == 3) { double f = 0; for (auto& L : P.factor_launches) if (L.kind == K_GEMM_B64 || L.kind == K_GEMM_B128) f += L.flops; return f; }
+    if (what == 3) { double f = 0; for (auto& L : P.factor_launches) if (L.kind == K_GEMM_B64 || L.kind == K_GEMM_T64) f += L.flops; return f; }
     return 0;
 }
 
@@ -198,7 +214,10 @@ static int64_t run_factor_list(Sim* s, const std::vector<Launch>& Ls) {
             } break;
         case K_DIAG: for (int t = 0; t < L.count; ++t) diag(*s, P.psteps[P.pslist[L.first + t]]); break;
         case K_PANEL: for (int t = 0; t < L.count; ++t) panel(*s, P.psteps[P.pslist[L.first + t]]); break;
-        case K_GEMM: case K_GEMM_B64: case K_GEMM_B128: for (int t = 0; t < L.count; ++t) gemm(*s, P.gemmt[L.first + t]); break;
+        case K_GEMM: for (int t = 0; t < L.count; ++t) gemm(*s, P.gemmt[L.first + t]); break;
+        case K_GEMM_B64: case K_GEMM_T64:                       // tile by tile, as the persistent kernel walks its list
+            for (int64_t q = L.tile0; q < L.tile0 + L.ntiles; ++q) gemm_tile(*s, P.gemmt[L.first + P.tiles[q].task], P.tiles[q], L.kind == K_GEMM_T64 ? 64 : BIG_TM, 64);
+            break;
         case K_FILLU:
             for (int t = 0; t < L.count; ++t) {
                 const FillTask& ft = P.fillt[L.first + t];

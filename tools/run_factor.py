@@ -46,7 +46,7 @@ for r in range(a.reps):
     fl = plan.factor()
     print(f"factor {r}: flag {fl} {plan.statf(2):.2f} ms, {plan.statf(0) / plan.statf(2) / 1e6:.1f} GFLOP/s, launches {plan.stat(0)}", flush=True)
     if a.profile:
-        kinds = ["asm", "asm_tail", "diag", "panel", "gemm_small", "gemm_dmma64", "gemm_dmma128"]
+        kinds = ["asm", "asm_tail", "diag", "panel", "gemm_small", "gemm_dmma_128x64", "gemm_dmma_64x64"]
         print("   " + "  ".join(f"{k}={plan.statf(10 + i):.2f}ms/{int(plan.statf(30 + i))}" for i, k in enumerate(kinds)))
         print(f"   dmma: {plan.statf(4) / max(plan.statf(5), 1e-9) / 1e9:.2f} TFLOP/s")
 bb = spk.matrices.rhs_for(A)
