@@ -34,9 +34,11 @@
 namespace spk {
 
 // 16-byte asynchronous copy; `bytes` (0, 8 or 16) are read from global memory, the rest of the 16 is zero-filled
+template <bool CA>
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int bytes) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
+    if (CA) asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
+    else asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -64,7 +66,7 @@ struct DmmaCfg {
 // WARPS_M x WARPS_N warps, each owning a (TM/WARPS_M) x (TN/WARPS_N) sub-tile of the block's C tile.
 template <int TM, int TN, int WARPS_M, int WARPS_N, int MINB, int DM_TK = 16, int DM_STAGES = 4>
 __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, MINB)
-k_gemm_dmma(DevCtx c, const GemmTask* __restrict__ tasks, const GemmTile* __restrict__ tiles, int ntiles, int32_t* __restrict__ counter) {
+k_gemm_dmma(DevCtx c, const GemmTask* __restrict__ tasks, const GemmTile* __restrict__ tiles, int ntiles, int32_t* __restrict__ counter, int flags) {
     using Cfg = DmmaCfg<TM, TN, DM_TK, DM_STAGES>;
     constexpr int DM_LDBK = Cfg::LDBK;
     constexpr int NT = WARPS_M * WARPS_N * 32;
@@ -73,7 +75,8 @@ k_gemm_dmma(DevCtx c, const GemmTask* __restrict__ tasks, const GemmTile* __rest
     constexpr int A_CHUNKS = TM * DM_TK / 2, B_CHUNKS = TN * DM_TK / 2;     // 16-byte chunks per stage
     static_assert(A_CHUNKS % NT == 0 && B_CHUNKS % NT == 0 && NT % TM == 0, "loader shapes");
     extern __shared__ __align__(16) double smem[];
-    __shared__ int s_tile;
+    __shared__ int s_tile, s_iter;
+    if (threadIdx.x == 0) s_iter = 0;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wm0 = (warp % WARPS_M) * WM, wn0 = (warp / WARPS_M) * WN;
@@ -81,11 +84,17 @@ k_gemm_dmma(DevCtx c, const GemmTask* __restrict__ tasks, const GemmTile* __rest
 
     pdl_trigger();
     pdl_wait();
+    const bool ca = flags & 1;                             // operand tiles through L1 (.ca) or L2 only (.cg)
+    if ((flags >> 8) && (blockIdx.x & 1)) {                // de-phase the two co-resident blocks of an SM (flags >> 8 = delay in 256 ns units)
+        const unsigned ns = (unsigned)(flags >> 8) * 256u;
+        for (unsigned waited = 0; waited < ns; waited += 1000u) __nanosleep(1000u);
+    }
     for (;;) {
-        if (tid == 0) s_tile = atomicAdd(counter, 1);
+        if (tid == 0) s_tile = (flags & 2) ? ((int)blockIdx.x + (int)gridDim.x * s_iter) : atomicAdd(counter, 1);
         __syncthreads();                                   // also: the previous tile's epilogue is done with the ring
         const int tile_id = s_tile;
         if (tile_id >= ntiles) break;
+        if (tid == 0) ++s_iter;
         const GemmTile tl = tiles[tile_id];
         const GemmTask g = tasks[tl.task];
         // origin moved to the previous even row / even k (16-byte aligned operand chunks)
@@ -125,7 +134,7 @@ k_gemm_dmma(DevCtx c, const GemmTask* __restrict__ tasks, const GemmTile* __rest
                 int valid = mp - (row0 + r); valid = valid < 0 ? 0 : (valid > 2 ? 2 : valid);
                 if (kg >= kp || kg < sb) valid = 0;                 // past the end, or the zeroed k-slice in front of an odd origin
                 const double* src = valid ? A + (size_t)(row0 + r) + (size_t)kg * ld : A;
-                cp_async16(As + kk * Cfg::LDA + r, src, valid * 8);
+                if (ca) cp_async16<true>(As + kk * Cfg::LDA + r, src, valid * 8); else cp_async16<false>(As + kk * Cfg::LDA + r, src, valid * 8);
             }
 #pragma unroll
             for (int e = tid; e < B_CHUNKS; e += NT) {              // consecutive threads -> consecutive k pairs
@@ -133,7 +142,7 @@ k_gemm_dmma(DevCtx c, const GemmTask* __restrict__ tasks, const GemmTile* __rest
                 int valid = kp - kg; valid = valid < 0 ? 0 : (valid > 2 ? 2 : valid);
                 if (col0 + r >= g.n) valid = 0;
                 const double* src = valid ? B + (size_t)kg + (size_t)(col0 + r) * ld : B;
-                cp_async16(Bs + r * DM_LDBK + kk, src, valid * 8);
+                if (ca) cp_async16<true>(Bs + r * DM_LDBK + kk, src, valid * 8); else cp_async16<false>(Bs + r * DM_LDBK + kk, src, valid * 8);
             }
         };
 
@@ -217,7 +226,7 @@ k_gemm_dmma(DevCtx c, const GemmTask* __restrict__ tasks, const GemmTile* __rest
 // the other's k loop); K_GEMM_T64 = 64 x 64 tiles, 4 warps, four blocks per SM, for launches whose 128-row tiles
 // would not fill the machine (the left-looking in-block updates on the critical path of the top fronts).
 // SPK_DMMA_VARIANT selects the pipeline shape of the 128 x 64 kernel (k per stage, ring depth).
-using GemmKernel = void (*)(DevCtx, const GemmTask*, const GemmTile*, int, int32_t*);
+using GemmKernel = void (*)(DevCtx, const GemmTask*, const GemmTile*, int, int32_t*, int);
 struct GemmVariant { GemmKernel fn; int threads; size_t smem; int blocks_per_sm; };
 inline GemmVariant gemm_dmma_variant(int kind, int variant) {
     if (kind == K_GEMM_T64) return {k_gemm_dmma<64, 64, 2, 2, 4, 16, 3>, 128, DmmaCfg<64, 64, 16, 3>::SMEM, 4};

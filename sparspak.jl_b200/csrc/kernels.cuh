@@ -122,6 +122,8 @@ __device__ __forceinline__ void asm_entry(const DevCtx& c, const DFront& C, cons
 // child entries and the ASM_COLS parent entries they go to are all loaded before the first store (no index
 // division, 2 * ASM_COLS independent loads in flight per thread); rows are contiguous in the child and run-wise
 // contiguous in the parent.  LDL^T: tiles strictly above the diagonal exit at once.
+// FILTER (distributed top-set parents): only the parent columns this part owns.
+template <bool FILTER>
 __global__ void __launch_bounds__(ASM_TPB) k_assemble(DevCtx c, const AsmTask* __restrict__ tasks,
                                                      const int32_t* __restrict__ pfx, int count) {
     int t = find_task(pfx, count, blockIdx.x);
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(ASM_TPB) k_assemble(DevCtx c, const AsmTask* _
     for (int cc = 0; cc < ASM_COLS; ++cc) {
         const int32_t j = j0 + cc;
         bool on = j < m && (c.lu || i >= j);
-        if (on && P.ownofs >= 0) on = c.fown[P.ownofs + rel[j]] == c.me;     // distributed parent: only the columns this part owns
+        if (FILTER) { if (on && P.ownofs >= 0) on = c.fown[P.ownofs + rel[j]] == c.me; }
         pofs[cc] = on ? (int64_t)rel[j] * P.ld : -1;
         v[cc] = on ? __ldcs(src + (int64_t)cc * C.ld) : 0.0;
     }

@@ -154,6 +154,7 @@ struct Plan {
     // multi-GPU (elimination-subtree partition): owner[f] = part that factors front f, or -1 for the TOP SET
     // (the ancestors of all subtree roots), which every part factors redundantly after the exchange.
     int32_t part = 0, nparts = 1;
+    int32_t force_splits = -1;                 // SPK_TOP_SPLITS=k: exactly k fronts split off the top of the tree (experiments)
     int32_t max_subtrees = 1 << 30;            // SPK_MAX_SUBTREES: cap on the number of subtrees (tests: parts left without one)
     std::vector<int32_t> owner;
     std::vector<int32_t> xchg;                 // subtree-root fronts (owner >= 0, parent in the top set)
@@ -462,6 +463,7 @@ inline void plan_env_overrides(Plan& P) {        // test / tuning knobs
     if (const char* e = getenv("SPK_PIPES")) P.pipes = std::min(4, std::max(1, atoi(e)));
     if (const char* e = getenv("SPK_SOLVE_LNZ")) P.solve_on_fronts = e[0] != '1';
     if (const char* e = getenv("SPK_PS_WIDTH")) P.ps_width = std::max(1, atoi(e));
+    if (const char* e = getenv("SPK_TOP_SPLITS")) P.force_splits = atoi(e);
     if (const char* e = getenv("SPK_GEMM_RESERVE")) P.gemm_reserve = std::max(0, atoi(e));
     if (const char* e = getenv("SPK_DIST_TOP")) P.dist_top_env = e[0] != '0';
 }
@@ -902,7 +904,7 @@ inline void partition(Plan& P) {
     const double rate = (P.lu ? 2.0 : 1.0) * 22e12 / 2.0;       // `own` counts multiply-adds of the LDL^T pattern
     const double tstep = 75e-6;
     // distributed top set: + one broadcast, one U rebuild and one strip update per outer block on the chain
-    const double tstep_top = P.dist_top ? 110e-6 : tstep;
+    const double tstep_top = P.dist_top ? 150e-6 : tstep;
     auto own = [&](int32_t f) { double W = P.fronts[f].W, m = P.fronts[f].m; return W * W * W / 3.0 + W * W * m + W * m * m + 1.0; };
     std::vector<double> chain(nf, 0.0);                          // dependent panel steps below and including f, in seconds
     for (int32_t f = 0; f < nf; ++f) {
@@ -928,6 +930,7 @@ inline void partition(Plan& P) {
     std::vector<int32_t> top, best_roots = roots, best_top;
     double best_cost = 1e300;
     for (int iter = 0; iter < 64; ++iter) {
+        if (P.force_splits >= 0 && iter == P.force_splits && roots.size() >= 2) { best_roots = roots; best_top = top; best_cost = 0.0; break; }   // SPK_TOP_SPLITS
         if ((roots.size() >= 2 && (int32_t)roots.size() <= P.max_subtrees) || P.nparts == 1) {
             double cost = top_time(top) + lpt_max(roots);
             if (cost < best_cost) { best_cost = cost; best_roots = roots; best_top = top; }

@@ -81,6 +81,7 @@ struct spk_plan {
     bool panel_smem_only = false;       // SPK_PANEL_SMEM=1: always use the shared-memory panel kernel
     bool diag_smem_only = false;        // SPK_DIAG_SMEM=1: always use the shared-memory diagonal kernel
     int dmma_variant = 4;               // SPK_DMMA_VARIANT (see gemm_dmma.cuh)
+    bool dmma_persist = false; int dmma_flags = 1;     // SPK_DMMA_PERSIST, SPK_DMMA_CA (bit 0), SPK_DMMA_STATIC (bit 1), SPK_DMMA_DEPHASE (us, bits 8..)
     bool values_in_fronts = false;      // inmatrix scattered straight into the fronts
     int64_t w_nrhs = 0, rhs_cap = 0;
     size_t dev_bytes = 0;
@@ -372,6 +373,13 @@ SPK_API spk_plan* spk_plan_create(int64_t n, int64_t nsuper, const int64_t* xsup
     }
     plan_env_overrides(p->P);
     if (const char* e = getenv("SPK_DMMA_VARIANT")) p->dmma_variant = atoi(e);
+    // persistent blocks hold their SM slots for the whole launch, which defeats the stream priorities the look-ahead
+    // relies on (measured: 243.6 ms persistent with 32 reserved slots vs 236.6 ms one block per tile); off by default
+    if (const char* e = getenv("SPK_DMMA_PERSIST")) p->dmma_persist = e[0] != '0';
+    if (const char* e = getenv("SPK_DMMA_CA")) p->dmma_flags = (p->dmma_flags & ~1) | (e[0] != '0' ? 1 : 0);
+    if (const char* e = getenv("SPK_DMMA_STATIC")) p->dmma_flags = (p->dmma_flags & ~2) | (e[0] != '0' ? 2 : 0);
+    if (const char* e = getenv("SPK_DMMA_DEPHASE")) p->dmma_flags = (p->dmma_flags & 255) | ((atoi(e) * 1000 / 256) << 8);
+    if (!p->dmma_persist) p->dmma_flags |= 2;         // one block per tile: tile = blockIdx.x
     if (const char* e = getenv("SPK_DIAG_SMEM")) p->diag_smem_only = e[0] == '1';
     if (const char* e = getenv("SPK_SOLVE_GRAPH")) p->solve_graphs = e[0] != '0';
     if (const char* e = getenv("SPK_DIAG_TG")) p->diag_tg = atoi(e);
@@ -514,7 +522,9 @@ static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L, 
     const bool lu = p->P.lu;
     switch (L.kind) {
     case K_ASM:
-        k_assemble<<<L.nblocks, ASM_TPB, 0, st>>>(c, p->d_asmt + L.first, pfx, L.count); break;
+        if (force && p->P.dist_top) k_assemble<true><<<L.nblocks, ASM_TPB, 0, st>>>(c, p->d_asmt + L.first, pfx, L.count);
+        else k_assemble<false><<<L.nblocks, ASM_TPB, 0, st>>>(c, p->d_asmt + L.first, pfx, L.count);
+        break;
     case K_ASM_TAIL:
         k_assemble_tail<<<L.count, 256, 0, st>>>(c, p->d_asmt + L.first, L.count); break;
     case K_DIAG: {
@@ -554,9 +564,9 @@ static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L, 
         GemmVariant v = gemm_dmma_variant(L.kind, p->dmma_variant);
         int cap = v.blocks_per_sm * p->num_sms - (L.reserve > 0 ? L.reserve * v.blocks_per_sm / 2 : 0);
         if (cap < p->num_sms) cap = p->num_sms;
-        const int grid = std::min<int>(L.ntiles, cap);
+        const int grid = p->dmma_persist ? std::min<int>(L.ntiles, cap) : L.ntiles;      // SPK_DMMA_PERSIST=0: one block per tile
         CK(launch_pdl(v.fn, dim3(grid), dim3(v.threads), v.smem, st, p->pdl_factor && p->pdl_gemm, c, (const GemmTask*)(p->d_gemmt + L.first),
-                      (const GemmTile*)(p->d_tiles + L.tile0), (int)L.ntiles, (int32_t*)(p->d_tilectr + L.ctr)));
+                      (const GemmTile*)(p->d_tiles + L.tile0), (int)L.ntiles, (int32_t*)(p->d_tilectr + L.ctr), (int)p->dmma_flags));
         break;
     }
     case K_FILLU:
