@@ -415,8 +415,13 @@ def _main(json_out):
                   "what": "one call of the stateless _ldltfactor!/_lufactor! drop-in (plan build + pageable lnz/unz H2D + factor + D2H)"}
 
     tmax = torch.tensor([factor_ms, solve_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    rank_phases = None
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ph = torch.tensor([phase_ms[0], phase_ms[1]], dtype=torch.float64, device="cuda")
+        allph = [torch.zeros_like(ph) for _ in range(world)]
+        dist.all_gather(allph, ph)
+        rank_phases = [[round(float(v), 2) for v in t.tolist()] for t in allph]     # per rank: own subtrees, top set (device events)
     factor_ms, solve_ms, e2e_ms = [float(v) for v in tmax.tolist()]
     if rank != 0:
         if world > 1:
@@ -448,7 +453,7 @@ def _main(json_out):
                      "kernel_flops": gemm_flops, "kernel_ms": gemm_ms, "launches": n_dmma_launches,
                      "flops_per_launch": gemm_flops / max(n_dmma_launches, 1),
                      "share_of_factor": gemm_ms / prof_total if prof_total else None},
-        "breakdown_ms": breakdown, "phase_ms": phase_ms,
+        "breakdown_ms": breakdown, "phase_ms": phase_ms, "rank_phase_ms": rank_phases,
         "wall_s_timed_region": wall,
     }
     if not args.no_cpu_baseline:

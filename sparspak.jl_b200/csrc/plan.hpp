@@ -20,6 +20,7 @@
 // (tests/hostsim) to validate the schedule independently of the kernels.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -901,7 +902,8 @@ inline void partition(Plan& P) {
     // when flops still balance better (96^3 on 8 GPUs: 8 subtrees + 6 replicated top fronts ran slower than
     // 4 subtrees + 2).  Keep splitting the largest splittable subtree (it joins the top set) and remember the
     // best configuration seen; parts may stay without a subtree if that is faster.
-    const double rate = (P.lu ? 2.0 : 1.0) * 22e12 / 2.0;       // `own` counts multiply-adds of the LDL^T pattern
+    // `own` below = the LDL^T flops of a front (LU: twice that); measured update rate ~24 TFLOP/s
+    const double rate = (P.lu ? 0.5 : 1.0) * 24e12;
     const double tstep = 75e-6;
     // distributed top set: + one broadcast, one U rebuild and one strip update per outer block on the chain
     const double tstep_top = P.dist_top ? 150e-6 : tstep;
@@ -933,7 +935,8 @@ inline void partition(Plan& P) {
         if (P.force_splits >= 0 && iter == P.force_splits && roots.size() >= 2) { best_roots = roots; best_top = top; best_cost = 0.0; break; }   // SPK_TOP_SPLITS
         if ((roots.size() >= 2 && (int32_t)roots.size() <= P.max_subtrees) || P.nparts == 1) {
             double cost = top_time(top) + lpt_max(roots);
-            if (cost < best_cost) { best_cost = cost; best_roots = roots; best_top = top; }
+            if (getenv("SPK_PARTITION_DEBUG")) fprintf(stderr, "[partition] parts=%d splits=%d subtrees=%zu top=%.1f ms subtrees(LPT max)=%.1f ms total=%.1f ms\n", P.nparts, iter, roots.size(), top_time(top) * 1e3, lpt_max(roots) * 1e3, cost * 1e3);
+            if (cost < 0.98 * best_cost) { best_cost = cost; best_roots = roots; best_top = top; }   // ties go to the shallower cut
         }
         int32_t pick = -1;
         for (size_t i = 0; i < roots.size(); ++i)
