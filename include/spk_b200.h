@@ -32,7 +32,9 @@ extern "C" {
 #define SPK_API
 #endif
 
-/* ---- stateless drop-ins: one call = upload, compute on the GPU, download ------------- */
+/* ---- stateless drop-ins: one call = upload, compute on the GPU, download -------------
+ * The plans behind these calls are CACHED per structure (and the factors stay resident: a solve that presents the
+ * arrays the last factor call wrote back does not upload them again); see spk_cache_clear below. */
 
 /* replaces _lufactor!(n,nsuper,xsuper,snode,xlindx,lindx,xlnz,lnz,xunz,unz,ipvt)
  * src/SparseMethod/SpkLUFactor.jl:60-255, called from _factor! SpkSparseBase.jl:384 */
@@ -139,6 +141,12 @@ SPK_API int64_t spk_plan_set_matrix(spk_plan* p, int64_t nnz, const int64_t* col
 SPK_API int64_t spk_plan_residual(spk_plan* p, const double* b, const double* x, int64_t nrhs, int64_t ld, double* res_or_null, double* relnorm);
 SPK_API int64_t spk_plan_refine(spk_plan* p, const double* b, double* x, int64_t nrhs, int64_t ld, int32_t maxit, double tol, double* relnorm);
 
+/* 1-norm condition estimate cond_1(A) ~ ||A||_1 * est(||inv(A)||_1) with the resident factors (needs
+ * spk_plan_set_matrix, spk_plan_set_perm and a factorisation).  LDL^T plans: Hager / Higham (LAPACK xLACON);
+ * LU plans: a probing LOWER BOUND (no transposed sweeps in the engine), flagged in info2[1].
+ * out2 = {||A||_1, estimate of ||inv(A)||_1} (may be NULL), info2 = {solves used, 1 if lower bound only}. */
+SPK_API double spk_plan_condest(spk_plan* p, double* out2, int32_t* info2);
+
 /* Float32 callers of a plan (the plan itself stays FP64) */
 SPK_API int64_t spk_plan_inmatrix_f32(spk_plan* p, int64_t nnz, const int64_t* dest_or_null, const float* nzval);
 SPK_API int64_t spk_plan_get_factors_f32(spk_plan* p, float* lnz, float* unz, int64_t* ipvt);
@@ -192,6 +200,8 @@ SPK_API int64_t spk_plan_stat(spk_plan* p, int32_t what);
  *       4 flops executed by the DMMA trailing-update kernels in the last factor, 5 ms spent in them
  *       (5 and 10+kind / 30+kind = ms / launches per kernel kind need profiling mode: spk_plan_stat(p, 100)) */
 SPK_API double  spk_plan_statf(spk_plan* p, int32_t what);
+/* frees the plans cached behind the stateless drop-ins (see spk_b200.cu: plan cache; SPK_PLAN_CACHE=<k>, 0 = off) */
+SPK_API void spk_cache_clear(void);
 SPK_API const char* spk_last_error(void);
 SPK_API int32_t spk_device_count(void);
 SPK_API const char* spk_version(void);

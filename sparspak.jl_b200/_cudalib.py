@@ -23,7 +23,7 @@ SYMBOLS = [
     "spk_plan_triangularsolve", "spk_plan_device_ptr", "spk_plan_device_len", "spk_plan_factor_phase",
     "spk_plan_solve_device", "spk_plan_solve_phase", "spk_nccl_unique_id", "spk_plan_comm_init", "spk_plan_factor_multi", "spk_plan_solve_multi",
     "spk_multi_create", "spk_multi_destroy", "spk_multi_plan", "spk_multi_inmatrix", "spk_multi_set_values", "spk_multi_factor",
-    "spk_multi_get_factors", "spk_multi_set_perm", "spk_multi_triangularsolve", "spk_plan_xchg_info", "spk_plan_stat", "spk_plan_statf", "spk_last_error", "spk_device_count", "spk_version",
+    "spk_multi_get_factors", "spk_multi_set_perm", "spk_multi_triangularsolve", "spk_plan_xchg_info", "spk_plan_stat", "spk_plan_statf", "spk_plan_condest", "spk_cache_clear", "spk_last_error", "spk_device_count", "spk_version",
 ]
 
 
@@ -115,6 +115,9 @@ def lib():
     L.spk_plan_factor_multi.restype = i64
     L.spk_plan_solve_multi.argtypes = [vp, vp, i64, i64]
     L.spk_plan_solve_multi.restype = i64
+    L.spk_plan_condest.argtypes = [vp, vp, vp]
+    L.spk_plan_condest.restype = dbl
+    L.spk_cache_clear.restype = None
     L.spk_multi_create.argtypes = [i64, i64, I64P, I64P, I64P, I64P, I64P, vp, i32]
     L.spk_multi_create.restype = vp
     L.spk_multi_destroy.argtypes = [vp]
@@ -215,6 +218,14 @@ class Plan:
         if rc < 0:
             self._ck(rc, "spk_plan_refine")
         return int(rc), rel
+
+    def condest(self):
+        """(cond_1 estimate, ||A||_1, estimate of ||inv(A)||_1, solves used, lower_bound_only)"""
+        out = np.zeros(2); info = np.zeros(2, np.int32)
+        c = float(self.L.spk_plan_condest(self.h, out.ctypes.data, info.ctypes.data))
+        if c < 0:
+            raise SpkError("spk_plan_condest failed: " + last_error())
+        return c, float(out[0]), float(out[1]), int(info[0]), bool(info[1])
 
     def reassemble(self):
         self._ck(self.L.spk_plan_reassemble(self.h), "spk_plan_reassemble")

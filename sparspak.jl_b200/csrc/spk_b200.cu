@@ -1331,95 +1331,234 @@ SPK_API double spk_plan_statf(spk_plan* p, int32_t what) {
 }
 
 // ---- stateless drop-ins -------------------------------------------------------------------
+// The reference's own call sites pass flat arrays only (SpkSparseBase.jl:384,409-411; SpkSparseSpdBase.jl:325,351),
+// so these entry points have no handle to keep.  Behind them sits a small PLAN CACHE keyed on the structure
+// (n, nsuper, LU / LDL^T, hash of xsuper / xlindx / lindx / xlnz): `_triangularsolve!` calls `_lulsolve!` then
+// `_luusolve!` for every right-hand side, and neither should re-analyse the structure, reallocate and zero tens
+// of GB of frontal storage, or — when the arrays are untouched since the factorisation that produced them —
+// upload the factors again.  A cached plan remembers the host address and a sampled fingerprint of the lnz / unz /
+// ipiv it wrote back; a solve that presents the same arrays uses the resident factors, anything else is uploaded.
+// SPK_PLAN_CACHE=0 disables the cache (every call builds and destroys its plan), SPK_PLAN_CACHE=<k> keeps k plans
+// (default 2); spk_cache_clear() frees them.
 static int64_t n_from_xsuper(int64_t nsuper, const int64_t* xsuper) { return xsuper[nsuper] - 1; }
+
+struct CacheEntry {
+    uint64_t key = 0; int64_t n = 0, nsuper = 0; bool lu = false;
+    spk_plan* plan = nullptr;
+    const void* h_lnz = nullptr; const void* h_unz = nullptr; const void* h_ipiv = nullptr;
+    uint64_t fp[3] = {0, 0, 0};                     // sampled fingerprints of lnz / unz / ipiv as written back
+    bool resident = false; bool f32 = false;
+    uint64_t stamp = 0;
+};
+static std::mutex g_cache_mu;
+static std::vector<CacheEntry> g_cache;
+static uint64_t g_cache_clock = 0;
+
+static uint64_t fnv(const void* data, size_t bytes, uint64_t h) {
+    const uint64_t* w = (const uint64_t*)data;
+    for (size_t i = 0; i < bytes / 8; ++i) { h ^= w[i]; h *= 1099511628211ull; }
+    return h;
+}
+static uint64_t structure_key(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* xlindx, const int64_t* lindx, const int64_t* xlnz, bool lu) {
+    uint64_t h = 1469598103934665603ull ^ (uint64_t)n * 31 ^ (uint64_t)nsuper * 131 ^ (lu ? 0x9e3779b97f4a7c15ull : 0);
+    h = fnv(xsuper, (size_t)(nsuper + 1) * 8, h);
+    h = fnv(xlindx, (size_t)(nsuper + 1) * 8, h);
+    h = fnv(lindx, (size_t)(xlindx[nsuper] - 1) * 8, h);
+    h = fnv(xlnz, (size_t)(n + 1) * 8, h);
+    return h;
+}
+// sampled fingerprint of one factor array (4096 evenly spaced entries + the last one); es = bytes per value
+static uint64_t array_fingerprint(const void* a, int64_t len, int es) {
+    uint64_t h = 1469598103934665603ull;
+    if (!a || len <= 0) return h;
+    const int64_t step = std::max<int64_t>(1, len / 4096);
+    for (int64_t i = 0; i < len; i += step) { uint64_t v = 0; memcpy(&v, (const char*)a + i * es, es); h ^= v + (uint64_t)i; h *= 1099511628211ull; }
+    uint64_t v = 0; memcpy(&v, (const char*)a + (len - 1) * es, es); h ^= v; h *= 1099511628211ull;
+    return h;
+}
+static int cache_capacity() {
+    static int cap = -1;
+    if (cap < 0) { const char* e = getenv("SPK_PLAN_CACHE"); cap = e ? std::max(0, atoi(e)) : 2; }
+    return cap;
+}
+// returns the cached plan for this structure (building it on a miss); *slot = its cache entry or nullptr when uncached
+static spk_plan* cached_plan(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* snode, const int64_t* xlindx,
+                             const int64_t* lindx, const int64_t* xlnz, const int64_t* xunz, bool lu, CacheEntry** slot) {
+    *slot = nullptr;
+    std::vector<int64_t> sn, xu;
+    if (!snode) { sn.resize(n); for (int64_t s = 0; s < nsuper; ++s) for (int64_t j = xsuper[s]; j < xsuper[s + 1]; ++j) sn[j - 1] = s + 1; snode = sn.data(); }
+    if (lu && !xunz) {                                   // `_lulsolve!` gets no xunz: rebuild it from the structure
+        xu.resize(n + 1);
+        int64_t up = 1;
+        for (int64_t s = 0; s < nsuper; ++s) {
+            int64_t w = xsuper[s + 1] - xsuper[s], len = xlindx[s + 1] - xlindx[s];
+            for (int64_t j = xsuper[s]; j < xsuper[s + 1]; ++j) { xu[j - 1] = up; up += len - w; }
+        }
+        xu[n] = up; xunz = xu.data();
+    }
+    if (cache_capacity() == 0) return spk_plan_create(n, nsuper, xsuper, snode, xlindx, lindx, xlnz, lu ? xunz : nullptr, 0, 0, 1);
+    const uint64_t key = structure_key(n, nsuper, xsuper, xlindx, lindx, xlnz, lu);
+    for (CacheEntry& e : g_cache)
+        if (e.key == key && e.n == n && e.nsuper == nsuper && e.lu == lu) { e.stamp = ++g_cache_clock; *slot = &e; return e.plan; }
+    if ((int)g_cache.size() >= cache_capacity()) {       // evict the least recently used plan BEFORE allocating the new arena
+        size_t old = 0;
+        for (size_t i = 1; i < g_cache.size(); ++i) if (g_cache[i].stamp < g_cache[old].stamp) old = i;
+        spk_plan_destroy(g_cache[old].plan);
+        g_cache.erase(g_cache.begin() + old);
+    }
+    spk_plan* p = spk_plan_create(n, nsuper, xsuper, snode, xlindx, lindx, xlnz, lu ? xunz : nullptr, 0, 0, 1);
+    if (!p) return nullptr;
+    CacheEntry e; e.key = key; e.n = n; e.nsuper = nsuper; e.lu = lu; e.plan = p; e.stamp = ++g_cache_clock;
+    g_cache.push_back(e);
+    *slot = &g_cache.back();
+    return p;
+}
+static void release_plan(spk_plan* p, CacheEntry* slot) { if (!slot && p) spk_plan_destroy(p); }
+
+SPK_API void spk_cache_clear(void) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (CacheEntry& e : g_cache) spk_plan_destroy(e.plan);
+    g_cache.clear();
+}
+
+// device-side Float32 <-> Float64 conversion of the value arrays (the _f32 twins move half the bytes over the bus)
+__global__ void k_widen_f32(int64_t len, const float* __restrict__ in, double* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) out[i] = (double)in[i];
+}
+__global__ void k_narrow_f32(int64_t len, const double* __restrict__ in, float* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) out[i] = (float)in[i];
+}
+static int64_t upload_values(spk_plan* p, double* d_dst, const void* h_src, int64_t len, bool f32) {
+    if (len <= 0) return 0;
+    if (!f32) { CK(cudaMemcpyAsync(d_dst, h_src, len * sizeof(double), cudaMemcpyHostToDevice, p->stream)); return 0; }
+    float* tmp = nullptr;
+    CK(cudaMalloc((void**)&tmp, len * sizeof(float)));
+    cudaError_t e = cudaMemcpyAsync(tmp, h_src, len * sizeof(float), cudaMemcpyHostToDevice, p->stream);
+    if (e == cudaSuccess) { k_widen_f32<<<1184, 256, 0, p->stream>>>(len, tmp, d_dst); e = cudaStreamSynchronize(p->stream); }
+    cudaFree(tmp);
+    CK(e);
+    return 0;
+}
+static int64_t download_values(spk_plan* p, void* h_dst, const double* d_src, int64_t len, bool f32) {
+    if (len <= 0) return 0;
+    if (!f32) { CK(cudaMemcpyAsync(h_dst, d_src, len * sizeof(double), cudaMemcpyDeviceToHost, p->stream)); CK(cudaStreamSynchronize(p->stream)); return 0; }
+    float* tmp = nullptr;
+    CK(cudaMalloc((void**)&tmp, len * sizeof(float)));
+    k_narrow_f32<<<1184, 256, 0, p->stream>>>(len, d_src, tmp);
+    cudaError_t e = cudaMemcpyAsync(h_dst, tmp, len * sizeof(float), cudaMemcpyDeviceToHost, p->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+    cudaFree(tmp);
+    CK(e);
+    return 0;
+}
+
+// factor: values up (FP64 or FP32), factorisation, factors back in place; the plan stays cached with the factors resident
+static int64_t dropin_factor(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* snode, const int64_t* xlindx,
+                             const int64_t* lindx, const int64_t* xlnz, void* lnz, const int64_t* xunz, void* unz, int64_t* ipvt, bool lu, bool f32) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    CacheEntry* slot = nullptr;
+    spk_plan* p = cached_plan(n, nsuper, xsuper, snode, xlindx, lindx, xlnz, xunz, lu, &slot);
+    if (!p) return -100;
+    if (slot) slot->resident = false;
+    int64_t rc = cudaSetDevice(p->device) == cudaSuccess ? 0 : -100;
+    if (!rc) rc = upload_values(p, p->d_lnz, lnz, p->P.nlnz, f32);
+    if (!rc && lu) rc = upload_values(p, p->d_unz, unz, p->P.nunz, f32);
+    if (!rc && cudaStreamSynchronize(p->stream) != cudaSuccess) rc = -100;
+    int64_t flag = 0;
+    if (!rc) { p->factored = false; p->values_in_fronts = false; flag = spk_plan_factor(p); if (flag < -1) rc = flag; }
+    if (!rc) rc = download_values(p, lnz, p->d_lnz, p->P.nlnz, f32);
+    if (!rc && lu) rc = download_values(p, unz, p->d_unz, p->P.nunz, f32);
+    if (!rc && lu) rc = spk_plan_get_factors(p, nullptr, nullptr, ipvt);
+    if (!rc && slot) {
+        slot->h_lnz = lnz; slot->h_unz = lu ? unz : nullptr; slot->h_ipiv = lu ? ipvt : nullptr; slot->f32 = f32;
+        const int es = f32 ? 4 : 8;
+        slot->fp[0] = array_fingerprint(lnz, p->P.nlnz, es); slot->fp[1] = array_fingerprint(slot->h_unz, p->P.nunz, es); slot->fp[2] = array_fingerprint(slot->h_ipiv, n, 8);
+        slot->resident = true;
+    }
+    release_plan(p, slot);
+    return rc ? rc : flag;
+}
+
+// solve: which = 0 both sweeps (LDL^T), 1 forward (_lulsolve!), 2 backward (_luusolve!)
+static int64_t dropin_solve(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* xlindx, const int64_t* lindx,
+                            const int64_t* xlnz, const void* lnz, const int64_t* xunz, const void* unz, const int64_t* ipiv,
+                            void* rhs, bool lu, int which, bool f32) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    CacheEntry* slot = nullptr;
+    spk_plan* p = cached_plan(n, nsuper, xsuper, nullptr, xlindx, lindx, xlnz, xunz, lu, &slot);
+    if (!p) return -100;
+    int64_t rc = cudaSetDevice(p->device) == cudaSuccess ? 0 : -100;
+    // the forward sweep needs lnz + ipiv, the backward sweep lnz + unz; arrays not passed by the caller count as unchanged
+    bool resident = slot && slot->resident && p->factored && slot->f32 == f32 && slot->h_lnz == lnz &&
+                    (!unz || slot->h_unz == unz) && (!ipiv || slot->h_ipiv == ipiv);
+    const int es = f32 ? 4 : 8;                          // only the arrays handed to THIS call are looked at (the others may be gone)
+    if (resident) resident = slot->fp[0] == array_fingerprint(lnz, p->P.nlnz, es) && (!unz || slot->fp[1] == array_fingerprint(unz, p->P.nunz, es)) &&
+                             (!ipiv || slot->fp[2] == array_fingerprint(ipiv, n, 8));
+    if (!rc && !resident) {
+        if (slot) slot->resident = false;
+        rc = upload_values(p, p->d_lnz, lnz, p->P.nlnz, f32);
+        if (!rc && lu) {
+            if (unz) rc = upload_values(p, p->d_unz, unz, p->P.nunz, f32);
+            else if (cudaMemsetAsync(p->d_unz, 0, std::max<int64_t>(p->P.nunz, 1) * sizeof(double), p->stream) != cudaSuccess) rc = -100;
+        }
+        if (!rc && lu && ipiv) {
+            std::vector<int32_t> ip((size_t)n);
+            for (int64_t i = 0; i < n; ++i) ip[i] = (int32_t)ipiv[i];
+            if (cudaMemcpy(p->d_ipiv, ip.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) rc = -100;
+        }
+        if (!rc) {   // the sweeps read the frontal matrices: rebuild them from the uploaded factors
+            DevCtx c = make_ctx(p);
+            if (cudaMemsetAsync(p->d_F, 0, p->P.arena * sizeof(double), p->stream) != cudaSuccess) rc = -100;
+            if (!rc) {
+                if (lu) k_chunks<false><<<p->chunk_blocks, 256, 0, p->stream>>>(c, p->d_chunkpfx, (int)p->P.chunks.size());
+                else k_chunks<false, true><<<p->chunk_blocks, 256, 0, p->stream>>>(c, p->d_chunkpfx, (int)p->P.chunks.size());   // + U = D L^T
+                if (cudaStreamSynchronize(p->stream) != cudaSuccess) rc = -100;
+            }
+        }
+        if (!rc) {
+            p->factored = true;
+            // a forward-only call leaves unz / a backward-only call leaves ipiv unset: not a complete resident copy
+            if (slot && (!lu || (unz && ipiv))) {
+                slot->h_lnz = lnz; slot->h_unz = unz; slot->h_ipiv = ipiv; slot->f32 = f32;
+                slot->fp[0] = array_fingerprint(lnz, p->P.nlnz, es); slot->fp[1] = array_fingerprint(unz, p->P.nunz, es); slot->fp[2] = array_fingerprint(ipiv, n, 8);
+                slot->resident = true;
+            }
+        }
+    }
+    if (!rc) {
+        if (!f32) rc = spk_plan_solve(p, (double*)rhs, 1, n, which);
+        else {
+            std::vector<double> r((size_t)n);
+            for (int64_t i = 0; i < n; ++i) r[i] = ((float*)rhs)[i];
+            rc = spk_plan_solve(p, r.data(), 1, n, which);
+            if (!rc) for (int64_t i = 0; i < n; ++i) ((float*)rhs)[i] = (float)r[i];
+        }
+    }
+    release_plan(p, slot);
+    return rc ? rc : 1;
+}
 
 SPK_API int64_t spk_lufactor_f64(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* snode,
                                  const int64_t* xlindx, const int64_t* lindx, const int64_t* xlnz, double* lnz,
                                  const int64_t* xunz, double* unz, int64_t* ipvt) {
-    spk_plan* p = spk_plan_create(n, nsuper, xsuper, snode, xlindx, lindx, xlnz, xunz, 0, 0, 1);
-    if (!p) return -100;
-    int64_t rc = spk_plan_set_values(p, lnz, unz);
-    int64_t flag = 0;
-    if (!rc) { flag = spk_plan_factor(p); if (flag < -1) rc = flag; }
-    if (!rc) rc = spk_plan_get_factors(p, lnz, unz, ipvt);
-    spk_plan_destroy(p);
-    return rc ? rc : flag;
+    return dropin_factor(n, nsuper, xsuper, snode, xlindx, lindx, xlnz, lnz, xunz, unz, ipvt, true, false);
 }
-
 SPK_API int64_t spk_ldltfactor_f64(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* snode,
                                    const int64_t* xlindx, const int64_t* lindx, const int64_t* xlnz, double* lnz) {
-    spk_plan* p = spk_plan_create(n, nsuper, xsuper, snode, xlindx, lindx, xlnz, nullptr, 0, 0, 1);
-    if (!p) return -100;
-    int64_t rc = spk_plan_set_values(p, lnz, nullptr);
-    int64_t flag = 0;
-    if (!rc) { flag = spk_plan_factor(p); if (flag < -1) rc = flag; }
-    if (!rc) rc = spk_plan_get_factors(p, lnz, nullptr, nullptr);
-    spk_plan_destroy(p);
-    return rc ? rc : flag;
+    return dropin_factor(n, nsuper, xsuper, snode, xlindx, lindx, xlnz, lnz, nullptr, nullptr, nullptr, false, false);
 }
-
-// the solve drop-ins get no snode / (for _lulsolve!) no xunz: rebuild what the plan needs
-static spk_plan* solve_plan(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* xlindx,
-                            const int64_t* lindx, const int64_t* xlnz, bool lu) {
-    std::vector<int64_t> snode(n), xunz;
-    for (int64_t s = 0; s < nsuper; ++s) for (int64_t j = xsuper[s]; j < xsuper[s + 1]; ++j) snode[j - 1] = s + 1;
-    if (lu) {
-        xunz.resize(n + 1);
-        int64_t up = 1;
-        for (int64_t s = 0; s < nsuper; ++s) {
-            int64_t w = xsuper[s + 1] - xsuper[s], len = xlindx[s + 1] - xlindx[s];
-            for (int64_t j = xsuper[s]; j < xsuper[s + 1]; ++j) { xunz[j - 1] = up; up += len - w; }
-        }
-        xunz[n] = up;
-    }
-    return spk_plan_create(n, nsuper, xsuper, snode.data(), xlindx, lindx, xlnz, lu ? xunz.data() : nullptr, 0, 0, 1);
-}
-
 SPK_API int64_t spk_lulsolve_f64(int64_t nsuper, const int64_t* xsuper, const int64_t* xlindx, const int64_t* lindx,
                                  const int64_t* xlnz, const double* lnz, const int64_t* ipiv, double* rhs) {
-    int64_t n = n_from_xsuper(nsuper, xsuper);
-    spk_plan* p = solve_plan(n, nsuper, xsuper, xlindx, lindx, xlnz, true);
-    if (!p) return -100;
-    // the forward sweep reads lnz and ipiv only; unz is left unset
-    int64_t rc = 0;
-    if (cudaMemcpy(p->d_lnz, lnz, p->P.nlnz * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) rc = -100;
-    if (!rc) {
-        std::vector<int32_t> ip(n);
-        for (int64_t i = 0; i < n; ++i) ip[i] = (int32_t)ipiv[i];
-        if (cudaMemcpy(p->d_ipiv, ip.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) rc = -100;
-    }
-    if (!rc) {   // the sweeps read the frontal matrices: build them from lnz (U is not needed by the forward sweep)
-        DevCtx c = make_ctx(p);
-        if (cudaMemset(p->d_unz, 0, std::max<int64_t>(p->P.nunz, 1) * sizeof(double)) != cudaSuccess) rc = -100;
-        if (!rc && cudaMemset(p->d_F, 0, p->P.arena * sizeof(double)) != cudaSuccess) rc = -100;
-        if (!rc) { k_chunks<false><<<p->chunk_blocks, 256, 0, p->stream>>>(c, p->d_chunkpfx, (int)p->P.chunks.size()); if (cudaStreamSynchronize(p->stream) != cudaSuccess) rc = -100; }
-    }
-    if (!rc) { p->factored = true; rc = spk_plan_solve(p, rhs, 1, n, 1); }
-    spk_plan_destroy(p);
-    return rc ? rc : 1;
+    return dropin_solve(n_from_xsuper(nsuper, xsuper), nsuper, xsuper, xlindx, lindx, xlnz, lnz, nullptr, nullptr, ipiv, rhs, true, 1, false);
 }
-
 SPK_API int64_t spk_luusolve_f64(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* xlindx,
                                  const int64_t* lindx, const int64_t* xlnz, const double* lnz, const int64_t* xunz,
                                  const double* unz, double* rhs) {
-    (void)xunz;
-    spk_plan* p = solve_plan(n, nsuper, xsuper, xlindx, lindx, xlnz, true);
-    if (!p) return -100;
-    int64_t rc = spk_plan_set_factors(p, lnz, unz, nullptr);
-    if (!rc) rc = spk_plan_solve(p, rhs, 1, n, 2);
-    spk_plan_destroy(p);
-    return rc ? rc : 1;
+    return dropin_solve(n, nsuper, xsuper, xlindx, lindx, xlnz, lnz, xunz, unz, nullptr, rhs, true, 2, false);
 }
-
 SPK_API int64_t spk_ldltsolve_f64(int64_t nsuper, const int64_t* xsuper, const int64_t* xlindx, const int64_t* lindx,
                                   const int64_t* xlnz, const double* lnz, double* rhs) {
-    int64_t n = n_from_xsuper(nsuper, xsuper);
-    spk_plan* p = solve_plan(n, nsuper, xsuper, xlindx, lindx, xlnz, false);
-    if (!p) return -100;
-    int64_t rc = spk_plan_set_factors(p, lnz, nullptr, nullptr);
-    if (!rc) rc = spk_plan_solve(p, rhs, 1, n, 0);
-    spk_plan_destroy(p);
-    return rc ? rc : 1;
+    return dropin_solve(n_from_xsuper(nsuper, xsuper), nsuper, xsuper, xlindx, lindx, xlnz, lnz, nullptr, nullptr, nullptr, rhs, false, 0, false);
 }
 
 // ---- residual and iterative refinement on the device --------------------
@@ -1524,52 +1663,117 @@ SPK_API int64_t spk_plan_refine(spk_plan* p, const double* b, double* x, int64_t
     return most;
 }
 
+
+// ---- 1-norm condition estimate with the resident factors ---------------------------------
+// The reference keeps its estimator only as commented-out Fortran (SpkSparseSpdSolver.jl:267-459).  This is the
+// Hager / Higham estimator (the algorithm of LAPACK's xLACON) of ||inv(A)||_1, driven by triangular solves with the
+// factors held on the device, times ||A||_1 computed from the device copy of A (spk_plan_set_matrix).
+//   LDL^T plans: A is symmetric, so the inv(A)^T products Hager's iteration needs are inv(A) products: the full
+//                algorithm, with Higham's alternating-sign safeguard vector.
+//   LU plans:    the engine has no transposed sweeps; the estimate is the largest ||inv(A) v||_1 / ||v||_1 over the
+//                safeguard vector, the uniform vector and four fixed random sign vectors — a LOWER BOUND
+//                (info[1] = 1 says so).
+// Returns cond_1 estimate (>= 1) or a negative error code; out[0] = ||A||_1, out[1] = estimate of ||inv(A)||_1.
+__global__ void k_csr_colabs(int64_t n, const int64_t* __restrict__ rp, const int32_t* __restrict__ ci, const double* __restrict__ av, double* __restrict__ colsum) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int64_t k = rp[i]; k < rp[i + 1]; ++k) atomicAdd(colsum + ci[k], fabs(av[k]));
+}
+SPK_API double spk_plan_condest(spk_plan* p, double* out2, int32_t* info2) {
+    if (!p || p->device < 0) { set_err("plan has no device"); return -100.0; }
+    if (cudaSetDevice(p->device) != cudaSuccess) return -100.0;
+    if (p->annz < 0) { set_err("spk_plan_condest: spk_plan_set_matrix not called"); return -100.0; }
+    if (!p->have_perm) { set_err("spk_plan_condest: spk_plan_set_perm not called"); return -100.0; }
+    if (!p->factored) { set_err("spk_plan_condest: no factors"); return -100.0; }
+    const int64_t n = p->P.n;
+    // ||A||_1 = max column sum of |a_ij|
+    double anorm = 0.0;
+    {
+        double* d_cs = nullptr;
+        if (cudaMalloc((void**)&d_cs, (size_t)n * sizeof(double)) != cudaSuccess) { set_err("cudaMalloc"); return -100.0; }
+        cudaMemsetAsync(d_cs, 0, (size_t)n * sizeof(double), p->stream);
+        k_csr_colabs<<<cdiv(n, 256), 256, 0, p->stream>>>(n, p->d_arp, p->d_aci, p->d_av, d_cs);
+        std::vector<double> cs((size_t)n);
+        cudaError_t e = cudaMemcpyAsync(cs.data(), d_cs, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, p->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+        cudaFree(d_cs);
+        if (e != cudaSuccess) { set_err(cudaGetErrorString(e)); return -100.0; }
+        for (double v : cs) anorm = std::max(anorm, v);
+    }
+    auto solve = [&](std::vector<double>& v) -> int64_t { return spk_plan_triangularsolve(p, v.data(), 1, n); };
+    auto norm1 = [&](const std::vector<double>& v) { double s1 = 0.0; for (double x : v) s1 += std::fabs(x); return s1; };
+    std::vector<double> x((size_t)n), y, z;
+    double est = 0.0; int iters = 0, lower_bound = 0;
+    if (!p->P.lu) {
+        for (int64_t i = 0; i < n; ++i) x[i] = 1.0 / (double)n;
+        int64_t jlast = -1;
+        for (int it = 0; it < 5; ++it) {
+            y = x; if (solve(y) < 0) return -100.0; ++iters;
+            const double e1 = norm1(y);
+            if (it > 0 && e1 <= est) break;                        // no increase: converged
+            est = e1;
+            z.resize((size_t)n);
+            for (int64_t i = 0; i < n; ++i) z[i] = y[i] >= 0.0 ? 1.0 : -1.0;
+            if (solve(z) < 0) return -100.0; ++iters;              // inv(A)^T sign(y) = inv(A) sign(y)
+            int64_t j = 0; double zmax = 0.0, ztx = 0.0;
+            for (int64_t i = 0; i < n; ++i) { if (std::fabs(z[i]) > zmax) { zmax = std::fabs(z[i]); j = i; } ztx += z[i] * x[i]; }
+            if (zmax <= ztx || j == jlast) break;
+            jlast = j;
+            std::fill(x.begin(), x.end(), 0.0); x[j] = 1.0;
+        }
+        // Higham's safeguard: x_i = (-1)^i (1 + i/(n-1)),  estimate 2 ||inv(A) x||_1 / (3 n)
+        for (int64_t i = 0; i < n; ++i) x[i] = ((i & 1) ? -1.0 : 1.0) * (1.0 + (n > 1 ? (double)i / (double)(n - 1) : 0.0));
+        y = x; if (solve(y) < 0) return -100.0; ++iters;
+        est = std::max(est, 2.0 * norm1(y) / (3.0 * (double)n));
+    } else {
+        lower_bound = 1;
+        uint64_t rng = 0x9876ull;
+        for (int probe = 0; probe < 6; ++probe) {
+            for (int64_t i = 0; i < n; ++i) {
+                if (probe == 0) x[i] = 1.0 / (double)n;
+                else if (probe == 1) x[i] = ((i & 1) ? -1.0 : 1.0) * (1.0 + (n > 1 ? (double)i / (double)(n - 1) : 0.0));
+                else { rng = rng * 6364136223846793005ull + 1442695040888963407ull; x[i] = ((rng >> 33) & 1) ? 1.0 : -1.0; }
+            }
+            const double xn = norm1(x);
+            y = x; if (solve(y) < 0) return -100.0; ++iters;
+            est = std::max(est, norm1(y) / xn);
+        }
+    }
+    if (out2) { out2[0] = anorm; out2[1] = est; }
+    if (info2) { info2[0] = iters; info2[1] = lower_bound; }
+    return anorm * est;
+}
+
 // ---- Float32 twins ---------------------------------------------------------------------------
 // The reference routes Float32 problems to sgemm/sgetrf/strsm (SpkSpdMMOps.jl:186-351).  On B200 the FP64
 // tensor pipe is the fastest pipe this path can use (tcgen05 has no FP32-accumulate-FP32-input kind short of
 // TF32 rounding), so the _f32 entry points widen on entry, run the FP64 engine and narrow on exit: results are
 // at least as accurate as an FP32 computation; the pivot sequence is the FP64 one.
-static std::vector<double> widen(const float* a, int64_t len) { std::vector<double> v((size_t)std::max<int64_t>(len, 0)); for (int64_t i = 0; i < len; ++i) v[i] = a[i]; return v; }
 static void narrow(const std::vector<double>& v, float* a) { for (size_t i = 0; i < v.size(); ++i) a[i] = (float)v[i]; }
+static std::vector<double> widen(const float* a, int64_t len) { std::vector<double> v((size_t)std::max<int64_t>(len, 0)); for (int64_t i = 0; i < len; ++i) v[i] = a[i]; return v; }
 
+// The value arrays cross the bus as Float32 and are widened / narrowed ON THE DEVICE (k_widen_f32 / k_narrow_f32).
 SPK_API int64_t spk_lufactor_f32(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* snode,
                                  const int64_t* xlindx, const int64_t* lindx, const int64_t* xlnz, float* lnz,
                                  const int64_t* xunz, float* unz, int64_t* ipvt) {
-    std::vector<double> l = widen(lnz, xlnz[n] - 1), u = widen(unz, xunz[n] - 1);
-    int64_t rc = spk_lufactor_f64(n, nsuper, xsuper, snode, xlindx, lindx, xlnz, l.data(), xunz, u.data(), ipvt);
-    if (rc >= -1) { narrow(l, lnz); narrow(u, unz); }
-    return rc;
+    return dropin_factor(n, nsuper, xsuper, snode, xlindx, lindx, xlnz, lnz, xunz, unz, ipvt, true, true);
 }
 SPK_API int64_t spk_ldltfactor_f32(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* snode,
                                    const int64_t* xlindx, const int64_t* lindx, const int64_t* xlnz, float* lnz) {
-    std::vector<double> l = widen(lnz, xlnz[n] - 1);
-    int64_t rc = spk_ldltfactor_f64(n, nsuper, xsuper, snode, xlindx, lindx, xlnz, l.data());
-    if (rc >= -1) narrow(l, lnz);
-    return rc;
+    return dropin_factor(n, nsuper, xsuper, snode, xlindx, lindx, xlnz, lnz, nullptr, nullptr, nullptr, false, true);
 }
 SPK_API int64_t spk_lulsolve_f32(int64_t nsuper, const int64_t* xsuper, const int64_t* xlindx, const int64_t* lindx,
                                  const int64_t* xlnz, const float* lnz, const int64_t* ipiv, float* rhs) {
-    const int64_t n = n_from_xsuper(nsuper, xsuper);
-    std::vector<double> l = widen(lnz, xlnz[n] - 1), r = widen(rhs, n);
-    int64_t rc = spk_lulsolve_f64(nsuper, xsuper, xlindx, lindx, xlnz, l.data(), ipiv, r.data());
-    if (rc == 1) narrow(r, rhs);
-    return rc;
+    return dropin_solve(n_from_xsuper(nsuper, xsuper), nsuper, xsuper, xlindx, lindx, xlnz, lnz, nullptr, nullptr, ipiv, rhs, true, 1, true);
 }
 SPK_API int64_t spk_luusolve_f32(int64_t n, int64_t nsuper, const int64_t* xsuper, const int64_t* xlindx,
                                  const int64_t* lindx, const int64_t* xlnz, const float* lnz, const int64_t* xunz,
                                  const float* unz, float* rhs) {
-    std::vector<double> l = widen(lnz, xlnz[n] - 1), u = widen(unz, xunz[n] - 1), r = widen(rhs, n);
-    int64_t rc = spk_luusolve_f64(n, nsuper, xsuper, xlindx, lindx, xlnz, l.data(), xunz, u.data(), r.data());
-    if (rc == 1) narrow(r, rhs);
-    return rc;
+    return dropin_solve(n, nsuper, xsuper, xlindx, lindx, xlnz, lnz, xunz, unz, nullptr, rhs, true, 2, true);
 }
 SPK_API int64_t spk_ldltsolve_f32(int64_t nsuper, const int64_t* xsuper, const int64_t* xlindx, const int64_t* lindx,
                                   const int64_t* xlnz, const float* lnz, float* rhs) {
-    const int64_t n = n_from_xsuper(nsuper, xsuper);
-    std::vector<double> l = widen(lnz, xlnz[n] - 1), r = widen(rhs, n);
-    int64_t rc = spk_ldltsolve_f64(nsuper, xsuper, xlindx, lindx, xlnz, l.data(), r.data());
-    if (rc == 1) narrow(r, rhs);
-    return rc;
+    return dropin_solve(n_from_xsuper(nsuper, xsuper), nsuper, xsuper, xlindx, lindx, xlnz, lnz, nullptr, nullptr, nullptr, rhs, false, 0, true);
 }
 // plan twins: values / right-hand sides cross the boundary as Float32, the plan stays FP64
 SPK_API int64_t spk_plan_inmatrix_f32(spk_plan* p, int64_t nnz, const int64_t* dest_or_null, const float* nzval) {
@@ -1578,9 +1782,10 @@ SPK_API int64_t spk_plan_inmatrix_f32(spk_plan* p, int64_t nnz, const int64_t* d
 }
 SPK_API int64_t spk_plan_get_factors_f32(spk_plan* p, float* lnz, float* unz, int64_t* ipvt) {
     NEED_DEV(p);
-    std::vector<double> l(lnz ? (size_t)p->P.nlnz : 0), u(unz ? (size_t)p->P.nunz : 0);
-    int64_t rc = spk_plan_get_factors(p, lnz ? l.data() : nullptr, unz ? u.data() : nullptr, ipvt);
-    if (!rc) { if (lnz) narrow(l, lnz); if (unz) narrow(u, unz); }
+    int64_t rc = 0;
+    if (lnz) rc = download_values(p, lnz, p->d_lnz, p->P.nlnz, true);          // narrowed on the device
+    if (!rc && unz && p->P.nunz > 0) rc = download_values(p, unz, p->d_unz, p->P.nunz, true);
+    if (!rc && ipvt) rc = spk_plan_get_factors(p, nullptr, nullptr, ipvt);
     return rc;
 }
 SPK_API int64_t spk_plan_triangularsolve_f32(spk_plan* p, float* b, int64_t nrhs, int64_t ldb) {

@@ -51,3 +51,20 @@ def test_product_sources_do_not_reference_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "spko_" not in txt and "import oracle" not in txt and "libspkoracle" not in txt, f
+
+
+def test_julia_shim_binds_only_declared_symbols_with_matching_arity():
+    """julia/SparspakB200.jl cannot run here (no Julia in the image): at least every `ccall((:sym, libspk), ...)` in
+    it must name a symbol the header declares, with as many argument types as the C prototype has parameters."""
+    hdr = open(os.path.join(ROOT, "include", "spk_b200.h")).read()
+    proto = {}
+    for m in re.finditer(r"SPK_API\s+[\w\s\*]+?\b(spk_\w+)\s*\(([^;]*?)\)\s*;", hdr, re.S):
+        args = m.group(2).strip()
+        proto[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+    jl = open(os.path.join(ROOT, "julia", "SparspakB200.jl")).read()
+    calls = re.findall(r"ccall\(\(:(spk_\w+), libspk\),\s*[\w{}\.]+,\s*\(([^()]*)\)", jl, re.S)
+    assert len(calls) >= 20
+    for name, argt in calls:
+        assert name in proto, f"{name} bound in the Julia shim but not declared in spk_b200.h"
+        n = len([a for a in argt.replace("\n", " ").split(",") if a.strip()])
+        assert n == proto[name], f"{name}: {n} ccall argument types, {proto[name]} C parameters"

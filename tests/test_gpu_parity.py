@@ -413,3 +413,87 @@ def test_solve_without_factors_is_an_error_and_inmatrix_map_guards():
     x = M.rhs_for(A); plan.triangularsolve(x)
     assert residual(sp.csc_matrix(A + bump), x, M.rhs_for(A)) < RESID_TOL
     plan.destroy()
+
+
+def test_condition_estimate_against_dense_cond1():
+    """Hager / Higham 1-norm estimate on the resident factors vs numpy.linalg.cond(A, 1).
+    The estimator never over-estimates ||inv(A)||_1 and is within a small factor of it (LAPACK's bar: 3)."""
+    rng = np.random.default_rng(31)
+    mats = [M.laplacian2d(12), M.laplacian3d(7)]
+    G = rng.standard_normal((60, 60)); D = np.diag(np.logspace(0, 6, 60))
+    mats.append(sp.csc_matrix(G @ D @ G.T + 1e-3 * np.eye(60)))               # ill-conditioned dense SPD
+    T = sp.diags([np.full(79, -1.0), np.linspace(2.0, 2.5, 80), np.full(79, -1.0)], [-1, 0, 1], format="csc")
+    mats.append(T)
+    for A in mats:
+        A = sp.csc_matrix(A)
+        s = prepare(A, True)
+        b = s.slvr
+        plan = _cudalib.Plan(b)
+        plan.set_values(b.lnz); assert plan.factor() == 0
+        plan.set_perm(b.order.rperm, b.order.rinvp); plan.set_matrix(A)
+        c, an, ainv, nsolves, lower = plan.condest()
+        Ad = A.toarray()
+        true_ainv = np.linalg.norm(np.linalg.inv(Ad), 1)
+        assert abs(an - np.linalg.norm(Ad, 1)) <= 1e-12 * an
+        assert not lower and nsolves <= 11
+        assert ainv <= true_ainv * (1 + 1e-8) and ainv >= true_ainv / 3.0
+        assert abs(c - an * ainv) <= 1e-12 * c
+        plan.destroy()
+    # LU plans: a flagged lower bound
+    A = M.convdiff3d(6)
+    s = prepare(A, False)
+    b = s.slvr
+    plan = _cudalib.Plan(b)
+    plan.set_values(b.lnz, b.unz); assert plan.factor() == 0
+    plan.set_perm(b.order.rperm, b.order.rinvp); plan.set_matrix(A)
+    c, an, ainv, nsolves, lower = plan.condest()
+    true_ainv = np.linalg.norm(np.linalg.inv(A.toarray()), 1)
+    assert lower and ainv <= true_ainv * (1 + 1e-8) and ainv >= true_ainv / 10.0
+    plan.destroy()
+
+
+def test_stateless_dropins_reuse_cached_plan_and_resident_factors():
+    """The reference's `_triangularsolve!` calls `_lulsolve!` + `_luusolve!` per right-hand side: behind the stateless
+    entry points the plan is cached per structure, and a solve that presents the arrays the last factor call wrote
+    back uses the resident factors; modified arrays (another address or other values) are uploaded again."""
+    import time
+    L = _cudalib.lib()
+    L.spk_cache_clear()
+    A = M.convdiff3d(12)
+    s = prepare(A, False, spk.nd_grid_order(12, 12, 12))
+    b = s.slvr
+    lnz = b.lnz.copy(); unz = b.unz.copy(); ipiv = np.zeros(b.n, np.int64)
+    assert L.spk_lufactor_f64(b.n, b.nsuper, b.xsuper, b.snode, b.xlindx, b.lindx, b.xlnz, lnz, b.xunz, unz, ipiv) == 0
+    bb = M.rhs_for(A)
+    for rep in range(3):                                                  # same arrays: resident factors
+        rhs = np.ascontiguousarray((rep + 1.0) * bb[b.order.rperm - 1])
+        assert L.spk_lulsolve_f64(b.nsuper, b.xsuper, b.xlindx, b.lindx, b.xlnz, lnz, ipiv, rhs) == 1
+        assert L.spk_luusolve_f64(b.n, b.nsuper, b.xsuper, b.xlindx, b.lindx, b.xlnz, lnz, b.xunz, unz, rhs) == 1
+        assert residual(A, rhs[b.order.rinvp - 1], (rep + 1.0) * bb) < RESID_TOL
+    # factors of ANOTHER matrix with the same structure, in other arrays: must not be confused with the resident ones
+    A2 = A.copy(); A2.data = A2.data * np.linspace(1.0, 2.0, A2.nnz)
+    s2 = prepare(A2, False, spk.nd_grid_order(12, 12, 12))
+    lo, uo, po, _ = oracle_factor(s2.slvr)
+    rhs = np.ascontiguousarray(M.rhs_for(A2)[b.order.rperm - 1])
+    assert L.spk_lulsolve_f64(b.nsuper, b.xsuper, b.xlindx, b.lindx, b.xlnz, lo, po, rhs) == 1
+    assert L.spk_luusolve_f64(b.n, b.nsuper, b.xsuper, b.xlindx, b.lindx, b.xlnz, lo, b.xunz, uo, rhs) == 1
+    assert residual(A2, rhs[b.order.rinvp - 1], M.rhs_for(A2)) < 1e-11
+    # values changed IN PLACE in the arrays of the first factorisation: fingerprint mismatch -> uploaded again
+    lnz[:] = lo; unz[:] = uo; ipiv[:] = po
+    rhs = np.ascontiguousarray(M.rhs_for(A2)[b.order.rperm - 1])
+    assert L.spk_lulsolve_f64(b.nsuper, b.xsuper, b.xlindx, b.lindx, b.xlnz, lnz, ipiv, rhs) == 1
+    assert L.spk_luusolve_f64(b.n, b.nsuper, b.xsuper, b.xlindx, b.lindx, b.xlnz, lnz, b.xunz, unz, rhs) == 1
+    assert residual(A2, rhs[b.order.rinvp - 1], M.rhs_for(A2)) < 1e-11
+    # SPD twin + a second structure (cache of two plans), then back to the first
+    As = M.laplacian3d(9)
+    ss = prepare(As, True, spk.nd_grid_order(9, 9, 9))
+    ls = ss.slvr.lnz.copy()
+    assert L.spk_ldltfactor_f64(ss.slvr.n, ss.slvr.nsuper, ss.slvr.xsuper, ss.slvr.snode, ss.slvr.xlindx, ss.slvr.lindx, ss.slvr.xlnz, ls) == 0
+    r2 = np.ascontiguousarray(M.rhs_for(As)[ss.slvr.order.rperm - 1])
+    assert L.spk_ldltsolve_f64(ss.slvr.nsuper, ss.slvr.xsuper, ss.slvr.xlindx, ss.slvr.lindx, ss.slvr.xlnz, ls, r2) == 1
+    assert residual(As, r2[ss.slvr.order.rinvp - 1], M.rhs_for(As)) < RESID_TOL
+    rhs = np.ascontiguousarray(M.rhs_for(A2)[b.order.rperm - 1])
+    assert L.spk_lulsolve_f64(b.nsuper, b.xsuper, b.xlindx, b.lindx, b.xlnz, lnz, ipiv, rhs) == 1
+    assert L.spk_luusolve_f64(b.n, b.nsuper, b.xsuper, b.xlindx, b.lindx, b.xlnz, lnz, b.xunz, unz, rhs) == 1
+    assert residual(A2, rhs[b.order.rinvp - 1], M.rhs_for(A2)) < 1e-11
+    L.spk_cache_clear()
