@@ -1594,6 +1594,232 @@ __global__ void __launch_bounds__(SV_ROWS, 1) k_pb_step(DevCtx c, const int32_t*
     }
 }
 
+
+// ------------------------------------------------------------------------------------
+// DATAFLOW sweeps on the big fronts of one level (K_PF_FLOW / K_PB_FLOW): one launch instead of one launch per panel
+// step.  A thread block owns ROWS of a front for the whole sweep — the pivot rows of a few consecutive panel steps,
+// or (forward) a slab of the rows below the front's columns — one row per thread, the row's running value in a
+// register.  The block that owns step j solves its diagonal block as soon as its rows have received the updates of
+// all earlier steps, writes x_j and raises flag j (release); every other block waits for the flag (acquire), reads
+// x_j (w doubles) and applies the step to its rows with the whole panel row in flight BEFORE it waits.  The chain of
+// dependent steps therefore costs one flag round trip + one in-block solve per step (~3 us) instead of a kernel
+// launch (~10 us), and the bulk of the panel streams from HBM behind it.
+// Blocks take their task by TICKET (atomic counter): tasks are listed in dependency order, so a block only ever waits
+// for blocks that started before it — no co-residency assumption, no deadlock when the grid exceeds the machine.
+__device__ __forceinline__ int ld_acquire(const int32_t* p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release(int32_t* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+constexpr int FLOW_NT = 128;
+inline size_t flow_smem_bytes(int maxw, int nr) { const size_t wp = maxw <= 64 ? 64 : (size_t)maxw; return (2 * (size_t)maxw * maxw + (size_t)nr * wp) * sizeof(double); }
+
+// val[u][q] -= sum_k M[r_u, col0 + k] * xs[q][k]  for the rows r_u of this thread inside [lo, hi)
+template <int NR, int RPT>
+__device__ __forceinline__ void flow_apply(const double* __restrict__ Fm, int ld, int col0, int w, int wp, const double* xs,
+                                           const int (&row)[RPT], int lo, int hi, double (&val)[RPT][NR], int nr) {
+#pragma unroll
+    for (int u = 0; u < RPT; ++u) {
+        const int r = row[u];
+        if (r < lo || r >= hi) continue;
+        const double* __restrict__ src = Fm + r + (size_t)col0 * ld;
+        for (int k0 = 0; k0 < w; k0 += 64) {
+            double v[64];
+#pragma unroll
+            for (int k = 0; k < 64; ++k) v[k] = __ldcs(src + (size_t)min(k0 + k, w - 1) * ld);
+#pragma unroll
+            for (int q = 0; q < NR; ++q) {
+                if (q >= nr) continue;
+                double acc = 0.0;
+#pragma unroll
+                for (int k = 0; k < 64; ++k) acc += (k0 + k < w) ? v[k] * xs[q * wp + k0 + k] : 0.0;
+                val[u][q] -= acc;
+            }
+        }
+    }
+}
+
+template <bool LU, int NR, int RPT>
+__global__ void __launch_bounds__(FLOW_NT) k_pf_flow(DevCtx c, const FlowTask* __restrict__ tasks, int32_t* ticket, int32_t* flags,
+                                                     int64_t flag_stride, int nrhs, int maxw) {
+    extern __shared__ double ssm[];
+    __shared__ int s_t;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) s_t = atomicAdd(ticket + blockIdx.y, 1);
+    __syncthreads();
+    const FlowTask t = tasks[s_t];
+    const DFront F = c.fronts[t.front];
+    const int q0 = blockIdx.y * NR, nr = min(NR, nrhs - q0);
+    double* wf0 = c.w + (size_t)q0 * c.wlen + F.wofs;
+    int32_t* fl = flags + (size_t)blockIdx.y * flag_stride + F.ps0;
+    const double* __restrict__ Fm = c.F + F.fofs;
+    const int ld = F.ld, wp = maxw <= 64 ? 64 : maxw;
+    double* Tb[2] = {ssm, ssm + (size_t)maxw * maxw};
+    double* xs = ssm + 2 * (size_t)maxw * maxw;
+    const bool pivot = t.jb > t.ja;
+    int R0, R1;
+    if (pivot) { const PStep a = c.psteps[F.ps0 + t.ja], b = c.psteps[F.ps0 + t.jb - 1]; R0 = a.o; R1 = b.o + b.w; }
+    else { R0 = t.r0; R1 = t.r1; }
+    int row[RPT]; double val[RPT][NR];
+#pragma unroll
+    for (int u = 0; u < RPT; ++u) {
+        row[u] = R0 + tid + u * FLOW_NT;
+        if (row[u] >= R1) row[u] = 1 << 30;
+#pragma unroll
+        for (int q = 0; q < NR; ++q) val[u][q] = (q < nr && row[u] < R1) ? wf0[(size_t)q * c.wlen + row[u]] : 0.0;
+    }
+    if (pivot) {                                            // diagonal blocks of my first two steps: staged while the updates arrive
+        for (int j = t.ja; j < min(t.jb, t.ja + 2); ++j) { const PStep ps = c.psteps[F.ps0 + j]; stage_block_async(Tb[(j - t.ja) & 1], Fm + (int64_t)ps.o + (int64_t)ps.o * ld, ld, ps.w); }
+    }
+    const int jend = pivot ? t.jb : F.nps;
+    for (int j = 0; j < jend; ++j) {
+        const PStep ps = c.psteps[F.ps0 + j];
+        const int w = ps.w, e0 = ps.o + w;
+        const bool mine = pivot && j >= t.ja;
+        if (mine) {
+#pragma unroll
+            for (int u = 0; u < RPT; ++u) if (row[u] >= ps.o && row[u] < e0)
+#pragma unroll
+                for (int q = 0; q < NR; ++q) if (q < nr) xs[q * wp + row[u] - ps.o] = val[u][q];
+            stage_wait();
+            __syncthreads();
+            for (int q = warp; q < nr; q += FLOW_NT / 32) pf_diag_warp<LU>(c, ps, Tb[(j - t.ja) & 1], xs + q * wp);
+            __syncthreads();
+            for (int e = tid; e < nr * w; e += FLOW_NT) { const int q = e / w, k = e - q * w; wf0[(size_t)q * c.wlen + ps.o + k] = xs[q * wp + k]; }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) st_release(fl + j, 1);
+            if (j + 2 < t.jb) { const PStep nx = c.psteps[F.ps0 + j + 2]; stage_block_async(Tb[(j - t.ja) & 1], Fm + (int64_t)nx.o + (int64_t)nx.o * ld, ld, nx.w); }
+            flow_apply<NR, RPT>(Fm, ld, ps.o, w, wp, xs, row, e0, R1, val, nr);
+        } else {
+            // RPT == 1, w <= 64: the thread's panel row is in flight before the flag is awaited
+            double v0[64];
+            const bool pre = RPT == 1 && w <= 64 && row[0] < R1;
+            if (pre) {
+                const double* __restrict__ src = Fm + row[0] + (size_t)ps.o * ld;
+#pragma unroll
+                for (int k = 0; k < 64; ++k) v0[k] = __ldcs(src + (size_t)min(k, w - 1) * ld);
+            }
+            if (tid == 0) while (ld_acquire(fl + j) == 0) { }
+            __syncthreads();
+            for (int e = tid; e < nr * wp; e += FLOW_NT) { const int q = e / wp, k = e - q * wp; xs[e] = k < w ? __ldcg(wf0 + (size_t)q * c.wlen + ps.o + k) : 0.0; }
+            __syncthreads();
+            if (RPT == 1 && w <= 64) {
+                if (pre) {
+#pragma unroll
+                    for (int q = 0; q < NR; ++q) {
+                        if (q >= nr) continue;
+                        double acc = 0.0;
+#pragma unroll
+                        for (int k = 0; k < 64; ++k) acc += v0[k] * xs[q * wp + k];      // xs zero-padded to 64
+                        val[0][q] -= acc;
+                    }
+                }
+            } else flow_apply<NR, RPT>(Fm, ld, ps.o, w, wp, xs, row, e0, R1, val, nr);
+        }
+        __syncthreads();                                    // xs is rewritten by the next step
+    }
+    if (!pivot) {
+#pragma unroll
+        for (int u = 0; u < RPT; ++u) if (row[u] < R1)
+#pragma unroll
+            for (int q = 0; q < NR; ++q) if (q < nr) wf0[(size_t)q * c.wlen + row[u]] = val[u][q];
+    }
+}
+
+// Backward: a block owns the pivot rows of steps [ja, jb); steps are solved last to first.  Row r of the U panel of
+// step j (LDL^T fronts hold U = D L^T above the diagonal) is F[r, o_j + k]: consecutive threads read consecutive rows.
+template <bool LU, int NR, int RPT>
+__global__ void __launch_bounds__(FLOW_NT) k_pb_flow(DevCtx c, const FlowTask* __restrict__ tasks, int32_t* ticket, int32_t* flags,
+                                                     int64_t flag_stride, double* __restrict__ rhs, int64_t ldrhs, int nrhs, int maxw) {
+    extern __shared__ double ssm[];
+    __shared__ int s_t;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) s_t = atomicAdd(ticket + blockIdx.y, 1);
+    __syncthreads();
+    const FlowTask t = tasks[s_t];
+    const DFront F = c.fronts[t.front];
+    const int q0 = blockIdx.y * NR, nr = min(NR, nrhs - q0);
+    double* wf0 = c.w + (size_t)q0 * c.wlen + F.wofs;
+    int32_t* fl = flags + (size_t)blockIdx.y * flag_stride + F.ps0;
+    const double* __restrict__ Fm = c.F + F.fofs;
+    const int ld = F.ld, wp = maxw <= 64 ? 64 : maxw;
+    double* Tb[2] = {ssm, ssm + (size_t)maxw * maxw};
+    double* xs = ssm + 2 * (size_t)maxw * maxw;
+    const PStep pa = c.psteps[F.ps0 + t.ja], pz = c.psteps[F.ps0 + t.jb - 1];
+    const int R0 = pa.o, R1 = pz.o + pz.w;
+    int row[RPT]; double val[RPT][NR];
+#pragma unroll
+    for (int u = 0; u < RPT; ++u) {
+        row[u] = R0 + tid + u * FLOW_NT;
+        if (row[u] >= R1) row[u] = 1 << 30;
+#pragma unroll
+        for (int q = 0; q < NR; ++q) val[u][q] = (q < nr && row[u] < R1) ? wf0[(size_t)q * c.wlen + row[u]] : 0.0;
+    }
+    for (int j = t.jb - 1; j >= max(t.ja, t.jb - 2); --j) { const PStep ps = c.psteps[F.ps0 + j]; stage_block_async(Tb[(t.jb - 1 - j) & 1], Fm + (int64_t)ps.o + (int64_t)ps.o * ld, ld, ps.w); }
+    // the unknowns below the front's columns are known (gathered from the parent): their contribution first
+    for (int c0 = F.W; c0 < F.R; c0 += wp) {
+        const int wc = min(wp, F.R - c0);
+        __syncthreads();
+        for (int e = tid; e < nr * wp; e += FLOW_NT) { const int q = e / wp, k = e - q * wp; xs[e] = k < wc ? wf0[(size_t)q * c.wlen + c0 + k] : 0.0; }
+        __syncthreads();
+        flow_apply<NR, RPT>(Fm, ld, c0, wc, wp, xs, row, R0, R1, val, nr);
+    }
+    __syncthreads();
+    for (int j = F.nps - 1; j >= t.ja; --j) {
+        const PStep ps = c.psteps[F.ps0 + j];
+        const int w = ps.w, e0 = ps.o + w;
+        const bool mine = j < t.jb;
+        if (mine) {
+            double* T = Tb[(t.jb - 1 - j) & 1];
+            stage_wait();
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < RPT; ++u) if (row[u] >= ps.o && row[u] < e0) {
+                const int k = row[u] - ps.o;
+#pragma unroll
+                for (int q = 0; q < NR; ++q) if (q < nr) xs[q * wp + k] = LU ? val[u][q] : val[u][q] / T[k + k * w];
+            }
+            __syncthreads();
+            for (int q = warp; q < nr; q += FLOW_NT / 32) pb_diag_warp<LU>(ps, T, xs + q * wp);
+            __syncthreads();
+            for (int e = tid; e < nr * w; e += FLOW_NT) {
+                const int q = e / w, k = e - q * w;
+                wf0[(size_t)q * c.wlen + ps.o + k] = xs[q * wp + k];
+                rhs[(size_t)(q0 + q) * ldrhs + ps.col0 + k] = xs[q * wp + k];
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) st_release(fl + j, 1);
+            if (j - 2 >= t.ja) { const PStep nx = c.psteps[F.ps0 + j - 2]; stage_block_async(T, Fm + (int64_t)nx.o + (int64_t)nx.o * ld, ld, nx.w); }
+            flow_apply<NR, RPT>(Fm, ld, ps.o, w, wp, xs, row, R0, ps.o, val, nr);       // my rows of earlier steps
+        } else {
+            double v0[64];
+            const bool pre = RPT == 1 && w <= 64 && row[0] < R1;
+            if (pre) {
+                const double* __restrict__ src = Fm + row[0] + (size_t)ps.o * ld;
+#pragma unroll
+                for (int k = 0; k < 64; ++k) v0[k] = __ldcs(src + (size_t)min(k, w - 1) * ld);
+            }
+            if (tid == 0) while (ld_acquire(fl + j) == 0) { }
+            __syncthreads();
+            for (int e = tid; e < nr * wp; e += FLOW_NT) { const int q = e / wp, k = e - q * wp; xs[e] = k < w ? __ldcg(wf0 + (size_t)q * c.wlen + ps.o + k) : 0.0; }
+            __syncthreads();
+            if (RPT == 1 && w <= 64) {
+                if (pre) {
+#pragma unroll
+                    for (int q = 0; q < NR; ++q) {
+                        if (q >= nr) continue;
+                        double acc = 0.0;
+#pragma unroll
+                        for (int k = 0; k < 64; ++k) acc += v0[k] * xs[q * wp + k];
+                        val[0][q] -= acc;
+                    }
+                }
+            } else flow_apply<NR, RPT>(Fm, ld, ps.o, w, wp, xs, row, R0, R1, val, nr);
+        }
+        __syncthreads();
+    }
+}
+
 // small fronts: one block walks all panel steps of the front, NR right-hand sides at a time (one warp per
 // right-hand side in the diagonal solves; every factor entry is read once per block)
 // NT = 256 threads, or 64 for the tiny fronts at the bottom of the tree: those blocks are pure latency (a chain of

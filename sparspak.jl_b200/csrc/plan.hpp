@@ -81,7 +81,9 @@ enum Kind : int32_t {
     K_PF_FRONT, K_PF_DIAG, K_PF_UPDATE, K_PB_FRONT, K_PB_UPDATE, K_PB_DIAG,
     K_PF_STEP, K_PB_STEP,     // fused: update + next diagonal block (forward), partial sums + diagonal block (backward)
     // distributed top set (multi-GPU LDL^T): broadcast of a column slab from its owner; U = D L^T rebuilt from a received panel
-    K_BCAST, K_FILLU
+    K_BCAST, K_FILLU,
+    // solve sweeps of the big fronts of a level as ONE flag-synchronised dataflow launch (k_pf_flow / k_pb_flow)
+    K_PF_FLOW, K_PB_FLOW
 };
 struct Launch {
     int32_t kind;
@@ -101,6 +103,9 @@ struct Launch {
     // distributed lists use three streams (0 panel, 1 trailing update, 2 communication) and wait_mask: bit s = wait
     // for the last record of stream s before launching
 };
+// one thread block of a dataflow solve launch: the pivot rows of panel steps [ja, jb) of a front (jb > ja), or a slab
+// [r0, r1) of the rows below its columns (forward sweep only)
+struct FlowTask { int32_t front, ja, jb, r0, r1; };
 struct Bcast { int64_t ofs, len; int32_t root, front; };          // in-place broadcast of F[ofs, ofs+len) from part `root`
 struct FillTask { int64_t fofs; int32_t ld, R, ob0, e; };          // U[ob0+k, c] = D_k * L[c, ob0+k] for k < e-ob0, e <= c < R
 
@@ -116,6 +121,7 @@ constexpr int BWD_COLS = 1;        // columns per block in the backward-solve up
 constexpr int PS_WIDTH = 64;       // target panel-step width (a wider single chunk stays alone)
 constexpr int OB_WIDTH = 512;      // target outer-block width (delayed trailing update)
 constexpr int OB_STEPS = 8;        // panel steps per outer block (aligned across the fronts of a level for the look-ahead)
+constexpr int FLOW_ROWS = 128;     // rows per thread block of the dataflow solve kernels (one per thread; wider single steps: two)
 constexpr int64_t SOLVE_SMALL = 65536;  // fronts with at most this many stored L entries are solved by one block
 constexpr int RELAX_ABS = 4;       // a chunk joins the chain if it adds at most this many rows ...
 constexpr double RELAX_FRAC = 0.02;//   ... or this fraction of its rows
@@ -150,6 +156,9 @@ struct Plan {
     std::vector<int32_t> pslist;              // panel-step ids, grouped per DIAG/PANEL launch
     std::vector<SolveTask> solvet;            // one per chunk
     std::vector<int32_t> gathert;
+    std::vector<FlowTask> flowt;              // thread blocks of the dataflow solve launches
+    int32_t nflowctr = 0;                     // ticket counters (one per dataflow launch)
+    bool solve_flow = true;                   // SPK_SOLVE_FLOW=0: one launch per panel step (k_pf_step / k_pb_step) instead
     std::vector<int32_t> blkpfx;
     std::vector<Launch> factor_launches, fwd_launches, bwd_launches;
     // multi-GPU (elimination-subtree partition): owner[f] = part that factors front f, or -1 for the TOP SET
@@ -463,6 +472,7 @@ inline void plan_env_overrides(Plan& P) {        // test / tuning knobs
     if (const char* e = getenv("SPK_MAX_SUBTREES")) P.max_subtrees = std::max(2, atoi(e));
     if (const char* e = getenv("SPK_PIPES")) P.pipes = std::min(4, std::max(1, atoi(e)));
     if (const char* e = getenv("SPK_SOLVE_LNZ")) P.solve_on_fronts = e[0] != '1';
+    if (const char* e = getenv("SPK_SOLVE_FLOW")) P.solve_flow = e[0] != '0';
     if (const char* e = getenv("SPK_PS_WIDTH")) P.ps_width = std::max(1, atoi(e));
     if (const char* e = getenv("SPK_TOP_SPLITS")) P.force_splits = atoi(e);
     if (const char* e = getenv("SPK_GEMM_RESERVE")) P.gemm_reserve = std::max(0, atoi(e));
@@ -595,6 +605,25 @@ inline void build_lists(Plan& P, const std::vector<uint8_t>& sel, std::vector<La
             sf.begin(K_PF_FRONT, (int32_t)P.gathert.size(), lev, 0);
             for (int32_t f : fr) if (smallf[f]) { P.gathert.push_back(f); int32_t mw = 0; for (int32_t q = 0; q < P.fronts[f].nps; ++q) mw = std::max(mw, P.psteps[P.fronts[f].ps0 + q].w); sf.add(1, 0, mw); }
             sf.end();
+            if (P.solve_flow && maxnps > 0) {
+                // dataflow sweep: per big front, blocks owning the pivot rows of a few consecutive panel steps (in step
+                // order: a block only ever waits for blocks listed before it), then blocks owning slabs of the rows below
+                sf.begin(K_PF_FLOW, (int32_t)P.flowt.size(), lev, 0);
+                sf.cur.ctr = P.nflowctr++;
+                for (int32_t f : fr) if (!smallf[f]) {
+                    const Front& F = P.fronts[f];
+                    for (int32_t j = 0; j < F.nps;) {
+                        int32_t j1 = j, rows = 0;
+                        while (j1 < F.nps && (j1 == j || rows + P.psteps[F.ps0 + j1].w <= FLOW_ROWS)) { rows += P.psteps[F.ps0 + j1].w; ++j1; }
+                        int32_t mw = 0; for (int32_t q = j; q < j1; ++q) mw = std::max(mw, P.psteps[F.ps0 + q].w);
+                        P.flowt.push_back(FlowTask{f, j, j1, 0, 0}); sf.add(1, 0, mw);
+                        j = j1;
+                    }
+                    for (int32_t r = F.W; r < F.R; r += FLOW_ROWS) { P.flowt.push_back(FlowTask{f, 0, 0, r, std::min(F.R, r + FLOW_ROWS)}); sf.add(1, 0, 0); }
+                }
+                sf.end();
+                continue;
+            }
             for (int32_t j = 0; j < maxnps; ++j) {
                 if (j == 0) {                       // later diagonal blocks are solved inside the previous fused step
                     sf.begin(K_PF_DIAG, (int32_t)P.gathert.size(), lev, j);
@@ -624,6 +653,22 @@ inline void build_lists(Plan& P, const std::vector<uint8_t>& sel, std::vector<La
             sb.begin(K_PB_FRONT, (int32_t)P.gathert.size(), lev, 0);
             for (int32_t f : fr) if (smallf[f]) { P.gathert.push_back(f); int32_t mw = 0; for (int32_t q = 0; q < P.fronts[f].nps; ++q) mw = std::max(mw, P.psteps[P.fronts[f].ps0 + q].w); sb.add(1, 0, mw); }
             sb.end();
+            if (P.solve_flow && maxnps > 0) {
+                sb.begin(K_PB_FLOW, (int32_t)P.flowt.size(), lev, 0);
+                sb.cur.ctr = P.nflowctr++;
+                for (int32_t f : fr) if (!smallf[f]) {
+                    const Front& F = P.fronts[f];
+                    for (int32_t j1 = F.nps; j1 > 0;) {                       // last steps first: the order of the backward sweep
+                        int32_t j = j1, rows = 0;
+                        while (j > 0 && (j == j1 || rows + P.psteps[F.ps0 + j - 1].w <= FLOW_ROWS)) { rows += P.psteps[F.ps0 + j - 1].w; --j; }
+                        int32_t mw = 0; for (int32_t q = j; q < j1; ++q) mw = std::max(mw, P.psteps[F.ps0 + q].w);
+                        P.flowt.push_back(FlowTask{f, j, j1, 0, 0}); sb.add(1, 0, mw);
+                        j1 = j;
+                    }
+                }
+                sb.end();
+                continue;
+            }
             for (int32_t j = maxnps - 1; j >= 0; --j) {
                 sb.begin(K_PB_STEP, (int32_t)P.gathert.size(), lev, j);
                 for (int32_t f : fr) if (!smallf[f] && P.fronts[f].nps > j) {

@@ -399,6 +399,15 @@ static int64_t run_solve_list(Sim* s, const std::vector<Launch>& Ls, double* rhs
             case K_PB_FRONT: { const Front& F = P.fronts[list[ti]]; for (int j = F.nps - 1; j >= 0; --j) pb_step(*s, P.psteps[F.ps0 + j], rhs); break; }
             case K_PB_UPDATE: break;                          // folded into pb_step at the K_PB_DIAG launch
             case K_PB_DIAG: pb_step(*s, P.psteps[list[ti]], rhs); break;
+            case K_PF_FLOW: {                                 // blocks of one front are consecutive: run the front once, in step order
+                const FlowTask& ft = P.flowt[L.first + ti];
+                if (ft.jb > ft.ja && ft.ja == 0) { const Front& F = P.fronts[ft.front]; for (int j = 0; j < F.nps; ++j) { pf_diag(*s, P.psteps[F.ps0 + j]); pf_update(*s, P.psteps[F.ps0 + j]); } }
+                break; }
+            case K_PB_FLOW: {
+                const FlowTask& ft = P.flowt[L.first + ti];
+                const Front& F = P.fronts[ft.front];
+                if (ft.jb == F.nps) for (int j = F.nps - 1; j >= 0; --j) pb_step(*s, P.psteps[F.ps0 + j], rhs);
+                break; }
             case K_PF_STEP: { const PStep& ps = P.psteps[list[ti]]; pf_update(*s, ps); const Front& F = P.fronts[ps.front]; if (list[ti] + 1 < F.ps0 + F.nps) pf_diag(*s, P.psteps[list[ti] + 1]); break; }
             case K_PB_STEP: pb_step(*s, P.psteps[list[ti]], rhs); break;
             default: return -100;
