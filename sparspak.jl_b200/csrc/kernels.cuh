@@ -1596,50 +1596,61 @@ __global__ void __launch_bounds__(SV_ROWS, 1) k_pb_step(DevCtx c, const int32_t*
 
 
 // ------------------------------------------------------------------------------------
-// DATAFLOW sweeps on the big fronts of one level (K_PF_FLOW / K_PB_FLOW): one launch instead of one launch per panel
-// step.  A thread block owns ROWS of a front for the whole sweep — the pivot rows of a few consecutive panel steps,
-// or (forward) a slab of the rows below the front's columns — one row per thread, the row's running value in a
-// register.  The block that owns step j solves its diagonal block as soon as its rows have received the updates of
-// all earlier steps, writes x_j and raises flag j (release); every other block waits for the flag (acquire), reads
-// x_j (w doubles) and applies the step to its rows with the whole panel row in flight BEFORE it waits.  The chain of
-// dependent steps therefore costs one flag round trip + one in-block solve per step (~3 us) instead of a kernel
-// launch (~10 us), and the bulk of the panel streams from HBM behind it.
+// DATAFLOW sweeps on the fronts with many panel steps (K_PF_FLOW / K_PB_FLOW): one launch per level instead of one
+// launch per panel step.  A thread block owns ROWS of a front for the whole sweep — the pivot rows of a few
+// consecutive panel steps, or (forward) a slab of the rows below the front's columns — one row per thread, the
+// row's running value in a register.  The block that owns step j solves its diagonal block as soon as its rows have
+// received the updates of all earlier steps and writes x_j into a MAILBOX that was pre-filled with a sentinel (an
+// all-ones NaN); every other block has the panel row of step j in flight already (it depends on the factors only),
+// polls the w mailbox words until they are no longer the sentinel — data and "ready" signal in ONE L2 round trip,
+// no fence, no flag — and applies the step to its rows.  The chain of dependent steps costs an in-block solve plus
+// one L2 round trip per step instead of a kernel launch, and the panels stream from HBM (L2-prefetched two steps
+// ahead) behind it.
 // Blocks take their task by TICKET (atomic counter): tasks are listed in dependency order, so a block only ever waits
 // for blocks that started before it — no co-residency assumption, no deadlock when the grid exceeds the machine.
-__device__ __forceinline__ int ld_acquire(const int32_t* p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
-__device__ __forceinline__ void st_release(int32_t* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-
 constexpr int FLOW_NT = 128;
+constexpr unsigned long long FLOW_EMPTY = 0xFFFFFFFFFFFFFFFFull;      // mailbox sentinel (cudaMemset 0xFF)
 inline size_t flow_smem_bytes(int maxw, int nr) { const size_t wp = maxw <= 64 ? 64 : (size_t)maxw; return (2 * (size_t)maxw * maxw + (size_t)nr * wp) * sizeof(double); }
 
-// val[u][q] -= sum_k M[r_u, col0 + k] * xs[q][k]  for the rows r_u of this thread inside [lo, hi)
-template <int NR, int RPT>
+__device__ __forceinline__ double flow_poll(const double* p) {
+    unsigned long long v;
+    do { asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); } while (v == FLOW_EMPTY);
+    return __longlong_as_double((long long)v);
+}
+__device__ __forceinline__ void flow_post(double* p, double x) { asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(x) : "memory"); }
+
+// val[u][q] -= sum_k M[r_u, col0 + k] * xs[q][k]  for the rows r_u, u >= U0, of this thread inside [lo, hi)
+template <int NR, int RPT, int U0>
 __device__ __forceinline__ void flow_apply(const double* __restrict__ Fm, int ld, int col0, int w, int wp, const double* xs,
                                            const int (&row)[RPT], int lo, int hi, double (&val)[RPT][NR], int nr) {
 #pragma unroll
-    for (int u = 0; u < RPT; ++u) {
+    for (int u = U0; u < RPT; ++u) {
         const int r = row[u];
         if (r < lo || r >= hi) continue;
         const double* __restrict__ src = Fm + r + (size_t)col0 * ld;
-        for (int k0 = 0; k0 < w; k0 += 64) {
-            double v[64];
+        for (int k0 = 0; k0 < w; k0 += 16) {
+            double v[16];
 #pragma unroll
-            for (int k = 0; k < 64; ++k) v[k] = __ldcs(src + (size_t)min(k0 + k, w - 1) * ld);
+            for (int k = 0; k < 16; ++k) v[k] = __ldcs(src + (size_t)min(k0 + k, w - 1) * ld);
 #pragma unroll
             for (int q = 0; q < NR; ++q) {
                 if (q >= nr) continue;
                 double acc = 0.0;
 #pragma unroll
-                for (int k = 0; k < 64; ++k) acc += (k0 + k < w) ? v[k] * xs[q * wp + k0 + k] : 0.0;
+                for (int k = 0; k < 16; ++k) acc += (k0 + k < w) ? v[k] * xs[q * wp + k0 + k] : 0.0;
                 val[u][q] -= acc;
             }
         }
     }
 }
+// pull the panel row segments this block will need for the step starting at column `col0` towards L2
+__device__ __forceinline__ void flow_prefetch(const double* __restrict__ Fm, int ld, int col0, int w, int r, bool ok) {
+    if (ok && (threadIdx.x & 15) == 0) for (int k = 0; k < w; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(Fm + r + (size_t)(col0 + k) * ld));
+}
 
 template <bool LU, int NR, int RPT>
-__global__ void __launch_bounds__(FLOW_NT) k_pf_flow(DevCtx c, const FlowTask* __restrict__ tasks, int32_t* ticket, int32_t* flags,
-                                                     int64_t flag_stride, int nrhs, int maxw) {
+__global__ void __launch_bounds__(FLOW_NT) k_pf_flow(DevCtx c, const FlowTask* __restrict__ tasks, int32_t* ticket, double* __restrict__ box,
+                                                     int64_t box_stride, int nrhs, int maxw) {
     extern __shared__ double ssm[];
     __shared__ int s_t;
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -1649,7 +1660,7 @@ __global__ void __launch_bounds__(FLOW_NT) k_pf_flow(DevCtx c, const FlowTask* _
     const DFront F = c.fronts[t.front];
     const int q0 = blockIdx.y * NR, nr = min(NR, nrhs - q0);
     double* wf0 = c.w + (size_t)q0 * c.wlen + F.wofs;
-    int32_t* fl = flags + (size_t)blockIdx.y * flag_stride + F.ps0;
+    double* bx = box + (size_t)q0 * box_stride + F.F0;           // x of front column k, right-hand side q: bx[q * box_stride + k]
     const double* __restrict__ Fm = c.F + F.fofs;
     const int ld = F.ld, wp = maxw <= 64 ? 64 : maxw;
     double* Tb[2] = {ssm, ssm + (size_t)maxw * maxw};
@@ -1670,10 +1681,20 @@ __global__ void __launch_bounds__(FLOW_NT) k_pf_flow(DevCtx c, const FlowTask* _
         for (int j = t.ja; j < min(t.jb, t.ja + 2); ++j) { const PStep ps = c.psteps[F.ps0 + j]; stage_block_async(Tb[(j - t.ja) & 1], Fm + (int64_t)ps.o + (int64_t)ps.o * ld, ld, ps.w); }
     }
     const int jend = pivot ? t.jb : F.nps;
+    PStep ps = c.psteps[F.ps0];
     for (int j = 0; j < jend; ++j) {
-        const PStep ps = c.psteps[F.ps0 + j];
+        const PStep nx = c.psteps[F.ps0 + min(j + 1, F.nps - 1)];      // next step's record: in flight during this step
         const int w = ps.w, e0 = ps.o + w;
         const bool mine = pivot && j >= t.ja;
+        // the thread's panel row of this step (beyond the step's own rows): in flight before x_j is known
+        const bool act = row[0] < R1 && row[0] >= e0;
+        double v[64];
+        if (w <= 64) {
+            const double* __restrict__ src = Fm + (act ? row[0] : 0) + (size_t)ps.o * ld;
+#pragma unroll
+            for (int k = 0; k < 64; ++k) v[k] = act ? __ldcs(src + (size_t)min(k, w - 1) * ld) : 0.0;
+        }
+        if (j + 2 < jend) { const PStep p2 = c.psteps[F.ps0 + j + 2]; flow_prefetch(Fm, ld, p2.o, p2.w, row[0], row[0] < R1 && row[0] >= p2.o + p2.w); }
         if (mine) {
 #pragma unroll
             for (int u = 0; u < RPT; ++u) if (row[u] >= ps.o && row[u] < e0)
@@ -1683,39 +1704,31 @@ __global__ void __launch_bounds__(FLOW_NT) k_pf_flow(DevCtx c, const FlowTask* _
             __syncthreads();
             for (int q = warp; q < nr; q += FLOW_NT / 32) pf_diag_warp<LU>(c, ps, Tb[(j - t.ja) & 1], xs + q * wp);
             __syncthreads();
-            for (int e = tid; e < nr * w; e += FLOW_NT) { const int q = e / w, k = e - q * w; wf0[(size_t)q * c.wlen + ps.o + k] = xs[q * wp + k]; }
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) st_release(fl + j, 1);
-            if (j + 2 < t.jb) { const PStep nx = c.psteps[F.ps0 + j + 2]; stage_block_async(Tb[(j - t.ja) & 1], Fm + (int64_t)nx.o + (int64_t)nx.o * ld, ld, nx.w); }
-            flow_apply<NR, RPT>(Fm, ld, ps.o, w, wp, xs, row, e0, R1, val, nr);
-        } else {
-            // RPT == 1, w <= 64: the thread's panel row is in flight before the flag is awaited
-            double v0[64];
-            const bool pre = RPT == 1 && w <= 64 && row[0] < R1;
-            if (pre) {
-                const double* __restrict__ src = Fm + row[0] + (size_t)ps.o * ld;
-#pragma unroll
-                for (int k = 0; k < 64; ++k) v0[k] = __ldcs(src + (size_t)min(k, w - 1) * ld);
+            for (int e = tid; e < nr * w; e += FLOW_NT) {
+                const int q = e / w, k = e - q * w;
+                flow_post(bx + (size_t)q * box_stride + ps.o + k, xs[q * wp + k]);
+                wf0[(size_t)q * c.wlen + ps.o + k] = xs[q * wp + k];
             }
-            if (tid == 0) while (ld_acquire(fl + j) == 0) { }
+            if (j + 2 < t.jb) { const PStep p2 = c.psteps[F.ps0 + j + 2]; stage_block_async(Tb[(j - t.ja) & 1], Fm + (int64_t)p2.o + (int64_t)p2.o * ld, ld, p2.w); }
+        } else {
+            for (int e = tid; e < nr * wp; e += FLOW_NT) { const int q = e / wp, k = e - q * wp; xs[e] = k < w ? flow_poll(bx + (size_t)q * box_stride + ps.o + k) : 0.0; }
             __syncthreads();
-            for (int e = tid; e < nr * wp; e += FLOW_NT) { const int q = e / wp, k = e - q * wp; xs[e] = k < w ? __ldcg(wf0 + (size_t)q * c.wlen + ps.o + k) : 0.0; }
-            __syncthreads();
-            if (RPT == 1 && w <= 64) {
-                if (pre) {
-#pragma unroll
-                    for (int q = 0; q < NR; ++q) {
-                        if (q >= nr) continue;
-                        double acc = 0.0;
-#pragma unroll
-                        for (int k = 0; k < 64; ++k) acc += v0[k] * xs[q * wp + k];      // xs zero-padded to 64
-                        val[0][q] -= acc;
-                    }
-                }
-            } else flow_apply<NR, RPT>(Fm, ld, ps.o, w, wp, xs, row, e0, R1, val, nr);
         }
+        if (w <= 64) {
+            if (act) {
+#pragma unroll
+                for (int q = 0; q < NR; ++q) {
+                    if (q >= nr) continue;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 64; ++k) acc += (k < w) ? v[k] * xs[q * wp + k] : 0.0;
+                    val[0][q] -= acc;
+                }
+            }
+            flow_apply<NR, RPT, 1>(Fm, ld, ps.o, w, wp, xs, row, e0, R1, val, nr);
+        } else flow_apply<NR, RPT, 0>(Fm, ld, ps.o, w, wp, xs, row, e0, R1, val, nr);
         __syncthreads();                                    // xs is rewritten by the next step
+        ps = nx;
     }
     if (!pivot) {
 #pragma unroll
@@ -1728,8 +1741,8 @@ __global__ void __launch_bounds__(FLOW_NT) k_pf_flow(DevCtx c, const FlowTask* _
 // Backward: a block owns the pivot rows of steps [ja, jb); steps are solved last to first.  Row r of the U panel of
 // step j (LDL^T fronts hold U = D L^T above the diagonal) is F[r, o_j + k]: consecutive threads read consecutive rows.
 template <bool LU, int NR, int RPT>
-__global__ void __launch_bounds__(FLOW_NT) k_pb_flow(DevCtx c, const FlowTask* __restrict__ tasks, int32_t* ticket, int32_t* flags,
-                                                     int64_t flag_stride, double* __restrict__ rhs, int64_t ldrhs, int nrhs, int maxw) {
+__global__ void __launch_bounds__(FLOW_NT) k_pb_flow(DevCtx c, const FlowTask* __restrict__ tasks, int32_t* ticket, double* __restrict__ box,
+                                                     int64_t box_stride, double* __restrict__ rhs, int64_t ldrhs, int nrhs, int maxw) {
     extern __shared__ double ssm[];
     __shared__ int s_t;
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -1739,7 +1752,7 @@ __global__ void __launch_bounds__(FLOW_NT) k_pb_flow(DevCtx c, const FlowTask* _
     const DFront F = c.fronts[t.front];
     const int q0 = blockIdx.y * NR, nr = min(NR, nrhs - q0);
     double* wf0 = c.w + (size_t)q0 * c.wlen + F.wofs;
-    int32_t* fl = flags + (size_t)blockIdx.y * flag_stride + F.ps0;
+    double* bx = box + (size_t)q0 * box_stride + F.F0;
     const double* __restrict__ Fm = c.F + F.fofs;
     const int ld = F.ld, wp = maxw <= 64 ? 64 : maxw;
     double* Tb[2] = {ssm, ssm + (size_t)maxw * maxw};
@@ -1761,13 +1774,22 @@ __global__ void __launch_bounds__(FLOW_NT) k_pb_flow(DevCtx c, const FlowTask* _
         __syncthreads();
         for (int e = tid; e < nr * wp; e += FLOW_NT) { const int q = e / wp, k = e - q * wp; xs[e] = k < wc ? wf0[(size_t)q * c.wlen + c0 + k] : 0.0; }
         __syncthreads();
-        flow_apply<NR, RPT>(Fm, ld, c0, wc, wp, xs, row, R0, R1, val, nr);
+        flow_apply<NR, RPT, 0>(Fm, ld, c0, wc, wp, xs, row, R0, R1, val, nr);
     }
     __syncthreads();
+    PStep ps = c.psteps[F.ps0 + F.nps - 1];
     for (int j = F.nps - 1; j >= t.ja; --j) {
-        const PStep ps = c.psteps[F.ps0 + j];
+        const PStep nx = c.psteps[F.ps0 + max(j - 1, 0)];
         const int w = ps.w, e0 = ps.o + w;
         const bool mine = j < t.jb;
+        const bool act = row[0] < ps.o;                         // my rows above the step (all of them when the step is not mine)
+        double v[64];
+        if (w <= 64) {
+            const double* __restrict__ src = Fm + (act ? row[0] : 0) + (size_t)ps.o * ld;
+#pragma unroll
+            for (int k = 0; k < 64; ++k) v[k] = act ? __ldcs(src + (size_t)min(k, w - 1) * ld) : 0.0;
+        }
+        if (j - 2 >= t.ja) { const PStep p2 = c.psteps[F.ps0 + j - 2]; flow_prefetch(Fm, ld, p2.o, p2.w, row[0], row[0] < p2.o); }
         if (mine) {
             double* T = Tb[(t.jb - 1 - j) & 1];
             stage_wait();
@@ -1783,40 +1805,30 @@ __global__ void __launch_bounds__(FLOW_NT) k_pb_flow(DevCtx c, const FlowTask* _
             __syncthreads();
             for (int e = tid; e < nr * w; e += FLOW_NT) {
                 const int q = e / w, k = e - q * w;
+                flow_post(bx + (size_t)q * box_stride + ps.o + k, xs[q * wp + k]);
                 wf0[(size_t)q * c.wlen + ps.o + k] = xs[q * wp + k];
                 rhs[(size_t)(q0 + q) * ldrhs + ps.col0 + k] = xs[q * wp + k];
             }
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) st_release(fl + j, 1);
-            if (j - 2 >= t.ja) { const PStep nx = c.psteps[F.ps0 + j - 2]; stage_block_async(T, Fm + (int64_t)nx.o + (int64_t)nx.o * ld, ld, nx.w); }
-            flow_apply<NR, RPT>(Fm, ld, ps.o, w, wp, xs, row, R0, ps.o, val, nr);       // my rows of earlier steps
+            if (j - 2 >= t.ja) { const PStep p2 = c.psteps[F.ps0 + j - 2]; stage_block_async(T, Fm + (int64_t)p2.o + (int64_t)p2.o * ld, ld, p2.w); }
         } else {
-            double v0[64];
-            const bool pre = RPT == 1 && w <= 64 && row[0] < R1;
-            if (pre) {
-                const double* __restrict__ src = Fm + row[0] + (size_t)ps.o * ld;
-#pragma unroll
-                for (int k = 0; k < 64; ++k) v0[k] = __ldcs(src + (size_t)min(k, w - 1) * ld);
-            }
-            if (tid == 0) while (ld_acquire(fl + j) == 0) { }
+            for (int e = tid; e < nr * wp; e += FLOW_NT) { const int q = e / wp, k = e - q * wp; xs[e] = k < w ? flow_poll(bx + (size_t)q * box_stride + ps.o + k) : 0.0; }
             __syncthreads();
-            for (int e = tid; e < nr * wp; e += FLOW_NT) { const int q = e / wp, k = e - q * wp; xs[e] = k < w ? __ldcg(wf0 + (size_t)q * c.wlen + ps.o + k) : 0.0; }
-            __syncthreads();
-            if (RPT == 1 && w <= 64) {
-                if (pre) {
-#pragma unroll
-                    for (int q = 0; q < NR; ++q) {
-                        if (q >= nr) continue;
-                        double acc = 0.0;
-#pragma unroll
-                        for (int k = 0; k < 64; ++k) acc += v0[k] * xs[q * wp + k];
-                        val[0][q] -= acc;
-                    }
-                }
-            } else flow_apply<NR, RPT>(Fm, ld, ps.o, w, wp, xs, row, R0, R1, val, nr);
         }
+        if (w <= 64) {
+            if (act) {
+#pragma unroll
+                for (int q = 0; q < NR; ++q) {
+                    if (q >= nr) continue;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 64; ++k) acc += (k < w) ? v[k] * xs[q * wp + k] : 0.0;
+                    val[0][q] -= acc;
+                }
+            }
+            flow_apply<NR, RPT, 1>(Fm, ld, ps.o, w, wp, xs, row, R0, ps.o, val, nr);
+        } else flow_apply<NR, RPT, 0>(Fm, ld, ps.o, w, wp, xs, row, R0, ps.o, val, nr);
         __syncthreads();
+        ps = nx;
     }
 }
 

@@ -121,6 +121,7 @@ constexpr int BWD_COLS = 1;        // columns per block in the backward-solve up
 constexpr int PS_WIDTH = 64;       // target panel-step width (a wider single chunk stays alone)
 constexpr int OB_WIDTH = 512;      // target outer-block width (delayed trailing update)
 constexpr int OB_STEPS = 8;        // panel steps per outer block (aligned across the fronts of a level for the look-ahead)
+constexpr int FLOW_MIN_STEPS = 8;  // fronts with at least this many panel steps take the dataflow solve kernels
 constexpr int FLOW_ROWS = 128;     // rows per thread block of the dataflow solve kernels (one per thread; wider single steps: two)
 constexpr int64_t SOLVE_SMALL = 65536;  // fronts with at most this many stored L entries are solved by one block
 constexpr int RELAX_ABS = 4;       // a chunk joins the chain if it adds at most this many rows ...
@@ -158,6 +159,7 @@ struct Plan {
     std::vector<int32_t> gathert;
     std::vector<FlowTask> flowt;              // thread blocks of the dataflow solve launches
     int32_t nflowctr = 0;                     // ticket counters (one per dataflow launch)
+    int32_t flow_min_steps = FLOW_MIN_STEPS;  // SPK_FLOW_MIN_STEPS
     bool solve_flow = true;                   // SPK_SOLVE_FLOW=0: one launch per panel step (k_pf_step / k_pb_step) instead
     std::vector<int32_t> blkpfx;
     std::vector<Launch> factor_launches, fwd_launches, bwd_launches;
@@ -473,6 +475,7 @@ inline void plan_env_overrides(Plan& P) {        // test / tuning knobs
     if (const char* e = getenv("SPK_PIPES")) P.pipes = std::min(4, std::max(1, atoi(e)));
     if (const char* e = getenv("SPK_SOLVE_LNZ")) P.solve_on_fronts = e[0] != '1';
     if (const char* e = getenv("SPK_SOLVE_FLOW")) P.solve_flow = e[0] != '0';
+    if (const char* e = getenv("SPK_FLOW_MIN_STEPS")) P.flow_min_steps = std::max(1, atoi(e));
     if (const char* e = getenv("SPK_PS_WIDTH")) P.ps_width = std::max(1, atoi(e));
     if (const char* e = getenv("SPK_TOP_SPLITS")) P.force_splits = atoi(e);
     if (const char* e = getenv("SPK_GEMM_RESERVE")) P.gemm_reserve = std::max(0, atoi(e));
@@ -593,24 +596,31 @@ inline void build_lists(Plan& P, const std::vector<uint8_t>& sel, std::vector<La
     // ---- solves on the frontal matrices: one step per panel step.  Small fronts: one block walks the whole
     // front.  Large fronts: a (diag, update) launch pair per panel step.
     if (P.solve_on_fronts) {
-        std::vector<uint8_t> smallf(nf);
-        for (int32_t f = 0; f < nf; ++f) smallf[f] = (int64_t)P.fronts[f].R * P.fronts[f].W <= P.solve_small;
+        // three classes: small fronts (one block walks the front), fronts with many panel steps (dataflow launch),
+        // the rest (one launch per panel step); `stepf` = the last class
+        std::vector<uint8_t> smallf(nf), flowf(nf), stepf(nf);
+        for (int32_t f = 0; f < nf; ++f) {
+            smallf[f] = (int64_t)P.fronts[f].R * P.fronts[f].W <= P.solve_small;
+            flowf[f] = !smallf[f] && P.solve_flow && P.fronts[f].nps >= P.flow_min_steps;
+            stepf[f] = !smallf[f] && !flowf[f];
+        }
         LaunchBuilder sf(P, fwd_out);
         for (int32_t lev = 0; lev < P.nlevels; ++lev) {
             const std::vector<int32_t>& fr = bylevel[lev];
             int32_t maxnps = 0;
             sf.begin(K_FWD_GATHER, (int32_t)P.gathert.size(), lev, 0);
-            for (int32_t f : fr) { P.gathert.push_back(f); sf.add(1); if (!smallf[f]) maxnps = std::max(maxnps, P.fronts[f].nps); }
+            bool anyflow = false;
+            for (int32_t f : fr) { P.gathert.push_back(f); sf.add(1); if (stepf[f]) maxnps = std::max(maxnps, P.fronts[f].nps); anyflow |= flowf[f] != 0; }
             sf.end();
             sf.begin(K_PF_FRONT, (int32_t)P.gathert.size(), lev, 0);
             for (int32_t f : fr) if (smallf[f]) { P.gathert.push_back(f); int32_t mw = 0; for (int32_t q = 0; q < P.fronts[f].nps; ++q) mw = std::max(mw, P.psteps[P.fronts[f].ps0 + q].w); sf.add(1, 0, mw); }
             sf.end();
-            if (P.solve_flow && maxnps > 0) {
+            if (anyflow) {
                 // dataflow sweep: per big front, blocks owning the pivot rows of a few consecutive panel steps (in step
                 // order: a block only ever waits for blocks listed before it), then blocks owning slabs of the rows below
                 sf.begin(K_PF_FLOW, (int32_t)P.flowt.size(), lev, 0);
                 sf.cur.ctr = P.nflowctr++;
-                for (int32_t f : fr) if (!smallf[f]) {
+                for (int32_t f : fr) if (flowf[f]) {
                     const Front& F = P.fronts[f];
                     for (int32_t j = 0; j < F.nps;) {
                         int32_t j1 = j, rows = 0;
@@ -622,16 +632,15 @@ inline void build_lists(Plan& P, const std::vector<uint8_t>& sel, std::vector<La
                     for (int32_t r = F.W; r < F.R; r += FLOW_ROWS) { P.flowt.push_back(FlowTask{f, 0, 0, r, std::min(F.R, r + FLOW_ROWS)}); sf.add(1, 0, 0); }
                 }
                 sf.end();
-                continue;
             }
             for (int32_t j = 0; j < maxnps; ++j) {
                 if (j == 0) {                       // later diagonal blocks are solved inside the previous fused step
                     sf.begin(K_PF_DIAG, (int32_t)P.gathert.size(), lev, j);
-                    for (int32_t f : fr) if (!smallf[f] && P.fronts[f].nps > j) { P.gathert.push_back(P.fronts[f].ps0 + j); sf.add(1, 0, P.psteps[P.fronts[f].ps0 + j].w); }
+                    for (int32_t f : fr) if (stepf[f] && P.fronts[f].nps > j) { P.gathert.push_back(P.fronts[f].ps0 + j); sf.add(1, 0, P.psteps[P.fronts[f].ps0 + j].w); }
                     sf.end();
                 }
                 sf.begin(K_PF_STEP, (int32_t)P.gathert.size(), lev, j);
-                for (int32_t f : fr) if (!smallf[f] && P.fronts[f].nps > j) {
+                for (int32_t f : fr) if (stepf[f] && P.fronts[f].nps > j) {
                     const PStep& ps = P.psteps[P.fronts[f].ps0 + j];
                     int32_t below = ps.R - ps.o - ps.w;
                     int32_t wn = P.fronts[f].nps > j + 1 ? P.psteps[P.fronts[f].ps0 + j + 1].w : 0;
@@ -645,18 +654,20 @@ inline void build_lists(Plan& P, const std::vector<uint8_t>& sel, std::vector<La
             const std::vector<int32_t>& fr = bylevel[lev];
             int32_t maxnps = 0;
             sb.begin(K_BWD_GATHER, (int32_t)P.gathert.size(), lev, 0);
+            bool anyflow = false;
             for (int32_t f : fr) {
-                if (!smallf[f]) maxnps = std::max(maxnps, P.fronts[f].nps);
+                if (stepf[f]) maxnps = std::max(maxnps, P.fronts[f].nps);
+                anyflow |= flowf[f] != 0;
                 if (P.fronts[f].m > 0) { P.gathert.push_back(f); sb.add(cdiv(P.fronts[f].m, 256)); }
             }
             sb.end();
             sb.begin(K_PB_FRONT, (int32_t)P.gathert.size(), lev, 0);
             for (int32_t f : fr) if (smallf[f]) { P.gathert.push_back(f); int32_t mw = 0; for (int32_t q = 0; q < P.fronts[f].nps; ++q) mw = std::max(mw, P.psteps[P.fronts[f].ps0 + q].w); sb.add(1, 0, mw); }
             sb.end();
-            if (P.solve_flow && maxnps > 0) {
+            if (anyflow) {
                 sb.begin(K_PB_FLOW, (int32_t)P.flowt.size(), lev, 0);
                 sb.cur.ctr = P.nflowctr++;
-                for (int32_t f : fr) if (!smallf[f]) {
+                for (int32_t f : fr) if (flowf[f]) {
                     const Front& F = P.fronts[f];
                     for (int32_t j1 = F.nps; j1 > 0;) {                       // last steps first: the order of the backward sweep
                         int32_t j = j1, rows = 0;
@@ -667,11 +678,10 @@ inline void build_lists(Plan& P, const std::vector<uint8_t>& sel, std::vector<La
                     }
                 }
                 sb.end();
-                continue;
             }
             for (int32_t j = maxnps - 1; j >= 0; --j) {
                 sb.begin(K_PB_STEP, (int32_t)P.gathert.size(), lev, j);
-                for (int32_t f : fr) if (!smallf[f] && P.fronts[f].nps > j) {
+                for (int32_t f : fr) if (stepf[f] && P.fronts[f].nps > j) {
                     const PStep& ps = P.psteps[P.fronts[f].ps0 + j];
                     int32_t below = ps.R - ps.o - ps.w;
                     P.gathert.push_back(P.fronts[f].ps0 + j); sb.add(std::max(1, cdiv(below, SV_ROWS)), 0, ps.w);

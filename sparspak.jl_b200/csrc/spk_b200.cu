@@ -46,7 +46,8 @@ struct spk_plan {
     ncclComm_t comm = nullptr; bool comm_owned = false;  // communicator over the parts (spk_plan_comm_init / spk_multi_create)
     int8_t* d_fown = nullptr; FillTask* d_fillt = nullptr;
     GemmTile* d_tiles = nullptr; int32_t* d_tilectr = nullptr; int num_sms = 148;
-    FlowTask* d_flowt = nullptr; int32_t* d_flow = nullptr; int64_t flow_ints = 0;   // dataflow solve: tasks; [tickets | flags] (zeroed per sweep pair)
+    FlowTask* d_flowt = nullptr; int32_t* d_flow = nullptr; int64_t flow_ints = 0;   // dataflow solve: tasks; ticket counters (zeroed per solve)
+    double* d_box = nullptr;            // dataflow solve: x mailboxes, [forward | backward] x (rhs of a batch) x n, sentinel-filled per solve
     double ms_xchg = 0;
     // tree pipelines (Plan::pipes): stream / event pair per pipeline; pair 0 = (stream, stream2, evs0, evs1)
     cudaStream_t pst[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
@@ -228,6 +229,7 @@ SPK_API void spk_plan_destroy(spk_plan* p) {
         if (p->comm && p->comm_owned && nccl_api()) nccl_api()->CommDestroy(p->comm);
         if (p->d_flowt) cudaFree(p->d_flowt);
         if (p->d_flow) cudaFree(p->d_flow);
+        if (p->d_box) cudaFree(p->d_box);
         if (p->d_tiles) cudaFree(p->d_tiles);
         if (p->d_tilectr) cudaFree(p->d_tilectr);
         if (p->d_fown) cudaFree(p->d_fown);
@@ -326,7 +328,7 @@ static int64_t plan_upload(spk_plan* p) {
     CK(upload(&p->d_gemmt, P.gemmt));
     CK(upload(&p->d_solvet, P.solvet));
     CK(upload(&p->d_flowt, P.flowt));
-    p->flow_ints = ((int64_t)P.nflowctr + (int64_t)P.psteps.size()) * 4;       // 4 right-hand-side groups per batch of 32
+    p->flow_ints = (int64_t)P.nflowctr * 4;                                      // 4 right-hand-side groups per batch of 32
     CK(cudaMalloc((void**)&p->d_flow, (size_t)std::max<int64_t>(p->flow_ints, 1) * sizeof(int32_t)));
     CK(upload(&p->d_tiles, P.tiles));
     CK(cudaMalloc((void**)&p->d_tilectr, (size_t)std::max(P.nctr, 1) * sizeof(int32_t)));
@@ -871,6 +873,9 @@ static int64_t ensure_w(spk_plan* p, int64_t nrhs) {
         if (p->d_pb) cudaFree(p->d_pb);
         p->d_pb = nullptr;
         CK(cudaMalloc((void**)&p->d_pb, std::max<size_t>((size_t)p->P.pblen * nrhs, 1) * sizeof(double)));
+        if (p->d_box) cudaFree(p->d_box);
+        p->d_box = nullptr;
+        if (p->P.nflowctr > 0) CK(cudaMalloc((void**)&p->d_box, (size_t)2 * p->P.n * nrhs * sizeof(double)));
         p->w_nrhs = nrhs;
     }
     return 0;
@@ -935,13 +940,13 @@ static int64_t run_solve_launches(spk_plan* p, const DevCtx& c, const std::vecto
             const dim3 g(L.count, nrhs == 1 ? 1 : ngrp);
             const FlowTask* tk = p->d_flowt + L.first;
             int32_t* ticket = p->d_flow + (size_t)L.ctr * 4;
-            int32_t* flags = p->d_flow + (size_t)p->P.nflowctr * 4;
-            const int64_t fstride = (int64_t)p->P.psteps.size();
+            const int64_t bstride = p->P.n;
+            double* box = p->d_box + (fwd ? 0 : (size_t)p->w_nrhs * p->P.n);
             const bool wide = mw > FLOW_NT;                   // a single panel step wider than one row per thread
 #define SPK_FLOW(LUv, NRv, RPTv)                                                                                                      \
             do {                                                                                                                     \
-                if (fwd) k_pf_flow<LUv, NRv, RPTv><<<g, FLOW_NT, sm, st>>>(c, tk, ticket, flags, fstride, (int)nrhs, mw);             \
-                else k_pb_flow<LUv, NRv, RPTv><<<g, FLOW_NT, sm, st>>>(c, tk, ticket, flags, fstride, d_rhs, (int64_t)ldrhs, (int)nrhs, mw); \
+                if (fwd) k_pf_flow<LUv, NRv, RPTv><<<g, FLOW_NT, sm, st>>>(c, tk, ticket, box, bstride, (int)nrhs, mw);               \
+                else k_pb_flow<LUv, NRv, RPTv><<<g, FLOW_NT, sm, st>>>(c, tk, ticket, box, bstride, d_rhs, (int64_t)ldrhs, (int)nrhs, mw); \
             } while (0)
             if (lu) { if (nr == 1) { if (wide) SPK_FLOW(true, 1, 2); else SPK_FLOW(true, 1, 1); } else { if (wide) SPK_FLOW(true, SOLVE_NR, 2); else SPK_FLOW(true, SOLVE_NR, 1); } }
             else { if (nr == 1) { if (wide) SPK_FLOW(false, 1, 2); else SPK_FLOW(false, 1, 1); } else { if (wide) SPK_FLOW(false, SOLVE_NR, 2); else SPK_FLOW(false, SOLVE_NR, 1); } }
@@ -1017,7 +1022,7 @@ static int64_t enqueue_solve(spk_plan* p, double* d_rhs, int64_t nrhs, int64_t l
         double* b = d_rhs + (size_t)r0 * ldrhs;
         const int nf = (int)p->P.fronts.size();
         int64_t rc = 0;
-        if (p->flow_ints > 0) CK(cudaMemsetAsync(p->d_flow, 0, (size_t)p->flow_ints * sizeof(int32_t), st));   // tickets + flags of the dataflow launches
+        if (p->flow_ints > 0) { CK(cudaMemsetAsync(p->d_flow, 0, (size_t)p->flow_ints * sizeof(int32_t), st)); CK(cudaMemsetAsync(p->d_box, 0xFF, (size_t)2 * p->P.n * p->w_nrhs * sizeof(double), st)); }   // tickets; mailboxes := sentinel
         if (which == 2) { k_copy_front_x<<<dim3(nf, (unsigned)nb), 64, 0, st>>>(c, nf, b, ldrhs, 0); ++p->launches_solve; }
         if (which == 0 || which == 1) { rc = run_solve_launches(p, c, p->P.fwd_launches, b, nb, ldrhs); if (rc) return rc; }
         if (which == 1) { k_copy_front_x<<<dim3(nf, (unsigned)nb), 64, 0, st>>>(c, nf, b, ldrhs, 1); ++p->launches_solve; }
@@ -1126,7 +1131,7 @@ SPK_API int64_t spk_plan_solve_phase(spk_plan* p, double* d_rhs, int64_t nrhs, i
     DevCtx c = make_ctx(p);
     cudaStream_t st = p->stream;
     CK(cudaEventRecord(p->ev0, st));
-    if (phase == 0 && p->flow_ints > 0) CK(cudaMemsetAsync(p->d_flow, 0, (size_t)p->flow_ints * sizeof(int32_t), st));
+    if (phase == 0 && p->flow_ints > 0) { CK(cudaMemsetAsync(p->d_flow, 0, (size_t)p->flow_ints * sizeof(int32_t), st)); CK(cudaMemsetAsync(p->d_box, 0xFF, (size_t)2 * p->P.n * p->w_nrhs * sizeof(double), st)); }
     if (phase == 0) { p->launches_solve = 0; rc = run_solve_launches(p, c, p->P.fwd_local, d_rhs, nrhs, ldrhs); }
     else if (phase == 1) { rc = run_solve_launches(p, c, p->P.fwd_top, d_rhs, nrhs, ldrhs); if (!rc) rc = run_solve_launches(p, c, p->P.bwd_top, d_rhs, nrhs, ldrhs); }
     else rc = run_solve_launches(p, c, p->P.bwd_local, d_rhs, nrhs, ldrhs);
@@ -1157,7 +1162,7 @@ SPK_API int64_t spk_plan_solve_multi(spk_plan* p, double* d_rhs, int64_t nrhs, i
         int64_t rc = ensure_w(p, 32); if (rc) return rc;
         DevCtx c = make_ctx(p);
         double* b = d_rhs + (size_t)r0 * ldrhs;
-        if (p->flow_ints > 0) CK(cudaMemsetAsync(p->d_flow, 0, (size_t)p->flow_ints * sizeof(int32_t), st));
+        if (p->flow_ints > 0) { CK(cudaMemsetAsync(p->d_flow, 0, (size_t)p->flow_ints * sizeof(int32_t), st)); CK(cudaMemsetAsync(p->d_box, 0xFF, (size_t)2 * p->P.n * p->w_nrhs * sizeof(double), st)); }
         rc = run_solve_launches(p, c, P.fwd_local, b, nb, ldrhs); if (rc) return rc;
         NK(N->GroupStart());
         for (int32_t f : P.xchg) {
