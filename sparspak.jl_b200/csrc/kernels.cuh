@@ -1129,9 +1129,11 @@ __global__ void __launch_bounds__(256) k_bwd_front(DevCtx c, const int32_t* __re
 // Executed by ONE warp on shared memory (column sweep, __syncwarp between columns): no block barriers.
 // Each lane keeps the unknowns lane, lane+32, lane+64 in registers; x_k is broadcast with one shuffle
 // per column, so a column costs a shuffle + FMA instead of a shared-memory round trip (w <= 96).
+__device__ int g_solve_dbg = 0;                            // SPK_SOLVE_DBG (timing experiments only): 1 = skip the in-block solves
 template <bool LU>
 __device__ __forceinline__ void pf_diag_warp(const DevCtx& c, const PStep& ps, const double* Ts, double* xs) {
     const int lane = threadIdx.x & 31, w = ps.w;
+    if (g_solve_dbg & 1) return;
     if (w > 96) {                                           // generic shared-memory sweep
         if (LU) {
             const int32_t* ipiv = c.ipiv + ps.col0; const int32_t* subw = c.subw + ps.sub0;
@@ -1184,6 +1186,7 @@ __device__ __forceinline__ void pf_diag_warp(const DevCtx& c, const PStep& ps, c
 template <bool LU>
 __device__ __forceinline__ void pb_diag_warp(const PStep& ps, const double* Ts, double* xs) {
     const int lane = threadIdx.x & 31, w = ps.w;
+    if (g_solve_dbg & 1) return;
     if (w > 96) {
         for (int k = w - 1; k >= 0; --k) {
             if (LU) { if (lane == 0) xs[k] /= Ts[k + k * w]; __syncwarp(); }
@@ -1612,9 +1615,15 @@ constexpr int FLOW_NT = 128;
 constexpr unsigned long long FLOW_EMPTY = 0xFFFFFFFFFFFFFFFFull;      // mailbox sentinel (cudaMemset 0xFF)
 inline size_t flow_smem_bytes(int maxw, int nr) { const size_t wp = maxw <= 64 ? 64 : (size_t)maxw; return (2 * (size_t)maxw * maxw + (size_t)nr * wp) * sizeof(double); }
 
+__device__ int g_flow_backoff = 64;                        // ns between polls of a mailbox word (SPK_FLOW_BACKOFF)
 __device__ __forceinline__ double flow_poll(const double* p) {
     unsigned long long v;
-    do { asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); } while (v == FLOW_EMPTY);
+    const unsigned ns = (unsigned)g_flow_backoff;
+    for (;;) {
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        if (v != FLOW_EMPTY) break;
+        if (ns) __nanosleep(ns);                            // ~100 blocks wait for the same x_j: do not hammer its L2 slice
+    }
     return __longlong_as_double((long long)v);
 }
 __device__ __forceinline__ void flow_post(double* p, double x) { asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(x) : "memory"); }

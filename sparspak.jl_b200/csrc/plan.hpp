@@ -160,7 +160,10 @@ struct Plan {
     std::vector<FlowTask> flowt;              // thread blocks of the dataflow solve launches
     int32_t nflowctr = 0;                     // ticket counters (one per dataflow launch)
     int32_t flow_min_steps = FLOW_MIN_STEPS;  // SPK_FLOW_MIN_STEPS
-    bool solve_flow = true;                   // SPK_SOLVE_FLOW=0: one launch per panel step (k_pf_step / k_pb_step) instead
+    // SPK_SOLVE_FLOW=1: dataflow sweeps (one flag-free, mailbox-synchronised launch per level for the fronts with many
+    // panel steps).  MEASURED SLOWER than one launch per panel step (96^3: 20.4 vs 13.6 ms): a step costs ~11 us either
+    // way, of which ~3.5 us is the in-block triangular solve — the launch is not what bounds the chain.  Off by default.
+    bool solve_flow = false;
     std::vector<int32_t> blkpfx;
     std::vector<Launch> factor_launches, fwd_launches, bwd_launches;
     // multi-GPU (elimination-subtree partition): owner[f] = part that factors front f, or -1 for the TOP SET

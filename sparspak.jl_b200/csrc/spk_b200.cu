@@ -155,6 +155,8 @@ static int64_t init_kernel_attributes(int device) {
     SPK_SMEM((k_pb_flow<true, 1, 1>)); SPK_SMEM((k_pb_flow<true, 1, 2>)); SPK_SMEM((k_pb_flow<true, SOLVE_NR, 1>)); SPK_SMEM((k_pb_flow<true, SOLVE_NR, 2>));
     SPK_SMEM((k_pb_flow<false, 1, 1>)); SPK_SMEM((k_pb_flow<false, 1, 2>)); SPK_SMEM((k_pb_flow<false, SOLVE_NR, 1>)); SPK_SMEM((k_pb_flow<false, SOLVE_NR, 2>));
 #undef SPK_SMEM
+    if (const char* e = getenv("SPK_SOLVE_DBG")) { int v = atoi(e); CK(cudaMemcpyToSymbol(g_solve_dbg, &v, sizeof(int))); }
+    if (const char* e = getenv("SPK_FLOW_BACKOFF")) { int ns = atoi(e); CK(cudaMemcpyToSymbol(g_flow_backoff, &ns, sizeof(int))); }
     CK(gemm_dmma_init());
     done[device] = true;
     return 0;

@@ -256,6 +256,10 @@ VARIANTS = [
     {"SPK_SOLVE_GRAPH": "0", "SPK_SOLVE_SMALL": "0"},
     {"SPK_STORE_OVERLAP": "0", "SPK_LL": "0"},  # one write-back kernel at the end; right-looking in-block updates (LDLt)
     {"SPK_PANEL_REG_MINW": "0", "SPK_PDL_FACTOR": "1"},   # register panel kernel for every width <= 64; PDL in the factorisation
+    {"SPK_SOLVE_FLOW": "1", "SPK_FLOW_MIN_STEPS": "1", "SPK_SOLVE_SMALL": "0"},   # dataflow solve sweeps (mailbox-synchronised), every front
+    {"SPK_SOLVE_FLOW": "1", "SPK_FLOW_MIN_STEPS": "2", "SPK_PS_WIDTH": "16"},     # dataflow sweeps mixed with the per-step path, many steps
+    {"SPK_DMMA_PERSIST": "1", "SPK_GEMM_RESERVE": "16"},  # persistent DMMA blocks with reserved slots
+    {"SPK_DMMA_CA": "0", "SPK_DMMA_VARIANT": "6"},        # L2-only operand loads, 4-stage ring
 ]
 
 
