@@ -33,6 +33,7 @@ struct DevCtx {
     int32_t lu;
     int32_t me;                      // this part (multi-GPU)
     const int8_t* fown;              // column owners of the distributed top-set fronts
+    const double* tinvf; const double* tinvb;   // explicit inverses of the panel steps' diagonal blocks (solve), or NULL
 };
 
 // Programmatic dependent launch: a kernel launched with the programmatic-serialization attribute may start
@@ -1129,11 +1130,57 @@ __global__ void __launch_bounds__(256) k_bwd_front(DevCtx c, const int32_t* __re
 // Executed by ONE warp on shared memory (column sweep, __syncwarp between columns): no block barriers.
 // Each lane keeps the unknowns lane, lane+32, lane+64 in registers; x_k is broadcast with one shuffle
 // per column, so a column costs a shuffle + FMA instead of a shared-memory round trip (w <= 96).
+
+// ---- explicit inverses of the diagonal blocks (solve) ---------------------------------------------------------------
+// The in-block triangular solve is a chain of w dependent steps (~3.5 us of the ~11 us a panel step of a sweep costs).
+// After a factorisation k_diag_inverse applies the forward / backward in-block operators of every panel step to the
+// identity once; the sweeps then stage that w x w matrix instead of the diagonal block and apply it as a matrix-vector
+// product (w independent dot products).  Forward: M_f = L11^{-1} P (LU: interchanges of all pivot sub-blocks folded
+// in, so M_f is a general matrix; LDL^T: unit lower triangular).  Backward: M_b = U11^{-1} (LU) or L11^{-T} (LDL^T).
+// LDL^T keeps D on the diagonal of both (the callers divide by it); the product treats that diagonal as 1.
+__device__ __forceinline__ const double* diag_src(const DevCtx& c, const PStep& ps, bool fwd, int& ld) {
+    if (c.tinvf) { ld = ps.w; return (fwd ? c.tinvf : c.tinvb) + ps.iofs; }
+    ld = ps.ld;
+    return c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld;
+}
+// xs := M xs by one warp (M staged column-major with leading dimension w); UNIT: the diagonal of M counts as 1
+template <bool UNIT>
+__device__ __forceinline__ void inv_apply_warp(const double* __restrict__ Ms, double* xs, int w) {
+    const int lane = threadIdx.x & 31;
+    if (w <= 96) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        const int i0 = lane, i1 = lane + 32, i2 = lane + 64;
+        for (int k = 0; k < w; ++k) {
+            const double xk = xs[k];
+            const double* __restrict__ col = Ms + k * w;
+            if (i0 < w) a0 += ((UNIT && k == i0) ? 1.0 : col[i0]) * xk;
+            if (i1 < w) a1 += ((UNIT && k == i1) ? 1.0 : col[i1]) * xk;
+            if (i2 < w) a2 += ((UNIT && k == i2) ? 1.0 : col[i2]) * xk;
+        }
+        __syncwarp();
+        if (i0 < w) xs[i0] = a0; if (i1 < w) xs[i1] = a1; if (i2 < w) xs[i2] = a2;
+        __syncwarp();
+        return;
+    }
+    double acc[8];                                          // w <= 256
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] = 0.0;
+    for (int k = 0; k < w; ++k) {
+        const double xk = xs[k];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int i = lane + 32 * u; if (i < w) acc[u] += ((UNIT && k == i) ? 1.0 : Ms[i + k * w]) * xk; }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int i = lane + 32 * u; if (i < w) xs[i] = acc[u]; }
+    __syncwarp();
+}
 __device__ int g_solve_dbg = 0;                            // SPK_SOLVE_DBG (timing experiments only): 1 = skip the in-block solves
 template <bool LU>
 __device__ __forceinline__ void pf_diag_warp(const DevCtx& c, const PStep& ps, const double* Ts, double* xs) {
     const int lane = threadIdx.x & 31, w = ps.w;
     if (g_solve_dbg & 1) return;
+    if (c.tinvf) { inv_apply_warp<!LU>(Ts, xs, w); return; }          // Ts holds M_f
     if (w > 96) {                                           // generic shared-memory sweep
         if (LU) {
             const int32_t* ipiv = c.ipiv + ps.col0; const int32_t* subw = c.subw + ps.sub0;
@@ -1184,9 +1231,10 @@ __device__ __forceinline__ void pf_diag_warp(const DevCtx& c, const PStep& ps, c
 }
 // pb_diag: backward in-block solve.  LU: x := inv(U11) y.  LDL^T: x := inv(L11^T) y (y already divided by D).
 template <bool LU>
-__device__ __forceinline__ void pb_diag_warp(const PStep& ps, const double* Ts, double* xs) {
+__device__ __forceinline__ void pb_diag_warp(const DevCtx& c, const PStep& ps, const double* Ts, double* xs) {
     const int lane = threadIdx.x & 31, w = ps.w;
     if (g_solve_dbg & 1) return;
+    if (c.tinvf) { inv_apply_warp<!LU>(Ts, xs, w); return; }          // Ts holds M_b
     if (w > 96) {
         for (int k = w - 1; k >= 0; --k) {
             if (LU) { if (lane == 0) xs[k] /= Ts[k + k * w]; __syncwarp(); }
@@ -1393,7 +1441,7 @@ __global__ void __launch_bounds__(128) k_pf_diag(DevCtx c, const int32_t* __rest
     const DFront F = c.fronts[ps.front];
     double* wf = c.w + (size_t)blockIdx.y * c.wlen + F.wofs;
     double* Ts = ssm; double* xs = ssm + ps.w * ps.w;
-    block_g2s<128>(Ts, ps.w, c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld, ps.ld, ps.w);
+    { int sld; const double* src = diag_src(c, ps, true, sld); block_g2s<128>(Ts, ps.w, src, sld, ps.w); }
     for (int k = threadIdx.x; k < ps.w; k += blockDim.x) xs[k] = wf[ps.o + k];
     __syncthreads();
     if (threadIdx.x < 32) pf_diag_warp<LU>(c, ps, Ts, xs);
@@ -1438,7 +1486,7 @@ __global__ void __launch_bounds__(128) k_pb_diag(DevCtx c, const int32_t* __rest
     double* wf = c.w + (size_t)blockIdx.y * c.wlen + F.wofs;
     const double* pb = c.pb + (size_t)blockIdx.y * c.pblen + F.pbofs;
     double* Ts = ssm; double* xs = ssm + ps.w * ps.w;
-    block_g2s<128>(Ts, ps.w, c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld, ps.ld, ps.w);
+    { int sld; const double* src = diag_src(c, ps, false, sld); block_g2s<128>(Ts, ps.w, src, sld, ps.w); }
     const int nblk = (ps.R - ps.o - ps.w + SV_ROWS - 1) / SV_ROWS;
     __syncthreads();
     for (int k = threadIdx.x; k < ps.w; k += blockDim.x) {
@@ -1448,7 +1496,7 @@ __global__ void __launch_bounds__(128) k_pb_diag(DevCtx c, const int32_t* __rest
         xs[k] = LU ? y - s : (ps.w <= 64 ? (y - s) / Ts[k + k * ps.w] : y / Ts[k + k * ps.w] - s);   // w <= 64: sums of U = D L^T entries
     }
     __syncthreads();
-    if (threadIdx.x < 32) pb_diag_warp<LU>(ps, Ts, xs);
+    if (threadIdx.x < 32) pb_diag_warp<LU>(c, ps, Ts, xs);
     __syncthreads();
     double* out = rhs + (size_t)blockIdx.y * ldrhs + ps.col0;
     for (int k = threadIdx.x; k < ps.w; k += blockDim.x) { wf[ps.o + k] = xs[k]; out[k] = xs[k]; }
@@ -1477,7 +1525,7 @@ __global__ void __launch_bounds__(SV_ROWS) k_pf_step(DevCtx c, const int32_t* __
     PStep nx;
     if (next) {
         nx = c.psteps[pid + 1];
-        stage_block_async(Ts, c.F + nx.fofs + (int64_t)nx.o + (int64_t)nx.o * nx.ld, nx.ld, nx.w);
+        { int sld; const double* src = diag_src(c, nx, true, sld); stage_block_async(Ts, src, sld, nx.w); }
     }
     const int e0 = ps.o + ps.w;
     const int r0 = e0 + lb * SV_ROWS, r1 = min(ps.R, e0 + (lb + 1) * SV_ROWS);
@@ -1547,7 +1595,7 @@ __global__ void __launch_bounds__(SV_ROWS, 1) k_pb_step(DevCtx c, const int32_t*
     double* Ts = ssm; double* xs = ssm + w * w;                // xs: NR x w, then 8 x w partial sums
     double* red = xs + NR * w;
     // every block stages the diagonal block while it forms its partial sums: the one that arrives last needs it at once
-    stage_block_async(Ts, c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld, ps.ld, w);
+    { int sld; const double* src = diag_src(c, ps, false, sld); stage_block_async(Ts, src, sld, w); }
     if (nblk > 0) {
         const int r0 = e0 + lb * SV_ROWS, r1 = min(ps.R, e0 + (lb + 1) * SV_ROWS);
         if (w <= 64) {
@@ -1588,7 +1636,7 @@ __global__ void __launch_bounds__(SV_ROWS, 1) k_pb_step(DevCtx c, const int32_t*
         xs[e] = LU ? y - sum : (w <= 64 ? (y - sum) / Ts[k + k * w] : y / Ts[k + k * w] - sum);       // w <= 64: sums of U = D L^T entries
     }
     __syncthreads();
-    if ((threadIdx.x >> 5) < nr) pb_diag_warp<LU>(ps, Ts, xs + (threadIdx.x >> 5) * w);              // one warp per right-hand side
+    if ((threadIdx.x >> 5) < nr) pb_diag_warp<LU>(c, ps, Ts, xs + (threadIdx.x >> 5) * w);              // one warp per right-hand side
     __syncthreads();
     for (int e = threadIdx.x; e < nr * w; e += blockDim.x) {
         const int q = e / w, k = e - q * w;
@@ -1597,6 +1645,57 @@ __global__ void __launch_bounds__(SV_ROWS, 1) k_pb_step(DevCtx c, const int32_t*
     }
 }
 
+
+
+// One block per panel step: applies the in-block forward and backward operators to the identity (thread c owns column
+// c of the result, kept in shared memory with an odd leading dimension: conflict-free although the threads walk
+// different columns), with the arithmetic of pf_diag_warp / pb_diag_warp.  Output: compact w x w, column-major.
+inline size_t inverse_smem_bytes(int w) { return (size_t)2 * w * (w | 1) * sizeof(double); }
+template <bool LU>
+__global__ void __launch_bounds__(64) k_diag_inverse(DevCtx c, const int32_t* __restrict__ list, double* __restrict__ outf, double* __restrict__ outb) {
+    extern __shared__ double ssm[];
+    const PStep ps = c.psteps[list[blockIdx.x]];
+    if (ps.fofs < 0) return;                               // a front this part holds no storage for
+    const int w = ps.w, lp = w | 1;
+    double* T = ssm; double* M = ssm + (size_t)w * lp;
+    const double* __restrict__ G = c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld;
+    for (int e = threadIdx.x; e < w * w; e += blockDim.x) { const int i = e % w, j = e / w; T[i + j * lp] = G[i + (int64_t)j * ps.ld]; }
+    __syncthreads();
+    // ---- forward operator
+    for (int col = threadIdx.x; col < w; col += blockDim.x) {
+        double* x = M + (size_t)col * lp;
+        for (int i = 0; i < w; ++i) x[i] = i == col ? 1.0 : 0.0;
+        if (LU) {
+            const int32_t* ipiv = c.ipiv + ps.col0; const int32_t* subw = c.subw + ps.sub0;
+            int s0 = 0;
+            for (int b = 0; b < ps.nsub; ++b) {
+                const int s1 = s0 + subw[b];
+                for (int k = s0; k < s1; ++k) { const int ip = s0 + ipiv[k] - 1; if (ip != k) { const double t = x[k]; x[k] = x[ip]; x[ip] = t; } }
+                for (int k = s0; k < s1; ++k) { const double xk = x[k]; if (xk != 0.0) for (int i = k + 1; i < w; ++i) x[i] -= xk * T[i + k * lp]; }
+                s0 = s1;
+            }
+        } else {
+            for (int k = col; k < w - 1; ++k) { const double xk = x[k]; for (int i = k + 1; i < w; ++i) x[i] -= xk * T[i + k * lp]; }
+            x[col] = T[col + col * lp];                      // D on the diagonal (the product treats it as 1)
+        }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < w * w; e += blockDim.x) { const int i = e % w, j = e / w; outf[ps.iofs + e] = M[i + j * lp]; }
+    __syncthreads();
+    // ---- backward operator
+    for (int col = threadIdx.x; col < w; col += blockDim.x) {
+        double* x = M + (size_t)col * lp;
+        for (int i = 0; i < w; ++i) x[i] = i == col ? 1.0 : 0.0;
+        if (LU) {
+            for (int k = col; k >= 0; --k) { x[k] /= T[k + k * lp]; const double xk = x[k]; for (int i = 0; i < k; ++i) x[i] -= xk * T[i + k * lp]; }
+        } else {
+            for (int k = col; k >= 1; --k) { const double xk = x[k]; for (int i = 0; i < k; ++i) x[i] -= xk * T[k + i * lp]; }
+            x[col] = T[col + col * lp];
+        }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < w * w; e += blockDim.x) { const int i = e % w, j = e / w; outb[ps.iofs + e] = M[i + j * lp]; }
+}
 
 // ------------------------------------------------------------------------------------
 // DATAFLOW sweeps on the fronts with many panel steps (K_PF_FLOW / K_PB_FLOW): one launch per level instead of one
@@ -1687,7 +1786,7 @@ __global__ void __launch_bounds__(FLOW_NT) k_pf_flow(DevCtx c, const FlowTask* _
         for (int q = 0; q < NR; ++q) val[u][q] = (q < nr && row[u] < R1) ? wf0[(size_t)q * c.wlen + row[u]] : 0.0;
     }
     if (pivot) {                                            // diagonal blocks of my first two steps: staged while the updates arrive
-        for (int j = t.ja; j < min(t.jb, t.ja + 2); ++j) { const PStep ps = c.psteps[F.ps0 + j]; stage_block_async(Tb[(j - t.ja) & 1], Fm + (int64_t)ps.o + (int64_t)ps.o * ld, ld, ps.w); }
+        for (int j = t.ja; j < min(t.jb, t.ja + 2); ++j) { const PStep ps = c.psteps[F.ps0 + j]; int sld; const double* src = diag_src(c, ps, true, sld); stage_block_async(Tb[(j - t.ja) & 1], src, sld, ps.w); }
     }
     const int jend = pivot ? t.jb : F.nps;
     PStep ps = c.psteps[F.ps0];
@@ -1718,7 +1817,7 @@ __global__ void __launch_bounds__(FLOW_NT) k_pf_flow(DevCtx c, const FlowTask* _
                 flow_post(bx + (size_t)q * box_stride + ps.o + k, xs[q * wp + k]);
                 wf0[(size_t)q * c.wlen + ps.o + k] = xs[q * wp + k];
             }
-            if (j + 2 < t.jb) { const PStep p2 = c.psteps[F.ps0 + j + 2]; stage_block_async(Tb[(j - t.ja) & 1], Fm + (int64_t)p2.o + (int64_t)p2.o * ld, ld, p2.w); }
+            if (j + 2 < t.jb) { const PStep p2 = c.psteps[F.ps0 + j + 2]; int sld; const double* src = diag_src(c, p2, true, sld); stage_block_async(Tb[(j - t.ja) & 1], src, sld, p2.w); }
         } else {
             for (int e = tid; e < nr * wp; e += FLOW_NT) { const int q = e / wp, k = e - q * wp; xs[e] = k < w ? flow_poll(bx + (size_t)q * box_stride + ps.o + k) : 0.0; }
             __syncthreads();
@@ -1776,7 +1875,7 @@ __global__ void __launch_bounds__(FLOW_NT) k_pb_flow(DevCtx c, const FlowTask* _
 #pragma unroll
         for (int q = 0; q < NR; ++q) val[u][q] = (q < nr && row[u] < R1) ? wf0[(size_t)q * c.wlen + row[u]] : 0.0;
     }
-    for (int j = t.jb - 1; j >= max(t.ja, t.jb - 2); --j) { const PStep ps = c.psteps[F.ps0 + j]; stage_block_async(Tb[(t.jb - 1 - j) & 1], Fm + (int64_t)ps.o + (int64_t)ps.o * ld, ld, ps.w); }
+    for (int j = t.jb - 1; j >= max(t.ja, t.jb - 2); --j) { const PStep ps = c.psteps[F.ps0 + j]; int sld; const double* src = diag_src(c, ps, false, sld); stage_block_async(Tb[(t.jb - 1 - j) & 1], src, sld, ps.w); }
     // the unknowns below the front's columns are known (gathered from the parent): their contribution first
     for (int c0 = F.W; c0 < F.R; c0 += wp) {
         const int wc = min(wp, F.R - c0);
@@ -1810,7 +1909,7 @@ __global__ void __launch_bounds__(FLOW_NT) k_pb_flow(DevCtx c, const FlowTask* _
                 for (int q = 0; q < NR; ++q) if (q < nr) xs[q * wp + k] = LU ? val[u][q] : val[u][q] / T[k + k * w];
             }
             __syncthreads();
-            for (int q = warp; q < nr; q += FLOW_NT / 32) pb_diag_warp<LU>(ps, T, xs + q * wp);
+            for (int q = warp; q < nr; q += FLOW_NT / 32) pb_diag_warp<LU>(c, ps, T, xs + q * wp);
             __syncthreads();
             for (int e = tid; e < nr * w; e += FLOW_NT) {
                 const int q = e / w, k = e - q * w;
@@ -1818,7 +1917,7 @@ __global__ void __launch_bounds__(FLOW_NT) k_pb_flow(DevCtx c, const FlowTask* _
                 wf0[(size_t)q * c.wlen + ps.o + k] = xs[q * wp + k];
                 rhs[(size_t)(q0 + q) * ldrhs + ps.col0 + k] = xs[q * wp + k];
             }
-            if (j - 2 >= t.ja) { const PStep p2 = c.psteps[F.ps0 + j - 2]; stage_block_async(T, Fm + (int64_t)p2.o + (int64_t)p2.o * ld, ld, p2.w); }
+            if (j - 2 >= t.ja) { const PStep p2 = c.psteps[F.ps0 + j - 2]; int sld; const double* src = diag_src(c, p2, false, sld); stage_block_async(T, src, sld, p2.w); }
         } else {
             for (int e = tid; e < nr * wp; e += FLOW_NT) { const int q = e / wp, k = e - q * wp; xs[e] = k < w ? flow_poll(bx + (size_t)q * box_stride + ps.o + k) : 0.0; }
             __syncthreads();
@@ -1857,7 +1956,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 8) k_pf_front(DevCtx c, co
         const int w = ps.w;
         const int xst = (NR > 1 && w <= 64) ? 64 : w;          // x of one right-hand side, zero-padded to 64 (unconditional FMAs)
         double* Ts = ssm; double* xs = ssm + w * w;             // xs: NR x xst
-        block_g2s<NT>(Ts, w, c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld, ps.ld, w);
+        { int sld; const double* src = diag_src(c, ps, true, sld); block_g2s<NT>(Ts, w, src, sld, w); }
         for (int e = threadIdx.x; e < nr * xst; e += blockDim.x) { const int q = e / xst, k = e - q * xst; xs[e] = k < w ? wf0[(size_t)q * c.wlen + ps.o + k] : 0.0; }
         __syncthreads();
         for (int q = warp; q < nr; q += NT / 32) pf_diag_warp<LU>(c, ps, Ts, xs + q * xst);
@@ -1903,7 +2002,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 8) k_pb_front(DevCtx c, co
         const PStep ps = c.psteps[F.ps0 + j];
         const int w = ps.w, e0 = ps.o + w;
         double* Ts = ssm; double* xs = ssm + w * w; double* red = xs + NR * w;        // red: NR x 8 warps x w (NR == 1: 8 x w)
-        block_g2s<NT>(Ts, w, c.F + ps.fofs + (int64_t)ps.o + (int64_t)ps.o * ps.ld, ps.ld, w);
+        { int sld; const double* src = diag_src(c, ps, false, sld); block_g2s<NT>(Ts, w, src, sld, w); }
         if (NR == 1 || w > 64) {
             for (int q = 0; q < nr; ++q) { pb_partial<LU>(c, ps, wf0 + (size_t)q * c.wlen, e0, ps.R, red, xs + q * w); __syncthreads(); }
         } else {
@@ -1950,7 +2049,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 8) k_pb_front(DevCtx c, co
             xs[e] = LU ? y - xs[e] : (w <= 64 ? (y - xs[e]) / Ts[k + k * w] : y / Ts[k + k * w] - xs[e]);   // w <= 64: sums of U = D L^T entries
         }
         __syncthreads();
-        for (int q = warp; q < nr; q += NT / 32) pb_diag_warp<LU>(ps, Ts, xs + q * w);
+        for (int q = warp; q < nr; q += NT / 32) pb_diag_warp<LU>(c, ps, Ts, xs + q * w);
         __syncthreads();
         for (int e = threadIdx.x; e < nr * w; e += blockDim.x) { const int q = e / w, k = e - q * w; wf0[(size_t)q * c.wlen + ps.o + k] = xs[e]; }
         __syncthreads();

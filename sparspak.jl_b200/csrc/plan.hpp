@@ -58,6 +58,7 @@ struct Front {
 struct PStep {
     int64_t fofs, col0;   // front matrix; global first column (ipiv index)
     int32_t ld, R, o, w, ob_end, sub0, nsub, front;
+    int64_t iofs;         // its w x w slot in the arrays of inverted diagonal blocks (solve)
 };
 
 struct GemmTask {         // C -= A * B   inside one frontal matrix (offsets relative to the arena)
@@ -138,7 +139,7 @@ struct Plan {
     std::vector<int32_t> rel;                 // relative indices, all fronts
     std::vector<int32_t> pos;                 // per-chunk stored-row -> front-row maps
     std::vector<int32_t> col2chunk;
-    int64_t arena = 0, wlen = 0, pblen = 0;
+    int64_t arena = 0, wlen = 0, pblen = 0, tinv_len = 0;
     bool solve_on_fronts = true;              // solve sweeps read the frontal matrices (panel steps) instead of lnz/unz (chunks)
     int32_t nlevels = 0, maxnj = 0, maxR = 0, maxpw = 0;
     double flops_struct = 0, nnzL = 0;        // sum cc^2 (or 2 sum cc^2 - sum cc), sum cc
@@ -348,6 +349,7 @@ inline bool analyze(Plan& P, int64_t n, int64_t nsuper, const int64_t* xsuper, c
             int32_t w = 0, ns = 0;
             while (t < F.nch && (ns == 0 || w + P.chunks[F.c0 + t].nj <= P.ps_width)) { w += P.chunks[F.c0 + t].nj; P.subw.push_back(P.chunks[F.c0 + t].nj); ++ns; ++t; }
             ps.w = w; ps.nsub = ns;
+            ps.iofs = P.tinv_len; P.tinv_len += (int64_t)w * w;
             P.maxpw = std::max(P.maxpw, w);
             P.psteps.push_back(ps);
         }

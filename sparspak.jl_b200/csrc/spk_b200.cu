@@ -47,6 +47,8 @@ struct spk_plan {
     int8_t* d_fown = nullptr; FillTask* d_fillt = nullptr;
     GemmTile* d_tiles = nullptr; int32_t* d_tilectr = nullptr; int num_sms = 148;
     FlowTask* d_flowt = nullptr; int32_t* d_flow = nullptr; int64_t flow_ints = 0;   // dataflow solve: tasks; ticket counters (zeroed per solve)
+    double *d_tinvf = nullptr, *d_tinvb = nullptr; bool use_inv = true, inv_ready = false;   // inverted diagonal blocks (SPK_SOLVE_INV=0: off)
+    int32_t *d_invlist = nullptr; int32_t inv_nsmall = 0, inv_nlarge = 0, inv_maxw_small = 32;
     double* d_box = nullptr;            // dataflow solve: x mailboxes, [forward | backward] x (rhs of a batch) x n, sentinel-filled per solve
     double ms_xchg = 0;
     // tree pipelines (Plan::pipes): stream / event pair per pipeline; pair 0 = (stream, stream2, evs0, evs1)
@@ -119,6 +121,7 @@ static DevCtx make_ctx(spk_plan* p) {
     c.childlist = p->d_childlist; c.rel = p->d_rel; c.pos = p->d_pos;
     c.solvet = p->d_solvet; c.wlen = p->P.wlen; c.lu = p->P.lu ? 1 : 0;
     c.me = p->P.part; c.fown = p->d_fown;
+    c.tinvf = p->inv_ready ? p->d_tinvf : nullptr; c.tinvb = p->inv_ready ? p->d_tinvb : nullptr;
     return c;
 }
 
@@ -150,6 +153,7 @@ static int64_t init_kernel_attributes(int device) {
     SPK_SMEM((k_pf_step<true, SOLVE_NR>)); SPK_SMEM((k_pf_step<false, SOLVE_NR>)); SPK_SMEM((k_pb_step<true, SOLVE_NR>)); SPK_SMEM((k_pb_step<false, SOLVE_NR>));
     SPK_SMEM(k_pf_diag<true>); SPK_SMEM(k_pf_diag<false>); SPK_SMEM(k_pb_diag<true>); SPK_SMEM(k_pb_diag<false>);
     SPK_SMEM(k_pb_update<true>); SPK_SMEM(k_pb_update<false>);
+    SPK_SMEM(k_diag_inverse<true>); SPK_SMEM(k_diag_inverse<false>);
     SPK_SMEM((k_pf_flow<true, 1, 1>)); SPK_SMEM((k_pf_flow<true, 1, 2>)); SPK_SMEM((k_pf_flow<true, SOLVE_NR, 1>)); SPK_SMEM((k_pf_flow<true, SOLVE_NR, 2>));
     SPK_SMEM((k_pf_flow<false, 1, 1>)); SPK_SMEM((k_pf_flow<false, 1, 2>)); SPK_SMEM((k_pf_flow<false, SOLVE_NR, 1>)); SPK_SMEM((k_pf_flow<false, SOLVE_NR, 2>));
     SPK_SMEM((k_pb_flow<true, 1, 1>)); SPK_SMEM((k_pb_flow<true, 1, 2>)); SPK_SMEM((k_pb_flow<true, SOLVE_NR, 1>)); SPK_SMEM((k_pb_flow<true, SOLVE_NR, 2>));
@@ -232,6 +236,9 @@ SPK_API void spk_plan_destroy(spk_plan* p) {
         if (p->d_flowt) cudaFree(p->d_flowt);
         if (p->d_flow) cudaFree(p->d_flow);
         if (p->d_box) cudaFree(p->d_box);
+        if (p->d_tinvf) cudaFree(p->d_tinvf);
+        if (p->d_tinvb) cudaFree(p->d_tinvb);
+        if (p->d_invlist) cudaFree(p->d_invlist);
         if (p->d_tiles) cudaFree(p->d_tiles);
         if (p->d_tilectr) cudaFree(p->d_tilectr);
         if (p->d_fown) cudaFree(p->d_fown);
@@ -329,6 +336,15 @@ static int64_t plan_upload(spk_plan* p) {
     CK(upload(&p->d_asmt, P.asmt));
     CK(upload(&p->d_gemmt, P.gemmt));
     CK(upload(&p->d_solvet, P.solvet));
+    if (p->use_inv && P.maxpw <= 110 && P.solve_on_fronts) {       // two w x (w|1) blocks of the widest step must fit in shared memory
+        CK(cudaMalloc((void**)&p->d_tinvf, (size_t)std::max<int64_t>(P.tinv_len, 1) * sizeof(double)));
+        CK(cudaMalloc((void**)&p->d_tinvb, (size_t)std::max<int64_t>(P.tinv_len, 1) * sizeof(double)));
+        std::vector<int32_t> small, large;
+        for (size_t i = 0; i < P.psteps.size(); ++i) if (P.psteps[i].fofs >= 0) (P.psteps[i].w <= p->inv_maxw_small ? small : large).push_back((int32_t)i);
+        p->inv_nsmall = (int32_t)small.size(); p->inv_nlarge = (int32_t)large.size();
+        small.insert(small.end(), large.begin(), large.end());
+        CK(upload(&p->d_invlist, small));
+    } else p->use_inv = false;
     CK(upload(&p->d_flowt, P.flowt));
     p->flow_ints = (int64_t)P.nflowctr * 4;                                      // 4 right-hand-side groups per batch of 32
     CK(cudaMalloc((void**)&p->d_flow, (size_t)std::max<int64_t>(p->flow_ints, 1) * sizeof(int32_t)));
@@ -389,6 +405,7 @@ SPK_API spk_plan* spk_plan_create(int64_t n, int64_t nsuper, const int64_t* xsup
     if (const char* e = getenv("SPK_DMMA_VARIANT")) p->dmma_variant = atoi(e);
     // persistent blocks hold their SM slots for the whole launch, which defeats the stream priorities the look-ahead
     // relies on (measured: 243.6 ms persistent with 32 reserved slots vs 236.6 ms one block per tile); off by default
+    if (const char* e = getenv("SPK_SOLVE_INV")) p->use_inv = e[0] != '0';
     if (const char* e = getenv("SPK_DMMA_PERSIST")) p->dmma_persist = e[0] != '0';
     if (const char* e = getenv("SPK_DMMA_CA")) p->dmma_flags = (p->dmma_flags & ~1) | (e[0] != '0' ? 1 : 0);
     if (const char* e = getenv("SPK_DMMA_STATIC")) p->dmma_flags = (p->dmma_flags & ~2) | (e[0] != '0' ? 2 : 0);
@@ -416,6 +433,8 @@ SPK_API spk_plan* spk_plan_create(int64_t n, int64_t nsuper, const int64_t* xsup
 }
 
 #define NEED_DEV(p) do { if (!(p) || (p)->device < 0) { set_err("plan has no device"); return -100; } CK(cudaSetDevice((p)->device)); } while (0)
+
+static int64_t build_inverses(spk_plan* p, cudaStream_t st);
 
 SPK_API int64_t spk_plan_set_values(spk_plan* p, const double* lnz, const double* unz) {
     NEED_DEV(p);
@@ -445,6 +464,7 @@ SPK_API int64_t spk_plan_set_factors(spk_plan* p, const double* lnz, const doubl
         CK(cudaMemsetAsync(p->d_F, 0, p->P.arena * sizeof(double), p->stream));
         if (p->P.lu) k_chunks<false><<<p->chunk_blocks, 256, 0, p->stream>>>(c, p->d_chunkpfx, (int)p->P.chunks.size());
         else k_chunks<false, true><<<p->chunk_blocks, 256, 0, p->stream>>>(c, p->d_chunkpfx, (int)p->P.chunks.size());   // + U = D L^T
+        int64_t rci = build_inverses(p, p->stream); if (rci) return rci;
         CK(cudaStreamSynchronize(p->stream));
     }
     p->factored = true;
@@ -521,6 +541,28 @@ SPK_API int64_t spk_plan_reassemble(spk_plan* p) {
     k_scatter_values<<<cdiv(p->nz_last, 256), 256, 0, p->stream>>>(p->nz_last, p->d_dest, p->d_nzval, p->d_F);
     CK(cudaGetLastError());
     p->factored = false; p->values_in_fronts = true;
+    return 0;
+}
+
+// explicit inverses of the diagonal blocks of every panel step this part holds (solve, see k_diag_inverse)
+static int64_t build_inverses(spk_plan* p, cudaStream_t st) {
+    if (!p->use_inv) return 0;
+    p->inv_ready = false;
+    DevCtx c = make_ctx(p);
+    const bool lu = p->P.lu;
+    if (p->inv_nsmall > 0) {
+        const size_t sm = inverse_smem_bytes(p->inv_maxw_small);
+        if (lu) k_diag_inverse<true><<<p->inv_nsmall, 64, sm, st>>>(c, p->d_invlist, p->d_tinvf, p->d_tinvb);
+        else k_diag_inverse<false><<<p->inv_nsmall, 64, sm, st>>>(c, p->d_invlist, p->d_tinvf, p->d_tinvb);
+    }
+    if (p->inv_nlarge > 0) {
+        const size_t sm = inverse_smem_bytes(p->P.maxpw);
+        if (lu) k_diag_inverse<true><<<p->inv_nlarge, 64, sm, st>>>(c, p->d_invlist + p->inv_nsmall, p->d_tinvf, p->d_tinvb);
+        else k_diag_inverse<false><<<p->inv_nlarge, 64, sm, st>>>(c, p->d_invlist + p->inv_nsmall, p->d_tinvf, p->d_tinvb);
+    }
+    CK(cudaGetLastError());
+    p->launches_factor += 2;
+    p->inv_ready = true;
     return 0;
 }
 
@@ -670,6 +712,7 @@ SPK_API int64_t spk_plan_factor_phase(spk_plan* p, int32_t phase) {
                 k_chunks_store_list<<<p->st_blocks[1][lv], 256, 0, st>>>(c, p->d_stlist + p->st_list0[1][lv], p->d_stpfx + p->st_pfx0[1][lv], p->st_count[1][lv]);
                 ++p->launches_factor;
             }
+        { int64_t rci = build_inverses(p, st); if (rci) return rci; }
         CK(cudaGetLastError());
         CK(cudaEventRecord(p->ev1, st));
         CK(cudaStreamSynchronize(st));
@@ -686,6 +729,7 @@ SPK_API int64_t spk_plan_factor_phase(spk_plan* p, int32_t phase) {
         CK(cudaMemsetAsync(p->d_iflag, 0, sizeof(int32_t), st));
         CK(cudaMemsetAsync(p->d_tilectr, 0, (size_t)std::max(P.nctr, 1) * sizeof(int32_t), st));    // tile counters of the persistent DMMA launches
         p->launches_factor = 0; p->gemm_flops = 0; p->gemm_ms = 0;
+        p->inv_ready = false;
         if (!p->values_in_fronts) {
             // gather the assembled matrix (reference layout) into the zeroed frontal matrices
             CK(cudaMemsetAsync(p->d_F, 0, P.arena * sizeof(double), st));
@@ -769,6 +813,7 @@ SPK_API int64_t spk_plan_factor_phase(spk_plan* p, int32_t phase) {
         k_chunks<true><<<p->chunk_blocks, 256, 0, st>>>(c, p->d_chunkpfx, (int)P.chunks.size());
         ++p->launches_factor;
     }
+    if (phase < 0) { int64_t rci = build_inverses(p, st); if (rci) return rci; }
     CK(cudaGetLastError());
     CK(cudaEventRecord(phase == 0 ? p->evg1 : p->ev1, st));
     if (phase == 0 && p->phase0_async) return 0;        // spk_plan_factor_multi: phase 1 follows without a host synchronisation
@@ -876,6 +921,9 @@ static int64_t ensure_w(spk_plan* p, int64_t nrhs) {
         p->d_pb = nullptr;
         CK(cudaMalloc((void**)&p->d_pb, std::max<size_t>((size_t)p->P.pblen * nrhs, 1) * sizeof(double)));
         if (p->d_box) cudaFree(p->d_box);
+        if (p->d_tinvf) cudaFree(p->d_tinvf);
+        if (p->d_tinvb) cudaFree(p->d_tinvb);
+        if (p->d_invlist) cudaFree(p->d_invlist);
         p->d_box = nullptr;
         if (p->P.nflowctr > 0) CK(cudaMalloc((void**)&p->d_box, (size_t)2 * p->P.n * nrhs * sizeof(double)));
         p->w_nrhs = nrhs;
@@ -1554,6 +1602,7 @@ static int64_t dropin_solve(int64_t n, int64_t nsuper, const int64_t* xsuper, co
             if (!rc) {
                 if (lu) k_chunks<false><<<p->chunk_blocks, 256, 0, p->stream>>>(c, p->d_chunkpfx, (int)p->P.chunks.size());
                 else k_chunks<false, true><<<p->chunk_blocks, 256, 0, p->stream>>>(c, p->d_chunkpfx, (int)p->P.chunks.size());   // + U = D L^T
+                if (build_inverses(p, p->stream) != 0) rc = -100;
                 if (cudaStreamSynchronize(p->stream) != cudaSuccess) rc = -100;
             }
         }
