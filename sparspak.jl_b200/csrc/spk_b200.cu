@@ -921,9 +921,6 @@ static int64_t ensure_w(spk_plan* p, int64_t nrhs) {
         p->d_pb = nullptr;
         CK(cudaMalloc((void**)&p->d_pb, std::max<size_t>((size_t)p->P.pblen * nrhs, 1) * sizeof(double)));
         if (p->d_box) cudaFree(p->d_box);
-        if (p->d_tinvf) cudaFree(p->d_tinvf);
-        if (p->d_tinvb) cudaFree(p->d_tinvb);
-        if (p->d_invlist) cudaFree(p->d_invlist);
         p->d_box = nullptr;
         if (p->P.nflowctr > 0) CK(cudaMalloc((void**)&p->d_box, (size_t)2 * p->P.n * nrhs * sizeof(double)));
         p->w_nrhs = nrhs;
