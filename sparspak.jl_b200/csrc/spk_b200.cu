@@ -49,6 +49,10 @@ struct spk_plan {
     FlowTask* d_flowt = nullptr; int32_t* d_flow = nullptr; int64_t flow_ints = 0;   // dataflow solve: tasks; ticket counters (zeroed per solve)
     double *d_tinvf = nullptr, *d_tinvb = nullptr; bool use_inv = true, inv_ready = false;   // inverted diagonal blocks (SPK_SOLVE_INV=0: off)
     int32_t *d_invlist = nullptr; int32_t inv_nsmall = 0, inv_nlarge = 0, inv_maxw_small = 32;
+    // SPK_SOLVE_INV bits: 1 = step / flow kernels (big fronts), 2 = one-block-per-front kernels.  Default: LU 3, LDL^T 0
+    // (measured at 80^3 LU: 11.1 -> 6.1 ms, the in-block solve with its interchanges is the expensive part of a step;
+    //  at 96^3 LDL^T: 13.9 -> 17.1 ms, the register / shuffle sweep over a unit triangle is already cheap).
+    int inv_mask = -1;
     double* d_box = nullptr;            // dataflow solve: x mailboxes, [forward | backward] x (rhs of a batch) x n, sentinel-filled per solve
     double ms_xchg = 0;
     // tree pipelines (Plan::pipes): stream / event pair per pipeline; pair 0 = (stream, stream2, evs0, evs1)
@@ -336,6 +340,8 @@ static int64_t plan_upload(spk_plan* p) {
     CK(upload(&p->d_asmt, P.asmt));
     CK(upload(&p->d_gemmt, P.gemmt));
     CK(upload(&p->d_solvet, P.solvet));
+    if (p->inv_mask < 0) p->inv_mask = P.lu ? 3 : 0;
+    p->use_inv = p->inv_mask != 0;
     if (p->use_inv && P.maxpw <= 110 && P.solve_on_fronts) {       // two w x (w|1) blocks of the widest step must fit in shared memory
         CK(cudaMalloc((void**)&p->d_tinvf, (size_t)std::max<int64_t>(P.tinv_len, 1) * sizeof(double)));
         CK(cudaMalloc((void**)&p->d_tinvb, (size_t)std::max<int64_t>(P.tinv_len, 1) * sizeof(double)));
@@ -405,7 +411,7 @@ SPK_API spk_plan* spk_plan_create(int64_t n, int64_t nsuper, const int64_t* xsup
     if (const char* e = getenv("SPK_DMMA_VARIANT")) p->dmma_variant = atoi(e);
     // persistent blocks hold their SM slots for the whole launch, which defeats the stream priorities the look-ahead
     // relies on (measured: 243.6 ms persistent with 32 reserved slots vs 236.6 ms one block per tile); off by default
-    if (const char* e = getenv("SPK_SOLVE_INV")) p->use_inv = e[0] != '0';
+    if (const char* e = getenv("SPK_SOLVE_INV")) p->inv_mask = atoi(e) & 3;
     if (const char* e = getenv("SPK_DMMA_PERSIST")) p->dmma_persist = e[0] != '0';
     if (const char* e = getenv("SPK_DMMA_CA")) p->dmma_flags = (p->dmma_flags & ~1) | (e[0] != '0' ? 1 : 0);
     if (const char* e = getenv("SPK_DMMA_STATIC")) p->dmma_flags = (p->dmma_flags & ~2) | (e[0] != '0' ? 2 : 0);
@@ -928,11 +934,14 @@ static int64_t ensure_w(spk_plan* p, int64_t nrhs) {
     return 0;
 }
 
-static int64_t run_solve_launches(spk_plan* p, const DevCtx& c, const std::vector<Launch>& Ls, double* d_rhs,
+static int64_t run_solve_launches(spk_plan* p, const DevCtx& c0, const std::vector<Launch>& Ls, double* d_rhs,
                                   int64_t nrhs, int64_t ldrhs) {
     cudaStream_t st = p->stream;
     const bool lu = p->P.lu;
+    DevCtx c_noinv = c0; c_noinv.tinvf = nullptr; c_noinv.tinvb = nullptr;
     for (const Launch& L : Ls) {
+        const bool frontk = L.kind == K_PF_FRONT || L.kind == K_PB_FRONT;
+        const DevCtx& c = (p->inv_mask & (frontk ? 2 : 1)) ? c0 : c_noinv;      // inverted diagonal blocks per kernel class
         const int32_t* pfx = p->d_blkpfx + L.pfx;
         const int32_t* list = p->d_gathert + L.first;
         dim3 grid(L.nblocks, (unsigned)nrhs);

@@ -260,8 +260,9 @@ VARIANTS = [
     {"SPK_SOLVE_FLOW": "1", "SPK_FLOW_MIN_STEPS": "2", "SPK_PS_WIDTH": "16"},     # dataflow sweeps mixed with the per-step path, many steps
     {"SPK_DMMA_PERSIST": "1", "SPK_GEMM_RESERVE": "16"},  # persistent DMMA blocks with reserved slots
     {"SPK_DMMA_CA": "0", "SPK_DMMA_VARIANT": "6"},        # L2-only operand loads, 4-stage ring
-    {"SPK_SOLVE_INV": "0"},                               # in-block triangular solves instead of the inverted diagonal blocks
-    {"SPK_SOLVE_INV": "0", "SPK_SOLVE_SMALL": "0"},
+    {"SPK_SOLVE_INV": "0"},                               # in-block triangular solves everywhere (LU default: inverted diagonal blocks)
+    {"SPK_SOLVE_INV": "3", "SPK_SOLVE_SMALL": "0"},       # inverted diagonal blocks everywhere (LDL^T default: none)
+    {"SPK_SOLVE_INV": "1"}, {"SPK_SOLVE_INV": "2"},
 ]
 
 
