@@ -1131,6 +1131,88 @@ __global__ void __launch_bounds__(256) k_bwd_front(DevCtx c, const int32_t* __re
 // Each lane keeps the unknowns lane, lane+32, lane+64 in registers; x_k is broadcast with one shuffle
 // per column, so a column costs a shuffle + FMA instead of a shared-memory round trip (w <= 96).
 
+
+// ------------------------------------------------------------------------------------
+// FUSED small-front kernel (K_FRONT_SMALL): a front of at most FUSED_MAXR rows is handled by ONE thread block in
+// shared memory — load (the values scattered by inmatrix), extend-add of all children in their fixed order, partial
+// factorisation of its W columns (right-looking, column by column; LU: partial pivoting restricted to each chunk's
+// own rows, first maximum wins, interchanges applied from the chunk's first column rightwards, block-local ipiv —
+// the rules of k_diag / k_panel), store.  The bottom levels of the tree hold tens of thousands of such fronts; the
+// kernel-per-operation path spends ~10 launches and as many global round trips per level on them for < 1 % of the
+// flops.  LDL^T fronts leave U = D L^T above the diagonal as the other kernels do.
+constexpr int FS_NT = 64;
+inline size_t front_small_smem_bytes(int maxR) { return (size_t)maxR * (maxR | 1) * sizeof(double); }
+template <bool LU>
+__global__ void __launch_bounds__(FS_NT) k_front_small(DevCtx c, const int32_t* __restrict__ flist) {
+    extern __shared__ double S[];
+    __shared__ int s_piv;
+    const DFront F = c.fronts[flist[blockIdx.x]];
+    const int R = F.R, lds = R | 1, tid = threadIdx.x;
+    double* __restrict__ G = c.F + F.fofs;
+    for (int e = tid; e < R * R; e += FS_NT) { const int j = e / R, i = e - j * R; S[i + j * lds] = G[i + (int64_t)j * F.ld]; }
+    __syncthreads();
+    for (int ch = 0; ch < F.nchild; ++ch) {                 // children in plan order: the same sums as k_assemble
+        const DFront C = c.fronts[c.childlist[F.child0 + ch]];
+        const int32_t* __restrict__ rel = c.rel + C.relofs;
+        const int m = C.m;
+        const double* __restrict__ CS = c.F + C.fofs + C.W + (int64_t)C.W * C.ld;
+        for (int e = tid; e < m * m; e += FS_NT) {
+            const int j = e / m, i = e - j * m;
+            if (!LU && i < j) continue;
+            S[rel[i] + rel[j] * lds] += CS[i + (int64_t)j * C.ld];
+        }
+        __syncthreads();
+    }
+    for (int js = 0; js < F.nps; ++js) {
+        const PStep ps = c.psteps[F.ps0 + js];
+        int s0 = ps.o;
+        for (int b = 0; b < ps.nsub; ++b) {
+            const int s1 = s0 + c.subw[ps.sub0 + b];
+            for (int k = s0; k < s1; ++k) {
+                if (LU) {
+                    if (tid < 32) {                         // first maximum of |S[k.., k]| over the chunk's rows
+                        double best = -1.0; int bi = k;
+                        for (int i = k + tid; i < s1; i += 32) { const double v = fabs(S[i + k * lds]); if (v > best) { best = v; bi = i; } }
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) {
+                            const double ov = __shfl_xor_sync(0xffffffffu, best, off); const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+                        }
+                        if (tid == 0) { s_piv = bi; c.ipiv[F.F0 + k] = bi - s0 + 1; }
+                    }
+                    __syncthreads();
+                    const int kp = s_piv;
+                    const double pv = S[kp + k * lds];
+                    if (pv == 0.0) { if (tid == 0) *c.iflag = -1; }
+                    else {
+                        if (kp != k) for (int j = s0 + tid; j < R; j += FS_NT) { const double t = S[k + j * lds]; S[k + j * lds] = S[kp + j * lds]; S[kp + j * lds] = t; }
+                        __syncthreads();
+                        const double inv = 1.0 / S[k + k * lds];
+                        for (int i = k + 1 + tid; i < R; i += FS_NT) S[i + k * lds] *= inv;
+                    }
+                    __syncthreads();
+                    for (int j = k + 1 + tid; j < R; j += FS_NT) {
+                        const double uj = S[k + j * lds];
+                        if (uj != 0.0) for (int i = k + 1; i < R; ++i) S[i + j * lds] -= S[i + k * lds] * uj;
+                    }
+                } else {
+                    const double d = S[k + k * lds];
+                    if (d == 0.0 && tid == 0) *c.iflag = -1;
+                    for (int i = k + 1 + tid; i < R; i += FS_NT) { const double u = S[i + k * lds]; S[k + i * lds] = u; S[i + k * lds] = u / d; }   // U = D L^T above, L below
+                    __syncthreads();
+                    for (int j = k + 1 + tid; j < R; j += FS_NT) {
+                        const double uj = S[k + j * lds];
+                        if (uj != 0.0) for (int i = j; i < R; ++i) S[i + j * lds] -= S[i + k * lds] * uj;
+                    }
+                }
+                __syncthreads();
+            }
+            s0 = s1;
+        }
+    }
+    for (int e = tid; e < R * R; e += FS_NT) { const int j = e / R, i = e - j * R; G[i + (int64_t)j * F.ld] = S[i + j * lds]; }
+}
+
 // ---- explicit inverses of the diagonal blocks (solve) ---------------------------------------------------------------
 // The in-block triangular solve is a chain of w dependent steps (~3.5 us of the ~11 us a panel step of a sweep costs).
 // After a factorisation k_diag_inverse applies the forward / backward in-block operators of every panel step to the

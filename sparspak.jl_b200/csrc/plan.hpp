@@ -84,7 +84,9 @@ enum Kind : int32_t {
     // distributed top set (multi-GPU LDL^T): broadcast of a column slab from its owner; U = D L^T rebuilt from a received panel
     K_BCAST, K_FILLU,
     // solve sweeps of the big fronts of a level as ONE flag-synchronised dataflow launch (k_pf_flow / k_pb_flow)
-    K_PF_FLOW, K_PB_FLOW
+    K_PF_FLOW, K_PB_FLOW,
+    // a whole small front (R <= FUSED_MAXR) in one thread block: load, extend-add, partial factorisation, store
+    K_FRONT_SMALL
 };
 struct Launch {
     int32_t kind;
@@ -122,6 +124,7 @@ constexpr int BWD_COLS = 1;        // columns per block in the backward-solve up
 constexpr int PS_WIDTH = 64;       // target panel-step width (a wider single chunk stays alone)
 constexpr int OB_WIDTH = 512;      // target outer-block width (delayed trailing update)
 constexpr int OB_STEPS = 8;        // panel steps per outer block (aligned across the fronts of a level for the look-ahead)
+constexpr int FUSED_MAXR = 64;     // fronts of at most this many rows are factored by the fused one-block kernel (k_front_small)
 constexpr int FLOW_MIN_STEPS = 8;  // fronts with at least this many panel steps take the dataflow solve kernels
 constexpr int FLOW_ROWS = 128;     // rows per thread block of the dataflow solve kernels (one per thread; wider single steps: two)
 constexpr int64_t SOLVE_SMALL = 65536;  // fronts with at most this many stored L entries are solved by one block
@@ -160,6 +163,7 @@ struct Plan {
     std::vector<int32_t> gathert;
     std::vector<FlowTask> flowt;              // thread blocks of the dataflow solve launches
     int32_t nflowctr = 0;                     // ticket counters (one per dataflow launch)
+    int32_t fused_maxr = FUSED_MAXR;          // SPK_FUSED_MAXR (0 = off)
     int32_t flow_min_steps = FLOW_MIN_STEPS;  // SPK_FLOW_MIN_STEPS
     // SPK_SOLVE_FLOW=1: dataflow sweeps (one flag-free, mailbox-synchronised launch per level for the fronts with many
     // panel steps).  MEASURED SLOWER than one launch per panel step (96^3: 20.4 vs 13.6 ms): a step costs ~11 us either
@@ -479,6 +483,7 @@ inline void plan_env_overrides(Plan& P) {        // test / tuning knobs
     if (const char* e = getenv("SPK_MAX_SUBTREES")) P.max_subtrees = std::max(2, atoi(e));
     if (const char* e = getenv("SPK_PIPES")) P.pipes = std::min(4, std::max(1, atoi(e)));
     if (const char* e = getenv("SPK_SOLVE_LNZ")) P.solve_on_fronts = e[0] != '1';
+    if (const char* e = getenv("SPK_FUSED_MAXR")) P.fused_maxr = std::min(FUSED_MAXR, std::max(0, atoi(e)));
     if (const char* e = getenv("SPK_SOLVE_FLOW")) P.solve_flow = e[0] != '0';
     if (const char* e = getenv("SPK_FLOW_MIN_STEPS")) P.flow_min_steps = std::max(1, atoi(e));
     if (const char* e = getenv("SPK_PS_WIDTH")) P.ps_width = std::max(1, atoi(e));
@@ -497,7 +502,14 @@ inline void build_lists(Plan& P, const std::vector<uint8_t>& sel, std::vector<La
 
     LaunchBuilder fb(P, factor_out);
     for (int32_t lev = 0; lev < P.nlevels; ++lev) {
-        const std::vector<int32_t>& fr = bylevel[lev];
+        // ---- small fronts: one fused launch (load, extend-add, partial factorisation, store in one block per front)
+        std::vector<int32_t> fr;                                  // the fronts that take the kernel-per-operation path
+        fb.begin(K_FRONT_SMALL, (int32_t)P.pslist.size(), lev, 0, 0, 1, 1);
+        for (int32_t f : bylevel[lev]) {
+            if (P.fronts[f].R <= P.fused_maxr) { P.pslist.push_back(f); fb.add(1, 0, P.fronts[f].R); }
+            else fr.push_back(f);
+        }
+        fb.end();
         int32_t maxch = 0, maxnps = 0;
         for (int32_t f : fr) { maxch = std::max(maxch, P.fronts[f].nchild); maxnps = std::max(maxnps, P.fronts[f].nps); }
         // ---- extend-add of the children's update matrices

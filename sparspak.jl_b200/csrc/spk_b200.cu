@@ -631,6 +631,12 @@ static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L, 
                       (const GemmTile*)(p->d_tiles + L.tile0), (int)L.ntiles, (int32_t*)(p->d_tilectr + L.ctr), (int)p->dmma_flags));
         break;
     }
+    case K_FRONT_SMALL: {
+        const size_t sm = front_small_smem_bytes(std::max(L.maxw, 1));
+        if (lu) k_front_small<true><<<L.count, FS_NT, sm, st>>>(c, p->d_pslist + L.first);
+        else k_front_small<false><<<L.count, FS_NT, sm, st>>>(c, p->d_pslist + L.first);
+        break;
+    }
     case K_FILLU:
         k_fill_u<<<L.nblocks, 256, 0, st>>>(c, p->d_fillt + L.first, pfx, L.count); break;
     default:

@@ -218,6 +218,17 @@ static int64_t run_factor_list(Sim* s, const std::vector<Launch>& Ls) {
         case K_GEMM_B64: case K_GEMM_T64:                       // tile by tile, as the persistent kernel walks its list
             for (int64_t q = L.tile0; q < L.tile0 + L.ntiles; ++q) gemm_tile(*s, P.gemmt[L.first + P.tiles[q].task], P.tiles[q], L.kind == K_GEMM_T64 ? 64 : BIG_TM, 64);
             break;
+        case K_FRONT_SMALL:                                      // fused small fronts: extend-add, then step by step with right-looking updates
+            for (int t = 0; t < L.count; ++t) {
+                const Front& F = P.fronts[P.pslist[L.first + t]];
+                for (int r = 0; r < F.nchild; ++r) assemble(*s, P.fronts[P.childlist[F.child0 + r]], F);
+                for (int j = 0; j < F.nps; ++j) {
+                    const PStep& ps = P.psteps[F.ps0 + j];
+                    diag(*s, ps); panel(*s, ps);
+                    const int e = ps.o + ps.w;
+                    if (e < F.R) gemm(*s, front_gemm(P, F, e, F.R - e, e, F.R - e, ps.o, ps.w));
+                }
+            } break;
         case K_FILLU:
             for (int t = 0; t < L.count; ++t) {
                 const FillTask& ft = P.fillt[L.first + t];
