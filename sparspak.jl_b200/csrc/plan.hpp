@@ -163,6 +163,7 @@ struct Plan {
     std::vector<int32_t> gathert;
     std::vector<FlowTask> flowt;              // thread blocks of the dataflow solve launches
     int32_t nflowctr = 0;                     // ticket counters (one per dataflow launch)
+    bool levels_by_depth = true;              // SPK_LEVELS=height: levels by height above the leaves
     int32_t fused_maxr = FUSED_MAXR;          // SPK_FUSED_MAXR (0 = off)
     int32_t flow_min_steps = FLOW_MIN_STEPS;  // SPK_FLOW_MIN_STEPS
     // SPK_SOLVE_FLOW=1: dataflow sweeps (one flag-free, mailbox-synchronised launch per level for the fronts with many
@@ -342,6 +343,16 @@ inline bool analyze(Plan& P, int64_t n, int64_t nsuper, const int64_t* xsuper, c
     }
     P.nlevels = 0;
     for (int32_t f = 0; f < nf; ++f) P.nlevels = std::max(P.nlevels, P.fronts[f].level + 1);
+    // Levels by DEPTH below the root (as late as possible) instead of height above the leaves: siblings whose subtrees
+    // differ in height by one would otherwise sit alone in consecutive levels, and a level with a single big front is
+    // bound by that front's chain of dependent panel steps (96^3: the four second-level separators end up in one
+    // level instead of three).  SPK_LEVELS=height restores the height levels.
+    if (P.levels_by_depth) {
+        for (int32_t f = nf - 1; f >= 0; --f) {
+            Front& F = P.fronts[f];
+            F.level = F.parent < 0 ? P.nlevels - 1 : P.fronts[F.parent].level - 1;
+        }
+    }
     // panel steps: greedy groups of consecutive chunks up to PS_WIDTH columns; outer blocks up to OB_WIDTH
     for (int32_t f = 0; f < nf; ++f) {
         Front& F = P.fronts[f];
@@ -483,6 +494,7 @@ inline void plan_env_overrides(Plan& P) {        // test / tuning knobs
     if (const char* e = getenv("SPK_MAX_SUBTREES")) P.max_subtrees = std::max(2, atoi(e));
     if (const char* e = getenv("SPK_PIPES")) P.pipes = std::min(4, std::max(1, atoi(e)));
     if (const char* e = getenv("SPK_SOLVE_LNZ")) P.solve_on_fronts = e[0] != '1';
+    if (const char* e = getenv("SPK_LEVELS")) P.levels_by_depth = e[0] != 'h';
     if (const char* e = getenv("SPK_FUSED_MAXR")) P.fused_maxr = std::min(FUSED_MAXR, std::max(0, atoi(e)));
     if (const char* e = getenv("SPK_SOLVE_FLOW")) P.solve_flow = e[0] != '0';
     if (const char* e = getenv("SPK_FLOW_MIN_STEPS")) P.flow_min_steps = std::max(1, atoi(e));
