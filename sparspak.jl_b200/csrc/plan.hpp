@@ -896,7 +896,19 @@ inline void build_lists_dist(Plan& P, std::vector<Launch>& out) {
                 fb.add(cdiv(below, PANEL_ROWS), 0, ps.w);
             }
             fb.end();
-            // ---- end of an outer block: broadcast the factored column slab, rebuild U = D L^T from it, delayed updates
+            // ---- the factored columns of THIS step travel at once (in place, from the owner): the broadcast of a block's
+            // columns overlaps the owner's chain over the block's remaining steps instead of following it.  A step's
+            // column slab is final after its panel kernel (stream 0); on the receivers only the U rebuild of earlier
+            // blocks (stream 0) touches these columns — the trailing updates (stream 1) never do.
+            begin(K_BCAST, (int32_t)P.bcasts.size(), lev, j, 2, 1);
+            for (int32_t f : fr) if (P.fronts[f].nps > j) {
+                const Front& F = P.fronts[f];
+                const PStep& ps = P.psteps[F.ps0 + j];
+                P.bcasts.push_back(Bcast{F.fofs + (int64_t)ps.o * F.ld, (int64_t)F.ld * ps.w, P.fown[P.ownofs[f] + ps.o], f});
+                fb.add(1);
+            }
+            fb.end();
+            // ---- end of an outer block: rebuild U = D L^T from the received columns, delayed updates
             const bool boundary = ((j + 1) % P.ob_steps) == 0;
             struct End { int32_t f, ob0, e, e2; bool last; };
             std::vector<End> ends;
@@ -911,17 +923,8 @@ inline void build_lists_dist(Plan& P, std::vector<Launch>& out) {
                 ends.push_back(End{f, ob0, e, last ? e : P.psteps[F.ps0 + j + 1].ob_end, last});
             }
             if (ends.empty()) continue;
-            // the slab is final once the owner's chain is done (stream 0); on the receivers only the U rebuild of the
-            // previous block (stream 0) touches these columns — the trailing updates (stream 1) never do
-            begin(K_BCAST, (int32_t)P.bcasts.size(), lev, j, 2, 1);
             bool all_mine = true;
-            for (const End& E : ends) {
-                all_mine = all_mine && P.fown[P.ownofs[E.f] + E.ob0] == me;
-                const Front& F = P.fronts[E.f];
-                P.bcasts.push_back(Bcast{F.fofs + (int64_t)E.ob0 * F.ld, (int64_t)F.ld * (E.e - E.ob0), P.fown[P.ownofs[E.f] + E.ob0], E.f});
-                fb.add(1);
-            }
-            fb.end();
+            for (const End& E : ends) all_mine = all_mine && P.fown[P.ownofs[E.f] + E.ob0] == me;
             begin(K_FILLU, (int32_t)P.fillt.size(), lev, j, 0, all_mine ? 0 : 4);      // the owner already holds the panel
             for (const End& E : ends) {
                 const Front& F = P.fronts[E.f];
