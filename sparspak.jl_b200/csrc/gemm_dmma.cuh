@@ -222,14 +222,20 @@ k_gemm_dmma(DevCtx c, const GemmTask* __restrict__ tasks, const GemmTile* __rest
     }
 }
 
-// Tile shapes: K_GEMM_B64 = 128 x 64 tiles, 8 warps, two co-resident blocks per SM (one block's epilogue overlaps
-// the other's k loop); K_GEMM_T64 = 64 x 64 tiles, 4 warps, four blocks per SM, for launches whose 128-row tiles
-// would not fill the machine (the left-looking in-block updates on the critical path of the top fronts).
-// SPK_DMMA_VARIANT selects the pipeline shape of the 128 x 64 kernel (k per stage, ring depth).
+// Tile shapes.  K_GEMM_T64 = 64 x 64 tiles, 4 warps, four co-resident blocks per SM, k streamed 8 at a time through a
+// 4-stage ring: the DEFAULT for every DMMA launch.  Measured on the delayed updates' own shapes (tools/ubench_dmma.cu,
+// lower-triangular m = n = 9000, k = 456): 31.1 TFLOP/s against 27.7 for the 128 x 64 / 8-warp / 2-per-SM shape, 26.5
+// against 23.4 at m = n = 4000 — four small independent blocks keep the DMMA pipe fed through each other's barriers,
+// prologues and epilogues better than two large ones, and short k-steps shorten the fill of a k = 456 tile.  Larger
+// block or warp tiles (128 x 128, 256 x 64, 64 x 32 per warp) were all slower.  K_GEMM_B64 = 128 x 64 tiles, 8 warps,
+// two blocks per SM (SPK_DMMA_BIG=1 selects it for launches with enough tiles; SPK_DMMA_VARIANT = its pipeline shape).
 using GemmKernel = void (*)(DevCtx, const GemmTask*, const GemmTile*, int, int32_t*, int);
 struct GemmVariant { GemmKernel fn; int threads; size_t smem; int blocks_per_sm; };
-inline GemmVariant gemm_dmma_variant(int kind, int variant) {
-    if (kind == K_GEMM_T64) return {k_gemm_dmma<64, 64, 2, 2, 4, 16, 3>, 128, DmmaCfg<64, 64, 16, 3>::SMEM, 4};
+inline GemmVariant gemm_dmma_variant(int kind, int variant, int variant64 = 8) {
+    if (kind == K_GEMM_T64) {
+        if (variant64 == 4) return {k_gemm_dmma<64, 64, 2, 2, 4, 16, 3>, 128, DmmaCfg<64, 64, 16, 3>::SMEM, 4};
+        return {k_gemm_dmma<64, 64, 2, 2, 4, 8, 4>, 128, DmmaCfg<64, 64, 8, 4>::SMEM, 4};
+    }
     if (variant == 3) return {k_gemm_dmma<BIG_TM, 64, 4, 2, 2, 32, 2>, 256, DmmaCfg<BIG_TM, 64, 32, 2>::SMEM, 2};
     if (variant == 5) return {k_gemm_dmma<BIG_TM, 64, 4, 2, 2, 8, 6>, 256, DmmaCfg<BIG_TM, 64, 8, 6>::SMEM, 2};
     if (variant == 6) return {k_gemm_dmma<BIG_TM, 64, 4, 2, 2, 16, 4>, 256, DmmaCfg<BIG_TM, 64, 16, 4>::SMEM, 2};
@@ -237,11 +243,12 @@ inline GemmVariant gemm_dmma_variant(int kind, int variant) {
 }
 inline cudaError_t gemm_dmma_init() {
     for (int kind : {(int)K_GEMM_B64, (int)K_GEMM_T64})
-        for (int variant : {3, 4, 5, 6}) {
-            GemmVariant v = gemm_dmma_variant(kind, variant);
-            cudaError_t e = cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem);
-            if (e != cudaSuccess) return e;
-        }
+        for (int variant : {3, 4, 5, 6})
+            for (int variant64 : {4, 8}) {
+                GemmVariant v = gemm_dmma_variant(kind, variant, variant64);
+                cudaError_t e = cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem);
+                if (e != cudaSuccess) return e;
+            }
     return cudaSuccess;
 }
 

@@ -150,6 +150,8 @@ struct Plan {
     int64_t solve_small = SOLVE_SMALL;
     int ob_width = OB_WIDTH, ps_width = PS_WIDTH, ob_steps = OB_STEPS;
     bool lookahead = true;
+    bool split_rest = false;                   // SPK_SPLIT_REST=1: the delayed trailing update of an outer block in two launches; the next strips wait for the first only (measured: no gain, the stream is never idle)
+    bool dmma_big = false;                     // SPK_DMMA_BIG=1: 128 x 64 DMMA tiles for launches with >= DMMA_FILL of them
     bool left_inblock = true;                  // SPK_LL=0: right-looking rank-w updates inside an outer block (LU always)
     int relax_abs = RELAX_ABS; double relax_frac = RELAX_FRAC;
     // schedules
@@ -445,7 +447,7 @@ struct GemmBatch {
         if (!dmma.empty()) {
             int64_t big = 0;
             for (const Item& it : dmma) dmma_tiles(it.t, BIG_TM, 64, 0, nullptr, &big);
-            const bool t64 = big < DMMA_FILL;                       // 128-row tiles would leave SMs idle
+            const bool t64 = !P.dmma_big || big < DMMA_FILL;        // default: 64 x 64 tiles everywhere (measured faster); SPK_DMMA_BIG=1: 128-row tiles when they fill the machine
             const int tm = t64 ? 64 : BIG_TM;
             fb.begin(t64 ? K_GEMM_T64 : K_GEMM_B64, (int32_t)P.gemmt.size(), lev, step, stream, wait_other, record);
             fb.cur.tile0 = (int64_t)P.tiles.size(); fb.cur.ctr = P.nctr++; fb.cur.reserve = reserve;
@@ -502,6 +504,8 @@ inline void plan_env_overrides(Plan& P) {        // test / tuning knobs
     if (const char* e = getenv("SPK_TOP_SPLITS")) P.force_splits = atoi(e);
     if (const char* e = getenv("SPK_GEMM_RESERVE")) P.gemm_reserve = std::max(0, atoi(e));
     if (const char* e = getenv("SPK_DIST_TOP")) P.dist_top_env = e[0] != '0';
+    if (const char* e = getenv("SPK_SPLIT_REST")) P.split_rest = e[0] != '0';
+    if (const char* e = getenv("SPK_DMMA_BIG")) P.dmma_big = e[0] != '0';
 }
 
 // Launch lists for the fronts selected by `sel` (all of them, one part's subtrees, or the top set).
@@ -577,7 +581,7 @@ inline void build_lists(Plan& P, const std::vector<uint8_t>& sel, std::vector<La
             // panel stream, the REST (the bulk of the flops) to the trailing-update stream, where it overlaps
             // the diagonal / panel kernels of the next block (look-ahead).  A front's last step sends its whole
             // remaining update (the update matrix S) to the trailing-update stream.
-            GemmBatch gp, gg;
+            GemmBatch gp, ga, gg;
             const bool boundary = ((j + 1) % P.ob_steps) == 0;
             for (int32_t f : fr) if (P.fronts[f].nps > j) {
                 const Front& F = P.fronts[f];
@@ -610,13 +614,34 @@ inline void build_lists(Plan& P, const std::vector<uint8_t>& sel, std::vector<La
                             GemmTask h = front_gemm(P, F, e, e2 - e, e2, F.R - e2, ob0, kb);  // row strip
                             gp.add(P, h, gemm_flops(h));
                         }
-                        GemmTask r = front_gemm(P, F, e2, F.R - e2, e2, F.R - e2, ob0, kb);   // the rest
-                        gg.add(P, r, gemm_flops(r));
+                        // The rest.  SPLIT: the part of it that the NEXT boundary's strips update again (the columns —
+                        // LU: and rows — of the block after the next one) goes first, as a launch of its own that
+                        // records the "early" event; the next strips wait for that event only and then run beside
+                        // the remainder instead of between two bulk updates (0.3 ms of an idle trailing-update
+                        // stream per outer block at the top of the tree).
+                        const int32_t jn = j + 1 + P.ob_steps;                                // first step of the block after the next
+                        const int32_t e3 = (P.split_rest && jn < F.nps) ? P.psteps[F.ps0 + jn].ob_end : F.R;
+                        if (e3 < F.R) {
+                            GemmTask ra = front_gemm(P, F, e2, F.R - e2, e2, e3 - e2, ob0, kb);
+                            ga.add(P, ra, gemm_flops(ra));
+                            if (lu) {
+                                GemmTask rh = front_gemm(P, F, e2, e3 - e2, e3, F.R - e3, ob0, kb);
+                                ga.add(P, rh, gemm_flops(rh));
+                            }
+                            GemmTask rb = front_gemm(P, F, e3, F.R - e3, e3, F.R - e3, ob0, kb);
+                            gg.add(P, rb, gemm_flops(rb));
+                        } else {
+                            GemmTask r = front_gemm(P, F, e2, F.R - e2, e2, F.R - e2, ob0, kb);
+                            (P.split_rest ? ga : gg).add(P, r, gemm_flops(r));                // nothing behind it: all of it is "early"
+                        }
                     }
                 }
             }
-            // strips must wait for the previous block's REST (same target region); rests wait for this step's panels
-            gp.emit(P, fb, lev, j, 0, boundary ? 1 : 0, 1);
+            // strips wait for the EARLY part of the previous block's rest (same target region: record bit 2 / wait bit 2;
+            // without the split: for all of it); rests wait for this step's panels.  Every launch of the trailing-update
+            // stream records the ordinary event too (the next level waits for the last of them).
+            gp.emit(P, fb, lev, j, 0, boundary ? (P.split_rest ? 2 : 1) : 0, 1);
+            ga.emit(P, fb, lev, j, 1, 1, 3);
             // the bulk update runs beside the next block's diagonal / panel chain: leave that chain some block slots
             gg.emit(P, fb, lev, j, 1, 1, 1, (j + 1 < maxnps) ? P.gemm_reserve : 0);
         }

@@ -58,6 +58,7 @@ struct spk_plan {
     // tree pipelines (Plan::pipes): stream / event pair per pipeline; pair 0 = (stream, stream2, evs0, evs1)
     cudaStream_t pst[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
     cudaEvent_t pev[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+    cudaEvent_t pev2[4] = {nullptr, nullptr, nullptr, nullptr};      // "early" event of a pair's trailing-update stream (split rest updates)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evg0 = nullptr, evg1 = nullptr;
     // device state
     double *d_pb = nullptr, *d_F = nullptr, *d_lnz = nullptr, *d_unz = nullptr, *d_w = nullptr, *d_rhs = nullptr, *d_tmp = nullptr;
@@ -88,7 +89,7 @@ struct spk_plan {
     int panel_reg_minw = 32;            // SPK_PANEL_REG_MINW
     bool panel_smem_only = false;       // SPK_PANEL_SMEM=1: always use the shared-memory panel kernel
     bool diag_smem_only = false;        // SPK_DIAG_SMEM=1: always use the shared-memory diagonal kernel
-    int dmma_variant = 4;               // SPK_DMMA_VARIANT (see gemm_dmma.cuh)
+    int dmma_variant = 4, dmma_variant64 = 8;   // SPK_DMMA_VARIANT, SPK_DMMA_VARIANT64 (see gemm_dmma.cuh)
     bool dmma_persist = false; int dmma_flags = 1;     // SPK_DMMA_PERSIST, SPK_DMMA_CA (bit 0), SPK_DMMA_STATIC (bit 1), SPK_DMMA_DEPHASE (us, bits 8..)
     bool values_in_fronts = false;      // inmatrix scattered straight into the fronts
     int64_t w_nrhs = 0, rhs_cap = 0;
@@ -258,6 +259,7 @@ SPK_API void spk_plan_destroy(spk_plan* p) {
         if (p->d_stlist) cudaFree(p->d_stlist);
         if (p->d_stpfx) cudaFree(p->d_stpfx);
         for (int v = 1; v < 4; ++v) for (int q = 0; q < 2; ++q) { if (p->pst[v][q]) cudaStreamDestroy(p->pst[v][q]); if (p->pev[v][q]) cudaEventDestroy(p->pev[v][q]); }
+        for (int v = 0; v < 4; ++v) if (p->pev2[v]) cudaEventDestroy(p->pev2[v]);
         if (p->stream) cudaStreamDestroy(p->stream);
     }
     delete p;
@@ -274,6 +276,7 @@ static int64_t plan_upload(spk_plan* p) {
         CK(cudaEventCreateWithFlags(&p->evs0, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&p->evs1, cudaEventDisableTiming));
         p->pst[0][0] = p->stream; p->pst[0][1] = p->stream2; p->pev[0][0] = p->evs0; p->pev[0][1] = p->evs1;
+        for (int v = 0; v < 4; ++v) CK(cudaEventCreateWithFlags(&p->pev2[v], cudaEventDisableTiming));
         CK(cudaStreamCreateWithPriority(&p->stream3, cudaStreamNonBlocking, lo));
         CK(cudaStreamCreateWithPriority(&p->stream_c, cudaStreamNonBlocking, hi));
         CK(cudaEventCreateWithFlags(&p->evsc, cudaEventDisableTiming));
@@ -409,6 +412,7 @@ SPK_API spk_plan* spk_plan_create(int64_t n, int64_t nsuper, const int64_t* xsup
     }
     plan_env_overrides(p->P);
     if (const char* e = getenv("SPK_DMMA_VARIANT")) p->dmma_variant = atoi(e);
+    if (const char* e = getenv("SPK_DMMA_VARIANT64")) p->dmma_variant64 = atoi(e);
     // persistent blocks hold their SM slots for the whole launch, which defeats the stream priorities the look-ahead
     // relies on (measured: 243.6 ms persistent with 32 reserved slots vs 236.6 ms one block per tile); off by default
     if (const char* e = getenv("SPK_SOLVE_INV")) p->inv_mask = atoi(e) & 3;
@@ -579,7 +583,8 @@ static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L, 
     if (force) { st = force; two_streams = false; }     // the caller handles waits / records (lists with broadcasts)
     else if (two_streams) {
         st = p->pst[pair][L.stream ? 1 : 0];
-        if (L.wait_other) CK(cudaStreamWaitEvent(st, p->pev[pair][L.stream ? 0 : 1], 0));
+        if (L.wait_other & 1) CK(cudaStreamWaitEvent(st, p->pev[pair][L.stream ? 0 : 1], 0));
+        if (L.wait_other & 2) CK(cudaStreamWaitEvent(st, p->pev2[pair], 0));          // the early part of the previous trailing update only
     }
     const bool lu = p->P.lu;
     switch (L.kind) {
@@ -623,7 +628,7 @@ static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L, 
         break;
     case K_GEMM_B64:
     case K_GEMM_T64: {
-        GemmVariant v = gemm_dmma_variant(L.kind, p->dmma_variant);
+        GemmVariant v = gemm_dmma_variant(L.kind, p->dmma_variant, p->dmma_variant64);
         int cap = v.blocks_per_sm * p->num_sms - (L.reserve > 0 ? L.reserve * v.blocks_per_sm / 2 : 0);
         if (cap < p->num_sms) cap = p->num_sms;
         const int grid = p->dmma_persist ? std::min<int>(L.ntiles, cap) : L.ntiles;      // SPK_DMMA_PERSIST=0: one block per tile
@@ -642,7 +647,8 @@ static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L, 
     default:
         set_err("bad launch kind"); return -100;
     }
-    if (two_streams && L.record) CK(cudaEventRecord(p->pev[pair][L.stream ? 1 : 0], st));
+    if (two_streams && (L.record & 1)) CK(cudaEventRecord(p->pev[pair][L.stream ? 1 : 0], st));
+    if (two_streams && (L.record & 2)) CK(cudaEventRecord(p->pev2[pair], st));
     return 0;
 }
 
@@ -662,7 +668,8 @@ static int64_t run_top_list(spk_plan* p, const DevCtx& c, const std::vector<Laun
     for (const Launch& L : Ls) {
         const int sid = L.stream < 3 ? L.stream : 0;
         cudaStream_t st = S[sid];
-        if (L.wait_other && sid < 2) CK(cudaStreamWaitEvent(st, E[1 - sid], 0));              // replicated lists (two-stream look-ahead)
+        if ((L.wait_other & 1) && sid < 2) CK(cudaStreamWaitEvent(st, E[1 - sid], 0));        // replicated lists (two-stream look-ahead)
+        if ((L.wait_other & 2) && sid < 2) CK(cudaStreamWaitEvent(st, p->pev2[0], 0));
         for (int q = 0; q < 3; ++q) if (((L.wait_mask >> q) & 1) && q != sid) CK(cudaStreamWaitEvent(st, E[q], 0));
         if (L.kind == K_BCAST) {
             if (!p->comm || !N) { set_err("multi-part plan without a communicator (spk_plan_comm_init)"); return -100; }
@@ -677,7 +684,8 @@ static int64_t run_top_list(spk_plan* p, const DevCtx& c, const std::vector<Laun
         } else {
             int64_t rc = run_factor_launch(p, c, L, false, 0, st);
             if (rc) return rc;
-            if (L.record) CK(cudaEventRecord(E[sid], st));
+            if (L.record & 1) CK(cudaEventRecord(E[sid], st));
+            if (L.record & 2) CK(cudaEventRecord(p->pev2[0], st));
             if (!p->profile && (L.kind == K_GEMM_B64 || L.kind == K_GEMM_T64)) p->gemm_flops += L.flops;   // profiling mode times phase 0 only
         }
         ++p->launches_factor;
