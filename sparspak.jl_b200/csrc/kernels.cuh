@@ -1312,17 +1312,23 @@ __device__ __forceinline__ void pf_diag_warp(const DevCtx& c, const PStep& ps, c
     __syncwarp();
 }
 // pb_diag: backward in-block solve.  LU: x := inv(U11) y.  LDL^T: x := inv(L11^T) y (y already divided by D).
+// Leading dimension of the staged diagonal block in the backward kernels.  The LDL^T in-block solve walks ROWS of
+// L11 (L[k,i], i < k): with the compact leading dimension w = 64 all 32 lanes hit one bank (a 32-way conflict on
+// every one of the w steps, ~3 us of the ~11 us a backward panel step costs); an odd leading dimension is
+// conflict-free for rows and columns alike.  LU (column access) and the inverted blocks (M_b, compact) keep w.
+template <bool LU>
+__device__ __forceinline__ int pb_tl(const DevCtx& c, int w) { return (LU || c.tinvf) ? w : (w | 1); }
 template <bool LU>
 __device__ __forceinline__ void pb_diag_warp(const DevCtx& c, const PStep& ps, const double* Ts, double* xs) {
-    const int lane = threadIdx.x & 31, w = ps.w;
+    const int lane = threadIdx.x & 31, w = ps.w, tl = pb_tl<LU>(c, w);
     if (g_solve_dbg & 1) return;
     if (c.tinvf) { inv_apply_warp<!LU>(Ts, xs, w); return; }          // Ts holds M_b
     if (w > 96) {
         for (int k = w - 1; k >= 0; --k) {
-            if (LU) { if (lane == 0) xs[k] /= Ts[k + k * w]; __syncwarp(); }
+            if (LU) { if (lane == 0) xs[k] /= Ts[k + k * tl]; __syncwarp(); }
             const double xk = xs[k];
-            if (LU) { for (int i = lane; i < k; i += 32) xs[i] -= xk * Ts[i + k * w]; }
-            else { for (int i = lane; i < k; i += 32) xs[i] -= xk * Ts[k + i * w]; }
+            if (LU) { for (int i = lane; i < k; i += 32) xs[i] -= xk * Ts[i + k * tl]; }
+            else { for (int i = lane; i < k; i += 32) xs[i] -= xk * Ts[k + i * tl]; }
             __syncwarp();
         }
         return;
@@ -1332,17 +1338,17 @@ __device__ __forceinline__ void pb_diag_warp(const DevCtx& c, const PStep& ps, c
         const int slot = k >> 5, src = k & 31;
         double xk = __shfl_sync(0xffffffffu, slot == 0 ? x0 : (slot == 1 ? x1 : x2), src);
         if (LU) {
-            xk /= Ts[k + k * w];
+            xk /= Ts[k + k * tl];
             if (lane == src) { if (slot == 0) x0 = xk; else if (slot == 1) x1 = xk; else x2 = xk; }
-            const double* __restrict__ col = Ts + k * w;                     // U[i,k], i < k
+            const double* __restrict__ col = Ts + k * tl;                    // U[i,k], i < k
             if (lane < k) x0 -= xk * col[lane];
             if (lane + 32 < k) x1 -= xk * col[lane + 32];
             if (lane + 64 < k) x2 -= xk * col[lane + 64];
         } else {
-            const double* __restrict__ rowk = Ts + k;                        // L[k,i] = Ts[k + i*w], i < k
-            if (lane < k) x0 -= xk * rowk[lane * w];
-            if (lane + 32 < k) x1 -= xk * rowk[(lane + 32) * w];
-            if (lane + 64 < k) x2 -= xk * rowk[(lane + 64) * w];
+            const double* __restrict__ rowk = Ts + k;                        // L[k,i] = Ts[k + i*tl], i < k (tl odd: conflict-free)
+            if (lane < k) x0 -= xk * rowk[lane * tl];
+            if (lane + 32 < k) x1 -= xk * rowk[(lane + 32) * tl];
+            if (lane + 64 < k) x2 -= xk * rowk[(lane + 64) * tl];
         }
     }
     if (lane < w) xs[lane] = x0; if (lane + 32 < w) xs[lane + 32] = x1; if (lane + 64 < w) xs[lane + 64] = x2;
@@ -1389,10 +1395,10 @@ __device__ __forceinline__ void pf_update_rows(const DevCtx& c, const PStep& ps,
 }
 // asynchronous staging of a w x w block (column-major, leading dimension w in shared memory): issued early,
 // waited for with stage_wait() once the block is needed
-__device__ __forceinline__ void stage_block_async(double* S, const double* __restrict__ G, int ld, int w) {
+__device__ __forceinline__ void stage_block_async(double* S, const double* __restrict__ G, int ld, int w, int lds) {
     for (int e = threadIdx.x; e < w * w; e += blockDim.x) {
         const int j = e / w, i = e - j * w;
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(S + e);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(S + i + j * lds);
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(G + i + (size_t)j * ld));
     }
     asm volatile("cp.async.commit_group;");
@@ -1507,13 +1513,13 @@ __device__ __forceinline__ void pb_apply64(const PStep& ps, const double* wf, in
     }
 }
 
-inline size_t pstep_smem_bytes(int w) { return ((size_t)w * w + (size_t)w + 8 * (size_t)w) * sizeof(double); }
+inline size_t pstep_smem_bytes(int w) { return ((size_t)(w | 1) * w + (size_t)w + 8 * (size_t)w) * sizeof(double); }
 // the fused step / front kernels with NR right-hand sides per block: T, NR x (padded) x, NR x next x or the
 // (NR x) 8 warps x w partial sums
 constexpr int SOLVE_NR = 8;                             // right-hand sides per block when nrhs > 1 (== warps per block)
 inline size_t pstep_smem_bytes_mr(int w, int nr, bool front) {
     const size_t xst = w <= 64 ? 64 : (size_t)w;      // stride of one right-hand side's x (zero-padded to 64: unconditional FMAs)
-    return ((size_t)w * w + (size_t)(2 * nr) * xst + (size_t)(8 * (front ? nr : 1)) * (w + 8) + 8) * sizeof(double);
+    return ((size_t)(w | 1) * w + (size_t)(2 * nr) * xst + (size_t)(8 * (front ? nr : 1)) * (w + 8) + 8) * sizeof(double);
 }
 
 template <bool LU>
@@ -1567,15 +1573,16 @@ __global__ void __launch_bounds__(128) k_pb_diag(DevCtx c, const int32_t* __rest
     const DFront F = c.fronts[ps.front];
     double* wf = c.w + (size_t)blockIdx.y * c.wlen + F.wofs;
     const double* pb = c.pb + (size_t)blockIdx.y * c.pblen + F.pbofs;
-    double* Ts = ssm; double* xs = ssm + ps.w * ps.w;
-    { int sld; const double* src = diag_src(c, ps, false, sld); block_g2s<128>(Ts, ps.w, src, sld, ps.w); }
+    const int tl = pb_tl<LU>(c, ps.w);
+    double* Ts = ssm; double* xs = ssm + (ps.w | 1) * ps.w;
+    { int sld; const double* src = diag_src(c, ps, false, sld); block_g2s<128>(Ts, tl, src, sld, ps.w); }
     const int nblk = (ps.R - ps.o - ps.w + SV_ROWS - 1) / SV_ROWS;
     __syncthreads();
     for (int k = threadIdx.x; k < ps.w; k += blockDim.x) {
         double s = 0.0;
         for (int q = 0; q < nblk; ++q) s += pb[(size_t)q * maxpw + k];
         const double y = wf[ps.o + k];
-        xs[k] = LU ? y - s : (ps.w <= 64 ? (y - s) / Ts[k + k * ps.w] : y / Ts[k + k * ps.w] - s);   // w <= 64: sums of U = D L^T entries
+        xs[k] = LU ? y - s : (ps.w <= 64 ? (y - s) / Ts[k + k * tl] : y / Ts[k + k * tl] - s);   // w <= 64: sums of U = D L^T entries
     }
     __syncthreads();
     if (threadIdx.x < 32) pb_diag_warp<LU>(c, ps, Ts, xs);
@@ -1607,7 +1614,7 @@ __global__ void __launch_bounds__(SV_ROWS) k_pf_step(DevCtx c, const int32_t* __
     PStep nx;
     if (next) {
         nx = c.psteps[pid + 1];
-        { int sld; const double* src = diag_src(c, nx, true, sld); stage_block_async(Ts, src, sld, nx.w); }
+        { int sld; const double* src = diag_src(c, nx, true, sld); stage_block_async(Ts, src, sld, nx.w, nx.w); }
     }
     const int e0 = ps.o + ps.w;
     const int r0 = e0 + lb * SV_ROWS, r1 = min(ps.R, e0 + (lb + 1) * SV_ROWS);
@@ -1674,10 +1681,11 @@ __global__ void __launch_bounds__(SV_ROWS, 1) k_pb_step(DevCtx c, const int32_t*
     double* pb0 = c.pb + (size_t)q0 * c.pblen + F.pbofs;
     const int e0 = ps.o + ps.w, below = ps.R - e0, w = ps.w;
     const int nblk = (below + SV_ROWS - 1) / SV_ROWS;
-    double* Ts = ssm; double* xs = ssm + w * w;                // xs: NR x w, then 8 x w partial sums
+    const int tl = pb_tl<LU>(c, w);
+    double* Ts = ssm; double* xs = ssm + (w | 1) * w;          // xs: NR x w, then 8 x w partial sums
     double* red = xs + NR * w;
     // every block stages the diagonal block while it forms its partial sums: the one that arrives last needs it at once
-    { int sld; const double* src = diag_src(c, ps, false, sld); stage_block_async(Ts, src, sld, w); }
+    { int sld; const double* src = diag_src(c, ps, false, sld); stage_block_async(Ts, src, sld, w, tl); }
     if (nblk > 0) {
         const int r0 = e0 + lb * SV_ROWS, r1 = min(ps.R, e0 + (lb + 1) * SV_ROWS);
         if (w <= 64) {
@@ -1715,7 +1723,7 @@ __global__ void __launch_bounds__(SV_ROWS, 1) k_pb_step(DevCtx c, const int32_t*
         double sum = 0.0;
         for (int b2 = 0; b2 < nblk; ++b2) sum += __ldcg(pb + (size_t)b2 * maxpw + k);
         const double y = wf0[(size_t)q * c.wlen + ps.o + k];
-        xs[e] = LU ? y - sum : (w <= 64 ? (y - sum) / Ts[k + k * w] : y / Ts[k + k * w] - sum);       // w <= 64: sums of U = D L^T entries
+        xs[e] = LU ? y - sum : (w <= 64 ? (y - sum) / Ts[k + k * tl] : y / Ts[k + k * tl] - sum);     // w <= 64: sums of U = D L^T entries
     }
     __syncthreads();
     if ((threadIdx.x >> 5) < nr) pb_diag_warp<LU>(c, ps, Ts, xs + (threadIdx.x >> 5) * w);              // one warp per right-hand side
@@ -1794,7 +1802,7 @@ __global__ void __launch_bounds__(64) k_diag_inverse(DevCtx c, const int32_t* __
 // for blocks that started before it — no co-residency assumption, no deadlock when the grid exceeds the machine.
 constexpr int FLOW_NT = 128;
 constexpr unsigned long long FLOW_EMPTY = 0xFFFFFFFFFFFFFFFFull;      // mailbox sentinel (cudaMemset 0xFF)
-inline size_t flow_smem_bytes(int maxw, int nr) { const size_t wp = maxw <= 64 ? 64 : (size_t)maxw; return (2 * (size_t)maxw * maxw + (size_t)nr * wp) * sizeof(double); }
+inline size_t flow_smem_bytes(int maxw, int nr) { const size_t wp = maxw <= 64 ? 64 : (size_t)maxw; return (2 * (size_t)(maxw | 1) * maxw + (size_t)nr * wp) * sizeof(double); }
 
 __device__ int g_flow_backoff = 64;                        // ns between polls of a mailbox word (SPK_FLOW_BACKOFF)
 __device__ __forceinline__ double flow_poll(const double* p) {
@@ -1868,7 +1876,7 @@ __global__ void __launch_bounds__(FLOW_NT) k_pf_flow(DevCtx c, const FlowTask* _
         for (int q = 0; q < NR; ++q) val[u][q] = (q < nr && row[u] < R1) ? wf0[(size_t)q * c.wlen + row[u]] : 0.0;
     }
     if (pivot) {                                            // diagonal blocks of my first two steps: staged while the updates arrive
-        for (int j = t.ja; j < min(t.jb, t.ja + 2); ++j) { const PStep ps = c.psteps[F.ps0 + j]; int sld; const double* src = diag_src(c, ps, true, sld); stage_block_async(Tb[(j - t.ja) & 1], src, sld, ps.w); }
+        for (int j = t.ja; j < min(t.jb, t.ja + 2); ++j) { const PStep ps = c.psteps[F.ps0 + j]; int sld; const double* src = diag_src(c, ps, true, sld); stage_block_async(Tb[(j - t.ja) & 1], src, sld, ps.w, ps.w); }
     }
     const int jend = pivot ? t.jb : F.nps;
     PStep ps = c.psteps[F.ps0];
@@ -1899,7 +1907,7 @@ __global__ void __launch_bounds__(FLOW_NT) k_pf_flow(DevCtx c, const FlowTask* _
                 flow_post(bx + (size_t)q * box_stride + ps.o + k, xs[q * wp + k]);
                 wf0[(size_t)q * c.wlen + ps.o + k] = xs[q * wp + k];
             }
-            if (j + 2 < t.jb) { const PStep p2 = c.psteps[F.ps0 + j + 2]; int sld; const double* src = diag_src(c, p2, true, sld); stage_block_async(Tb[(j - t.ja) & 1], src, sld, p2.w); }
+            if (j + 2 < t.jb) { const PStep p2 = c.psteps[F.ps0 + j + 2]; int sld; const double* src = diag_src(c, p2, true, sld); stage_block_async(Tb[(j - t.ja) & 1], src, sld, p2.w, p2.w); }
         } else {
             for (int e = tid; e < nr * wp; e += FLOW_NT) { const int q = e / wp, k = e - q * wp; xs[e] = k < w ? flow_poll(bx + (size_t)q * box_stride + ps.o + k) : 0.0; }
             __syncthreads();
@@ -1945,8 +1953,8 @@ __global__ void __launch_bounds__(FLOW_NT) k_pb_flow(DevCtx c, const FlowTask* _
     double* bx = box + (size_t)q0 * box_stride + F.F0;
     const double* __restrict__ Fm = c.F + F.fofs;
     const int ld = F.ld, wp = maxw <= 64 ? 64 : maxw;
-    double* Tb[2] = {ssm, ssm + (size_t)maxw * maxw};
-    double* xs = ssm + 2 * (size_t)maxw * maxw;
+    double* Tb[2] = {ssm, ssm + (size_t)(maxw | 1) * maxw};
+    double* xs = ssm + 2 * (size_t)(maxw | 1) * maxw;
     const PStep pa = c.psteps[F.ps0 + t.ja], pz = c.psteps[F.ps0 + t.jb - 1];
     const int R0 = pa.o, R1 = pz.o + pz.w;
     int row[RPT]; double val[RPT][NR];
@@ -1957,7 +1965,7 @@ __global__ void __launch_bounds__(FLOW_NT) k_pb_flow(DevCtx c, const FlowTask* _
 #pragma unroll
         for (int q = 0; q < NR; ++q) val[u][q] = (q < nr && row[u] < R1) ? wf0[(size_t)q * c.wlen + row[u]] : 0.0;
     }
-    for (int j = t.jb - 1; j >= max(t.ja, t.jb - 2); --j) { const PStep ps = c.psteps[F.ps0 + j]; int sld; const double* src = diag_src(c, ps, false, sld); stage_block_async(Tb[(t.jb - 1 - j) & 1], src, sld, ps.w); }
+    for (int j = t.jb - 1; j >= max(t.ja, t.jb - 2); --j) { const PStep ps = c.psteps[F.ps0 + j]; int sld; const double* src = diag_src(c, ps, false, sld); stage_block_async(Tb[(t.jb - 1 - j) & 1], src, sld, ps.w, pb_tl<LU>(c, ps.w)); }
     // the unknowns below the front's columns are known (gathered from the parent): their contribution first
     for (int c0 = F.W; c0 < F.R; c0 += wp) {
         const int wc = min(wp, F.R - c0);
@@ -1988,7 +1996,7 @@ __global__ void __launch_bounds__(FLOW_NT) k_pb_flow(DevCtx c, const FlowTask* _
             for (int u = 0; u < RPT; ++u) if (row[u] >= ps.o && row[u] < e0) {
                 const int k = row[u] - ps.o;
 #pragma unroll
-                for (int q = 0; q < NR; ++q) if (q < nr) xs[q * wp + k] = LU ? val[u][q] : val[u][q] / T[k + k * w];
+                for (int q = 0; q < NR; ++q) if (q < nr) xs[q * wp + k] = LU ? val[u][q] : val[u][q] / T[k + k * pb_tl<LU>(c, w)];
             }
             __syncthreads();
             for (int q = warp; q < nr; q += FLOW_NT / 32) pb_diag_warp<LU>(c, ps, T, xs + q * wp);
@@ -1999,7 +2007,7 @@ __global__ void __launch_bounds__(FLOW_NT) k_pb_flow(DevCtx c, const FlowTask* _
                 wf0[(size_t)q * c.wlen + ps.o + k] = xs[q * wp + k];
                 rhs[(size_t)(q0 + q) * ldrhs + ps.col0 + k] = xs[q * wp + k];
             }
-            if (j - 2 >= t.ja) { const PStep p2 = c.psteps[F.ps0 + j - 2]; int sld; const double* src = diag_src(c, p2, false, sld); stage_block_async(T, src, sld, p2.w); }
+            if (j - 2 >= t.ja) { const PStep p2 = c.psteps[F.ps0 + j - 2]; int sld; const double* src = diag_src(c, p2, false, sld); stage_block_async(T, src, sld, p2.w, pb_tl<LU>(c, p2.w)); }
         } else {
             for (int e = tid; e < nr * wp; e += FLOW_NT) { const int q = e / wp, k = e - q * wp; xs[e] = k < w ? flow_poll(bx + (size_t)q * box_stride + ps.o + k) : 0.0; }
             __syncthreads();
@@ -2083,8 +2091,9 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 8) k_pb_front(DevCtx c, co
     for (int j = F.nps - 1; j >= 0; --j) {
         const PStep ps = c.psteps[F.ps0 + j];
         const int w = ps.w, e0 = ps.o + w;
-        double* Ts = ssm; double* xs = ssm + w * w; double* red = xs + NR * w;        // red: NR x 8 warps x w (NR == 1: 8 x w)
-        { int sld; const double* src = diag_src(c, ps, false, sld); block_g2s<NT>(Ts, w, src, sld, w); }
+        const int tl = pb_tl<LU>(c, w);
+        double* Ts = ssm; double* xs = ssm + (w | 1) * w; double* red = xs + NR * w;  // red: NR x 8 warps x w (NR == 1: 8 x w)
+        { int sld; const double* src = diag_src(c, ps, false, sld); block_g2s<NT>(Ts, tl, src, sld, w); }
         if (NR == 1 || w > 64) {
             for (int q = 0; q < nr; ++q) { pb_partial<LU>(c, ps, wf0 + (size_t)q * c.wlen, e0, ps.R, red, xs + q * w); __syncthreads(); }
         } else {
@@ -2128,7 +2137,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 8) k_pb_front(DevCtx c, co
         for (int e = threadIdx.x; e < nr * w; e += blockDim.x) {
             const int q = e / w, k = e - q * w;
             const double y = wf0[(size_t)q * c.wlen + ps.o + k];
-            xs[e] = LU ? y - xs[e] : (w <= 64 ? (y - xs[e]) / Ts[k + k * w] : y / Ts[k + k * w] - xs[e]);   // w <= 64: sums of U = D L^T entries
+            xs[e] = LU ? y - xs[e] : (w <= 64 ? (y - xs[e]) / Ts[k + k * tl] : y / Ts[k + k * tl] - xs[e]);   // w <= 64: sums of U = D L^T entries
         }
         __syncthreads();
         for (int q = warp; q < nr; q += NT / 32) pb_diag_warp<LU>(c, ps, Ts, xs + q * w);

@@ -532,8 +532,12 @@ SPK_API int64_t spk_plan_inmatrix(spk_plan* p, int64_t nnz, const int64_t* dest,
         CK(cudaMemcpy(p->d_dest, ad.data(), nnz * sizeof(int64_t), cudaMemcpyHostToDevice));
         p->map_nnz = nnz;
     }
+    // the arena clear (HBM-bound, ms) runs on the second stream beside the upload of A's values (PCIe-bound)
+    CK(cudaEventRecord(p->ev3a, p->stream)); CK(cudaStreamWaitEvent(p->stream2, p->ev3a, 0));
+    CK(cudaMemsetAsync(p->d_F, 0, p->P.arena * sizeof(double), p->stream2));
+    CK(cudaEventRecord(p->ev3b, p->stream2));
     CK(cudaMemcpyAsync(p->d_nzval, nzval, nnz * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-    CK(cudaMemsetAsync(p->d_F, 0, p->P.arena * sizeof(double), p->stream));
+    CK(cudaStreamWaitEvent(p->stream, p->ev3b, 0));
     if (nnz > 0) k_scatter_values<<<cdiv(nnz, 256), 256, 0, p->stream>>>(nnz, p->d_dest, p->d_nzval, p->d_F);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(p->stream));

@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-( timeout 120 ./tools/ubench_dmma 9000 456 1; timeout 120 ./tools/ubench_dmma 9000 456 1 0 3; timeout 120 ./tools/ubench_dmma 4000 456 1; timeout 120 ./tools/ubench_dmma 9000 200 1;  timeout 120 ./tools/ubench_dmma 2000 456 1) > gpurun_out/d_ubench3.txt 2>&1
-cat gpurun_out/d_ubench3.txt
+( for k in 64 200 400; do timeout 120 ./tools/ubench_dmma 13000 $k 0 0 3 64; done; timeout 120 ./tools/ubench_dmma 4000 400 0 0 3 64; timeout 120 ./tools/ubench_dmma 13000 456 0 0 3 512;  timeout 120 ./tools/ubench_dmma 9000 456 1 0 3 ) > gpurun_out/d_ubench4.txt 2>&1
+cat gpurun_out/d_ubench4.txt

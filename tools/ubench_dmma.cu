@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
+#include <cstring>
 #include <vector>
 #include <cuda_runtime.h>
 #include "plan.hpp"
@@ -37,7 +38,8 @@ struct Variant { const char* name; GemmKernel fn; int threads; size_t smem; int 
 
 int main(int argc, char** argv) {
     int m = argc > 1 ? atoi(argv[1]) : 9000, k = argc > 2 ? atoi(argv[2]) : 456, lower = argc > 3 ? atoi(argv[3]) : 1;
-    int odd = argc > 4 ? atoi(argv[4]) : 0; int flags = argc > 5 ? atoi(argv[5]) : 1;                     // 1: odd panel offsets (exercises the shifted-origin path)
+    int odd = argc > 4 ? atoi(argv[4]) : 0; int flags = argc > 5 ? atoi(argv[5]) : 1;
+    int n = argc > 6 ? atoi(argv[6]) : m;                       // columns of C (default square; a narrow n = the in-block left-looking updates)                     // 1: odd panel offsets (exercises the shifted-origin path)
     int reps = 5;
     CK(cudaSetDevice(0));
     CK(gemm_dmma_init());
@@ -50,11 +52,11 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&F, nel * sizeof(double))); CK(cudaMalloc(&F0, nel * sizeof(double)));
     k_fill<<<1024, 256>>>(F0, nel, 12345u); CK(cudaDeviceSynchronize());
     GemmTask g{};
-    g.ld = ld; g.m = m; g.n = m; g.k = k;
+    g.ld = ld; g.m = m; g.n = n; g.k = k;
     const int e = o + k;
     g.a0 = (int64_t)e + (int64_t)o * ld; g.c0 = (int64_t)e + (int64_t)e * ld; g.b0 = (int64_t)o + (int64_t)e * ld;
     g.lower = (uint8_t)lower; g.roff = 0;
-    double flops = 2.0 * m * (double)m * k; if (lower) flops -= (double)m * m * k;
+    double flops = 2.0 * m * (double)n * k; if (lower) flops -= (double)n * n * k;
     GemmTask* d_task; CK(cudaMalloc(&d_task, sizeof(GemmTask))); CK(cudaMemcpy(d_task, &g, sizeof(g), cudaMemcpyHostToDevice));
     int32_t* d_ctr; CK(cudaMalloc(&d_ctr, 64 * sizeof(int32_t)));
     // samples
@@ -62,7 +64,7 @@ int main(int argc, char** argv) {
     std::vector<int> si(ns), sj(ns);
     unsigned s = 777;
     for (int i = 0; i < ns; ++i) {
-        s = s * 1664525u + 1013904223u; int a = (s >> 8) % m; s = s * 1664525u + 1013904223u; int b = (s >> 8) % m;
+        s = s * 1664525u + 1013904223u; int a = (s >> 8) % m; s = s * 1664525u + 1013904223u; int b = (s >> 8) % n;
         if (lower && a < b) std::swap(a, b);
         si[i] = a; sj[i] = b;
     }
@@ -85,21 +87,21 @@ int main(int argc, char** argv) {
     addv("64x64 tk16 s3", K_GEMM_T64, 4, 64);
 #define ADDK(name, TM, TN, WM, WN, MINB, TK, ST) vars.push_back({name, k_gemm_dmma<TM, TN, WM, WN, MINB, TK, ST>, WM * WN * 32, DmmaCfg<TM, TN, TK, ST>::SMEM, TM, TN})
     ADDK("64x64 tk8 s4", 64, 64, 2, 2, 4, 8, 4);
-    ADDK("64x64 tk8 s3", 64, 64, 2, 2, 4, 8, 3);
-    ADDK("64x64 tk8 s5", 64, 64, 2, 2, 4, 8, 5);
-    ADDK("64x64 tk4 s6", 64, 64, 2, 2, 4, 4, 6);
-    ADDK("64x64 tk4 s8", 64, 64, 2, 2, 4, 4, 8);
-    ADDK("64x64 tk8 s4 minb5", 64, 64, 2, 2, 5, 8, 4);
-    ADDK("64x32 2wp tk8 s4", 64, 32, 2, 1, 8, 8, 4);
+    ADDK("64x64 8wp(32x16) tk8 s4", 64, 64, 2, 4, 2, 8, 4);
+    ADDK("64x64 8wp(16x32) tk8 s4", 64, 64, 4, 2, 2, 8, 4);
+    ADDK("64x64 16wp(16x16) tk16 s3", 64, 64, 4, 4, 1, 16, 3);
     ADDK("32x64 2wp tk8 s4", 32, 64, 1, 2, 8, 8, 4);
-    ADDK("64x64 tk12? no", 64, 64, 2, 2, 4, 16, 2);
-    ADDK("128x64 tk8 s4", 128, 64, 4, 2, 2, 8, 4);
-    ADDK("128x64 tk8 s3", 128, 64, 4, 2, 2, 8, 3);
-    ADDK("128x64 tk8 s5", 128, 64, 4, 2, 2, 8, 5);
-    ADDK("128x32 4wp tk8 s4", 128, 32, 4, 1, 4, 8, 4);
+    ADDK("32x64 4wp(16x32) tk8 s4", 32, 64, 2, 2, 4, 8, 4);
+    ADDK("64x32 2wp tk8 s4", 64, 32, 2, 1, 8, 8, 4);
+    ADDK("64x32 4wp(32x16) tk8 s4", 64, 32, 2, 2, 4, 8, 4);
+    ADDK("32x32 4wp(16x16) tk8 s4", 32, 32, 2, 2, 4, 8, 4);
+    ADDK("32x32 1wp tk8 s4", 32, 32, 1, 1, 8, 8, 4);
     DevCtx c{}; c.F = F;
-    printf("m=n=%d k=%d lower=%d odd=%d ld=%d  flops=%.3e\n", m, k, lower, odd, ld, flops);
+    printf("m=%d n=%d k=%d lower=%d odd=%d ld=%d  flops=%.3e\n", m, n, k, lower, odd, ld, flops);
+    const char* only = getenv("UB_ONLY");                     // run one variant (by substring of its name): ncu captures
+    if (const char* r = getenv("UB_REPS")) reps = atoi(r);
     for (const Variant& v : vars) {
+        if (only && !strstr(v.name, only)) continue;
         std::vector<GemmTile> tiles;
         dmma_tiles(g, v.tm, v.tn, 0, &tiles, nullptr);
         GemmTile* d_tiles; CK(cudaMalloc(&d_tiles, tiles.size() * sizeof(GemmTile)));
