@@ -108,6 +108,9 @@ SCHED = [
     {"SPK_OB_STEPS": "2", "SPK_PS_WIDTH": "8", "SPK_LOOKAHEAD": "0"},
     {"SPK_OB_STEPS": "1", "SPK_PS_WIDTH": "16", "SPK_STORE_OVERLAP": "0"},
     {"SPK_OB_STEPS": "3", "SPK_PS_WIDTH": "24", "SPK_LL": "0"},
+    {"SPK_OB_STEPS": "2", "SPK_PS_WIDTH": "16", "SPK_SPLIT_REST": "1"},      # trailing update in two launches, strips wait for the first
+    {"SPK_OB_STEPS": "1", "SPK_PS_WIDTH": "8", "SPK_SPLIT_REST": "1", "SPK_DMMA_BIG": "1"},
+    {"SPK_OB_STEPS": "2", "SPK_PS_WIDTH": "24", "SPK_DMMA_BIG": "1", "SPK_DMMA_VARIANT64": "4"},   # 128 x 64 DMMA tiles where they fill the machine, old 64 x 64 pipeline
 ]
 
 

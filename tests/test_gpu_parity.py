@@ -263,6 +263,7 @@ VARIANTS = [
     {"SPK_SOLVE_INV": "0"},                               # in-block triangular solves everywhere (LU default: inverted diagonal blocks)
     {"SPK_SOLVE_INV": "3", "SPK_SOLVE_SMALL": "0"},       # inverted diagonal blocks everywhere (LDL^T default: none)
     {"SPK_SOLVE_INV": "1"}, {"SPK_SOLVE_INV": "2"},
+    {"SPK_DMMA_BIG": "1"}, {"SPK_DMMA_VARIANT64": "4"},   # 128 x 64 DMMA tiles / the 16-deep 3-stage pipeline of the 64 x 64 kernel
 ]
 
 
