@@ -1,0 +1,7 @@
+mkdir -p gpurun_out
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29524 bench.py --gpus 4 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/z_bench_n4.json 2> gpurun_out/z_bench_n4.err; echo "bench n4 rc=$?"
+python - <<'PY'
+import json
+d = json.load(open("gpurun_out/z_bench_n4.json"))
+print("N=4 TF %.2f" % (d["value"]/1e3), "factor_ms %.1f" % (d["factor_s"]*1e3), "solve_ms %.2f" % (d["solve_s"]*1e3), "e2e %.2f" % (d["e2e"]["value"]/1e3), "GiB %.1f" % (d["device_bytes"]/2**30), "resid %.1e" % d["residual"], d.get("phase_ms"), d.get("rank_phase_ms"), d["parallelism"])
+PY
