@@ -229,9 +229,12 @@ k_gemm_dmma(DevCtx c, const GemmTask* __restrict__ tasks, const GemmTile* __rest
 // prologues and epilogues better than two large ones, and short k-steps shorten the fill of a k = 456 tile.  Larger
 // block or warp tiles (128 x 128, 256 x 64, 64 x 32 per warp) were all slower.  K_GEMM_B64 = 128 x 64 tiles, 8 warps,
 // two blocks per SM (SPK_DMMA_BIG=1 selects it for launches with enough tiles; SPK_DMMA_VARIANT = its pipeline shape).
+// Launches with fewer than Plan::dmma_narrow 64 x 64 tiles (the in-block updates of the top fronts: n = 64, ~200 tiles on 148
+// SMs) run 64 x 32 tiles, 4 warps of 32 x 16: twice the blocks, 37 vs 43 us at 13000 x 64 x 400.
 using GemmKernel = void (*)(DevCtx, const GemmTask*, const GemmTile*, int, int32_t*, int);
 struct GemmVariant { GemmKernel fn; int threads; size_t smem; int blocks_per_sm; };
-inline GemmVariant gemm_dmma_variant(int kind, int variant, int variant64 = 8) {
+inline GemmVariant gemm_dmma_variant(int kind, int variant, int variant64 = 8, int tile_n = 64) {
+    if (kind == K_GEMM_T64 && tile_n == 32) return {k_gemm_dmma<64, 32, 2, 2, 4, 8, 4>, 128, DmmaCfg<64, 32, 8, 4>::SMEM, 4};   // under-filled launches
     if (kind == K_GEMM_T64) {
         if (variant64 == 4) return {k_gemm_dmma<64, 64, 2, 2, 4, 16, 3>, 128, DmmaCfg<64, 64, 16, 3>::SMEM, 4};
         return {k_gemm_dmma<64, 64, 2, 2, 4, 8, 4>, 128, DmmaCfg<64, 64, 8, 4>::SMEM, 4};
@@ -244,8 +247,8 @@ inline GemmVariant gemm_dmma_variant(int kind, int variant, int variant64 = 8) {
 inline cudaError_t gemm_dmma_init() {
     for (int kind : {(int)K_GEMM_B64, (int)K_GEMM_T64})
         for (int variant : {3, 4, 5, 6})
-            for (int variant64 : {4, 8}) {
-                GemmVariant v = gemm_dmma_variant(kind, variant, variant64);
+            for (int variant64 : {4, 8, 32}) {
+                GemmVariant v = gemm_dmma_variant(kind, variant, variant64 == 32 ? 8 : variant64, variant64 == 32 ? 32 : 64);
                 cudaError_t e = cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem);
                 if (e != cudaSuccess) return e;
             }

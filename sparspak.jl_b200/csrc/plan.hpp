@@ -102,6 +102,7 @@ struct Launch {
     // counter `ctr`, and `reserve`: leave that many block slots of the machine free (trailing updates that run beside
     // the latency-critical diagonal / panel chain of the next outer block)
     int64_t tile0; int32_t ntiles, ctr; int32_t reserve;
+    int32_t tile_m = 0, tile_n = 0;   // C tile of a DMMA launch (128 x 64, 64 x 64, or 64 x 32 for launches that do not fill the machine)
     uint8_t stream, wait_other, record, wait_mask;   // wait_other: wait for the other stream's last record first
     // distributed lists use three streams (0 panel, 1 trailing update, 2 communication) and wait_mask: bit s = wait
     // for the last record of stream s before launching
@@ -151,6 +152,7 @@ struct Plan {
     int ob_width = OB_WIDTH, ps_width = PS_WIDTH, ob_steps = OB_STEPS;
     bool lookahead = true;
     bool split_rest = false;                   // SPK_SPLIT_REST=1: the delayed trailing update of an outer block in two launches; the next strips wait for the first only (measured: no gain, the stream is never idle)
+    int32_t dmma_narrow = 296;                 // SPK_DMMA_NARROW: DMMA launches with fewer 64 x 64 tiles than this (2 per SM) run 64 x 32 tiles (0 = never)
     bool dmma_big = false;                     // SPK_DMMA_BIG=1: 128 x 64 DMMA tiles for launches with >= DMMA_FILL of them
     bool left_inblock = true;                  // SPK_LL=0: right-looking rank-w updates inside an outer block (LU always)
     int relax_abs = RELAX_ABS; double relax_frac = RELAX_FRAC;
@@ -449,13 +451,20 @@ struct GemmBatch {
             for (const Item& it : dmma) dmma_tiles(it.t, BIG_TM, 64, 0, nullptr, &big);
             const bool t64 = !P.dmma_big || big < DMMA_FILL;        // default: 64 x 64 tiles everywhere (measured faster); SPK_DMMA_BIG=1: 128-row tiles when they fill the machine
             const int tm = t64 ? 64 : BIG_TM;
+            // launches that would leave SM slots empty even with 64 x 64 tiles (the in-block updates of the top fronts, on the
+            // critical path of every panel step): 64 x 32 tiles, twice the blocks (tools/ubench_dmma.cu: 37 vs 43 us at
+            // 13000 x 64 x 400)
+            int64_t n64 = 0;
+            if (t64 && P.dmma_narrow > 0) for (const Item& it : dmma) dmma_tiles(it.t, 64, 64, 0, nullptr, &n64);
+            const int tn = (t64 && P.dmma_narrow > 0 && n64 < P.dmma_narrow) ? 32 : 64;
             fb.begin(t64 ? K_GEMM_T64 : K_GEMM_B64, (int32_t)P.gemmt.size(), lev, step, stream, wait_other, record);
             fb.cur.tile0 = (int64_t)P.tiles.size(); fb.cur.ctr = P.nctr++; fb.cur.reserve = reserve;
+            fb.cur.tile_m = tm; fb.cur.tile_n = tn;
             int32_t rel = 0;
             for (const Item& it : dmma) {
                 P.gemmt.push_back(it.t);
                 const size_t n0 = P.tiles.size();
-                dmma_tiles(it.t, tm, 64, rel++, &P.tiles, nullptr);
+                dmma_tiles(it.t, tm, tn, rel++, &P.tiles, nullptr);
                 fb.add((int32_t)(P.tiles.size() - n0), it.flops, std::max(it.t.m, it.t.n));
             }
             fb.cur.ntiles = (int32_t)(P.tiles.size() - (size_t)fb.cur.tile0);
@@ -506,6 +515,7 @@ inline void plan_env_overrides(Plan& P) {        // test / tuning knobs
     if (const char* e = getenv("SPK_DIST_TOP")) P.dist_top_env = e[0] != '0';
     if (const char* e = getenv("SPK_SPLIT_REST")) P.split_rest = e[0] != '0';
     if (const char* e = getenv("SPK_DMMA_BIG")) P.dmma_big = e[0] != '0';
+    if (const char* e = getenv("SPK_DMMA_NARROW")) P.dmma_narrow = std::max(0, atoi(e));
 }
 
 // Launch lists for the fronts selected by `sel` (all of them, one part's subtrees, or the top set).

@@ -632,7 +632,7 @@ static int64_t run_factor_launch(spk_plan* p, const DevCtx& c, const Launch& L, 
         break;
     case K_GEMM_B64:
     case K_GEMM_T64: {
-        GemmVariant v = gemm_dmma_variant(L.kind, p->dmma_variant, p->dmma_variant64);
+        GemmVariant v = gemm_dmma_variant(L.kind, p->dmma_variant, p->dmma_variant64, L.tile_n);
         int cap = v.blocks_per_sm * p->num_sms - (L.reserve > 0 ? L.reserve * v.blocks_per_sm / 2 : 0);
         if (cap < p->num_sms) cap = p->num_sms;
         const int grid = p->dmma_persist ? std::min<int>(L.ntiles, cap) : L.ntiles;      // SPK_DMMA_PERSIST=0: one block per tile

@@ -216,7 +216,7 @@ static int64_t run_factor_list(Sim* s, const std::vector<Launch>& Ls) {
         case K_PANEL: for (int t = 0; t < L.count; ++t) panel(*s, P.psteps[P.pslist[L.first + t]]); break;
         case K_GEMM: for (int t = 0; t < L.count; ++t) gemm(*s, P.gemmt[L.first + t]); break;
         case K_GEMM_B64: case K_GEMM_T64:                       // tile by tile, as the persistent kernel walks its list
-            for (int64_t q = L.tile0; q < L.tile0 + L.ntiles; ++q) gemm_tile(*s, P.gemmt[L.first + P.tiles[q].task], P.tiles[q], L.kind == K_GEMM_T64 ? 64 : BIG_TM, 64);
+            for (int64_t q = L.tile0; q < L.tile0 + L.ntiles; ++q) gemm_tile(*s, P.gemmt[L.first + P.tiles[q].task], P.tiles[q], L.tile_m, L.tile_n);
             break;
         case K_FRONT_SMALL:                                      // fused small fronts: extend-add, then step by step with right-looking updates
             for (int t = 0; t < L.count; ++t) {
