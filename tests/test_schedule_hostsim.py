@@ -67,3 +67,32 @@ def test_hostsim_large_front_solve_path(spd, monkeypatch):
     rhs = np.ascontiguousarray(bb[b.order.rperm - 1])
     x = sim.solve(rhs)[b.order.rinvp - 1]
     assert residual(A, x, bb) < 1e-13
+
+
+SCHED_KNOBS = [
+    {"SPK_OB_STEPS": "2", "SPK_PS_WIDTH": "8"},                                   # many outer blocks: strip / rest / delayed updates
+    {"SPK_OB_STEPS": "2", "SPK_PS_WIDTH": "8", "SPK_SPLIT_REST": "1"},            # delayed update in two launches (early part first)
+    {"SPK_OB_STEPS": "1", "SPK_PS_WIDTH": "16", "SPK_SPLIT_REST": "1", "SPK_DMMA_NARROW": "0"},
+    {"SPK_OB_STEPS": "3", "SPK_PS_WIDTH": "8", "SPK_DMMA_BIG": "1", "SPK_DMMA_NARROW": "100000"},   # 128-row and 64 x 32 tile lists
+]
+
+
+@pytest.mark.parametrize("spd", [False, True])
+@pytest.mark.parametrize("env", SCHED_KNOBS, ids=["+".join(f"{k[4:]}={v}" for k, v in e.items()) for e in SCHED_KNOBS])
+def test_hostsim_schedule_knobs(spd, env, monkeypatch):
+    """The launch lists built under the schedule / tile-shape knobs (split delayed update, 128 x 64 / 64 x 64 / 64 x 32
+    DMMA tile lists) are complete and correctly ordered: executed serially on the host they reproduce the oracle."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    g = 10
+    A = M.convdiff3d(g) if not spd else M.laplacian3d(g)
+    s = prepare(A, spd, spk.nd_grid_order(g, g, g))
+    b = s.slvr
+    lo, uo, po, fo = oracle_factor(b)
+    ls, us, ps, fs = HostSim(b).factor()
+    assert fs == fo == 0
+    nl = int(b.xlnz[b.n]) - 1
+    assert rel_err(ls, lo[:nl], spd_mask(b)[:nl]) < 1e-12
+    if not spd:
+        assert np.array_equal(ps, po)
+        assert rel_err(us, uo) < 1e-12
