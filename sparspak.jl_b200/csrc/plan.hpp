@@ -25,9 +25,25 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <memory>
+#include <utility>
+#include <thread>
+#include <atomic>
 #include <algorithm>
 
 namespace spk {
+
+// std::vector allocator whose default construction leaves trivially constructible elements uninitialised
+// (resize() without the zero fill: the position maps are 0.5 GB at 96^3 and every entry is written right after)
+template <class T>
+struct NoInitAlloc : std::allocator<T> {
+    template <class U> struct rebind { using other = NoInitAlloc<U>; };
+    NoInitAlloc() = default;
+    template <class U> NoInitAlloc(const NoInitAlloc<U>&) {}
+    template <class U, class... A> void construct(U* p, A&&... a) {
+        if constexpr (sizeof...(A) == 0) ::new ((void*)p) U; else ::new ((void*)p) U(std::forward<A>(a)...);
+    }
+};
 
 struct Chunk {            // one reference supernode
     int64_t fj;           // first column (0-based)
@@ -141,7 +157,7 @@ struct Plan {
     std::vector<int32_t> subw;                // pivot sub-block widths of all panel steps
     std::vector<int32_t> childlist;
     std::vector<int32_t> rel;                 // relative indices, all fronts
-    std::vector<int32_t> pos;                 // per-chunk stored-row -> front-row maps
+    std::vector<int32_t, NoInitAlloc<int32_t>> pos;   // per-chunk stored-row -> front-row maps (every entry written by analyze(): not zero-filled first)
     std::vector<int32_t> col2chunk;
     int64_t arena = 0, wlen = 0, pblen = 0, tinv_len = 0;
     bool solve_on_fronts = true;              // solve sweeps read the frontal matrices (panel steps) instead of lnz/unz (chunks)
@@ -238,7 +254,7 @@ inline bool analyze(Plan& P, int64_t n, int64_t nsuper, const int64_t* xsuper, c
         c.posofs = posofs; posofs += c.jlen;
         P.maxnj = std::max(P.maxnj, c.nj);
     }
-    P.pos.assign(posofs, 0);
+    P.pos.resize(posofs);
     P.col2chunk.assign(n, 0);
     for (int64_t s = 0; s < nsuper; ++s) for (int32_t j = 0; j < P.chunks[s].nj; ++j) P.col2chunk[P.chunks[s].fj + j] = (int32_t)s;
 
@@ -272,28 +288,55 @@ inline bool analyze(Plan& P, int64_t n, int64_t nsuper, const int64_t* xsuper, c
     }
     const int32_t nf = (int32_t)P.fronts.size();
     // per-chunk position maps: own columns map to o..o+nj-1; below rows are located in the front's
-    // row list = [columns of the chain] ++ [below rows of the last chunk]
-    for (int32_t f = 0; f < nf; ++f) {
-        const Front& F = P.fronts[f];
-        const Chunk& last = P.chunks[F.c0 + F.nch - 1];
-        const int64_t* below = lindx + (xlindx[F.c0 + F.nch - 1] - 1) + last.nj;   // m entries, 1-based, sorted
-        for (int32_t t = 0; t < F.nch; ++t) {
-            const Chunk& c = P.chunks[F.c0 + t];
-            int32_t* pos = P.pos.data() + c.posofs;
-            const int64_t* rows = lindx + (xlindx[F.c0 + t] - 1);
-            int32_t q = 0;
-            for (int32_t i = 0; i < c.jlen; ++i) {
-                int64_t r = rows[i] - 1;            // 0-based global row
-                if (r < F.F0 + F.W) {               // a column of the chain
-                    if (r < c.fj) { P.error = "row above supernode"; return false; }
-                    pos[i] = (int32_t)(r - F.F0);
-                } else {
-                    while (q < F.m && below[q] - 1 < r) ++q;
-                    if (q >= F.m || below[q] - 1 != r) { P.error = "chain rows do not nest"; return false; }
-                    pos[i] = F.W + q;
+    // row list = [columns of the chain] ++ [below rows of the last chunk].  One entry per stored row of every chunk
+    // (96^3: 1.3e8): fronts are independent and write disjoint ranges, so the loop is dealt to host threads in
+    // contiguous front ranges of about equal size (the result does not depend on the thread count).
+    {
+        std::atomic<int> bad{0};                        // 1 = row above supernode, 2 = chain rows do not nest
+        auto work = [&](int32_t f0, int32_t f1) {
+            for (int32_t f = f0; f < f1 && !bad.load(std::memory_order_relaxed); ++f) {
+                const Front& F = P.fronts[f];
+                const Chunk& last = P.chunks[F.c0 + F.nch - 1];
+                const int64_t* below = lindx + (xlindx[F.c0 + F.nch - 1] - 1) + last.nj;   // m entries, 1-based, sorted
+                for (int32_t t = 0; t < F.nch; ++t) {
+                    const Chunk& c = P.chunks[F.c0 + t];
+                    int32_t* pos = P.pos.data() + c.posofs;
+                    const int64_t* rows = lindx + (xlindx[F.c0 + t] - 1);
+                    int32_t q = 0;
+                    for (int32_t i = 0; i < c.jlen; ++i) {
+                        int64_t r = rows[i] - 1;            // 0-based global row
+                        if (r < F.F0 + F.W) {               // a column of the chain
+                            if (r < c.fj) { bad.store(1); return; }
+                            pos[i] = (int32_t)(r - F.F0);
+                        } else {
+                            while (q < F.m && below[q] - 1 < r) ++q;
+                            if (q >= F.m || below[q] - 1 != r) { bad.store(2); return; }
+                            pos[i] = F.W + q;
+                        }
+                    }
                 }
             }
+        };
+        int nth = 1;
+        if (posofs > (int64_t)1 << 22) {
+            nth = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+            if (const char* e = getenv("SPK_HOST_THREADS")) nth = std::max(1, atoi(e));
         }
+        if (nth <= 1) work(0, nf);
+        else {
+            std::vector<std::thread> th;
+            int32_t f0 = 0;
+            for (int t = 0; t < nth && f0 < nf; ++t) {
+                const int64_t target = posofs / nth * (t + 1);
+                int32_t f1 = f0;
+                while (f1 < nf && (t == nth - 1 || P.chunks[P.fronts[f1].c0].posofs < target)) ++f1;
+                if (f1 > f0) th.emplace_back(work, f0, f1);
+                f0 = f1;
+            }
+            for (auto& x : th) x.join();
+        }
+        if (bad.load() == 1) { P.error = "row above supernode"; return false; }
+        if (bad.load() == 2) { P.error = "chain rows do not nest"; return false; }
     }
     // front tree, relative indices, arena
     int64_t relofs = 0, fofs = 0, wofs = 0;

@@ -27,8 +27,8 @@ static void set_err(const std::string& s) { g_err = s; }
         }                                                                                     \
     } while (0)
 
-template <class T>
-static cudaError_t upload(T** d, const std::vector<T>& h) {
+template <class T, class A>
+static cudaError_t upload(T** d, const std::vector<T, A>& h) {
     *d = nullptr;
     size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
     cudaError_t e = cudaMalloc((void**)d, bytes);
