@@ -330,7 +330,7 @@ inline bool analyze(Plan& P, int64_t n, int64_t nsuper, const int64_t* xsuper, c
                 const int64_t target = posofs / nth * (t + 1);
                 int32_t f1 = f0;
                 while (f1 < nf && (t == nth - 1 || P.chunks[P.fronts[f1].c0].posofs < target)) ++f1;
-                if (f1 > f0) th.emplace_back(work, f0, f1);
+                if (f1 > f0) { try { th.emplace_back(work, f0, f1); } catch (...) { work(f0, f1); } }   // no thread to be had: this range inline
                 f0 = f1;
             }
             for (auto& x : th) x.join();
