@@ -190,6 +190,8 @@ API int64_t sim_stat(void* h, int what) {
     case 11: return (int64_t)P.psteps.size();
     case 12: { int64_t k = 0; for (auto& f : P.fronts) k += (int64_t)f.m * f.m; return k; }
     case 13: return P.dist_top ? 1 : 0;
+    case 20: { uint64_t h = 1469598103934665603ull; for (int32_t v : P.pos) { h ^= (uint32_t)v; h *= 1099511628211ull; } return (int64_t)(h >> 1); }   // position-map fingerprint
+    case 21: return (int64_t)P.pos.size();
     case 14: { int64_t k = 0; for (int32_t o : P.owner) if (o == -1) ++k; return k; }
     default: return 0; }
 }

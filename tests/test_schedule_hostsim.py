@@ -96,3 +96,18 @@ def test_hostsim_schedule_knobs(spd, env, monkeypatch):
     if not spd:
         assert np.array_equal(ps, po)
         assert rel_err(us, uo) < 1e-12
+
+
+def test_position_maps_do_not_depend_on_host_threads(monkeypatch):
+    """analyze() builds the per-chunk position maps with host threads over disjoint front ranges once they are
+    large (> 4 Mi entries): the result must be the serial one for every thread count."""
+    g = 48
+    A = M.laplacian3d(g)
+    s = prepare(A, True, spk.nd_grid_order(g, g, g))
+    fp = set()
+    for nth in ("1", "2", "7", "33"):
+        monkeypatch.setenv("SPK_HOST_THREADS", nth)
+        sim = HostSim(s.slvr, alloc=False)
+        assert sim.stat(21) > (1 << 22)              # large enough for the threaded path
+        fp.add(sim.stat(20))
+    assert len(fp) == 1
